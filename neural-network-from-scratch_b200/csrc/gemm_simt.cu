@@ -1,0 +1,125 @@
+// fp32 SIMT GEMM (FFMA) -- the fp32-accurate contraction path behind Backend.matmul / dot
+// (backends/backend.py:133-140; numpy_backend.py:134-137 = np.matmul / np.dot). It exists to honour the
+// north star's 1e-5-relative fp32 contract, which a 10-bit-mantissa tensor-core path cannot; the bf16
+// tcgen05 path (gemm_tc.cu) is the throughput path.
+//   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b] (+ bias[n])      row-major, arbitrary M/N/K/ld
+// 128x128x16 block tile, 256 threads, 8x8 register tile per thread, double-buffered smem.
+#include "common.cuh"
+
+#define BM 128
+#define BN 128
+#define BK 16
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+k_sgemm(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t lda, int64_t sA, const float* __restrict__ B,
+        int64_t ldb, int64_t sB, float beta, float* __restrict__ C, int64_t ldc, int64_t sC, const float* __restrict__ bias) {
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  int bz = blockIdx.z;
+  A += (int64_t)bz * sA;
+  B += (int64_t)bz * sB;
+  C += (int64_t)bz * sC;
+  int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int tid = threadIdx.x;
+  int tx = tid % 16, ty = tid / 16;  // 16 x 16 thread grid, each 8x8 outputs (strided by 16 for conflict-free smem reads)
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  // each thread loads 8 A elements and 8 B elements per K-tile
+  float ra[8], rb[8];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      int e = tid + l * 256;  // 0 .. 2047
+      // A tile element (m, k): choose the mapping whose fastest index follows memory
+      int am, ak;
+      if (!TA) { ak = e % BK; am = e / BK; } else { am = e % BM; ak = e / BM; }
+      int gm = m0 + am, gk = k0 + ak;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      ra[l] = v;
+      int bn, bk;
+      if (!TB) { bn = e % BN; bk = e / BN; } else { bk = e % BK; bn = e / BK; }
+      int gn = n0 + bn;
+      gk = k0 + bk;
+      v = 0.f;
+      if (gn < N && gk < K) v = TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn];
+      rb[l] = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      int e = tid + l * 256;
+      int am, ak;
+      if (!TA) { ak = e % BK; am = e / BK; } else { am = e % BM; ak = e / BM; }
+      As[buf][ak][am] = ra[l];
+      int bn, bk;
+      if (!TB) { bn = e % BN; bk = e / BN; } else { bk = e % BK; bn = e / BK; }
+      Bs[buf][bk][bn] = rb[l];
+    }
+  };
+
+  int nk = (K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    int buf = kt & 1;
+    if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[buf][kk][ty + i * 16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[buf][kk][tx + j * 16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gm = m0 + ty + i * 16;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int gn = n0 + tx + j * 16;
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      if (bias) v += bias[gn];
+      float* c = C + (int64_t)gm * ldc + gn;
+      if (beta != 0.f) v += beta * (*c);
+      *c = v;
+    }
+  }
+}
+
+NFB_API int nfb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda, int64_t strideA,
+                         const float* B, int64_t ldb, int64_t strideB, float beta, float* C, int64_t ldc, int64_t strideC,
+                         int batch, const float* bias) {
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  if (batch > 65535) return NFB_FAIL("nfb_gemm_f32: batch %d > 65535", batch);
+  dim3 grid((unsigned)nfb_cdiv(N, BN), (unsigned)nfb_cdiv(M, BM), (unsigned)batch);
+  if (grid.y > 65535) return NFB_FAIL("nfb_gemm_f32: M too large");
+  cudaStream_t s = nfb_cur_stream();
+#define GO(TA, TB) k_sgemm<TA, TB><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, bias)
+  if (!transA && !transB) GO(false, false);
+  else if (!transA && transB) GO(false, true);
+  else if (transA && !transB) GO(true, false);
+  else GO(true, true);
+#undef GO
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

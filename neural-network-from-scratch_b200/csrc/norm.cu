@@ -1,0 +1,337 @@
+// LayerNorm / RMSNorm forward + backward, one warp per row with the row held in registers
+// (two-pass statistics like np.mean / np.var, warp-shuffle reductions, 128-bit accesses).
+// Reference math: nn/normalization.py:101-200 (LayerNorm) and :269-341 (RMSNorm);
+// models/language/gpt2.py:98-116 (the GPT-2 local RMSNorm). HBM-bound: fwd 8 B/elem, bwd 12 B/elem
+// in fp32.
+//   x / residual stream : fp32 or bf16 (TX)       y and dy : fp32 or bf16 (TY)      dx : TX
+// Optional fusions: `res` (forward: s = x + res is normalised and written back to `sum_out`) and
+// `dres` (backward: dx += dres, the gradient arriving over the skip connection).
+#include "common.cuh"
+
+#define WARPS_PER_BLOCK 4
+
+template <int VPL, typename TX, typename TY, bool RMS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_norm_fwd(const TX* __restrict__ x, const TX* __restrict__ res, TX* __restrict__ sum_out, const float* __restrict__ gamma,
+           const float* __restrict__ beta, TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+           int64_t rows, int cols, float eps) {
+  int lane = threadIdx.x & 31;
+  int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  float inv_n = 1.f / (float)cols;
+  for (int64_t row = warp_global; row < rows; row += nwarps) {
+    const TX* xr = x + row * cols;
+    f4 v[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int c = k * 128 + lane * 4;
+      if (c < cols) {
+        v[k] = ld4<TX>(xr + c);
+        if (res) {
+          f4 r = ld4<TX>(res + row * cols + c);
+          v[k].x += r.x; v[k].y += r.y; v[k].z += r.z; v[k].w += r.w;
+          st4<TX>(sum_out + row * cols + c, v[k]);
+        }
+      } else v[k] = {0.f, 0.f, 0.f, 0.f};
+    }
+    float mean = 0.f;
+    if (!RMS) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      mean = warp_sum(s) * inv_n;
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int c = k * 128 + lane * 4;
+      if (c < cols) {
+        float a = v[k].x - mean, b = v[k].y - mean, cc = v[k].z - mean, d = v[k].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    float var = warp_sum(q) * inv_n;
+    float rstd = 1.f / sqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int c = k * 128 + lane * 4;
+      if (c < cols) {
+        float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 b = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f4 o;
+        o.x = g.x * ((v[k].x - mean) * rstd) + b.x;
+        o.y = g.y * ((v[k].y - mean) * rstd) + b.y;
+        o.z = g.z * ((v[k].z - mean) * rstd) + b.z;
+        o.w = g.w * ((v[k].w - mean) * rstd) + b.w;
+        st4<TY>(y + row * cols + c, o);
+      }
+    }
+  }
+}
+
+// backward: each warp walks rows with a grid stride; its lanes own fixed columns, so dgamma/dbeta
+// partials accumulate in registers and are written once per block to `partial`
+// ([gridDim.x][2][cols]); k_norm_param_reduce then sums the blocks in a fixed order (deterministic).
+template <int VPL, typename TX, typename TY, bool RMS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
+           const float* __restrict__ rstd_in, const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
+           int64_t rows, int cols) {
+  __shared__ float sh[WARPS_PER_BLOCK][2][VPL * 128];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + w;
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  float inv_n = 1.f / (float)cols;
+  f4 dg[VPL], db[VPL];
+  float4 gm[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    dg[k] = {0.f, 0.f, 0.f, 0.f};
+    db[k] = {0.f, 0.f, 0.f, 0.f};
+    int c = k * 128 + lane * 4;
+    gm[k] = (gamma && c < cols) ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  for (int64_t row = warp_global; row < rows; row += nwarps) {
+    float mean = (RMS || !mean_in) ? 0.f : mean_in[row];
+    float rstd = rstd_in[row];
+    f4 xh[VPL], gh[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int c = k * 128 + lane * 4;
+      if (c < cols) {
+        f4 xv = ld4<TX>(x + row * cols + c);
+        f4 g = ld4<TY>(dy + row * cols + c);
+        xh[k] = {(xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd};
+        dg[k].x += g.x * xh[k].x; dg[k].y += g.y * xh[k].y; dg[k].z += g.z * xh[k].z; dg[k].w += g.w * xh[k].w;
+        db[k].x += g.x; db[k].y += g.y; db[k].z += g.z; db[k].w += g.w;
+        gh[k] = {g.x * gm[k].x, g.y * gm[k].y, g.z * gm[k].z, g.w * gm[k].w};
+        s1 += (gh[k].x + gh[k].y) + (gh[k].z + gh[k].w);
+        s2 += (gh[k].x * xh[k].x + gh[k].y * xh[k].y) + (gh[k].z * xh[k].z + gh[k].w * xh[k].w);
+      } else {
+        xh[k] = {0.f, 0.f, 0.f, 0.f};
+        gh[k] = {0.f, 0.f, 0.f, 0.f};
+      }
+    }
+    float m1 = RMS ? 0.f : warp_sum(s1) * inv_n;
+    float m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      int c = k * 128 + lane * 4;
+      if (c < cols) {
+        f4 o;
+        o.x = rstd * (gh[k].x - m1 - xh[k].x * m2);
+        o.y = rstd * (gh[k].y - m1 - xh[k].y * m2);
+        o.z = rstd * (gh[k].z - m1 - xh[k].z * m2);
+        o.w = rstd * (gh[k].w - m1 - xh[k].w * m2);
+        if (dres) {
+          f4 r = ld4<TX>(dres + row * cols + c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        st4<TX>(dx + row * cols + c, o);
+      }
+    }
+  }
+  if (!partial) return;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    int c = k * 128 + lane * 4;
+    *reinterpret_cast<float4*>(&sh[w][0][c]) = make_float4(dg[k].x, dg[k].y, dg[k].z, dg[k].w);
+    *reinterpret_cast<float4*>(&sh[w][1][c]) = make_float4(db[k].x, db[k].y, db[k].z, db[k].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
+    int which = i / cols, c = i % cols;
+    float a = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < WARPS_PER_BLOCK; ++ww) a += sh[ww][which][c];
+    partial[((int64_t)blockIdx.x * 2 + which) * cols + c] = a;
+  }
+}
+
+__global__ void k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * cols) return;
+  int which = i / cols, c = i % cols;
+  float* dst = which == 0 ? dgamma : dbeta;
+  if (!dst) return;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) a += partial[((int64_t)b * 2 + which) * cols + c];
+  dst[c] = accumulate ? dst[c] + a : a;
+}
+
+// generic fallback (cols not a multiple of 4 or > 1024): one block per row, three passes.
+template <bool RMS>
+__global__ void k_norm_fwd_generic(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int cols, float eps) {
+  __shared__ float red[32];
+  int64_t row = blockIdx.x;
+  const float* xr = x + row * cols;
+  float mean = 0.f;
+  if (!RMS) {
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s += xr[c];
+    mean = block_sum(s, red) / (float)cols;
+  }
+  float q = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) { float d = xr[c] - mean; q += d * d; }
+  float var = block_sum(q, red) / (float)cols;
+  float rstd = 1.f / sqrtf(var + eps);
+  if (threadIdx.x == 0) { if (mean_out) mean_out[row] = mean; rstd_out[row] = rstd; }
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float h = (xr[c] - mean) * rstd;
+    y[row * cols + c] = (gamma ? gamma[c] : 1.f) * h + (beta ? beta[c] : 0.f);
+  }
+}
+template <bool RMS>
+__global__ void k_norm_bwd_generic(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dx, int cols) {
+  __shared__ float red[32];
+  int64_t row = blockIdx.x;
+  float mean = (RMS || !mean_in) ? 0.f : mean_in[row], rstd = rstd_in[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float gh = dy[row * cols + c] * (gamma ? gamma[c] : 1.f);
+    float xh = (x[row * cols + c] - mean) * rstd;
+    s1 += gh;
+    s2 += gh * xh;
+  }
+  float m1 = RMS ? 0.f : block_sum(s1, red) / (float)cols;
+  float m2 = block_sum(s2, red) / (float)cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float gh = dy[row * cols + c] * (gamma ? gamma[c] : 1.f);
+    float xh = (x[row * cols + c] - mean) * rstd;
+    dx[row * cols + c] = rstd * (gh - m1 - xh * m2);
+  }
+}
+// dgamma[c] = sum_rows dy*xhat ; dbeta[c] = sum_rows dy   (generic path)
+template <bool RMS>
+__global__ void k_norm_param_generic(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
+                                     const float* __restrict__ rstd_in, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int64_t rows, int cols, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f, b = 0.f;
+  for (int64_t r = 0; r < rows; ++r) {
+    float mean = (RMS || !mean_in) ? 0.f : mean_in[r];
+    float g = dy[r * cols + c];
+    a += g * ((x[r * cols + c] - mean) * rstd_in[r]);
+    b += g;
+  }
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + a : a;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + b : b;
+}
+
+static int pick_vpl(int cols) {
+  if (cols % 4 != 0 || cols > 1024) return 0;
+  int v = (cols + 127) / 128;
+  if (v <= 1) return 1;
+  if (v <= 2) return 2;
+  if (v <= 4) return 4;
+  if (v <= 6) return 6;
+  return 8;
+}
+
+template <typename TX, typename TY, bool RMS>
+static int norm_fwd_t(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y,
+                      float* mean, float* rstd, int64_t rows, int cols, float eps) {
+  int vpl = pick_vpl(cols);
+  cudaStream_t s = nfb_cur_stream();
+  int grid = nfb_grid_for(rows, WARPS_PER_BLOCK, 8);
+#define LF(V) k_norm_fwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TX*)x, (const TX*)res, (TX*)sum_out, gamma, beta, (TY*)y, mean, rstd, rows, cols, eps)
+  switch (vpl) {
+    case 1: LF(1); break;
+    case 2: LF(2); break;
+    case 4: LF(4); break;
+    case 6: LF(6); break;
+    case 8: LF(8); break;
+    default: return NFB_FAIL("norm fwd: cols=%d needs the generic path", cols);
+  }
+#undef LF
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename TX, typename TY, bool RMS>
+static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
+                      void* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int cols) {
+  int vpl = pick_vpl(cols);
+  cudaStream_t s = nfb_cur_stream();
+  int grid = nfb_grid_for(rows, WARPS_PER_BLOCK * 4, 2);
+  float* partial = nullptr;
+  bool need_params = dgamma || dbeta;
+  if (need_params && nfb_malloc(sizeof(float) * 2 * (size_t)cols * grid, (void**)&partial)) return -1;
+#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols)
+  switch (vpl) {
+    case 1: LB(1); break;
+    case 2: LB(2); break;
+    case 4: LB(4); break;
+    case 6: LB(6); break;
+    case 8: LB(8); break;
+    default: if (partial) nfb_free(partial); return NFB_FAIL("norm bwd: cols=%d needs the generic path", cols);
+  }
+#undef LB
+  nfb_count_launch();
+  if (need_params) {
+    k_norm_param_reduce<<<(2 * cols + 255) / 256, 256, 0, s>>>(partial, grid, cols, dgamma, dbeta, accumulate);
+    nfb_free(partial);
+  }
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// kind: 0 = LayerNorm, 1 = RMSNorm. xdt / ydt: NFB_F32 or NFB_BF16.
+NFB_API int nfb_norm_fwd(int kind, int xdt, int ydt, const void* x, const void* res, void* sum_out, const float* gamma,
+                         const float* beta, void* y, float* mean, float* rstd, int64_t rows, int cols, float eps) {
+  if (rows == 0) return 0;
+  if (pick_vpl(cols) == 0) {
+    if (xdt != NFB_F32 || ydt != NFB_F32 || res) return NFB_FAIL("nfb_norm_fwd: generic path (cols=%d) is fp32 only, no residual", cols);
+    cudaStream_t s = nfb_cur_stream();
+    if (kind == 0) k_norm_fwd_generic<false><<<(unsigned)rows, 256, 0, s>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, cols, eps);
+    else k_norm_fwd_generic<true><<<(unsigned)rows, 256, 0, s>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, cols, eps);
+    NFB_LAUNCH_CHECK();
+    return 0;
+  }
+#define DISPATCH(TX, TY)                                                                                            \
+  return kind == 0 ? norm_fwd_t<TX, TY, false>(x, res, sum_out, gamma, beta, y, mean, rstd, rows, cols, eps)        \
+                   : norm_fwd_t<TX, TY, true>(x, res, sum_out, gamma, beta, y, mean, rstd, rows, cols, eps)
+  if (xdt == NFB_F32 && ydt == NFB_F32) { DISPATCH(float, float); }
+  if (xdt == NFB_F32 && ydt == NFB_BF16) { DISPATCH(float, __nv_bfloat16); }
+  if (xdt == NFB_BF16 && ydt == NFB_BF16) { DISPATCH(__nv_bfloat16, __nv_bfloat16); }
+#undef DISPATCH
+  return NFB_FAIL("nfb_norm_fwd: unsupported dtype pair (%d,%d)", xdt, ydt);
+}
+
+NFB_API int nfb_norm_bwd(int kind, int xdt, int ydt, const void* dy, const void* x, const float* gamma, const float* mean,
+                         const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int accumulate,
+                         int64_t rows, int cols) {
+  if (rows == 0) return 0;
+  if (pick_vpl(cols) == 0) {
+    if (xdt != NFB_F32 || ydt != NFB_F32 || dres) return NFB_FAIL("nfb_norm_bwd: generic path (cols=%d) is fp32 only, no residual", cols);
+    cudaStream_t s = nfb_cur_stream();
+    if (kind == 0) {
+      k_norm_bwd_generic<false><<<(unsigned)rows, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx, cols);
+      nfb_count_launch();
+      if (dgamma || dbeta) k_norm_param_generic<false><<<(cols + 127) / 128, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd, dgamma, dbeta, rows, cols, accumulate);
+    } else {
+      k_norm_bwd_generic<true><<<(unsigned)rows, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx, cols);
+      nfb_count_launch();
+      if (dgamma || dbeta) k_norm_param_generic<true><<<(cols + 127) / 128, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd, dgamma, dbeta, rows, cols, accumulate);
+    }
+    NFB_LAUNCH_CHECK();
+    return 0;
+  }
+#define DISPATCH(TX, TY)                                                                                                   \
+  return kind == 0 ? norm_bwd_t<TX, TY, false>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols)  \
+                   : norm_bwd_t<TX, TY, true>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols)
+  if (xdt == NFB_F32 && ydt == NFB_F32) { DISPATCH(float, float); }
+  if (xdt == NFB_F32 && ydt == NFB_BF16) { DISPATCH(float, __nv_bfloat16); }
+  if (xdt == NFB_BF16 && ydt == NFB_BF16) { DISPATCH(__nv_bfloat16, __nv_bfloat16); }
+#undef DISPATCH
+  return NFB_FAIL("nfb_norm_bwd: unsupported dtype pair (%d,%d)", xdt, ydt);
+}

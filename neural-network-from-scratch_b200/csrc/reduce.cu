@@ -1,0 +1,198 @@
+// Reductions over a [outer, R, inner] view (the host permutes/reshapes so the reduced axes are the
+// middle block): sum / mean / max / min / prod, argmax / argmin, and the squared-L2 norm used by
+// gradient clipping. Semantics follow numpy_backend.py:138-160 of the reference (np.sum/mean/max/
+// min/argmax/argmin); NaNs propagate through max/min as in NumPy.
+#include "common.cuh"
+#include <float.h>
+
+enum RedOp { R_SUM = 0, R_MEAN = 1, R_MAX = 2, R_MIN = 3, R_PROD = 4 };
+
+template <typename A> __device__ __forceinline__ A red_identity(int op);
+template <> __device__ __forceinline__ float red_identity<float>(int op) {
+  return op == R_MAX ? -INFINITY : (op == R_MIN ? INFINITY : (op == R_PROD ? 1.f : 0.f));
+}
+template <> __device__ __forceinline__ double red_identity<double>(int op) {
+  return op == R_MAX ? -INFINITY : (op == R_MIN ? INFINITY : (op == R_PROD ? 1.0 : 0.0));
+}
+template <> __device__ __forceinline__ long long red_identity<long long>(int op) {
+  return op == R_MAX ? LLONG_MIN : (op == R_MIN ? LLONG_MAX : (op == R_PROD ? 1 : 0));
+}
+template <typename A> __device__ __forceinline__ A red_combine(int op, A a, A b) {
+  switch (op) {
+    case R_MAX: return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+    case R_MIN: return (a != a) ? a : ((b != b) ? b : (a < b ? a : b));
+    case R_PROD: return a * b;
+    default: return a + b;
+  }
+}
+template <typename A> __device__ __forceinline__ A shfl_xor_t(A v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+template <typename A> __device__ __forceinline__ A warp_red(int op, A v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_combine<A>(op, v, shfl_xor_t<A>(v, o));
+  return v;
+}
+
+// inner == 1: one block per (outer, chunk) row segment
+template <typename T, typename A, typename O>
+__global__ void k_reduce_rows(int op, const T* __restrict__ x, O* __restrict__ out, int64_t R, int64_t chunk_len, int chunks, double post_scale) {
+  __shared__ A red[32];
+  int64_t row = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  int64_t lo = ch * chunk_len, hi = lo + chunk_len < R ? lo + chunk_len : R;
+  const T* p = x + row * R;
+  A acc = red_identity<A>(op);
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = red_combine<A>(op, acc, (A)p[i]);
+  acc = warp_red<A>(op, acc);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) red[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    A r = lane < nw ? red[lane] : red_identity<A>(op);
+    r = warp_red<A>(op, r);
+    if (lane == 0) out[blockIdx.x] = (O)(post_scale == 1.0 ? r : (A)(r * (A)post_scale));
+  }
+}
+
+// inner > 1: block = 32 columns x 8 row-lanes; grid = (ceil(inner/32), chunks, outer)
+template <typename T, typename A, typename O>
+__global__ void k_reduce_cols(int op, const T* __restrict__ x, O* __restrict__ out, int64_t R, int64_t inner, int64_t chunk_len, int chunks, double post_scale) {
+  __shared__ A red[8][33];
+  int64_t o = blockIdx.z, ch = blockIdx.y;
+  int64_t col = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  int64_t lo = ch * chunk_len, hi = lo + chunk_len < R ? lo + chunk_len : R;
+  A acc = red_identity<A>(op);
+  if (col < inner) {
+    const T* p = x + o * R * inner + col;
+    for (int64_t r = lo + threadIdx.y; r < hi; r += 8) acc = red_combine<A>(op, acc, (A)p[r * inner]);
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < inner) {
+    A r = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = red_combine<A>(op, r, red[k][threadIdx.x]);
+    out[(o * chunks + ch) * inner + col] = (O)(post_scale == 1.0 ? r : (A)(r * (A)post_scale));
+  }
+}
+
+template <typename T, typename A>
+static int reduce_typed(int op, const T* x, T* out, int64_t outer, int64_t R, int64_t inner) {
+  cudaStream_t s = nfb_cur_stream();
+  int sms = nfb_sm_count();
+  double scale = (op == R_MEAN) ? 1.0 / (double)R : 1.0;
+  int kop = (op == R_MEAN) ? R_SUM : op;
+  if (inner == 1) {
+    int chunks = 1;
+    if (outer < 2 * sms && R >= 1 << 16) {
+      chunks = (int)((4 * (int64_t)sms + outer - 1) / outer);
+      int64_t max_chunks = R / 4096;
+      if (chunks > max_chunks) chunks = (int)max_chunks;
+      if (chunks < 1) chunks = 1;
+    }
+    int threads = R / chunks >= 2048 ? 512 : (R / chunks >= 256 ? 256 : 64);
+    if (chunks == 1) {
+      k_reduce_rows<T, A, T><<<(unsigned)outer, threads, 0, s>>>(kop, x, out, R, R, 1, scale);
+      NFB_LAUNCH_CHECK();
+      return 0;
+    }
+    int64_t chunk_len = nfb_cdiv(R, chunks);
+    A* tmp = nullptr;
+    if (nfb_malloc(sizeof(A) * outer * chunks, (void**)&tmp)) return -1;
+    k_reduce_rows<T, A, A><<<(unsigned)(outer * chunks), threads, 0, s>>>(kop, x, tmp, R, chunk_len, chunks, 1.0);
+    nfb_count_launch();
+    k_reduce_rows<A, A, T><<<(unsigned)outer, 64, 0, s>>>(kop, tmp, out, chunks, chunks, 1, scale);
+    nfb_free(tmp);
+    NFB_LAUNCH_CHECK();
+    return 0;
+  }
+  if (outer > 65535) return NFB_FAIL("nfb_reduce: outer extent %lld too large for the column kernel", (long long)outer);
+  int64_t col_blocks = nfb_cdiv(inner, 32);
+  int chunks = 1;
+  if (col_blocks * outer < 2 * sms && R >= 1024) {
+    chunks = (int)((4 * (int64_t)sms) / (col_blocks * outer));
+    int64_t max_chunks = R / 64;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+  }
+  dim3 block(32, 8);
+  if (chunks == 1) {
+    k_reduce_cols<T, A, T><<<dim3((unsigned)col_blocks, 1, (unsigned)outer), block, 0, s>>>(kop, x, out, R, inner, R, 1, scale);
+    NFB_LAUNCH_CHECK();
+    return 0;
+  }
+  int64_t chunk_len = nfb_cdiv(R, chunks);
+  A* tmp = nullptr;
+  if (nfb_malloc(sizeof(A) * outer * chunks * inner, (void**)&tmp)) return -1;
+  k_reduce_cols<T, A, A><<<dim3((unsigned)col_blocks, (unsigned)chunks, (unsigned)outer), block, 0, s>>>(kop, x, tmp, R, inner, chunk_len, chunks, 1.0);
+  nfb_count_launch();
+  k_reduce_cols<A, A, T><<<dim3((unsigned)col_blocks, 1, (unsigned)outer), block, 0, s>>>(kop, tmp, out, chunks, inner, chunks, 1, scale);
+  nfb_free(tmp);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+NFB_API int nfb_reduce(int op, int dtype, const void* x, void* out, int64_t outer, int64_t R, int64_t inner) {
+  if (outer * inner == 0) return 0;
+  if (R == 0) return NFB_FAIL("nfb_reduce: zero-size reduction axis");
+  switch (dtype) {
+    case NFB_F32: return reduce_typed<float, float>(op, (const float*)x, (float*)out, outer, R, inner);
+    case NFB_F64: return reduce_typed<double, double>(op, (const double*)x, (double*)out, outer, R, inner);
+    case NFB_I64: return reduce_typed<long long, long long>(op, (const long long*)x, (long long*)out, outer, R, inner);
+  }
+  return NFB_FAIL("nfb_reduce: unsupported dtype %d (cast to f32/f64/i64 first)", dtype);
+}
+
+// ---- argmax / argmin: first occurrence wins, NaN wins over everything (NumPy semantics) ----
+template <typename T>
+__device__ __forceinline__ bool arg_better(bool is_max, T v, int64_t i, T bv, int64_t bi) {
+  bool vnan = (v != v), bnan = (bv != bv);
+  if (bnan) return vnan && i < bi;  // keep the first NaN
+  if (vnan) return true;
+  if (v == bv) return i < bi;
+  return is_max ? (v > bv) : (v < bv);
+}
+template <typename T>
+__global__ void k_argreduce(int is_max, const T* __restrict__ x, int64_t* __restrict__ out, int64_t R, int64_t inner) {
+  __shared__ T sv[256];
+  __shared__ int64_t si[256];
+  int64_t o = blockIdx.x / inner, c = blockIdx.x % inner;
+  const T* p = x + o * R * inner + c;
+  T bv = p[0];
+  int64_t bi = 0;
+  for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
+    T v = p[r * inner];
+    if (arg_better<T>(is_max, v, r, bv, bi)) { bv = v; bi = r; }
+  }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      if (arg_better<T>(is_max, sv[threadIdx.x + s], si[threadIdx.x + s], sv[threadIdx.x], si[threadIdx.x])) {
+        sv[threadIdx.x] = sv[threadIdx.x + s];
+        si[threadIdx.x] = si[threadIdx.x + s];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = si[0];
+}
+NFB_API int nfb_argreduce(int is_max, int dtype, const void* x, int64_t* out, int64_t outer, int64_t R, int64_t inner) {
+  if (outer * inner == 0) return 0;
+  if (R == 0) return NFB_FAIL("nfb_argreduce: attempt to get argmax of an empty sequence");
+  int64_t blocks = outer * inner;
+  if (blocks > 2147483647LL) return NFB_FAIL("nfb_argreduce: too many output elements");
+  int threads = R >= 256 ? 256 : (R >= 64 ? 64 : 32);
+  cudaStream_t s = nfb_cur_stream();
+  switch (dtype) {
+    case NFB_F32: k_argreduce<float><<<(unsigned)blocks, threads, 0, s>>>(is_max, (const float*)x, out, R, inner); break;
+    case NFB_F64: k_argreduce<double><<<(unsigned)blocks, threads, 0, s>>>(is_max, (const double*)x, out, R, inner); break;
+    case NFB_I32: k_argreduce<int32_t><<<(unsigned)blocks, threads, 0, s>>>(is_max, (const int32_t*)x, out, R, inner); break;
+    case NFB_I64: k_argreduce<int64_t><<<(unsigned)blocks, threads, 0, s>>>(is_max, (const int64_t*)x, out, R, inner); break;
+    case NFB_BOOL: k_argreduce<uint8_t><<<(unsigned)blocks, threads, 0, s>>>(is_max, (const uint8_t*)x, out, R, inner); break;
+    default: return NFB_FAIL("nfb_argreduce: unsupported dtype %d", dtype);
+  }
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

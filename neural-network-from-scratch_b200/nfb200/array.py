@@ -606,6 +606,13 @@ def binary(op: str, a, b) -> B200Array:
         rt = _result_dtype(arr, sc, op)
         if op == "pow" and rt.kind in "iu" and float(sc) < 0 and not rev:
             raise ValueError("Integers to negative integer powers are not allowed.")
+        if op == "pow" and not rev and rt.kind == "f":
+            # ndarray.__pow__ fast paths for scalar exponents (exactly rounded, unlike a generic powf)
+            fast = {2: "square", 0.5: "sqrt", -1: "recip"}.get(sc if isinstance(sc, (int, float)) else float(sc))
+            if fast is not None:
+                return unary(fast, arr.astype(rt) if arr.dtype != rt else arr)
+            if sc == 1:
+                return (arr.astype(rt) if arr.dtype != rt else arr).copy()
         src = arr.astype(rt) if arr.dtype != rt else arr.contiguous()
         out = B200Array.empty(src.shape, np.bool_ if is_cmp else rt)
         if out.size:

@@ -1,0 +1,126 @@
+"""GPU parity of the tcgen05/TMEM bf16 GEMM against a float64 NumPy contraction of the
+SAME bf16-rounded operands (so the only error left is fp32 accumulation order): all four operand
+layouts (forward x.W^T, dgrad dY.W, wgrad dY^T.X), ragged M/N/K, every tile width, epilogues, split-K."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+def _to(be, a, dtype=None):
+    return be.from_numpy(np.asarray(a), dtype)
+
+
+def _ref(a, b, ta, tb):
+    A = _bf16(a).astype(np.float64)
+    B = _bf16(b).astype(np.float64)
+    return (A.T if ta else A) @ (B.T if tb else B)
+
+
+LAYOUTS = [(False, True), (False, False), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("ta,tb", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (512, 768, 768), (300, 200, 136), (129, 72, 72), (64, 40, 8), (4096, 2304, 768)])
+def test_gemm_layouts_and_ragged_shapes(be, ta, tb, M, N, K):
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    got = Kn.gemm_bf16(_to(be, a), _to(be, b), ta, tb).get()
+    want = _ref(a, b, ta, tb)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-4 * np.sqrt(K / 64))
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_every_tile_width(be, bn):
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(bn)
+    a = rng.standard_normal((384, 320)).astype(np.float32)
+    b = rng.standard_normal((1000, 320)).astype(np.float32)
+    _lib.call("nfb_gemm_bf16_force_tile", bn)
+    try:
+        got = Kn.gemm_bf16(_to(be, a), _to(be, b), False, True).get()
+        got2 = Kn.gemm_bf16(_to(be, a.T.copy()), _to(be, b.T.copy()), True, False).get()
+    finally:
+        _lib.call("nfb_gemm_bf16_force_tile", 0)
+    want = _ref(a, b, False, True)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=5e-4)
+    np.testing.assert_allclose(got2, want, rtol=2e-5, atol=5e-4)
+
+
+def test_many_tiles_persistent_schedule(be):
+    """More tiles than SMs: exercises smem-ring wrap-around and the double-buffered TMEM accumulator."""
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((2048, 192)).astype(np.float32)
+    b = rng.standard_normal((5000, 192)).astype(np.float32)
+    got = Kn.gemm_bf16(_to(be, a), _to(be, b), False, True).get()
+    np.testing.assert_allclose(got, _ref(a, b, False, True), rtol=2e-5, atol=5e-4)
+
+
+def test_unaligned_output_pitch_logits_shape(be):
+    """N = 50257-style odd row pitch: coalesced scalar stores, no alignment requirement on C."""
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((256, 128)).astype(np.float32)
+    w = rng.standard_normal((5027, 128)).astype(np.float32)
+    got = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True).get()
+    np.testing.assert_allclose(got, _ref(x, w, False, True), rtol=2e-5, atol=4e-4)
+
+
+def test_epilogues_bias_gelu_relu_residual_bf16_out(be):
+    from nfb200 import kernels as Kn
+    from oracle import np_ops as O
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((200, 256)).astype(np.float32)
+    w = (rng.standard_normal((384, 256)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(384).astype(np.float32)
+    res = rng.standard_normal((200, 384)).astype(np.float32)
+    z = _ref(x, w, False, True) + bias
+    y = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias)).get()
+    np.testing.assert_allclose(y, z, rtol=2e-5, atol=3e-4)
+    yg, aux = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), epilogue="gelu", aux=True)
+    np.testing.assert_allclose(yg.get(), O.gelu_tanh_fwd(z), rtol=1e-4, atol=3e-4)
+    np.testing.assert_allclose(aux.get(), z, rtol=1e-2, atol=1e-2)  # bf16 pre-activation
+    yr = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), epilogue="relu", residual=_to(be, res)).get()
+    np.testing.assert_allclose(yr, np.maximum(z, 0) + res, rtol=2e-5, atol=3e-4)
+    yb = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), out_dtype=be.bfloat16)
+    assert yb.dtype is be.bfloat16
+    np.testing.assert_allclose(yb.get(), z, rtol=1e-2, atol=1e-2)
+    yc = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), clip=0.5).get()
+    np.testing.assert_allclose(yc, np.clip(z, -0.5, 0.5), rtol=2e-5, atol=3e-4)
+
+
+@pytest.mark.parametrize("split_k", [0, 1, 3, 8])
+def test_wgrad_split_k_accumulate(be, split_k):
+    """dW (+)= dY^T X with K = tokens: split-K partial sums land with red.global.add on a pre-initialised C."""
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(4)
+    T, dout, din = 4096, 256, 384
+    dy = (rng.standard_normal((T, dout)) * 0.1).astype(np.float32)
+    x = rng.standard_normal((T, din)).astype(np.float32)
+    base = rng.standard_normal((dout, din)).astype(np.float32)
+    out = _to(be, base.copy())
+    Kn.gemm_bf16(_to(be, dy), _to(be, x), True, False, out=out, accumulate=True, split_k=split_k)
+    want = base + _ref(dy, x, True, False)
+    np.testing.assert_allclose(out.get(), want, rtol=3e-5, atol=2e-3)
+
+
+def test_gemm_f32_wrapper(be):
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((300, 200)).astype(np.float32)
+    w = rng.standard_normal((150, 200)).astype(np.float32)
+    b = rng.standard_normal(150).astype(np.float32)
+    got = Kn.gemm_f32(_to(be, x), _to(be, w), False, True, bias=_to(be, b)).get()
+    np.testing.assert_allclose(got, x.astype(np.float64) @ w.T.astype(np.float64) + b, rtol=1e-5, atol=2e-5)
+    got = Kn.gemm_f32(_to(be, x), _to(be, x), True, False).get()
+    np.testing.assert_allclose(got, x.T.astype(np.float64) @ x.astype(np.float64), rtol=1e-5, atol=3e-5)

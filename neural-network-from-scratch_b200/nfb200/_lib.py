@@ -95,9 +95,10 @@ _SIGNATURES = {
     "nfb_gemm_bf16": [i32, i32, i32, i32, i32, vp, i64, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, i32, i32, i32, f32],
     "nfb_gemm_bf16_force_tile": [i32],
     # attention
-    "nfb_rope": [i32, vp, i32, i32, i32, i32, i64, i64, i64, f32, i32],
-    "nfb_flash_attn_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
-    "nfb_flash_attn_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, f32, i32, vp],
+    "nfb_rope": [i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, i64, i64, i64, i32],
+    "nfb_flash_attn_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, vp],
+    "nfb_flash_attn_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64,
+                           i32, f32, i32, vp],
     # collectives
     "nfb_comm_load": [C.c_char_p],
     "nfb_comm_unique_id": [C.c_char_p, i32],

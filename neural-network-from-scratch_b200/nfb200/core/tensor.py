@@ -1,0 +1,587 @@
+"""Tensor + autograd core, reconstructed from the reference's call sites and tests (the reference
+snapshot is missing ``core/tensor.py``: SURVEY F1, contract in Appendix A) and re-designed so data
+and gradients stay RESIDENT on the device:
+
+  * ``tensor.data`` / ``tensor.grad`` are backend arrays -- ``np.ndarray`` on ``Device.cpu()``,
+    :class:`nfb200.array.B200Array` (HBM) on ``Device.cuda(i)``.  Nothing round-trips through the
+    host (the reference's ops do).
+  * ``backward()`` walks the graph ONCE in reverse creation order (a valid topological order)
+    instead of the reference's per-path recursion, accumulating fan-in gradients before a node's
+    backward runs.  The reference's +-10 gradient clip / NaN scrub is kept and
+    switchable (``set_grad_clip``); with fan-out > 1 it applies to the summed gradient (PARITY.md).
+  * gradient functions return the input gradients as a tuple; a function may accumulate into a
+    parameter's gradient buffer in place (wgrad GEMMs, scatter-add) and return ``ACCUMULATED``.
+"""
+from __future__ import annotations
+
+import itertools
+import logging
+import numbers
+from contextlib import contextmanager
+from typing import Any, Callable, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from ..array import B200Array, bfloat16
+from ..plugin import get_backend
+from .device import Device, DeviceType, as_device, get_default_device
+from .dtype import DType, get_default_dtype
+
+logger = logging.getLogger(__name__)
+
+TensorLike = Union["Tensor", np.ndarray, list, float, int]
+Shape = Tuple[int, ...]
+
+_grad_enabled = True
+_grad_clip = 10.0          # reference behaviour; None disables
+_seq = itertools.count()
+ACCUMULATED = object()     # sentinel: "gradient already added into the input's buffer in place"
+
+
+def is_grad_enabled() -> bool:
+    return _grad_enabled
+
+
+@contextmanager
+def no_grad():
+    global _grad_enabled
+    prev, _grad_enabled = _grad_enabled, False
+    try:
+        yield
+    finally:
+        _grad_enabled = prev
+
+
+@contextmanager
+def enable_grad():
+    global _grad_enabled
+    prev, _grad_enabled = _grad_enabled, True
+    try:
+        yield
+    finally:
+        _grad_enabled = prev
+
+
+def set_grad_clip(value: Optional[float]) -> None:
+    """Gradient clip applied to every upstream gradient (reference: 10.0).  None switches it off."""
+    global _grad_clip
+    _grad_clip = value
+
+
+def get_grad_clip() -> Optional[float]:
+    return _grad_clip
+
+
+def _clip(g):
+    """GradientFunction.apply semantics: scrub non-finite values, clip to [-c, c]."""
+    c = _grad_clip
+    if c is None or g is None:
+        return g
+    if isinstance(g, B200Array):
+        if g.dtype is bfloat16:
+            return g  # bf16 gradients are clipped where they are produced (GEMM epilogue `clip`)
+        return g.clip(-c, c) if _scrub_free(g) else np.nan_to_num(g, nan=0.0, posinf=c, neginf=-c).clip(-c, c)
+    g = np.asarray(g)
+    if not np.all(np.isfinite(g)):
+        logger.warning("Non-finite gradient encountered; applying nan_to_num")
+        g = np.nan_to_num(g, nan=0.0, posinf=c, neginf=-c)
+    return np.clip(g, -c, c)
+
+
+def _scrub_free(g) -> bool:
+    # U_CLIP keeps NaN, so a NaN check would need a device->host sync on every gradient.  The clip kernel
+    # already maps +-inf into range; NaNs are left to surface in the loss (documented in PARITY.md).
+    return True
+
+
+class GradientFunction:
+    """backward_fn(grad_output) -> tuple of gradients, one per entry of ``inputs`` (None / ACCUMULATED allowed)."""
+
+    __slots__ = ("backward_fn", "inputs", "name", "seq", "fused_acc")
+
+    def __init__(self, backward_fn: Callable, inputs: Sequence["Tensor"], name: Optional[str] = None, fused_acc: bool = False):
+        self.backward_fn = backward_fn
+        self.inputs = list(inputs)
+        self.name = name or getattr(backward_fn, "__name__", "op")
+        self.seq = next(_seq)
+        self.fused_acc = fused_acc  # backward_fn(g, acc0) returns input-0's TOTAL gradient (acc0 folded in)
+
+    def apply(self, grad_output) -> None:
+        """Reference-style entry point: clip, run, and push the results into the inputs (recursively)."""
+        g = _clip(grad_output)
+        try:
+            grads = self.backward_fn(g)
+        except Exception as e:
+            logger.error(f"Error in backward pass of {self.name}: {e}")
+            raise
+        if grads is None:
+            return
+        if not isinstance(grads, (tuple, list)):
+            grads = (grads,)
+        for inp, gi in zip(self.inputs, grads):
+            if gi is None or gi is ACCUMULATED or not isinstance(inp, Tensor) or not inp.requires_grad:
+                continue
+            inp.backward(gi)
+
+    def __repr__(self):
+        return f"GradientFunction({self.name})"
+
+
+def _backend_for(device: Device):
+    if device.type is DeviceType.CUDA:
+        # no NumPy fallback for cuda tensors: an unavailable B200 backend raises here (PARITY.md)
+        return get_backend("cuda")
+    if device.type is DeviceType.MPS:
+        raise RuntimeError("the mps backend is not part of this build")
+    return get_backend("numpy")
+
+
+def _resolve_dtype(dtype):
+    if dtype is None:
+        return None
+    if isinstance(dtype, DType):
+        return dtype.numpy_dtype
+    if dtype is bfloat16:
+        return bfloat16
+    return DType.from_numpy(dtype).numpy_dtype
+
+
+class Tensor:
+    __array_priority__ = 2000.0
+
+    def __init__(self, data: Any, requires_grad: bool = False, dtype=None, device=None, name: Optional[str] = None):
+        if not isinstance(requires_grad, (bool, np.bool_)):
+            raise TypeError("requires_grad must be bool")
+        if isinstance(data, str):
+            raise TypeError("Tensor data cannot be a string")
+        if isinstance(data, dict):
+            raise TypeError("Tensor data cannot be a dict")
+        want = _resolve_dtype(dtype)
+        if isinstance(data, Tensor):
+            device = device if device is not None else data._device
+            data = data._data
+        if isinstance(data, B200Array):
+            dev = as_device(device) if device is not None else Device.cuda(int(data.device.split(":")[1]))
+            self._device = dev
+            self._backend = _backend_for(dev)
+            if dev.is_cpu:
+                data = data.get()
+            elif want is not None and want != data.dtype:
+                data = data.astype(want)
+            self._data = data if not dev.is_cpu else self._coerce_host(data, want)
+        else:
+            dev = as_device(device)
+            self._device = dev
+            self._backend = _backend_for(dev)
+            host = self._coerce_host(data, want)
+            self._data = host if dev.is_cpu else self._backend.from_numpy(host)
+        self.requires_grad = bool(requires_grad)
+        self.name = name
+        self._grad = None
+        self._grad_fn: Optional[GradientFunction] = None
+        self._grad_slot = None        # persistent gradient-arena view (set by optimizers / DDP)
+        self._slot_zero = False
+        self._hooks = None
+        self._version = 0
+
+    @staticmethod
+    def _coerce_host(data, want):
+        try:
+            if isinstance(data, np.ndarray):
+                arr = data
+                if want is None and arr.dtype not in (np.float32, np.float64, np.int32, np.int64, np.bool_):
+                    if arr.dtype.kind == "f":
+                        arr = arr.astype(np.float32)
+                    elif arr.dtype.kind in "iu":
+                        arr = arr.astype(np.int64)
+                    elif arr.dtype.kind == "O":
+                        raise TypeError("object arrays are not supported")
+            else:
+                arr = np.array(data)
+                if arr.dtype.kind == "O" or arr.dtype.kind in "US":
+                    raise TypeError(f"cannot build a Tensor from {type(data).__name__}")
+                if want is None:
+                    if arr.dtype.kind == "f":
+                        arr = arr.astype(get_default_dtype().numpy_dtype)
+                    elif arr.dtype.kind in "iu" and not isinstance(data, np.generic):
+                        # Python ints / lists of ints: the reference stores float32 (default dtype) for list data
+                        arr = arr.astype(get_default_dtype().numpy_dtype)
+                    elif arr.dtype.kind == "b":
+                        pass
+        except (ValueError, TypeError) as e:
+            raise TypeError(f"cannot convert data to a Tensor: {e}") from e
+        if want is not None and want is not bfloat16 and arr.dtype != want:
+            arr = arr.astype(want)
+        return arr
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        if isinstance(value, Tensor):
+            value = value._data
+        if self._device.is_cpu:
+            self._data = value.get() if isinstance(value, B200Array) else np.asarray(value)
+        else:
+            new = value if isinstance(value, B200Array) else self._backend.from_numpy(np.asarray(value))
+            cur = self._data
+            if getattr(self, "_arena_bound", False) and isinstance(cur, B200Array) and cur.shape == new.shape and cur.dtype == new.dtype:
+                cur._assign(new)  # keep the flat-arena binding (optimizer / DDP buckets)
+            else:
+                self._data = new
+        self._version += 1
+
+    @property
+    def backend(self):
+        return self._backend
+
+    @property
+    def backend_data(self):
+        return self._data
+
+    @property
+    def device(self) -> Device:
+        return self._device
+
+    @property
+    def shape(self) -> Shape:
+        return tuple(self._data.shape)
+
+    @property
+    def ndim(self) -> int:
+        return len(self._data.shape)
+
+    @property
+    def size(self) -> int:
+        return int(self._data.size)
+
+    @property
+    def dtype(self) -> DType:
+        dt = self._data.dtype
+        if dt is bfloat16:
+            return DType.FLOAT32  # bf16 is backend-internal storage of an fp32-typed tensor
+        return DType.from_numpy(dt)
+
+    @property
+    def grad(self):
+        return self._grad
+
+    @grad.setter
+    def grad(self, value):
+        if value is None:
+            self._grad = None
+            return
+        if isinstance(value, Tensor):
+            value = value._data
+        if self._device.is_cpu:
+            self._grad = value.get() if isinstance(value, B200Array) else np.asarray(value)
+        else:
+            self._grad = value if isinstance(value, B200Array) else self._backend.from_numpy(np.asarray(value))
+
+    @property
+    def grad_fn(self):
+        return self._grad_fn
+
+    @grad_fn.setter
+    def grad_fn(self, fn):
+        self._grad_fn = fn
+
+    @property
+    def T(self) -> "Tensor":
+        from ..functional.shape import transpose
+        return transpose(self)
+
+    @property
+    def is_leaf(self) -> bool:
+        return self._grad_fn is None
+
+    # ------------------------------------------------------------------ autograd
+    def grad_buffer(self):
+        """The array gradients accumulate into (allocating / zero-filling the arena slot on first use)."""
+        if self._grad is None:
+            if self._grad_slot is not None:
+                if not self._slot_zero:
+                    self._grad_slot.fill(0.0)
+                self._slot_zero = False
+                self._grad = self._grad_slot
+            elif self._device.is_cpu:
+                self._grad = np.zeros(self.shape, dtype=self._data.dtype)
+            else:
+                self._grad = self._backend.zeros(self.shape, np.float32)
+        return self._grad
+
+    def _accumulate(self, g):
+        if self._hooks:
+            for h in list(self._hooks.values()):
+                r = h(g)
+                if r is not None:
+                    g = r
+        if self._grad is None:
+            if self._grad_slot is not None:
+                self._grad_slot._assign(g)
+                self._slot_zero = False
+                self._grad = self._grad_slot
+            else:
+                self._grad = g.copy() if isinstance(g, (np.ndarray, B200Array)) else np.asarray(g)
+        elif isinstance(self._grad, B200Array):
+            self._grad += g
+        else:
+            self._grad = self._grad + g
+
+    def _coerce_grad(self, g):
+        if isinstance(g, Tensor):
+            g = g._data
+        if self._device.is_cpu:
+            g = g.get() if isinstance(g, B200Array) else np.asarray(g, dtype=self._data.dtype if self._data.dtype.kind == "f" else np.float32)
+        elif not isinstance(g, B200Array):
+            g = self._backend.from_numpy(np.asarray(g, dtype=np.float32))
+        if tuple(g.shape) != self.shape:
+            if g.size == self.size:
+                g = g.reshape(self.shape)
+            else:
+                from ..functional.utils import reduce_gradient
+                g = reduce_gradient(g, self.shape)
+        return g
+
+    def backward(self, gradient=None) -> None:
+        if not self.requires_grad:
+            return
+        if gradient is None:
+            gradient = np.ones(self.shape, dtype=np.float32) if self._device.is_cpu else self._backend.ones(self.shape, np.float32)
+        run_backward(self, self._coerce_grad(gradient))
+
+    def zero_grad(self) -> None:
+        self._grad = None
+
+    def register_backward_hook(self, fn: Callable) -> int:
+        if self._hooks is None:
+            self._hooks = {}
+        hid = max(self._hooks.keys(), default=-1) + 1
+        self._hooks[hid] = fn
+        return hid
+
+    def remove_backward_hook(self, hid: int) -> None:
+        if self._hooks:
+            self._hooks.pop(hid, None)
+
+    # ------------------------------------------------------------------ conversion
+    def numpy(self) -> np.ndarray:
+        return self._data.get() if isinstance(self._data, B200Array) else np.asarray(self._data)
+
+    def item(self):
+        return self._data.item()
+
+    def tolist(self):
+        return self.numpy().tolist()
+
+    def clone(self) -> "Tensor":
+        return Tensor(self._data.copy(), requires_grad=self.requires_grad, device=self._device, name=self.name)
+
+    def detach(self) -> "Tensor":
+        return Tensor(self._data, requires_grad=False, device=self._device, name=self.name)
+
+    def to(self, device) -> "Tensor":
+        dev = as_device(device)
+        if dev == self._device:
+            return self
+        host = self.numpy()
+        out = Tensor(host, requires_grad=self.requires_grad, device=dev, name=self.name)
+        return out
+
+    def astype(self, dtype) -> "Tensor":
+        dt = _resolve_dtype(dtype)
+        return Tensor(self._data.astype(dt), requires_grad=self.requires_grad and np.dtype(dt).kind == "f", device=self._device, name=self.name)
+
+    def memory_usage(self) -> int:
+        n = int(self._data.nbytes)
+        if self._grad is not None:
+            n += int(self._grad.nbytes)
+        return n
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        nm = f", name={self.name!r}" if self.name else ""
+        return f"Tensor(shape={self.shape}, dtype={self.dtype}, device={self._device}, requires_grad={self.requires_grad}{nm})"
+
+    __str__ = __repr__
+
+    def __array__(self, dtype=None, copy=None):
+        if isinstance(self._data, B200Array):
+            raise TypeError("a cuda Tensor is not implicitly convertible to NumPy; call .numpy()")
+        return np.asarray(self._data, dtype=dtype)
+
+    # ------------------------------------------------------------------ shape ops / indexing (differentiable)
+    def reshape(self, *shape) -> "Tensor":
+        from ..functional.shape import reshape
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return reshape(self, shape)
+
+    def flatten(self):
+        """Flat view of the DATA (nn/embedding.py:49 iterates it as row indices)."""
+        return self._data.flatten() if not isinstance(self._data, B200Array) else self._data.reshape(-1)
+
+    def transpose(self, *axes) -> "Tensor":
+        from ..functional.shape import transpose
+        if len(axes) == 1 and (axes[0] is None or isinstance(axes[0], (tuple, list))):
+            axes = axes[0]
+        return transpose(self, axes if axes else None)
+
+    def __getitem__(self, key) -> "Tensor":
+        from ..functional.shape import getitem
+        return getitem(self, key)
+
+    # ------------------------------------------------------------------ arithmetic -> functional ops
+    def __add__(self, o):
+        from ..functional.arithmetic import add
+        return add(self, o)
+
+    __radd__ = __add__
+
+    def __iadd__(self, o):
+        from ..functional.arithmetic import add
+        return add(self, o)
+
+    def __sub__(self, o):
+        from ..functional.arithmetic import sub
+        return sub(self, o)
+
+    def __rsub__(self, o):
+        from ..functional.arithmetic import sub
+        return sub(o, self)
+
+    def __mul__(self, o):
+        from ..functional.arithmetic import mul
+        return mul(self, o)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        from ..functional.arithmetic import div
+        return div(self, o)
+
+    def __rtruediv__(self, o):
+        from ..functional.arithmetic import div
+        return div(o, self)
+
+    def __neg__(self):
+        from ..functional.arithmetic import neg
+        return neg(self)
+
+    def __matmul__(self, o):
+        from ..functional.arithmetic import matmul
+        return matmul(self, o)
+
+    def __rmatmul__(self, o):
+        from ..functional.arithmetic import matmul
+        return matmul(o, self)
+
+    def __pow__(self, p):
+        from ..functional.arithmetic import power
+        return power(self, p)
+
+    def _cmp(self, o, fn):
+        od = o._data if isinstance(o, Tensor) else o
+        return Tensor(fn(self._data, od), device=self._device)
+
+    def __lt__(self, o): return self._cmp(o, lambda a, b: a < b)
+    def __le__(self, o): return self._cmp(o, lambda a, b: a <= b)
+    def __gt__(self, o): return self._cmp(o, lambda a, b: a > b)
+    def __ge__(self, o): return self._cmp(o, lambda a, b: a >= b)
+
+    def sum(self, axis=None, keepdims=False):
+        from ..functional.reduction import sum as _sum
+        return _sum(self, axis, keepdims)
+
+    def mean(self, axis=None, keepdims=False):
+        from ..functional.reduction import mean as _mean
+        return _mean(self, axis, keepdims)
+
+
+def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable], name: str, device=None, fused_acc=False) -> Tensor:
+    """Wrap an op result; attach the gradient function when any input needs a gradient and grad mode is on."""
+    dev = device
+    if dev is None:
+        for t in inputs:
+            if isinstance(t, Tensor):
+                dev = t._device
+                break
+    rg = _grad_enabled and any(isinstance(t, Tensor) and t.requires_grad for t in inputs)
+    out = Tensor.__new__(Tensor)
+    out._device = dev if dev is not None else get_default_device()
+    out._backend = _backend_for(out._device)
+    out._data = data
+    out.requires_grad = bool(rg)
+    out.name = name
+    out._grad = None
+    out._grad_fn = GradientFunction(backward_fn, inputs, name, fused_acc) if (rg and backward_fn is not None) else None
+    out._grad_slot = None
+    out._slot_zero = False
+    out._hooks = None
+    out._version = 0
+    return out
+
+
+def run_backward(root: Tensor, grad) -> None:
+    """One reverse sweep over the graph in decreasing creation order (inputs are always created before outputs)."""
+    # collect reachable op nodes
+    nodes = {}
+    stack = [root]
+    seen = {id(root)}
+    while stack:
+        t = stack.pop()
+        fn = t._grad_fn
+        if fn is None:
+            continue
+        nodes[id(t)] = t
+        for inp in fn.inputs:
+            if isinstance(inp, Tensor) and inp.requires_grad and id(inp) not in seen:
+                seen.add(id(inp))
+                stack.append(inp)
+    pending = {id(root): grad}
+    if root._grad_fn is None:
+        root._accumulate(_clip(grad))
+        return
+    order = sorted(nodes.values(), key=lambda t: t._grad_fn.seq, reverse=True)
+    # the root keeps its gradient (reference: every tensor on the path has .grad set; we keep root + leaves)
+    root._grad = grad if root._grad is None else root._grad + grad
+    for t in order:
+        g = pending.pop(id(t), None)
+        if g is None:
+            continue
+        g = _clip(g)
+        fn = t._grad_fn
+        if t._hooks:
+            for h in list(t._hooks.values()):
+                r = h(g)
+                if r is not None:
+                    g = r
+        if fn.fused_acc:
+            first = fn.inputs[0]
+            acc0 = pending.pop(id(first), None) if (isinstance(first, Tensor) and first._grad_fn is not None) else None
+            grads = fn.backward_fn(g, acc0)
+        else:
+            acc0 = None
+            grads = fn.backward_fn(g)
+        if grads is None:
+            continue
+        if not isinstance(grads, (tuple, list)):
+            grads = (grads,)
+        for i, (inp, gi) in enumerate(zip(fn.inputs, grads)):
+            if gi is None or gi is ACCUMULATED or not isinstance(inp, Tensor) or not inp.requires_grad:
+                continue
+            if tuple(gi.shape) != inp.shape:
+                gi = inp._coerce_grad(gi)
+            if inp._grad_fn is None:
+                inp._accumulate(_clip(gi))
+            else:
+                prev = pending.get(id(inp))
+                if prev is None or (fn.fused_acc and i == 0):
+                    pending[id(inp)] = gi
+                else:
+                    pending[id(inp)] = prev + gi

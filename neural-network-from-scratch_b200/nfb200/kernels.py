@@ -121,3 +121,267 @@ def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None,
     call("nfb_gemm_f32", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, 1.0, a2.ptr, lda, 0, b2.ptr, ldb, 0, float(beta),
          out.ptr, out.strides[0] if M > 1 else N, 0, 1, bias_c.ptr if bias_c is not None else None)
     return out
+
+
+# ======================================================================================
+# Linear (nn/optimized.py:149-317, nn/linear.py:202-205): y = act(x @ W^T + b) [+ residual]
+# ======================================================================================
+def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtype=None, residual=None, w_bf16=None,
+                   precision=None, weight_layout="out_in"):
+    """x (..., in); W (out,in) [or (in,out) with weight_layout='in_out'].  Returns (y, ctx) where ctx is what
+    linear_backward needs.  precision None -> the module-level mode."""
+    precision = precision or _PRECISION
+    lead = x.shape[:-1]
+    k_in = x.shape[-1]
+    x2 = x.reshape(-1, k_in)
+    n_out = W.shape[0] if weight_layout == "out_in" else W.shape[1]
+    tb = weight_layout == "out_in"
+    act = activation.lower() if isinstance(activation, str) else None
+    if act not in (None, "gelu", "relu"):
+        act = None
+    res2 = None if residual is None else residual.reshape(-1, n_out)
+    if precision == "bf16":
+        xb = to_bf16(x2)
+        wb = w_bf16 if w_bf16 is not None else to_bf16(W)
+        odt = out_dtype if out_dtype is not None else (F32 if x.dtype == F32 else bfloat16)
+        if act == "gelu":
+            y, z = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue="gelu", aux=True)
+        else:
+            y = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue=act)
+            z = y if act == "relu" else None  # relu'(z) == (y > 0)
+        ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16")
+    else:
+        xf = x2 if x2.dtype == F32 else x2.astype(np.float32)
+        z = gemm_f32(xf, W, False, tb, bias=b)
+        if act == "gelu":
+            from . import array as A
+            y = A.unary("gelu_tanh", z)
+        elif act == "relu":
+            from . import array as A
+            y = A.unary("relu", z)
+        else:
+            y = z
+        if res2 is not None:
+            y = y + res2
+        ctx = (xf, W, None, z if act else None, act, weight_layout, b is not None, "fp32")
+    return y.reshape(lead + (n_out,)), ctx
+
+
+def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, dx_dtype=None, clip=0.0):
+    """Returns (dx, dW, db).  dW / db are ACCUMULATED into dW_out / db_out when given (gradient arena views),
+    otherwise freshly allocated.  dX = dZ W ; dW = dZ^T X ; db = column sums of dZ."""
+    from . import array as A
+    x2, W, wb, z, act, layout, has_bias, precision = ctx
+    lead = dy.shape[:-1]
+    n_out = dy.shape[-1]
+    dz = dy.reshape(-1, n_out)
+    out_in = layout == "out_in"
+    if precision == "bf16":
+        dz = to_bf16(dz)
+        if act == "gelu":
+            dz = A.unary_bwd("gelu_tanh", z.reshape(dz.shape), dz)
+        elif act == "relu":
+            dz = A.unary_bwd("relu", to_bf16(z.reshape(dz.shape)), dz)
+        dx = None
+        if need_dx:
+            odt = dx_dtype if dx_dtype is not None else bfloat16
+            # dX (T,in) = dZ (T,out) . W(out,in): B operand is W stored (K=out, N=in) -> trans_b=False
+            dx = gemm_bf16(dz, wb, False, not out_in, out_dtype=odt, clip=clip)
+        if dW_out is None:
+            dW_out = B200Array.full(W.shape, 0.0, np.float32)
+        if out_in:   # dW (out,in) = dZ^T (out,T) . X (T,in)
+            gemm_bf16(dz, x2, True, False, out=dW_out, accumulate=True)
+        else:        # dW (in,out) = X^T . dZ
+            gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
+        db = None
+        if has_bias:
+            s = A.reduce("sum", dz, 0, False)
+            if db_out is not None:
+                db_out += s
+                db = db_out
+            else:
+                db = s
+        return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
+    # ---- fp32 path
+    if dz.dtype != F32:
+        dz = dz.astype(np.float32)
+    dz = dz.contiguous()
+    if act == "gelu":
+        dz = A.unary_bwd("gelu_tanh", z.reshape(dz.shape), dz)
+    elif act == "relu":
+        dz = A.unary_bwd("relu", z.reshape(dz.shape), dz)
+    dx = None
+    if need_dx:
+        dx = gemm_f32(dz, W, False, not out_in)
+        if clip > 0:
+            dx = dx.clip(-clip, clip)
+        dx = dx.reshape(lead + (x2.shape[1],))
+    if out_in:
+        dW = gemm_f32(dz, x2, True, False, out=dW_out, beta=1.0 if dW_out is not None else 0.0)
+    else:
+        dW = gemm_f32(x2, dz, True, False, out=dW_out, beta=1.0 if dW_out is not None else 0.0)
+    db = None
+    if has_bias:
+        s = A.reduce("sum", dz, 0, False)
+        if db_out is not None:
+            db_out += s
+            db = db_out
+        else:
+            db = s
+    return dx, dW, db
+
+
+# ======================================================================================
+# RoPE + fused attention
+# ======================================================================================
+_ROPE_CACHE = {}
+
+
+def rope_tables(head_dim: int, seq_len: int, base: int = 10000):
+    """cos/sin tables (S, D/2) built with the reference's own NumPy expressions (gpt2.py:25-54) so angles are
+    bit-identical to the NumPy path; cached on device."""
+    key = (head_dim, seq_len, base)
+    hit = _ROPE_CACHE.get(key)
+    if hit is None:
+        inv_freq = 1.0 / (base ** (np.arange(0, head_dim, 2).astype(np.float32) / head_dim))
+        t = np.arange(seq_len, dtype=np.float32)
+        freqs = np.outer(t, inv_freq)
+        hit = (B200Array.from_numpy(np.cos(freqs).astype(np.float32)), B200Array.from_numpy(np.sin(freqs).astype(np.float32)))
+        _ROPE_CACHE[key] = hit
+    return hit
+
+
+def _bhsd_strides(x: B200Array):
+    """Logical (B,H,S,D) array -> (sb, ss, sh) element strides; requires unit stride along D."""
+    if x.ndim != 4 or x.strides[3] != 1:
+        raise ValueError("attention operands must be 4-D (B,H,S,D) with a contiguous last dimension")
+    return x.strides[0], x.strides[2], x.strides[1]
+
+
+def rope_inplace(x: B200Array, inverse=False, base=10000):
+    """Rotate a logical (B,H,S,D) array (any strides) in place."""
+    Bn, H, S, D = x.shape
+    cos_t, sin_t = rope_tables(D, S, base)
+    sb, ss, sh = _bhsd_strides(x)
+    call("nfb_rope", dtype_code(x.dtype), x.ptr, cos_t.ptr, sin_t.ptr, 1, 0, Bn, S, H, D, sb, ss, sh, 1 if inverse else 0)
+    return x
+
+
+def rope_packed_qk_inplace(qkv: B200Array, n_heads: int, inverse=False, base=10000):
+    """qkv: packed (B,S,3,H,D) [or (T=B*S,3*H*D) with B,S given by shape]: rotates the q and k parts in place."""
+    Bn, S, three, H, D = qkv.shape
+    cos_t, sin_t = rope_tables(D, S, base)
+    call("nfb_rope", dtype_code(qkv.dtype), qkv.ptr, cos_t.ptr, sin_t.ptr, 2, H * D, Bn, S, H, D, S * 3 * H * D, 3 * H * D, D,
+         1 if inverse else 0)
+    return qkv
+
+
+def _key_mask(mask, Bn, Skv):
+    if mask is None:
+        return None
+    m = mask if isinstance(mask, B200Array) else B200Array.from_numpy(np.asarray(mask, np.float32))
+    if m.dtype != F32:
+        m = m.astype(np.float32)
+    if m.size == Bn * Skv:
+        return m.reshape(Bn, Skv).contiguous()
+    if m.size == Skv:
+        return m.reshape(1, Skv).broadcast_to((Bn, Skv)).contiguous()
+    raise ValueError(f"attention mask must be an additive per-key mask broadcastable to (B,1,1,S_kv); got shape {m.shape}")
+
+
+def attention_forward(q: B200Array, k: B200Array, v: B200Array, scale: float, causal=False, mask=None, need_lse=True):
+    """Fused softmax(q k^T * scale [masks]) v.  q,k,v logical (B,H,S,D), bf16 (fp32 inputs are cast), D == 64.
+    Returns (o, lse): o logical (B,H,S,D) stored as (B,S,H,D) so o.transpose(0,2,1,3).reshape(B,S,H*D) is free."""
+    q, k, v = to_bf16(q), to_bf16(k), to_bf16(v)
+    Bn, H, S, D = q.shape
+    Skv = k.shape[2]
+    o_store = B200Array.empty((Bn, S, H, D), bfloat16)
+    lse = B200Array.empty((Bn, H, S), np.float32) if need_lse else None
+    km = _key_mask(mask, Bn, Skv)
+    qs, ks_, vs = _bhsd_strides(q), _bhsd_strides(k), _bhsd_strides(v)
+    if ks_ != vs:
+        v = v.contiguous()
+        k = k.contiguous()
+        ks_ = _bhsd_strides(k)
+    mode = (1 if causal else 0) | (2 if km is not None else 0)
+    call("nfb_flash_attn_fwd", _lib.BF16, q.ptr, k.ptr, v.ptr, o_store.ptr, lse.ptr if lse is not None else None, Bn, H, S, D,
+         qs[0], qs[1], qs[2], ks_[0], ks_[1], ks_[2], S * H * D, H * D, D, Skv, float(scale), mode, km.ptr if km is not None else None)
+    return o_store.transpose(0, 2, 1, 3), lse
+
+
+def attention_backward(dout: B200Array, q, k, v, o, lse, scale, causal=False, mask=None, packed=False):
+    """Returns (dq, dk, dv) as logical (B,H,S,D) bf16 arrays.  With packed=True the three live in ONE
+    (B,S,3,H,D) buffer (returned as a 4th value) laid out like a fused qkv projection output."""
+    q, k, v = to_bf16(q), to_bf16(k), to_bf16(v)
+    Bn, H, S, D = q.shape
+    Skv = k.shape[2]
+    dout = to_bf16(dout)
+    os_ = _bhsd_strides(o)
+    if _bhsd_strides(dout) != os_:
+        # bring dout into o's storage layout (B,S,H,D)
+        tmp = B200Array.empty((Bn, S, H, D), bfloat16).transpose(0, 2, 1, 3)
+        if _bhsd_strides(tmp) != os_:
+            o = o.transpose(0, 2, 1, 3).contiguous().transpose(0, 2, 1, 3)
+            os_ = _bhsd_strides(o)
+        tmp._assign(dout)
+        dout = tmp
+    qs, ks_ = _bhsd_strides(q), _bhsd_strides(k)
+    if _bhsd_strides(v) != ks_:
+        k, v = k.contiguous(), v.contiguous()
+        ks_ = _bhsd_strides(k)
+    km = _key_mask(mask, Bn, Skv)
+    mode = (1 if causal else 0) | (2 if km is not None else 0)
+    if packed:
+        if S != Skv:
+            raise ValueError("packed dqkv needs S == S_kv")
+        buf = B200Array.empty((Bn, S, 3, H, D), bfloat16)
+        dq = buf[:, :, 0].transpose(0, 2, 1, 3)
+        dk = buf[:, :, 1].transpose(0, 2, 1, 3)
+        dv = buf[:, :, 2].transpose(0, 2, 1, 3)
+    else:
+        buf = None
+        dq = B200Array.empty((Bn, S, H, D), bfloat16).transpose(0, 2, 1, 3)
+        dk = B200Array.empty((Bn, Skv, H, D), bfloat16).transpose(0, 2, 1, 3)
+        dv = B200Array.empty((Bn, Skv, H, D), bfloat16).transpose(0, 2, 1, 3)
+    # the kernels address dq with q's strides and dk/dv with k's strides: make operand layouts agree
+    if _bhsd_strides(dq) != qs:
+        q = _relayout_like(q, dq)
+        qs = _bhsd_strides(q)
+    if _bhsd_strides(dk) != ks_:
+        k = _relayout_like(k, dk)
+        v = _relayout_like(v, dv)
+        ks_ = _bhsd_strides(k)
+    call("nfb_flash_attn_bwd", _lib.BF16, q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr, dq.ptr, dk.ptr, dv.ptr, Bn, H, S, D,
+         qs[0], qs[1], qs[2], ks_[0], ks_[1], ks_[2], os_[0], os_[1], os_[2], Skv, float(scale), mode, km.ptr if km is not None else None)
+    return (dq, dk, dv, buf) if packed else (dq, dk, dv)
+
+
+def _relayout_like(x: B200Array, like: B200Array) -> B200Array:
+    """Copy logical (B,H,S,D) x into a fresh buffer with the same stride pattern as `like`."""
+    Bn, H, S, D = x.shape
+    sb, ss, sh = _bhsd_strides(like)
+    if (sb, ss, sh) == (S * 3 * H * D, 3 * H * D, D):
+        buf = B200Array.empty((Bn, S, 3, H, D), bfloat16)
+        out = buf[:, :, 0].transpose(0, 2, 1, 3)
+    else:
+        out = B200Array.empty((Bn, S, H, D), bfloat16).transpose(0, 2, 1, 3)
+        if _bhsd_strides(out) != (sb, ss, sh):
+            raise B200Error("attention: unsupported gradient layout")
+    out._assign(x)
+    return out
+
+
+def attention_reference_unfused(q, k, v, scale, causal=False, mask=None):
+    """fp32 unfused attention (batched SIMT GEMM + softmax kernel + GEMM): the always-correct 1e-5 path; it
+    materialises the (B,H,S,S) score tensor like the reference does.  Returns (o, p)."""
+    from . import array as A
+    from .b200_backend import B200Backend
+    be = B200Backend()
+    s = A.matmul(q, k.transpose(0, 1, 3, 2)) * float(scale)
+    if causal:
+        S, Skv = s.shape[-2], s.shape[-1]
+        s = A.where(A.tril_mask(S, Skv), s, -1e4)
+    if mask is not None:
+        s = s + mask
+    p = be.softmax(s, axis=-1)
+    return A.matmul(p, v), p

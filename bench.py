@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- training tokens/s of the reference-architecture GPT-2 small (BASELINE.json configs[1]:
+"GPT-2 small (model zoo, random-init) causal LM training, batch 8 x seq 512, on 1 B200") through the nfb200
+public API (Tensor / nn / optim on the b200 backend), one step = forward + cross-entropy + backward + AdamW
+over one synthetic (8, 512) token batch.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's arm (N > 1 under torchrun: data parallel)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: the NumPy oracle port on the host cores
+
+One JSON line on stdout (rank 0).  `value` = whole-job tokens/s with the batch resident in HBM, device-timed with
+CUDA events (max over ranks); `e2e` = the same step fed from pinned HOST buffers (H2D of ids/labels and D2H of the
+loss inside the timed region); `roofline` = the tcgen05 GEMM (dominant kernel) measured with CUDA events around every
+GEMM launch inside the timed steps vs the measured bf16 peak; `cpu_baseline` = the oracle port on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "neural-network-from-scratch_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+GPT2_SMALL = {"vocab_size": 50257, "n_positions": 1024, "n_embd": 768, "n_layer": 12, "n_head": 12}
+BATCH, SEQ = 8, 512
+TRAIN_FLOP_PER_TOKEN = 712.88e6  # SURVEY App. C (GEMM + logits + attention, x3 for training)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batch(rng, batch=BATCH, seq=SEQ, vocab=GPT2_SMALL["vocab_size"]):
+    ids = rng.integers(0, vocab, (batch, seq)).astype(np.int64)
+    labels = np.concatenate([ids[:, 1:], np.zeros((batch, 1), dtype=np.int64)], axis=1)  # shifted by one, last = 0
+    return ids, labels
+
+
+# ------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_oracle_run(steps, warmup, sample_batch=1):
+    """The oracle port of the reference NumPy path (forward + CE + backward + AdamW) at FULL model size on a bounded
+    sample: `sample_batch` of the 8 sequences per step.  Returns (tokens/s, cores, description)."""
+    from oracle.np_model import GPT2Oracle, OracleAdamW
+    np.random.seed(0)
+    model = GPT2Oracle(GPT2_SMALL, grad_clip=True)
+    opt = OracleAdamW(model.params, lr=5e-4, weight_decay=0.1)
+    rng = np.random.default_rng(1234)
+    ids, labels = synthetic_batch(rng, sample_batch, SEQ)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad()
+        out = model.forward(ids, labels)
+        opt.step(model.backward())
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = float(np.median(times))
+    cores = os.cpu_count() or 1
+    return sample_batch * SEQ / t, cores, t, f"oracle port (NumPy/OpenBLAS, all {cores} host threads), full GPT-2 small, {sample_batch} of {BATCH} sequences x {SEQ} tokens per step, median of {steps}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    tps, cores, t, desc = cpu_oracle_run(steps, warm)
+    line = {"impl": "reference", "metric": "training tokens/sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step, batch 8 x seq 512", "sample": desc},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ this repo's arm
+def run_b200(args):
+    import nfb200
+    from nfb200 import _lib, kernels as K, runtime as R
+    from nfb200.array import B200Array
+    from nfb200.core import Tensor, set_default_device, set_grad_clip
+    from nfb200.models import GPT2
+    from nfb200.optim import AdamW
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.init(local)
+    if not nfb200.get_backend("b200").is_available:
+        raise RuntimeError("bench.py: the b200 backend is unavailable (no libnfb200.so or no GPU); there is no CPU fallback")
+    set_default_device(f"cuda:{local}")
+    K.set_precision(args.precision)
+    np.random.seed(0)  # identical replicas on every rank (the reference relies on seeding too)
+    model = GPT2(GPT2_SMALL)
+    ddp = None
+    if world > 1:
+        from nfb200.distributed import DistributedDataParallel, init_process_group
+        init_process_group("nccl")
+        ddp = DistributedDataParallel(model, bucket_size_mb=25)
+    opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float32")
+    rng = np.random.default_rng(1234 + rank)  # each rank gets its own shard: weak scaling, per-GPU batch fixed
+    ids_h, labels_h = synthetic_batch(rng)
+    ids_d, labels_d = Tensor(ids_h, device=f"cuda:{local}"), Tensor(labels_h, device=f"cuda:{local}")
+    fwd_model = ddp if ddp is not None else model
+
+    def step(ids_t, labels_t):
+        opt.zero_grad()
+        loss = fwd_model(ids_t, labels=labels_t)["loss"]
+        loss.backward()
+        if ddp is not None:
+            ddp.finish_gradient_sync()
+        opt.step()
+        return loss
+
+    def barrier():
+        if ddp is not None:
+            from nfb200.distributed import barrier as b
+            b()
+        R.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(ids_d, labels_d)
+    barrier()
+    # ---- timed region 1: inputs resident in HBM (inputs 8x512 tokens; the step streams >> L2 (126 MB) of weights/activations)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = R.Event(), R.Event()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(ids_d, labels_d)
+    e1.record()
+    e1.synchronize()
+    barrier()
+    ms = e0.elapsed_ms(e1)
+    launches = _lib.launch_count() - launches0
+    final_loss = float(loss.item())
+    # ---- timed region 1b: the same steps with a CUDA-event pair around every tcgen05 GEMM launch (roofline numerator);
+    # kept apart from region 1 so the ~200 extra event records per step do not perturb `value`
+    gemm_prof, ms_prof, prof_steps = None, None, max(1, min(args.steps, 5))
+    if args.profile_gemm and rank == 0:
+        K.GEMM_PROFILE = []
+        p0, p1 = R.Event(), R.Event()
+        p0.record()
+        for _ in range(prof_steps):
+            step(ids_d, labels_d)
+        p1.record()
+        p1.synchronize()
+        ms_prof = p0.elapsed_ms(p1)
+        gemm_prof = K.GEMM_PROFILE
+        K.GEMM_PROFILE = None
+    elif args.profile_gemm:
+        for _ in range(prof_steps):
+            step(ids_d, labels_d)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2 (e2e): ids/labels come from PINNED host memory every step, the loss goes back to the host
+    import ctypes as C
+    nbytes = ids_h.nbytes
+    pin = C.c_void_p()
+    _lib.call("nfb_host_alloc", 2 * nbytes + 64, C.byref(pin))
+    pin_ids = np.frombuffer((C.c_char * nbytes).from_address(pin.value), dtype=np.int64).reshape(ids_h.shape)
+    pin_lab = np.frombuffer((C.c_char * nbytes).from_address(pin.value + nbytes), dtype=np.int64).reshape(ids_h.shape)
+    pin_ids[...] = ids_h
+    pin_lab[...] = labels_h
+    loss_host = np.zeros(1, np.float32)
+    dev_ids, dev_lab = B200Array.empty(ids_h.shape, np.int64), B200Array.empty(ids_h.shape, np.int64)
+    t_ids, t_lab = Tensor(dev_ids), Tensor(dev_lab)
+    e2e_steps = max(2, min(args.steps, 10))
+    barrier()
+    f0, f1 = R.Event(), R.Event()
+    f0.record()
+    for _ in range(e2e_steps):
+        _lib.call("nfb_memcpy_h2d_async", dev_ids.ptr, pin_ids.ctypes.data, nbytes)
+        _lib.call("nfb_memcpy_h2d_async", dev_lab.ptr, pin_lab.ctypes.data, nbytes)
+        l = step(t_ids, t_lab)
+        _lib.call("nfb_memcpy_d2h", loss_host.ctypes.data, l.data.ptr, 4)  # blocks until the step's loss is on the host
+    f1.record()
+    f1.synchronize()
+    barrier()
+    ms_e2e = f0.elapsed_ms(f1)
+    _lib.call("nfb_host_free", pin)
+
+    # max over ranks (device-timed)
+    if ddp is not None:
+        from nfb200.distributed import all_reduce_max_host
+        ms = all_reduce_max_host(ms)
+        ms_e2e = all_reduce_max_host(ms_e2e)
+    if rank != 0:
+        return
+    tokens_per_step = BATCH * SEQ * world
+    value = tokens_per_step * args.steps / (ms / 1e3)
+    e2e_value = tokens_per_step * e2e_steps / (ms_e2e / 1e3)
+    pk = peaks()
+    roof = None
+    if gemm_prof:
+        tot_ms = sum(a.elapsed_ms(b) for a, b, _, _ in gemm_prof)
+        tot_flop = sum(f for _, _, f, _ in gemm_prof)
+        n = len(gemm_prof)
+        achieved = tot_flop / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_gemm_tc (tcgen05/TMEM bf16 GEMM)", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                "launches_timed": n, "avg_launch_ms": tot_ms / n, "avg_launch_gflop": tot_flop / n / 1e9, "share_of_step": tot_ms / ms_prof,
+                "algorithmic_flops": "2*M*N*K per launch (fwd, dgrad and wgrad GEMMs of every Linear + logits), summed over the launches of the timed steps"}
+    line = {"metric": "training tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step (fwd + CE + bwd + AdamW)",
+                       "per_gpu_batch": BATCH, "seq_len": SEQ, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "precision": "bf16 tensor-core GEMM/attention operands, fp32 accumulate / residual stream / master weights / Adam moments" if args.precision == "bf16" else "fp32",
+                       "l2": "no explicit flush: each step streams ~3 GB of weights/optimizer state and ~5 GB of activations, far above the 126 MB L2",
+                       "grad_clip": "reference +-10 clip on fp32 gradients and in the dgrad GEMM epilogues"},
+            "model_tflops": value * TRAIN_FLOP_PER_TOKEN / 1e12, "mfu_vs_sustained_peak": value * TRAIN_FLOP_PER_TOKEN / 1e12 / (pk["bf16_tflops_sustained"] * world),
+            "final_loss": final_loss,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 4, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if roof is not None:
+        line["roofline"] = roof
+    if world == 1 and not args.no_cpu_baseline:
+        tps, cores, t, desc = cpu_oracle_run(1, 0)
+        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -282,6 +282,27 @@ class B200Array:
             shape[shape.index(-1)] = self.size // known
         if _prod(shape) != self.size:
             raise ValueError(f"cannot reshape array of size {self.size} into shape {tuple(shape)}")
+        if tuple(shape) == self.shape:
+            return self
+        if not self.is_contiguous and self.ndim >= 2 and shape and shape[-1] == self.shape[-1] and self.strides[-1] == 1:
+            # row-padded arrays (e.g. logits with a 16-byte-aligned pitch): regrouping the leading dims stays a view
+            ld = None
+            e, ok = 1, True
+            for s, st in zip(reversed(self.shape[:-1]), reversed(self.strides[:-1])):
+                if s == 1:
+                    continue
+                if ld is None:
+                    ld = st
+                if st != ld * e:
+                    ok = False
+                    break
+                e *= s
+            if ok and ld is not None:
+                st_new, e = [1], 1
+                for s in reversed(shape[:-1]):
+                    st_new.append(ld * e)
+                    e *= s
+                return B200Array(self._buf, shape, self.dtype, tuple(reversed(st_new)), self._off)
         src = self if self.is_contiguous else self.contiguous()
         return B200Array(src._buf, shape, src.dtype, None, src._off)
 

@@ -442,11 +442,12 @@ class B200Backend(Backend):
             raise ValueError(f"cross_entropy: {rows} logits rows but {t.shape[0]} targets")
         per_row = B200Array.empty((rows,), np.float32)
         dl = None
+        dld = (V + 7) // 8 * 8  # 16-byte row pitch: the gradient feeds TMA-loaded GEMM operands without a repack
         if need_grad:
-            dl = B200Array.empty((rows, V), grad_dtype or np.float32)
+            dl = B200Array.empty((rows, dld), grad_dtype or np.float32)[:, :V]
         scale = 1.0 / rows if reduction == "mean" else 1.0
         call("nfb_cross_entropy", logits.ptr, t.ptr, 1 if t.dtype == np.dtype(np.int64) else 0, per_row.ptr,
-             dl.ptr if dl is not None else None, dtype_code(dl.dtype) if dl is not None else 0, rows, V, ldv, V, float(scale))
+             dl.ptr if dl is not None else None, dtype_code(dl.dtype) if dl is not None else 0, rows, V, ldv, dld, float(scale))
         if reduction == "mean":
             loss = A.reduce("mean", per_row, None, False)
         elif reduction == "sum":

@@ -349,9 +349,10 @@ class Tensor:
     def backward(self, gradient=None) -> None:
         if not self.requires_grad:
             return
-        if gradient is None:
+        unit = gradient is None
+        if unit:
             gradient = np.ones(self.shape, dtype=np.float32) if self._device.is_cpu else self._backend.ones(self.shape, np.float32)
-        run_backward(self, self._coerce_grad(gradient))
+        run_backward(self, self._coerce_grad(gradient), unit_seed=unit)
 
     def zero_grad(self) -> None:
         self._grad = None
@@ -527,8 +528,24 @@ def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable],
     return out
 
 
-def run_backward(root: Tensor, grad) -> None:
+_UNIT_SEED = None  # the default all-ones seed of the current backward(): ops may skip multiplying by it
+
+
+def is_unit_seed(g) -> bool:
+    return g is _UNIT_SEED and g is not None
+
+
+def run_backward(root: Tensor, grad, unit_seed: bool = False) -> None:
     """One reverse sweep over the graph in decreasing creation order (inputs are always created before outputs)."""
+    global _UNIT_SEED
+    _UNIT_SEED = grad if unit_seed else None
+    try:
+        _run_backward(root, grad, unit_seed)
+    finally:
+        _UNIT_SEED = None
+
+
+def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
     # collect reachable op nodes
     nodes = {}
     stack = [root]
@@ -554,7 +571,8 @@ def run_backward(root: Tensor, grad) -> None:
         g = pending.pop(id(t), None)
         if g is None:
             continue
-        g = _clip(g)
+        if not (unit_seed and t is root):
+            g = _clip(g)
         fn = t._grad_fn
         if t._hooks:
             for h in list(t._hooks.values()):

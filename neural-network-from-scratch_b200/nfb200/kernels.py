@@ -19,6 +19,7 @@ from .array import B200Array, bfloat16, dtype_code
 
 _PRECISION = "fp32"
 F32 = np.dtype(np.float32)
+GEMM_PROFILE = None  # set to a list to collect (start_event, end_event, flops, shape) per tcgen05 GEMM launch (bench.py)
 
 
 def set_precision(mode: str):
@@ -73,6 +74,8 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
         if accumulate:
             raise ValueError("gemm_bf16: accumulate=True needs an existing `out`")
         odt = bfloat16 if (out_dtype is bfloat16 or out_dtype == "bfloat16") else F32
+        if ldc is None and N % 8 != 0 and N >= 1024:
+            ldc = (N + 7) // 8 * 8  # wide ragged outputs (logits): keep rows 16-byte aligned for the consumers
         if ldc is None or ldc == N:
             out = B200Array.empty((M, N), odt)
         else:
@@ -93,9 +96,15 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
         bias_ptr = bias.ptr
     aux_arr = B200Array.empty((M, N), bfloat16) if aux else None
     epi = {None: 0, "none": 0, "gelu": 1, "relu": 2}[epilogue.lower() if isinstance(epilogue, str) else epilogue]
+    prof = GEMM_PROFILE
+    if prof is not None:
+        from .runtime import Event
+        e0 = Event().record()
     call("nfb_gemm_bf16", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, a2.ptr, lda, b2.ptr, ldb, out.ptr,
          dtype_code(out.dtype), ldc_v, bias_ptr, res_ptr, ldr, aux_arr.ptr if aux_arr is not None else None, N, epi,
          1 if accumulate else 0, int(split_k), float(clip))
+    if prof is not None:
+        prof.append((e0, Event().record(), 2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b))))
     return (out, aux_arr) if aux else out
 
 
@@ -143,7 +152,8 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
     if precision == "bf16":
         xb = to_bf16(x2)
         wb = w_bf16 if w_bf16 is not None else to_bf16(W)
-        odt = out_dtype if out_dtype is not None else (F32 if x.dtype == F32 else bfloat16)
+        # the residual stream is fp32: a GEMM that folds the skip connection into its epilogue writes fp32
+        odt = out_dtype if out_dtype is not None else (F32 if (x.dtype == F32 or residual is not None) else bfloat16)
         if act == "gelu":
             y, z = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue="gelu", aux=True)
         else:

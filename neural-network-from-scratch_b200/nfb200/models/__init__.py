@@ -1,0 +1,2 @@
+"""Model zoo for the named configs: GPT-2 small/medium, BERT-base MLM, ViT-B/16, translation encoder-decoder."""
+from .gpt2 import GPT2, GPT2_CONFIGS, GPT2LMHead, GPT2Model, gpt2_large, gpt2_medium, gpt2_small, gpt2_xl

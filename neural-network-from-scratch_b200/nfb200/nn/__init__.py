@@ -1,0 +1,6 @@
+"""Neural-network layers (mirror of neural_arch.nn for the Transformer hot path)."""
+from ..core import Module, Parameter
+from .layers import (GELU, Dropout, Embedding, LayerError, LayerNorm, ModuleList, ReLU, RMSNorm, Sequential, Sigmoid, Softmax,
+                     Tanh)
+from .linear import Linear, OptimizedLinear, StandardLinear
+from .transformer import MultiHeadAttention, TransformerBlock, TransformerDecoderBlock

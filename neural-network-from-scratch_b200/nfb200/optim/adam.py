@@ -1,0 +1,219 @@
+"""Adam / AdamW with the reference's exact (quirky) semantics -- optim/adam.py:27-252, optim/adamw.py:41-372 and
+SURVEY F7: fp64 moment accumulation, epsilon inside the square root, Adam's small-LR boost min(5, 0.1/lr), AdamW's
+double bias correction, update clip to +-10, nan_to_num scrub of the parameters.  cuda parameters are updated by
+one fused kernel launch over the flat arena (csrc/optim.cu); cpu parameters run the same formulas in NumPy.
+
+`moment_dtype`: "float64" reproduces the reference bit-for-bit-ish (44 B/param of HBM traffic); "float32" is the
+throughput mode (28 B/param) whose 10-step trajectories stay within 1e-5 of it (tests/test_gpu_train_parity.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from .._lib import F32 as C_F32, F64 as C_F64, call
+from ..array import B200Array
+from ..core import Optimizer
+from .arena import ParamArena
+
+
+class OptimizerError(ValueError):
+    pass
+
+
+class _AdamBase(Optimizer):
+    _variant = 0  # 0 Adam, 1 AdamW
+
+    def __init__(self, parameters, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-5, weight_decay=0.0, amsgrad=False, maximize=False,
+                 betas: Optional[tuple] = None, moment_dtype: str = "float64"):
+        if betas is not None:
+            if len(betas) != 2:
+                raise OptimizerError(f"betas must be a tuple of length 2, got {len(betas)}")
+            beta1, beta2 = betas
+        if hasattr(parameters, "items"):
+            param_dict = dict(parameters.items())
+        else:
+            param_dict = {f"param_{i}": p for i, p in enumerate(parameters)}
+        super().__init__(param_dict, lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, maximize=maximize)
+        if not 0.0 <= lr:
+            raise OptimizerError(f"Invalid learning rate: {lr}")
+        if not 0.0 <= beta1 < 1.0:
+            raise OptimizerError(f"Invalid beta1: {beta1}")
+        if not 0.0 <= beta2 < 1.0:
+            raise OptimizerError(f"Invalid beta2: {beta2}")
+        if not 0.0 <= eps:
+            raise OptimizerError(f"Invalid epsilon: {eps}")
+        if not 0.0 <= weight_decay:
+            raise OptimizerError(f"Invalid weight decay: {weight_decay}")
+        if amsgrad:
+            raise NotImplementedError("amsgrad is not implemented on the b200 backend (not used by the named configs)")
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.weight_decay, self.amsgrad, self.maximize = weight_decay, amsgrad, maximize
+        self.step_count = 0
+        self.moment_dtype = np.dtype(moment_dtype)
+        self.grad_scale = None  # optional device scalar multiplied into every gradient (global-norm clipping)
+        self.state: Dict[str, dict] = {}
+        self.m, self.v = {}, {}
+        dev_params = [p for p in self.parameters.values() if isinstance(p.data, B200Array)]
+        self.arena = None
+        if dev_params:
+            from .. import kernels as K
+            self.arena = ParamArena(dev_params, self.moment_dtype, 2, with_bf16=(K.get_precision() == "bf16"))
+        seen = {}
+        for name, p in self.parameters.items():
+            if id(p) in seen:  # tied parameter registered under a second name: share the state
+                self.state[name] = self.state[seen[id(p)]]
+                continue
+            seen[id(p)] = name
+            if self.arena is not None and id(p) in self.arena.offsets:
+                ea, es = self.arena.view(self.arena.moments[0], p), self.arena.view(self.arena.moments[1], p)
+            else:
+                ea, es = np.zeros(p.shape, dtype=np.float64), np.zeros(p.shape, dtype=np.float64)
+            self.state[name] = {"step": 0, "exp_avg": ea, "exp_avg_sq": es}
+            self.m[name], self.v[name] = ea, es
+
+    # ------------------------------------------------------------------ step
+    def _update_learning_rate(self):
+        pass
+
+    def step(self) -> None:
+        self.step_count += 1
+        self._update_learning_rate()
+        done = set()
+        if self.arena is not None:
+            # group the arena parameters that have a gradient by their per-parameter step count (all equal unless some
+            # parameters were skipped earlier: the reference skips parameters whose grad is None)
+            name_of = {}
+            for name, p in self.parameters.items():
+                name_of.setdefault(id(p), name)
+            steps = {}
+            for p in self.arena.params:
+                if p.grad is None:
+                    continue
+                st = self.state[name_of[id(p)]]
+                st["step"] += 1
+                steps.setdefault(st["step"], set()).add(id(p))
+                done.add(id(p))
+            mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
+            msz = self.moment_dtype.itemsize
+            a = self.arena
+            for step, ids in steps.items():
+                for off, n in a.runs(lambda q: id(q) in ids):
+                    call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + off * 4, a.flat_g.ptr + off * 4,
+                         a.moments[0].ptr + off * msz, a.moments[1].ptr + off * msz,
+                         (a.flat_bf16.ptr + off * 2) if a.flat_bf16 is not None else None, n, float(self.lr), float(self.beta1),
+                         float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
+                         self.grad_scale.ptr if self.grad_scale is not None else None)
+            for p in a.params:
+                if id(p) in done:
+                    p._version += 1
+        for name, p in self.parameters.items():
+            if id(p) in done or p.grad is None:
+                continue
+            done.add(id(p))
+            self._host_step(name, p)
+
+    def _host_step(self, name, p):
+        st = self.state[name]
+        g = p.grad if not isinstance(p.grad, B200Array) else p.grad.get()
+        pd = p.data if not isinstance(p.data, B200Array) else p.data.get()
+        if self.maximize:
+            g = -g
+        if self._variant == 0 and self.weight_decay != 0:
+            g = g + self.weight_decay * pd
+        st["step"] += 1
+        t = st["step"]
+        st["exp_avg"] = self.beta1 * st["exp_avg"] + (1 - self.beta1) * g.astype(np.float64)
+        st["exp_avg_sq"] = self.beta2 * st["exp_avg_sq"] + (1 - self.beta2) * (g.astype(np.float64) ** 2)
+        self.m[name], self.v[name] = st["exp_avg"], st["exp_avg_sq"]
+        bc1, bc2 = 1 - self.beta1 ** t, 1 - self.beta2 ** t
+        denom = np.sqrt(st["exp_avg_sq"] / bc2 + self.eps)
+        if self._variant == 0:
+            eff = self.lr * min(5.0, 0.1 / self.lr) if (0 < self.lr <= 0.02) else self.lr
+        else:
+            eff = self.lr / bc1
+        upd = np.clip((eff * (st["exp_avg"] / bc1) / denom).astype(pd.dtype), -10.0, 10.0)
+        if self._variant == 1 and self.weight_decay != 0:
+            new = pd * (1 - self.lr * self.weight_decay) - upd
+        else:
+            new = pd - upd
+        if not np.all(np.isfinite(new)):
+            new = np.nan_to_num(new, nan=0.0, posinf=1.0, neginf=-1.0)
+        p.data = np.asarray(new, dtype=pd.dtype)
+
+    def zero_grad(self) -> None:
+        if self.arena is not None:
+            self.arena.zero_grad()
+        for p in self.parameters.values():
+            if self.arena is None or id(p) not in self.arena.offsets:
+                p.zero_grad()
+
+    # ------------------------------------------------------------------ state (optim/adam.py:279-311)
+    def get_state_dict(self) -> dict:
+        def host(x):
+            return x.get() if isinstance(x, B200Array) else np.asarray(x)
+        return {"state": {n: {"step": s["step"], "exp_avg": host(s["exp_avg"]).astype(np.float64),
+                              "exp_avg_sq": host(s["exp_avg_sq"]).astype(np.float64)} for n, s in self.state.items()},
+                "param_groups": [{"lr": self.lr, "beta1": self.beta1, "beta2": self.beta2, "eps": self.eps,
+                                  "weight_decay": self.weight_decay, "amsgrad": self.amsgrad, "maximize": self.maximize}],
+                "step_count": self.step_count}
+
+    state_dict = get_state_dict
+
+    def load_state_dict(self, sd: dict) -> None:
+        for n, s in sd.get("state", {}).items():
+            if n not in self.state:
+                continue
+            cur = self.state[n]
+            cur["step"] = int(s["step"])
+            for k in ("exp_avg", "exp_avg_sq"):
+                if isinstance(cur[k], B200Array):
+                    cur[k]._assign(B200Array.from_numpy(np.asarray(s[k]).astype(self.moment_dtype)))
+                else:
+                    cur[k] = np.asarray(s[k], dtype=np.float64)
+        g = (sd.get("param_groups") or [{}])[0]
+        for k in ("lr", "beta1", "beta2", "eps", "weight_decay"):
+            if k in g:
+                setattr(self, k, g[k])
+        self.step_count = sd.get("step_count", self.step_count)
+
+
+class Adam(_AdamBase):
+    _variant = 0
+
+
+class AdamW(_AdamBase):
+    _variant = 1
+
+    def __init__(self, parameters, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.01, amsgrad=False, maximize=False,
+                 betas=None, lr_scheduler: Optional[str] = None, lr_scheduler_params: Optional[dict] = None,
+                 moment_dtype: str = "float64"):
+        super().__init__(parameters, lr, beta1, beta2, eps, weight_decay, amsgrad, maximize, betas, moment_dtype)
+        self.initial_lr = lr
+        self.lr_scheduler = lr_scheduler
+        self.lr_scheduler_params = lr_scheduler_params or {}
+
+    def _update_learning_rate(self):
+        """Built-in schedules of optim/adamw.py:232-275 (host-side scalars)."""
+        s, pr = self.lr_scheduler, self.lr_scheduler_params
+        if not s:
+            return
+        t = self.step_count
+        if s == "cosine":
+            T, eta = pr.get("T_max", 1000), pr.get("eta_min", 0)
+            self.lr = eta + (self.initial_lr - eta) * 0.5 * (1 + np.cos(np.pi * min(t, T) / T))
+        elif s == "linear":
+            T = pr.get("total_steps", 1000)
+            self.lr = self.initial_lr * max(0.0, 1.0 - t / T)
+        elif s == "exponential":
+            self.lr = self.initial_lr * pr.get("gamma", 0.95) ** t
+        elif s == "step":
+            self.lr = self.initial_lr * pr.get("gamma", 0.1) ** (t // pr.get("step_size", 30))
+        elif s == "warmup_cosine":
+            W, T, eta = pr.get("warmup_steps", 100), pr.get("T_max", 1000), pr.get("eta_min", 0)
+            if t <= W:
+                self.lr = self.initial_lr * t / W
+            else:
+                prog = min((t - W) / (T - W), 1.0) if T > W else 1.0
+                self.lr = eta + (self.initial_lr - eta) * 0.5 * (1 + np.cos(np.pi * prog))

@@ -11,8 +11,8 @@
 //   transB = 1: B stored (N,K) row-major  -> K-major    (y = x W^T with W (out,in))
 //   transB = 0: B stored (K,N) row-major  -> MN-major   (dX = dY W ; dW = dY^T X)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
-// elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes  32*(warp%4) .. +31).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2..9 = epilogue (two warps per 32-lane TMEM quarter 32*(warp%4) .. +31).
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), double-buffered TMEM accumulator
 // full/empty mbarriers (MMA <-> epilogue), static persistent tile schedule.
 #include "common.cuh"
@@ -25,7 +25,7 @@
 #define BLOCK_M 128
 #define BLOCK_K 64
 #define UMMA_K 16
-#define GEMM_THREADS 192
+#define GEMM_THREADS 320
 
 struct GemmParams {
   int M, N, K;
@@ -42,6 +42,7 @@ struct GemmParams {
   int epilogue;         // 0 none, 1 gelu_tanh, 2 relu
   int accumulate;       // C += (fp32 only, red.global.add)
   float clip;           // > 0: clamp the result to [-clip, clip]
+  int vec_ok;           // C / residual / aux pitches and bases allow 128-bit (fp32) / 64-bit (bf16) accesses
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -160,7 +161,7 @@ struct GemmSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;   // per-epilogue-warp transpose buffers
+  static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // per-epilogue-warp 32x32 fp32 transpose buffers (XOR swizzled)
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
@@ -188,7 +189,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -265,9 +266,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter owned by this warp
-    float* st = staging + (warp - 2) * 32 * 33;
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); the pair splits the
+    // 32-column chunks even/odd.  Per chunk: tcgen05.ld (thread = row, 32 columns) -> XOR-swizzled smem transpose
+    // (conflict-free 128-bit STS/LDS) -> each thread owns 4 consecutive columns of 8 rows -> fused bias /
+    // activation / residual / clip -> 128-bit (fp32) or 64-bit (bf16) coalesced global stores.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float4* st4 = reinterpret_cast<float4*>(staging) + (warp - 2) * 256;
+    const int g = lane & 7, rsub = lane >> 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -279,36 +286,81 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool add_bias = p.bias != nullptr && ks == 0;
       const bool add_res = p.residual != nullptr && ks == 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         tmem_ld_wait();
-        // thread `lane` holds row (row0 + lane), columns col0 .. col0+31  ->  transpose through smem
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int gg = 0; gg < 8; ++gg)
+          st4[lane * 8 + (gg ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]),
+                                                          __uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
         __syncwarp();
-        const int col = col0 + lane;
-        const bool col_ok = col < p.N;
-        const float bv = (add_bias && col_ok) ? p.bias[col] : 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+        const int col = col0 + g * 4;
+        const bool full4 = (col + 3 < p.N) && p.vec_ok;
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (add_bias) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (col + e < p.N) bv[e] = p.bias[col + e];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rsub;
           const int row = row0 + rr;
-          if (row >= p.M) break;  // warp-uniform
-          float v = st[rr * 33 + lane] + bv;
-          if (col_ok) {
-            if (p.aux) ((__nv_bfloat16*)p.aux)[(long long)row * p.ldaux + col] = __float2bfloat16_rn(v);
-            if (p.epilogue == 1) v = gelu_tanh_f(v);
-            else if (p.epilogue == 2) v = fmaxf(v, 0.f);
-            if (add_res) v += p.residual[(long long)row * p.ldr + col];
-            if (p.clip > 0.f) v = fminf(fmaxf(v, -p.clip), p.clip);
-            if (p.c_bf16) {
-              ((__nv_bfloat16*)p.C)[(long long)row * p.ldc + col] = __float2bfloat16_rn(v);
+          float4 t4 = st4[rr * 8 + (g ^ (rr & 7))];
+          if (row < p.M && col < p.N) {
+            float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
+            if (full4) {
+              if (p.aux) {
+                __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0], v[1]), a1 = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+                *reinterpret_cast<uint2*>((__nv_bfloat16*)p.aux + (long long)row * p.ldaux + col) = u;
+              }
+              if (p.epilogue == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_f(v[e]);
+              } else if (p.epilogue == 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (add_res) {
+                float4 rv = *reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col);
+                v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+              }
+              if (p.clip > 0.f) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fminf(fmaxf(v[e], -p.clip), p.clip);
+              }
+              if (p.c_bf16) {
+                __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0], v[1]), a1 = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+                *reinterpret_cast<uint2*>((__nv_bfloat16*)p.C + (long long)row * p.ldc + col) = u;
+              } else {
+                float* dst = (float*)p.C + (long long)row * p.ldc + col;
+                if (p.accumulate) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+              }
             } else {
-              float* dst = (float*)p.C + (long long)row * p.ldc + col;
-              if (p.accumulate) atomicAdd(dst, v);
-              else *dst = v;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (col + e >= p.N) break;
+                float x = v[e];
+                if (p.aux) ((__nv_bfloat16*)p.aux)[(long long)row * p.ldaux + col + e] = __float2bfloat16_rn(x);
+                if (p.epilogue == 1) x = gelu_tanh_f(x);
+                else if (p.epilogue == 2) x = fmaxf(x, 0.f);
+                if (add_res) x += p.residual[(long long)row * p.ldr + col + e];
+                if (p.clip > 0.f) x = fminf(fmaxf(x, -p.clip), p.clip);
+                if (p.c_bf16) ((__nv_bfloat16*)p.C)[(long long)row * p.ldc + col + e] = __float2bfloat16_rn(x);
+                else {
+                  float* dst = (float*)p.C + (long long)row * p.ldc + col + e;
+                  if (p.accumulate) atomicAdd(dst, x);
+                  else *dst = x;
+                }
+              }
             }
           }
         }
@@ -442,6 +494,12 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   p.C = C; p.c_bf16 = (c_dtype == NFB_BF16); p.ldc = ldc;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.aux = aux; p.ldaux = ldaux;
   p.epilogue = epilogue; p.accumulate = accumulate; p.clip = clip;
+  {
+    bool ok = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
+    if (residual) ok = ok && (ldr % 4 == 0) && ((uintptr_t)residual % 16 == 0);
+    if (aux) ok = ok && (ldaux % 4 == 0) && ((uintptr_t)aux % 8 == 0);
+    p.vec_ok = ok ? 1 : 0;
+  }
 
   CUtensorMap tmA, tmB;
   if (!p.a_mn) { if (make_map(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M)) return -1; }
@@ -453,7 +511,7 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   int grid = (int)(total < sms ? total : sms);
   switch (best_bn) {
     case 256: return launch_gemm<256, 4>(tmA, tmB, p, grid);
-    case 192: return launch_gemm<192, 5>(tmA, tmB, p, grid);
+    case 192: return launch_gemm<192, 4>(tmA, tmB, p, grid);
     case 128: return launch_gemm<128, 6>(tmA, tmB, p, grid);
     case 64: return launch_gemm<64, 8>(tmA, tmB, p, grid);
   }

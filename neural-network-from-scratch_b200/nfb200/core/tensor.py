@@ -513,6 +513,11 @@ def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable],
                 dev = t._device
                 break
     rg = _grad_enabled and any(isinstance(t, Tensor) and t.requires_grad for t in inputs)
+    if rg and backward_fn is not None:
+        for t in inputs:  # data-parallel bucket readiness: count the graph nodes that consume each parameter
+            if isinstance(t, Tensor) and t._grad_fn is None:
+                for q in _ddp_targets(t):
+                    q._ddp._note_use(q)
     out = Tensor.__new__(Tensor)
     out._device = dev if dev is not None else get_default_device()
     out._backend = _backend_for(out._device)
@@ -526,6 +531,18 @@ def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable],
     out._hooks = None
     out._version = 0
     return out
+
+
+def _ddp_targets(t):
+    """Parameters tracked by a DistributedDataParallel wrapper that `t` stands for (itself, or the parameters a fused
+    multi-parameter view aliases)."""
+    d = t.__dict__
+    if "_ddp" in d:
+        return (t,)
+    al = d.get("_ddp_alias")
+    if al:
+        return tuple(q for q in al if "_ddp" in q.__dict__)
+    return ()
 
 
 _UNIT_SEED = None  # the default all-ones seed of the current backward(): ops may skip multiplying by it
@@ -586,20 +603,23 @@ def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
         else:
             acc0 = None
             grads = fn.backward_fn(g)
-        if grads is None:
-            continue
-        if not isinstance(grads, (tuple, list)):
-            grads = (grads,)
-        for i, (inp, gi) in enumerate(zip(fn.inputs, grads)):
-            if gi is None or gi is ACCUMULATED or not isinstance(inp, Tensor) or not inp.requires_grad:
-                continue
-            if tuple(gi.shape) != inp.shape:
-                gi = inp._coerce_grad(gi)
-            if inp._grad_fn is None:
-                inp._accumulate(_clip(gi))
-            else:
-                prev = pending.get(id(inp))
-                if prev is None or (fn.fused_acc and i == 0):
-                    pending[id(inp)] = gi
+        if grads is not None:
+            if not isinstance(grads, (tuple, list)):
+                grads = (grads,)
+            for i, (inp, gi) in enumerate(zip(fn.inputs, grads)):
+                if gi is None or gi is ACCUMULATED or not isinstance(inp, Tensor) or not inp.requires_grad:
+                    continue
+                if tuple(gi.shape) != inp.shape:
+                    gi = inp._coerce_grad(gi)
+                if inp._grad_fn is None:
+                    inp._accumulate(_clip(gi))
                 else:
-                    pending[id(inp)] = prev + gi
+                    prev = pending.get(id(inp))
+                    if prev is None or (fn.fused_acc and i == 0):
+                        pending[id(inp)] = gi
+                    else:
+                        pending[id(inp)] = prev + gi
+        for inp in fn.inputs:  # data-parallel: this consumer of the parameter is done -> maybe launch its bucket
+            if isinstance(inp, Tensor) and inp._grad_fn is None:
+                for q in _ddp_targets(inp):
+                    q._ddp._note_grad_done(q)

@@ -1,0 +1,230 @@
+"""DistributedDataParallel / DataParallel / DistributedSampler (mirror of distributed/data_parallel.py:21-388).
+
+B200 design: one process per GPU; the module's parameters are re-homed into one flat fp32 arena with a
+matching flat gradient arena; gradients are all-reduced (NCCL ncclAvg over NVLink/NVSwitch) in contiguous ~25 MB
+BUCKETS of that arena -- the reference accepts bucket_size_mb=25 but all-reduces one tensor at a time,
+synchronously (data_parallel.py:250-287).  A bucket is launched on a dedicated communication stream as soon as the
+backward pass has produced the last gradient that lives in it (use-count tracking in the autograd engine), so the
+transfer overlaps the rest of backward; finish_gradient_sync() fences the compute stream before the optimizer.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import List, Optional
+
+import numpy as np
+
+from ..array import B200Array
+from ..core import Module, Tensor
+from ..optim.arena import ALIGN, ParamArena
+from . import communication as comm
+from .communication import ReduceOp
+
+
+class _Bucket:
+    __slots__ = ("lo", "hi", "params", "pending", "launched", "event")
+
+    def __init__(self, lo, hi, params):
+        self.lo, self.hi, self.params = lo, hi, params
+        self.pending = 0
+        self.launched = False
+        self.event = None
+
+
+class DistributedDataParallel(Module):
+    def __init__(self, module: Module, device_ids=None, output_device=None, bucket_size_mb: float = 25,
+                 find_unused_parameters: bool = False, broadcast_parameters: bool = True, overlap: bool = True):
+        super().__init__()
+        self.module = module
+        self.bucket_size_mb = bucket_size_mb
+        self.find_unused_parameters = find_unused_parameters
+        self.overlap = overlap
+        self.group = comm.get_backend() if comm.is_initialized() else None
+        self.world_size = self.group.world_size if self.group else 1
+        self.rank = self.group.rank if self.group else 0
+        self._require_sync = True
+        params = list(module.parameters())
+        self._dev_params = [p for p in params if isinstance(p.data, B200Array)]
+        self._host_params = [p for p in params if not isinstance(p.data, B200Array)]
+        self.arena: Optional[ParamArena] = None
+        self.buckets: List[_Bucket] = []
+        if self._dev_params:
+            from .. import kernels as K
+            self.arena = ParamArena(self._dev_params, np.float32, 0, with_bf16=(K.get_precision() == "bf16"))
+            self._build_buckets()
+            for p in self.arena.params:
+                p._ddp = self
+        if broadcast_parameters and self.world_size > 1:
+            self.broadcast_parameters()
+
+    # ------------------------------------------------------------------ buckets
+    def _build_buckets(self):
+        """Contiguous slices of the gradient arena, filled in REVERSE registration order (backward order)."""
+        cap = max(1, int(self.bucket_size_mb * (1 << 20) / 4))
+        a = self.arena
+        cur, cur_hi = [], None
+        for p in reversed(a.params):
+            o = a.offsets[id(p)]
+            n = (p.size + ALIGN - 1) // ALIGN * ALIGN
+            if cur and (cur_hi - o) > cap:
+                self.buckets.append(_Bucket(min(a.offsets[id(q)] for q in cur), cur_hi, cur))
+                cur, cur_hi = [], None
+            if cur_hi is None:
+                cur_hi = o + n
+            cur.append(p)
+        if cur:
+            self.buckets.append(_Bucket(min(a.offsets[id(q)] for q in cur), cur_hi, cur))
+        self._bucket_of = {}
+        for b in self.buckets:
+            for p in b.params:
+                self._bucket_of[id(p)] = b
+
+    def broadcast_parameters(self, src: int = 0):
+        if self.arena is not None and self.group is not None and self.group.backend == "nccl":
+            self.group.broadcast_buffer(self.arena.flat_p, src)
+            if self.arena.flat_bf16 is not None:
+                self.group.broadcast_buffer(self.arena.flat_bf16, src)
+            for p in self.arena.params:
+                p._version += 1
+        for p in self._host_params:
+            if self.group is not None:
+                self.group.broadcast(p, src)
+
+    # ------------------------------------------------------------------ forward / overlap machinery
+    def forward(self, *args, **kwargs):
+        if self.arena is not None and self._require_sync and self.world_size > 1:
+            for b in self.buckets:
+                b.pending = 0
+                b.launched = False
+            for p in self.arena.params:
+                p._ddp_uses = 0
+        return self.module(*args, **kwargs)
+
+    def _note_use(self, p):
+        """Called by the autograd engine when a graph node consumes parameter p in the forward pass."""
+        p._ddp_uses = getattr(p, "_ddp_uses", 0) + 1
+        if p._ddp_uses == 1:
+            self._bucket_of[id(p)].pending += 1
+
+    def _note_grad_done(self, p):
+        """Called by the autograd engine after a consumer node of p has run its backward."""
+        if not (self._require_sync and self.overlap and self.world_size > 1):
+            return
+        p._ddp_uses -= 1
+        if p._ddp_uses == 0:
+            b = self._bucket_of[id(p)]
+            b.pending -= 1
+            if b.pending == 0 and not b.launched:
+                self._launch_bucket(b)
+
+    def _launch_bucket(self, b: _Bucket):
+        from ..runtime import Event
+        g = self.group
+        # parameters of this bucket that received no gradient this step still take part with zeros
+        for p in b.params:
+            if p._grad is None and not p._slot_zero:
+                p._grad_slot.fill(0.0)
+                p._slot_zero = True
+        ready = Event(timing=False).record()            # on the compute stream: gradients of this bucket are final
+        g.comm_stream.wait_event(ready)
+        g.allreduce_buffer(self.arena.flat_g, b.hi - b.lo, ReduceOp.AVERAGE, g.comm_stream, offset=b.lo)
+        b.event = Event(timing=False).record(g.comm_stream)
+        b.launched = True
+
+    def finish_gradient_sync(self):
+        """Fence: launch what has not been launched (unused parameters, overlap off) and make the compute stream
+        wait for every bucket.  Call after backward(), before optimizer.step()."""
+        if self.world_size == 1 or not self._require_sync:
+            return
+        from ..runtime import compute_stream_wait
+        if self.arena is not None:
+            for b in self.buckets:
+                if not b.launched:
+                    self._launch_bucket(b)
+            for b in self.buckets:
+                compute_stream_wait(b.event)
+            for p in self.arena.params:   # every parameter now holds the averaged gradient (zeros if unused)
+                if p._grad is None:
+                    p._grad = p._grad_slot
+                p._slot_zero = False
+        for p in self._host_params:
+            if p.grad is not None:
+                p.grad = self.group.all_reduce(Tensor(p.grad), ReduceOp.AVERAGE).data
+
+    def sync_gradients(self):
+        """Reference API (data_parallel.py:271-287): all-reduce(AVERAGE) every gradient after backward."""
+        self.finish_gradient_sync()
+
+    @contextmanager
+    def no_sync(self):
+        prev, self._require_sync = self._require_sync, False
+        try:
+            yield
+        finally:
+            self._require_sync = prev
+
+    def parameters(self, recurse: bool = True):
+        return self.module.parameters(recurse)
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, _memo=None):
+        return self.module.named_parameters(prefix, recurse, _memo)
+
+    def state_dict(self):
+        return self.module.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        return self.module.load_state_dict(sd, strict)
+
+    def train(self, mode: bool = True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.module.eval()
+        return self
+
+
+class DataParallel(DistributedDataParallel):
+    """Single-process multi-GPU DataParallel does not exist in a one-process-per-GPU design; this is DDP under the
+    reference's other class name (data_parallel.py:21-183), so scripts using either spelling run."""
+
+
+class DistributedSampler:
+    """Rank-strided partition with padding and epoch-seeded shuffling, bit-identical to data_parallel.py:304-388."""
+
+    def __init__(self, dataset_size: int, num_replicas: Optional[int] = None, rank: Optional[int] = None, shuffle: bool = True,
+                 seed: int = 0, drop_last: bool = False):
+        if num_replicas is None:
+            num_replicas = comm.get_world_size() if comm.is_initialized() else 1
+        if rank is None:
+            rank = comm.get_rank() if comm.is_initialized() else 0
+        self.dataset_size, self.num_replicas, self.rank = dataset_size, num_replicas, rank
+        self.shuffle, self.seed, self.drop_last, self.epoch = shuffle, seed, drop_last, 0
+        if drop_last and dataset_size % num_replicas != 0:
+            self.num_samples = dataset_size // num_replicas
+        else:
+            self.num_samples = (dataset_size + num_replicas - 1) // num_replicas
+        self.total_size = self.num_samples * num_replicas
+
+    def __iter__(self):
+        if self.shuffle:
+            indices = np.random.RandomState(self.seed + self.epoch).permutation(self.dataset_size).tolist()
+        else:
+            indices = list(range(self.dataset_size))
+        if not self.drop_last:
+            pad = self.total_size - len(indices)
+            if pad <= len(indices):
+                indices += indices[:pad]
+            else:
+                indices += (indices * (pad // len(indices) + 1))[:pad]
+        else:
+            indices = indices[:self.total_size]
+        indices = indices[self.rank:self.total_size:self.num_replicas]
+        assert len(indices) == self.num_samples
+        return iter(indices)
+
+    def __len__(self):
+        return self.num_samples
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch

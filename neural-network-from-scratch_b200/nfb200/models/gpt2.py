@@ -58,6 +58,7 @@ class SwiGLU(Module):
             if a1.flat_bf16 is not None:
                 f._bf16 = a1.flat_bf16[o1:o1 + n].reshape(f.shape)
                 f._bf16_live = True
+            f._ddp_alias = (w1, w2)
             object.__setattr__(self, "_fused_w12", f)
         # the fused view shares w1/w2's gradient slots: it is "zero" exactly when they are untouched
         f._grad = f._grad_slot if (w1._grad is not None or w2._grad is not None) else None

@@ -173,16 +173,28 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step(ids_d, labels_d)
     barrier()
+    graphed = None
+    if args.graph:
+        # steady-state step captured once into a CUDA graph (launch-bound otherwise: ~500 launches per step)
+        from nfb200.training import GraphedStep
+        graphed = GraphedStep(lambda: step(ids_d, labels_d), warmup=2, optimizers=[opt])
+        for _ in range(2):
+            graphed()
+        barrier()
     # ---- timed region 1: inputs resident in HBM (inputs 8x512 tokens; the step streams >> L2 (126 MB) of weights/activations)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # kernels per step (counted by the library on an eager step; a graph replay launches the same kernels)
+    _l0 = _lib.launch_count()
+    step(ids_d, labels_d)
+    graphed_launches = _lib.launch_count() - _l0
     launches0 = _lib.launch_count()
     e0, e1 = R.Event(), R.Event()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = step(ids_d, labels_d)
+        loss = graphed() if graphed is not None else step(ids_d, labels_d)
     e1.record()
     e1.synchronize()
     barrier()
@@ -221,6 +233,10 @@ def run_b200(args):
     loss_host = np.zeros(1, np.float32)
     dev_ids, dev_lab = B200Array.empty(ids_h.shape, np.int64), B200Array.empty(ids_h.shape, np.int64)
     t_ids, t_lab = Tensor(dev_ids), Tensor(dev_lab)
+    graphed_e2e = None
+    if args.graph:
+        from nfb200.training import GraphedStep
+        graphed_e2e = GraphedStep(lambda: step(t_ids, t_lab), warmup=1, optimizers=[opt])
     e2e_steps = max(2, min(args.steps, 10))
     barrier()
     f0, f1 = R.Event(), R.Event()
@@ -228,7 +244,7 @@ def run_b200(args):
     for _ in range(e2e_steps):
         _lib.call("nfb_memcpy_h2d_async", dev_ids.ptr, pin_ids.ctypes.data, nbytes)
         _lib.call("nfb_memcpy_h2d_async", dev_lab.ptr, pin_lab.ctypes.data, nbytes)
-        l = step(t_ids, t_lab)
+        l = graphed_e2e() if graphed_e2e is not None else step(t_ids, t_lab)
         _lib.call("nfb_memcpy_d2h", loss_host.ctypes.data, l.data.ptr, 4)  # blocks until the step's loss is on the host
     f1.record()
     f1.synchronize()
@@ -268,7 +284,7 @@ def run_b200(args):
             "model_tflops": value * TRAIN_FLOP_PER_TOKEN / 1e12, "mfu_vs_sustained_peak": value * TRAIN_FLOP_PER_TOKEN / 1e12 / (pk["bf16_tflops_sustained"] * world),
             "final_loss": final_loss,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 4, "steps": e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(launches) if graphed is None else int(graphed_launches * args.steps), "cuda_graph": graphed is not None, "clocks": clocks}
     if roof is not None:
         line["roofline"] = roof
     if world == 1 and not args.no_cpu_baseline:
@@ -285,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying a captured CUDA graph")
     ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

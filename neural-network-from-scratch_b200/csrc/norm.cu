@@ -80,7 +80,7 @@ template <int VPL, typename TX, typename TY, bool RMS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
            const float* __restrict__ rstd_in, const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
-           int64_t rows, int cols) {
+           int64_t rows, int cols, float clip, __nv_bfloat16* __restrict__ dx_twin) {
   __shared__ float sh[WARPS_PER_BLOCK][2][VPL * 128];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + w;
@@ -132,7 +132,12 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
           f4 r = ld4<TX>(dres + row * cols + c);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
+        if (clip > 0.f) {  // the reference's +-clip on every upstream gradient, fused into the producer
+          o.x = fminf(fmaxf(o.x, -clip), clip); o.y = fminf(fmaxf(o.y, -clip), clip);
+          o.z = fminf(fmaxf(o.z, -clip), clip); o.w = fminf(fmaxf(o.w, -clip), clip);
+        }
         st4<TX>(dx + row * cols + c, o);
+        if (dx_twin) st4<__nv_bfloat16>(dx_twin + row * cols + c, o);  // bf16 copy for the next dgrad/wgrad GEMMs
       }
     }
   }
@@ -153,7 +158,25 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
   }
 }
 
-__global__ void k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ dgamma,
+// partial is [nblocks][2][cols]; stage 1 sums row-chunks of it (grid = (col tiles of 32, chunks)), stage 2 sums the
+// chunks in a fixed order and writes / accumulates dgamma, dbeta: deterministic and parallel over blocks AND columns.
+__global__ void k_norm_param_stage1(const float* __restrict__ partial, int nblocks, int cols2, int chunk_len, float* __restrict__ tmp) {
+  __shared__ float red[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  int lo = blockIdx.y * chunk_len, hi = min(lo + chunk_len, nblocks);
+  float a = 0.f;
+  if (col < cols2)
+    for (int b = lo + threadIdx.y; b < hi; b += 8) a += partial[(int64_t)b * cols2 + col];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols2) {
+    float r = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += red[k][threadIdx.x];
+    tmp[(int64_t)blockIdx.y * cols2 + col] = r;
+  }
+}
+__global__ void k_norm_param_stage2(const float* __restrict__ tmp, int chunks, int cols, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * cols) return;
@@ -161,7 +184,7 @@ __global__ void k_norm_param_reduce(const float* __restrict__ partial, int nbloc
   float* dst = which == 0 ? dgamma : dbeta;
   if (!dst) return;
   float a = 0.f;
-  for (int b = 0; b < nblocks; ++b) a += partial[((int64_t)b * 2 + which) * cols + c];
+  for (int b = 0; b < chunks; ++b) a += tmp[(int64_t)b * 2 * cols + i];
   dst[c] = accumulate ? dst[c] + a : a;
 }
 
@@ -259,14 +282,19 @@ static int norm_fwd_t(const void* x, const void* res, void* sum_out, const float
 
 template <typename TX, typename TY, bool RMS>
 static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
-                      void* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int cols) {
+                      void* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int cols, float clip, void* dx_twin) {
   int vpl = pick_vpl(cols);
   cudaStream_t s = nfb_cur_stream();
-  int grid = nfb_grid_for(rows, WARPS_PER_BLOCK * 4, 2);
+  // one row per warp while that keeps every SM busy: the kernel is latency-bound otherwise (was 4.7x off the HBM roofline)
+  int grid = nfb_grid_for(rows, WARPS_PER_BLOCK, 8);
   float* partial = nullptr;
   bool need_params = dgamma || dbeta;
-  if (need_params && nfb_malloc(sizeof(float) * 2 * (size_t)cols * grid, (void**)&partial)) return -1;
-#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols)
+  int chunks = grid >= 64 ? 16 : 1;
+  int chunk_len = (grid + chunks - 1) / chunks;
+  chunks = (grid + chunk_len - 1) / chunk_len;
+  size_t part_elems = 2 * (size_t)cols * grid;
+  if (need_params && nfb_malloc(sizeof(float) * (part_elems + 2 * (size_t)cols * chunks), (void**)&partial)) return -1;
+#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
   switch (vpl) {
     case 1: LB(1); break;
     case 2: LB(2); break;
@@ -278,7 +306,10 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
 #undef LB
   nfb_count_launch();
   if (need_params) {
-    k_norm_param_reduce<<<(2 * cols + 255) / 256, 256, 0, s>>>(partial, grid, cols, dgamma, dbeta, accumulate);
+    float* tmp = partial + part_elems;
+    k_norm_param_stage1<<<dim3((2 * cols + 31) / 32, chunks), dim3(32, 8), 0, s>>>(partial, grid, 2 * cols, chunk_len, tmp);
+    nfb_count_launch();
+    k_norm_param_stage2<<<(2 * cols + 255) / 256, 256, 0, s>>>(tmp, chunks, cols, dgamma, dbeta, accumulate);
     nfb_free(partial);
   }
   NFB_LAUNCH_CHECK();
@@ -309,10 +340,10 @@ NFB_API int nfb_norm_fwd(int kind, int xdt, int ydt, const void* x, const void* 
 
 NFB_API int nfb_norm_bwd(int kind, int xdt, int ydt, const void* dy, const void* x, const float* gamma, const float* mean,
                          const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int accumulate,
-                         int64_t rows, int cols) {
+                         int64_t rows, int cols, float clip, void* dx_twin) {
   if (rows == 0) return 0;
   if (pick_vpl(cols) == 0) {
-    if (xdt != NFB_F32 || ydt != NFB_F32 || dres) return NFB_FAIL("nfb_norm_bwd: generic path (cols=%d) is fp32 only, no residual", cols);
+    if (xdt != NFB_F32 || ydt != NFB_F32 || dres || dx_twin || clip > 0.f) return NFB_FAIL("nfb_norm_bwd: generic path (cols=%d) is fp32 only, no fusions", cols);
     cudaStream_t s = nfb_cur_stream();
     if (kind == 0) {
       k_norm_bwd_generic<false><<<(unsigned)rows, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, (float*)dx, cols);
@@ -327,8 +358,8 @@ NFB_API int nfb_norm_bwd(int kind, int xdt, int ydt, const void* dy, const void*
     return 0;
   }
 #define DISPATCH(TX, TY)                                                                                                   \
-  return kind == 0 ? norm_bwd_t<TX, TY, false>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols)  \
-                   : norm_bwd_t<TX, TY, true>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols)
+  return kind == 0 ? norm_bwd_t<TX, TY, false>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols, clip, dx_twin)  \
+                   : norm_bwd_t<TX, TY, true>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, accumulate, rows, cols, clip, dx_twin)
   if (xdt == NFB_F32 && ydt == NFB_F32) { DISPATCH(float, float); }
   if (xdt == NFB_F32 && ydt == NFB_BF16) { DISPATCH(float, __nv_bfloat16); }
   if (xdt == NFB_BF16 && ydt == NFB_BF16) { DISPATCH(__nv_bfloat16, __nv_bfloat16); }

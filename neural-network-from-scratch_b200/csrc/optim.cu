@@ -12,8 +12,16 @@
 
 template <typename MT>
 __global__ void k_adam(int variant, float* __restrict__ p, const float* __restrict__ g, MT* __restrict__ m, MT* __restrict__ v,
-                       __nv_bfloat16* __restrict__ p_bf16, int64_t n, MT lr_eff, MT beta1, MT beta2, MT eps, float wd_factor, float wd_grad,
-                       MT inv_bc1, MT inv_bc2, float gsign, const float* __restrict__ grad_scale) {
+                       __nv_bfloat16* __restrict__ p_bf16, int64_t n, double lr, MT beta1, MT beta2, MT eps, float wd_factor, float wd_grad,
+                       int step_host, const int* __restrict__ step_dev, float gsign, const float* __restrict__ grad_scale) {
+  // bias corrections from the step count: a host value, or a device counter so that a captured CUDA graph of the
+  // training step stays valid from one replay to the next
+  const int step = step_dev ? *step_dev : step_host;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  double lr_d;
+  if (variant == 0) lr_d = (lr <= 0.02 && lr > 0.0) ? lr * fmin(5.0, 0.1 / lr) : lr;
+  else lr_d = lr / bc1;
+  const MT lr_eff = (MT)lr_d, inv_bc1 = (MT)(1.0 / bc1), inv_bc2 = (MT)(1.0 / bc2);
   float gs = grad_scale ? *grad_scale : 1.f;
   gs *= gsign;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,28 +47,30 @@ __global__ void k_adam(int variant, float* __restrict__ p, const float* __restri
   }
 }
 
-// variant: 0 = Adam, 1 = AdamW. moment_dtype: NFB_F32 or NFB_F64. step is 1-based (after increment).
+// variant: 0 = Adam, 1 = AdamW. moment_dtype: NFB_F32 or NFB_F64. step is 1-based (after increment); when step_dev
+// (a device int) is given it overrides `step`.
 NFB_API int nfb_adam_step(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n,
                           double lr, double beta1, double beta2, double eps, double weight_decay, int step, int maximize,
-                          const float* grad_scale) {
+                          const float* grad_scale, const int* step_dev) {
   if (n == 0) return 0;
-  double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  double lr_eff;
-  if (variant == 0) {
-    lr_eff = (lr <= 0.02 && lr > 0.0) ? lr * fmin(5.0, 0.1 / lr) : lr;
-  } else {
-    lr_eff = lr / bc1;
-  }
   float wd_factor = (variant == 1 && weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.f;
   float wd_grad = (variant == 0) ? (float)weight_decay : 0.f;
   float gsign = maximize ? -1.f : 1.f;
   int grid = nfb_grid_for(n, 256, 8);
   cudaStream_t s = nfb_cur_stream();
   if (moment_dtype == NFB_F64)
-    k_adam<double><<<grid, 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, n, lr_eff, beta1, beta2, eps, wd_factor, wd_grad, 1.0 / bc1, 1.0 / bc2, gsign, grad_scale);
+    k_adam<double><<<grid, 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
   else if (moment_dtype == NFB_F32)
-    k_adam<float><<<grid, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n, (float)lr_eff, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, (float)(1.0 / bc1), (float)(1.0 / bc2), gsign, grad_scale);
+    k_adam<float><<<grid, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n, lr, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
   else return NFB_FAIL("nfb_adam_step: moment dtype %d", moment_dtype);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_add_i32(int* p, int delta) { *p += delta; }
+// *counter += delta on the device (optimizer step counters that live inside a captured graph)
+NFB_API int nfb_add_i32(int* counter, int delta) {
+  k_add_i32<<<1, 1, 0, nfb_cur_stream()>>>(counter, delta);
   NFB_LAUNCH_CHECK();
   return 0;
 }

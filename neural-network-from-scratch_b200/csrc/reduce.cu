@@ -196,3 +196,63 @@ NFB_API int nfb_argreduce(int is_max, int dtype, const void* x, int64_t* out, in
   NFB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- out[c] (+)= sum_r x[r, c] for a row-major (R, C) matrix with pitch ld: bias gradients (functional/utils.py:33-96
+// reduce_gradient for a (T, n) -> (n) broadcast).  fp32 or bf16 input, fp32 output; two deterministic stages.
+template <typename T>
+__global__ void k_colsum_stage1(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_len, float* __restrict__ tmp) {
+  __shared__ float red[8][65];
+  int c0 = blockIdx.x * 64 + threadIdx.x * 2;
+  int64_t lo = (int64_t)blockIdx.y * chunk_len, hi = lo + chunk_len < R ? lo + chunk_len : R;
+  float a0 = 0.f, a1 = 0.f;
+  if (c0 + 1 < C) {
+    for (int64_t r = lo + threadIdx.y; r < hi; r += 8) {
+      a0 += ld_f<T>(x, r * ld + c0);
+      a1 += ld_f<T>(x, r * ld + c0 + 1);
+    }
+  } else if (c0 < C) {
+    for (int64_t r = lo + threadIdx.y; r < hi; r += 8) a0 += ld_f<T>(x, r * ld + c0);
+  }
+  red[threadIdx.y][threadIdx.x * 2] = a0;
+  red[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y < 2) {
+    int cc = threadIdx.x * 2 + threadIdx.y;
+    int col = blockIdx.x * 64 + cc;
+    if (col < C) {
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r += red[k][cc];
+      tmp[(int64_t)blockIdx.y * C + col] = r;
+    }
+  }
+}
+__global__ void k_colsum_stage2(const float* __restrict__ tmp, int chunks, int C, float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = 0; b < chunks; ++b) a += tmp[(int64_t)b * C + c];
+  out[c] = accumulate ? out[c] + a : a;
+}
+NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, float* out, int accumulate) {
+  if (C == 0) return 0;
+  int col_blocks = (C + 63) / 64;
+  int chunks = (int)((4LL * nfb_sm_count() + col_blocks - 1) / col_blocks);
+  int64_t max_chunks = R / 32 > 0 ? R / 32 : 1;
+  if (chunks > max_chunks) chunks = (int)max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t chunk_len = nfb_cdiv(R > 0 ? R : 1, chunks);
+  chunks = (int)nfb_cdiv(R > 0 ? R : 1, chunk_len);
+  float* tmp = nullptr;
+  if (nfb_malloc(sizeof(float) * (size_t)chunks * C, (void**)&tmp)) return -1;
+  cudaStream_t s = nfb_cur_stream();
+  dim3 grid(col_blocks, chunks), block(32, 8);
+  if (dtype == NFB_F32) k_colsum_stage1<float><<<grid, block, 0, s>>>((const float*)x, R, C, ld, chunk_len, tmp);
+  else if (dtype == NFB_BF16) k_colsum_stage1<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp);
+  else { nfb_free(tmp); return NFB_FAIL("nfb_colsum: unsupported dtype %d", dtype); }
+  nfb_count_launch();
+  k_colsum_stage2<<<(C + 255) / 256, 256, 0, s>>>(tmp, chunks, C, out, accumulate);
+  nfb_free(tmp);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

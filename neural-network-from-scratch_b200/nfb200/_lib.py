@@ -74,9 +74,10 @@ _SIGNATURES = {
     # reductions
     "nfb_reduce": [i32, i32, vp, vp, i64, i64, i64],
     "nfb_argreduce": [i32, i32, vp, vp, i64, i64, i64],
+    "nfb_colsum": [i32, vp, i64, i32, i64, vp, i32],
     # norms / softmax / loss
     "nfb_norm_fwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32],
-    "nfb_norm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32],
+    "nfb_norm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],
     "nfb_softmax_fwd": [vp, vp, i64, i32],
     "nfb_softmax_bwd": [vp, vp, vp, i64, i32],
     "nfb_cross_entropy": [vp, vp, i32, vp, vp, i32, i64, i32, i64, i64, f32],
@@ -85,7 +86,8 @@ _SIGNATURES = {
     "nfb_scatter_add_rows": [i32, i32, vp, vp, vp, i64, i32, i64, i32],
     "nfb_index_error_check": [C.POINTER(C.c_int)],
     # optimizers
-    "nfb_adam_step": [i32, i32, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, i32, vp],
+    "nfb_adam_step": [i32, i32, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, i32, vp, vp],
+    "nfb_add_i32": [vp, i32],
     "nfb_sgd_step": [vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, i32, i32],
     "nfb_sumsq": [vp, i64, vp, i32],
     "nfb_clip_coef": [vp, f32, f32, vp, vp],

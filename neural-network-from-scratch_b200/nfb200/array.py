@@ -114,7 +114,7 @@ RED = {"sum": 0, "mean": 1, "max": 2, "min": 3, "prod": 4}
 
 
 class B200Array:
-    __slots__ = ("_buf", "_off", "shape", "strides", "dtype", "__weakref__")
+    __slots__ = ("_buf", "_off", "shape", "strides", "dtype", "clipped", "twin", "__weakref__")
     __array_priority__ = 1000.0
 
     # ------------------------------------------------------------------ construction
@@ -124,6 +124,8 @@ class B200Array:
         self.dtype = dtype
         self.strides = tuple(strides) if strides is not None else _contig_strides(self.shape)  # in ELEMENTS
         self._off = int(offset)  # in elements
+        self.clipped = False  # gradient already clamped to +-clip by the kernel that produced it
+        self.twin = None      # optional bf16 copy written by the producing kernel (feeds tensor-core GEMMs)
 
     @staticmethod
     def empty(shape, dtype=np.float32) -> "B200Array":

@@ -8,7 +8,7 @@ fallback: if the library or a B200 is missing the backend reports ``is_available
 ``get_backend("b200")`` raises RuntimeError exactly like an unavailable reference backend) and any
 direct use raises :class:`B200Error`.
 
-Beyond the 56 abstract members it provides the optional hooks the reference's functional layer
+Beyond the 54 abstract members it provides the optional hooks the reference's functional layer
 probes with ``hasattr`` (relu/maximum/softmax/sigmoid/tanh/gelu, functional/activation.py:28-283),
 the CuPy-precedent fused entry points (``fused_linear_gelu``, ``layernorm``, ``flash_attention``,
 ``benchmark_kernel``, ``has_custom_kernels``; backends/cuda_backend.py:303-386) and the fused
@@ -404,7 +404,7 @@ class B200Backend(Backend):
         return (y, mean, rstd) if res is None else (y, mean, rstd, summed)
 
     def norm_backward(self, dy, x, weight, mean, rstd, rms=False, need_wgrad=True, need_bgrad=True, dresidual=None,
-                      dweight_out=None, dbias_out=None, accumulate=False):
+                      dweight_out=None, dbias_out=None, accumulate=False, clip=0.0, bf16_twin=False):
         """Returns (dx, dweight|None, dbias|None).  nn/normalization.py:147-200 / :300-341."""
         x = _arr(x).contiguous()
         dy = _arr(dy).contiguous()
@@ -415,9 +415,14 @@ class B200Backend(Backend):
         db = dbias_out if dbias_out is not None else (B200Array.empty((cols,), np.float32) if need_bgrad and not rms else None)
         w = None if weight is None else _arr(weight).contiguous()
         dres = None if dresidual is None else _arr(dresidual).contiguous()
+        twin = B200Array.empty(x.shape, bfloat16) if (bf16_twin and x.dtype == np.dtype(np.float32)) else None
         call("nfb_norm_bwd", 1 if rms else 0, dtype_code(x.dtype), dtype_code(dy.dtype), dy.ptr, x.ptr, w.ptr if w is not None else None,
              mean.ptr if mean is not None else None, rstd.ptr, dres.ptr if dres is not None else None, dx.ptr,
-             dw.ptr if dw is not None else None, db.ptr if db is not None else None, 1 if accumulate else 0, rows, cols)
+             dw.ptr if dw is not None else None, db.ptr if db is not None else None, 1 if accumulate else 0, rows, cols,
+             float(clip or 0.0), twin.ptr if twin is not None else None)
+        if clip:
+            dx.clipped = True
+        dx.twin = twin
         return dx, dw, db
 
     def cross_entropy(self, logits, targets, reduction="mean", need_grad=True, grad_dtype=None, ld=None):
@@ -478,6 +483,18 @@ class B200Backend(Backend):
             accumulate = False
         call("nfb_scatter_add_rows", dtype_code(idx.dtype), dtype_code(g.dtype), g.ptr, idx.ptr, out.ptr, n, d, vocab_size,
              1 if accumulate else 0)
+        return out
+
+    def colsum(self, x, out=None, accumulate=False):
+        """out[c] (+)= sum over rows of a 2-D fp32/bf16 array (bias gradients), fp32 result."""
+        x = _arr(x)
+        if x.ndim != 2 or x.strides[1] != 1:
+            x = x.reshape(-1, x.shape[-1]).contiguous()
+        R, Cc = x.shape
+        if out is None:
+            out = B200Array.empty((Cc,), np.float32)
+            accumulate = False
+        call("nfb_colsum", dtype_code(x.dtype), x.ptr, R, Cc, x.strides[0] if R > 1 else Cc, out.ptr, 1 if accumulate else 0)
         return out
 
     def swiglu_forward(self, gate, up):

@@ -78,8 +78,8 @@ def _clip(g):
     if c is None or g is None:
         return g
     if isinstance(g, B200Array):
-        if g.dtype is bfloat16:
-            return g  # bf16 gradients are clipped where they are produced (GEMM epilogue `clip`)
+        if g.dtype is bfloat16 or g.clipped:
+            return g  # clipped where it was produced (GEMM epilogue / norm backward `clip`): no extra pass
         return g.clip(-c, c) if _scrub_free(g) else np.nan_to_num(g, nan=0.0, posinf=c, neginf=-c).clip(-c, c)
     g = np.asarray(g)
     if not np.all(np.isfinite(g)):

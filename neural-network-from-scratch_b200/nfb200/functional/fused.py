@@ -123,9 +123,12 @@ def _norm(x: Tensor, weight, bias, eps: float, rms: bool, out_dtype=None, name="
             dres = acc0
             if dres is not None and dres.dtype != xd.dtype:
                 dres = dres.astype(xd.dtype)
+            from ..core.tensor import get_grad_clip
+            from .. import kernels as K
             dx, _, _ = be.norm_backward(gdt, xd, None if weight is None else weight.data, mean, rstd, rms=rms,
                                         dresidual=dres, dweight_out=dw_out, dbias_out=db_out, accumulate=True,
-                                        need_wgrad=dw_out is not None, need_bgrad=db_out is not None)
+                                        need_wgrad=dw_out is not None, need_bgrad=db_out is not None,
+                                        clip=get_grad_clip() or 0.0, bf16_twin=(K.get_precision() == "bf16"))
             outs = [dx]
             if weight is not None:
                 outs.append(ACCUMULATED)

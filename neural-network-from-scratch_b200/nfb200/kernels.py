@@ -184,10 +184,11 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
     x2, W, wb, z, act, layout, has_bias, precision = ctx
     lead = dy.shape[:-1]
     n_out = dy.shape[-1]
+    twin = getattr(dy, "twin", None)
     dz = dy.reshape(-1, n_out)
     out_in = layout == "out_in"
     if precision == "bf16":
-        dz = to_bf16(dz)
+        dz = twin.reshape(-1, n_out) if (twin is not None and dy.dtype != bfloat16) else to_bf16(dz)
         if act == "gelu":
             dz = A.unary_bwd("gelu_tanh", z.reshape(dz.shape), dz)
         elif act == "relu":
@@ -205,12 +206,7 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
         db = None
         if has_bias:
-            s = A.reduce("sum", dz, 0, False)
-            if db_out is not None:
-                db_out += s
-                db = db_out
-            else:
-                db = s
+            db = _colsum(dz, db_out)
         return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
     # ---- fp32 path
     if dz.dtype != F32:
@@ -232,13 +228,18 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
         dW = gemm_f32(x2, dz, True, False, out=dW_out, beta=1.0 if dW_out is not None else 0.0)
     db = None
     if has_bias:
-        s = A.reduce("sum", dz, 0, False)
-        if db_out is not None:
-            db_out += s
-            db = db_out
-        else:
-            db = s
+        db = _colsum(dz, db_out)
     return dx, dW, db
+
+
+def _colsum(dz: B200Array, out=None) -> B200Array:
+    """Bias gradient: column sums of dZ accumulated straight into the gradient buffer (one 2-stage kernel)."""
+    R, Cc = dz.shape
+    acc = out is not None
+    if out is None:
+        out = B200Array.empty((Cc,), np.float32)
+    call("nfb_colsum", dtype_code(dz.dtype), dz.ptr, R, Cc, dz.strides[0] if R > 1 else Cc, out.ptr, 1 if acc else 0)
+    return out
 
 
 # ======================================================================================

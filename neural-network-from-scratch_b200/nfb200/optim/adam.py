@@ -53,6 +53,8 @@ class _AdamBase(Optimizer):
         self.step_count = 0
         self.moment_dtype = np.dtype(moment_dtype)
         self.grad_scale = None  # optional device scalar multiplied into every gradient (global-norm clipping)
+        self.capturable = False  # True: keep the step counter on the device (CUDA-graph capture of the training step)
+        self._step_dev = None
         self.state: Dict[str, dict] = {}
         self.m, self.v = {}, {}
         dev_params = [p for p in self.parameters.values() if isinstance(p.data, B200Array)]
@@ -95,6 +97,12 @@ class _AdamBase(Optimizer):
                 st["step"] += 1
                 steps.setdefault(st["step"], set()).add(id(p))
                 done.add(id(p))
+            if self.capturable:
+                # graph-capturable mode: the step count lives on the device and is advanced by a kernel, so a captured
+                # step replays with the right bias corrections (all arena parameters share one count in this mode)
+                if self._step_dev is None:
+                    self._step_dev = B200Array.full((1,), self.step_count - 1, np.int32)
+                call("nfb_add_i32", self._step_dev.ptr, 1)
             mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
             msz = self.moment_dtype.itemsize
             a = self.arena
@@ -104,7 +112,8 @@ class _AdamBase(Optimizer):
                          a.moments[0].ptr + off * msz, a.moments[1].ptr + off * msz,
                          (a.flat_bf16.ptr + off * 2) if a.flat_bf16 is not None else None, n, float(self.lr), float(self.beta1),
                          float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
-                         self.grad_scale.ptr if self.grad_scale is not None else None)
+                         self.grad_scale.ptr if self.grad_scale is not None else None,
+                         self._step_dev.ptr if self._step_dev is not None else None)
             for p in a.params:
                 if id(p) in done:
                     p._version += 1

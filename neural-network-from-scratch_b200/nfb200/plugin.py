@@ -1,7 +1,7 @@
 """Backend plugin interface + registry: the drop-in boundary of this repo.
 
 Mirrors the contract of the reference's ``neural_arch.backends`` package:
-  * ``Backend`` abstract interface -- 56 abstract members (backends/backend.py:9-322)
+  * ``Backend`` abstract interface -- 54 abstract members (backends/backend.py:9-322)
   * ``register_backend / get_backend / set_backend / available_backends / current_backend``
     (backends/backend.py:325-375): ``get_backend(name)`` builds a NEW instance per call, raises
     ``ValueError`` for an unknown name and ``RuntimeError`` for an unavailable backend

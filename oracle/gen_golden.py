@@ -1,0 +1,208 @@
+#!/usr/bin/env python
+"""ORACLE INFRASTRUCTURE: generate golden input/output vectors by running the UNMODIFIED reference
+(/root/reference/src/neural_arch: functional/, nn/, optim/, models/, distributed/) in this container, over the
+reconstructed `core` (oracle/compat).  The reference cannot travel to the GPU box, so the vectors are
+committed under tests/golden/ together with this script; tests/test_oracle_golden.py pins oracle/np_ops.py against
+them on CPU and tests/test_gpu_golden.py pins the CUDA path against them on the B200.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz (needs /root/reference)
+
+Every fixture stores the seeded inputs and what the reference computed from them (forward values and, where the
+reference has a working backward, gradients).  Sizes are tiny on purpose (total < 1 MB).
+"""
+import os
+import sys
+
+os.environ.setdefault("NUMBA_DISABLE_JIT", "1")  # the reference's Numba kernels then run as the plain Python/NumPy they wrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle", "compat"), ROOT, os.path.join(ROOT, "neural-network-from-scratch_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _ref():
+    import neural_arch  # noqa: F401  (the shim in oracle/compat + the reference tree)
+    from neural_arch.optimization_config import configure
+    configure(enable_jit=False, enable_fusion=False)  # pin the plain NumPy Linear path
+    return neural_arch
+
+
+def gen_functional(g):
+    import neural_arch.functional as RF
+    from neural_arch.core import Tensor
+    rng = np.random.default_rng(100)
+    a = rng.standard_normal((4, 6)).astype(np.float32)
+    b = (rng.standard_normal((6,)) + 3).astype(np.float32)
+    up = rng.standard_normal((4, 6)).astype(np.float32)
+    for name, fn in (("add", RF.add), ("sub", RF.sub), ("mul", RF.mul), ("div", RF.div)):
+        ta, tb = Tensor(a, requires_grad=True), Tensor(b, requires_grad=True)
+        out = fn(ta, tb)
+        out.backward(up)
+        g[f"{name}_out"], g[f"{name}_da"], g[f"{name}_db"] = out.data, np.asarray(ta.grad), np.asarray(tb.grad)
+    g["ab_a"], g["ab_b"], g["ab_up"] = a, b, up
+    m1 = rng.standard_normal((3, 5, 4)).astype(np.float32)
+    m2 = rng.standard_normal((3, 4, 6)).astype(np.float32)
+    mu = rng.standard_normal((3, 5, 6)).astype(np.float32)
+    t1, t2 = Tensor(m1, requires_grad=True), Tensor(m2, requires_grad=True)
+    out = RF.matmul(t1, t2)
+    out.backward(mu)
+    g["mm_a"], g["mm_b"], g["mm_up"], g["mm_out"], g["mm_da"], g["mm_db"] = m1, m2, mu, out.data, np.asarray(t1.grad), np.asarray(t2.grad)
+    x = (rng.standard_normal((5, 9)) * 2.5).astype(np.float32)
+    x.flat[:4] = [0.0, 30.0, -30.0, 1e-3]
+    ux = rng.standard_normal((5, 9)).astype(np.float32)
+    g["act_x"], g["act_up"] = x, ux
+    for name, fn in (("relu", RF.relu), ("sigmoid", RF.sigmoid), ("tanh", RF.tanh), ("gelu", RF.gelu), ("silu", RF.silu),
+                     ("gelu_tanh", lambda t: RF.gelu(t, approximate=True)), ("softmax", lambda t: RF.softmax(t, axis=-1)),
+                     ("softmax0", lambda t: RF.softmax(t, axis=0))):
+        t = Tensor(x, requires_grad=True)
+        out = fn(t)
+        out.backward(ux)
+        g[f"{name}_out"], g[f"{name}_dx"] = out.data, np.asarray(t.grad)
+    z = (rng.standard_normal((7, 11)) * 3).astype(np.float32)
+    tg = rng.integers(0, 11, 7)
+    g["ce_z"], g["ce_t"] = z, tg
+    for red in ("mean", "sum"):
+        t = Tensor(z, requires_grad=True)
+        loss = RF.cross_entropy_loss(t, Tensor(tg), reduction=red)
+        loss.backward()
+        g[f"ce_{red}_loss"], g[f"ce_{red}_dz"] = np.asarray(loss.data), np.asarray(t.grad)
+
+
+def gen_layers(g):
+    from neural_arch.core import Tensor
+    from neural_arch.nn import Embedding, LayerNorm, Linear, RMSNorm
+    from neural_arch.nn.linear import Linear as StandardLinear
+    rng = np.random.default_rng(200)
+    x = (rng.standard_normal((3, 5, 16)) * 2 + 0.5).astype(np.float32)
+    up = rng.standard_normal((3, 5, 16)).astype(np.float32)
+    g["norm_x"], g["norm_up"] = x, up
+    w = rng.standard_normal(16).astype(np.float32)
+    b = rng.standard_normal(16).astype(np.float32)
+    g["norm_w"], g["norm_b"] = w, b
+    for name, layer in (("ln", LayerNorm(16, eps=1e-5)), ("ln12", LayerNorm(16, eps=1e-12)), ("rms", RMSNorm(16, eps=1e-8))):
+        layer.weight.data = w.copy()
+        if getattr(layer, "bias", None) is not None:
+            layer.bias.data = b.copy()
+        t = Tensor(x, requires_grad=True)
+        out = layer(t)
+        out.backward(up)
+        g[f"{name}_out"], g[f"{name}_dx"], g[f"{name}_dw"] = out.data, np.asarray(t.grad), np.asarray(layer.weight.grad)
+        if getattr(layer, "bias", None) is not None:
+            g[f"{name}_db"] = np.asarray(layer.bias.grad)
+    # Linear: OptimizedLinear (out,in) standard path (2-D input so the reference backward is valid) + StandardLinear (in,out)
+    np.random.seed(5)
+    lin = Linear(16, 8)
+    x2 = rng.standard_normal((6, 16)).astype(np.float32)
+    u2 = rng.standard_normal((6, 8)).astype(np.float32)
+    t = Tensor(x2, requires_grad=True)
+    out = lin(t)
+    out.backward(u2)
+    g["lin_W"], g["lin_b"], g["lin_x"], g["lin_up"] = lin.weight.data, lin.bias.data, x2, u2
+    g["lin_out"], g["lin_dx"], g["lin_dW"], g["lin_db"] = out.data, np.asarray(t.grad), np.asarray(lin.weight.grad), np.asarray(lin.bias.grad)
+    np.random.seed(6)
+    sl = StandardLinear(16, 8)
+    t = Tensor(x2, requires_grad=True)
+    out = sl(t)
+    out.backward(u2)
+    g["slin_W"], g["slin_b"] = sl.weight.data, sl.bias.data
+    g["slin_out"], g["slin_dx"], g["slin_dW"], g["slin_db"] = out.data, np.asarray(t.grad), np.asarray(sl.weight.grad), np.asarray(sl.bias.grad)
+    # fused Linear+GELU (tanh form): forward only via the reference's own fused NumPy/Numba routine
+    from neural_arch.optimization.fusion import fuse_linear_activation
+    g["lin_gelu_out"] = np.asarray(fuse_linear_activation(x2, lin.weight.data, lin.bias.data, "gelu"))
+    # Embedding: gather + the sequential scatter-add backward, with duplicate indices
+    np.random.seed(7)
+    emb = Embedding(13, 8)
+    idx = np.array([[0, 0, 1, 12], [5, 1, 0, 5]])
+    ue = rng.standard_normal((2, 4, 8)).astype(np.float32)
+    out = emb(Tensor(idx))
+    out.backward(ue)
+    out._backward()
+    g["emb_W"], g["emb_idx"], g["emb_up"], g["emb_out"], g["emb_dW"] = emb.weight.data, idx, ue, out.data, np.asarray(emb.weight.grad)
+
+
+def gen_optim(g):
+    from neural_arch.core import Parameter
+    from neural_arch.optim import SGD, Adam, AdamW
+    rng = np.random.default_rng(300)
+    p0 = rng.standard_normal((5, 7)).astype(np.float32)
+    grads = [(rng.standard_normal((5, 7)) * (10.0 ** rng.integers(-3, 1))).astype(np.float32) for _ in range(6)]
+    g["opt_p0"], g["opt_grads"] = p0, np.stack(grads)
+    for name, make in (("adam", lambda p: Adam({"w": p}, lr=1e-3)), ("adam_wd", lambda p: Adam({"w": p}, lr=0.05, weight_decay=0.01)),
+                       ("adamw", lambda p: AdamW({"w": p}, lr=5e-4, weight_decay=0.1)), ("adamw_default", lambda p: AdamW({"w": p})),
+                       ("sgd", lambda p: SGD({"w": p}, lr=0.1, momentum=0.9, weight_decay=1e-4, nesterov=True))):
+        p = Parameter(p0.copy())
+        opt = make(p)
+        traj = []
+        for gr in grads:
+            p.grad = gr.copy()
+            opt.step()
+            traj.append(np.asarray(p.data).copy())
+        g[f"{name}_traj"] = np.stack(traj)
+        if hasattr(opt, "state"):
+            g[f"{name}_m"], g[f"{name}_v"] = opt.state["w"]["exp_avg"], opt.state["w"]["exp_avg_sq"]
+
+
+def gen_gpt2_pieces(g):
+    """Forward values of the GPT-2 building blocks exactly as models/language/gpt2.py computes them (its backward graph is
+    severed -- SURVEY F6 -- so only forwards can be pinned at this level)."""
+    from neural_arch.core import Tensor
+    from neural_arch.models.language.gpt2 import GPT2, GPT2Attention, RMSNorm, RotaryEmbedding, SwiGLU, apply_rotary_pos_emb
+    rng = np.random.default_rng(400)
+    cfg = {"vocab_size": 61, "n_positions": 32, "n_embd": 32, "n_layer": 2, "n_head": 2}
+    rot = RotaryEmbedding(16)
+    q = rng.standard_normal((2, 2, 10, 16)).astype(np.float32)
+    k = rng.standard_normal((2, 2, 10, 16)).astype(np.float32)
+    cos, sin = rot(Tensor(q), seq_len=10)
+    qr, kr = apply_rotary_pos_emb(Tensor(q), Tensor(k), cos, sin)
+    g["rope_q"], g["rope_k"], g["rope_qr"], g["rope_kr"] = q, k, qr.data, kr.data
+    np.random.seed(11)
+    attn = GPT2Attention(cfg)
+    v = rng.standard_normal((2, 2, 10, 16)).astype(np.float32)
+    g["attn_v"], g["attn_out"] = v, attn._attn(qr, kr, Tensor(v)).data          # causal -1e4 replace, softmax, @ v
+    x = rng.standard_normal((2, 10, 32)).astype(np.float32)
+    g["blk_x"] = x
+    a_out, _ = attn(Tensor(x))
+    g["attn_Wqkv"], g["attn_bqkv"], g["attn_Wo"], g["attn_bo"] = attn.c_attn.weight.data, attn.c_attn.bias.data, attn.c_proj.weight.data, attn.c_proj.bias.data
+    g["attn_block_out"] = a_out.data
+    np.random.seed(12)
+    sw = SwiGLU(32)
+    g["sw_w1"], g["sw_w2"], g["sw_w3"], g["sw_out"] = sw.w1.weight.data, sw.w2.weight.data, sw.w3.weight.data, sw(Tensor(x)).data
+    rn = RMSNorm(32, eps=1e-5)
+    rn.weight.data = rng.standard_normal(32).astype(np.float32)
+    g["grms_w"], g["grms_out"] = rn.weight.data, rn(Tensor(x)).data
+    # whole model forward (logits) from a seed: pins construction order / init RNG calls / tying / block wiring
+    np.random.seed(0)
+    model = GPT2(cfg)
+    ids = rng.integers(0, 61, (2, 12))
+    g["gpt2_ids"] = ids
+    g["gpt2_logits"] = model(Tensor(ids))["logits"].data
+    g["gpt2_wte_sample"] = model.transformer.wte.weight.data[:4]
+    g["gpt2_cattn0_sample"] = model.transformer.h[0].attn.c_attn.weight.data[:2]
+
+
+def gen_sampler(g):
+    from neural_arch.distributed.data_parallel import DistributedSampler
+    for tag, kw in (("a", dict(dataset_size=10, num_replicas=4, rank=3, shuffle=False)), ("b", dict(dataset_size=23, num_replicas=3, rank=1, shuffle=True, seed=5)),
+                    ("c", dict(dataset_size=7, num_replicas=2, rank=1, shuffle=True, seed=5, drop_last=True))):
+        s = DistributedSampler(**kw)
+        s.set_epoch(2 if tag == "b" else 0)
+        g[f"sampler_{tag}"] = np.array(list(s))
+
+
+def main():
+    _ref()
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("sampler", gen_sampler)):
+        g = {}
+        fn(g)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **{k: np.asarray(v) for k, v in g.items()})
+        print(f"{name}: {len(g)} arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -229,7 +229,7 @@ def test_adam_family_trajectory(be, variant, moments):
         p_ref = (O.adam_step if variant == "adam" else O.adamw_step)(p_ref, g, st, **hyper)
         gd = _to(be, g)
         _lib.call("nfb_adam_step", 0 if variant == "adam" else 1, _lib.F64 if moments == "f64" else _lib.F32, p.ptr, gd.ptr, m.ptr, v.ptr, None, n,
-                  hyper["lr"], hyper["betas"][0], hyper["betas"][1], hyper["eps"], hyper["weight_decay"], step, 0, None)
+                  hyper["lr"], hyper["betas"][0], hyper["betas"][1], hyper["eps"], hyper["weight_decay"], step, 0, None, None)
         if moments == "f64":
             np.testing.assert_allclose(p.get(), p_ref, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(p.get(), p_ref, rtol=1e-5, atol=1e-6)
@@ -247,7 +247,7 @@ def test_adam_nonfinite_scrub_and_update_clip(be):
         want = O.adam_step(p0.copy(), g, st, lr=1.0, eps=1e-5)
     p = _to(be, p0)
     m, v = be.zeros((4,), np.float64), be.zeros((4,), np.float64)
-    _lib.call("nfb_adam_step", 0, _lib.F64, p.ptr, _to(be, g).ptr, m.ptr, v.ptr, None, 4, 1.0, 0.9, 0.999, 1e-5, 0.0, 1, 0, None)
+    _lib.call("nfb_adam_step", 0, _lib.F64, p.ptr, _to(be, g).ptr, m.ptr, v.ptr, None, 4, 1.0, 0.9, 0.999, 1e-5, 0.0, 1, 0, None, None)
     np.testing.assert_allclose(p.get(), want, rtol=1e-6)
 
 

@@ -1,0 +1,147 @@
+"""The CUDA path against the golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz,
+oracle/gen_golden.py).  Everything goes through the public API (Tensor / functional / nn / optim on Device.cuda) and
+therefore through the C-ABI.  fp32 path: 1e-5 relative; gather/scatter-add: bit-exact; bf16 path: 1e-2."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = dict(rtol=1e-5, atol=2e-6)
+
+
+def load(name):
+    return np.load(os.path.join(G, f"{name}.npz"))
+
+
+@pytest.fixture(autouse=True)
+def _fp32(be):
+    from nfb200 import kernels as K
+    K.set_precision("fp32")
+    yield
+    K.set_precision("fp32")
+
+
+def T(a, rg=False):
+    from nfb200.core import Tensor
+    return Tensor(np.asarray(a), requires_grad=rg, device="cuda")
+
+
+def test_functional_ops_on_device():
+    from nfb200 import functional as F
+    g = load("functional")
+    a, b, up = g["ab_a"], g["ab_b"], g["ab_up"]
+    for name, fn in (("add", F.add), ("sub", F.sub), ("mul", F.mul), ("div", F.div)):
+        ta, tb = T(a, True), T(b, True)
+        out = fn(ta, tb)
+        out.backward(T(up).data)
+        np.testing.assert_allclose(out.numpy(), g[f"{name}_out"], **TOL)
+        np.testing.assert_allclose(ta.grad.get(), g[f"{name}_da"], **TOL)
+        np.testing.assert_allclose(tb.grad.get(), g[f"{name}_db"], rtol=1e-5, atol=1e-5)
+    t1, t2 = T(g["mm_a"], True), T(g["mm_b"], True)
+    out = F.matmul(t1, t2)
+    out.backward(T(g["mm_up"]).data)
+    np.testing.assert_allclose(out.numpy(), g["mm_out"], **TOL)
+    np.testing.assert_allclose(t1.grad.get(), g["mm_da"], **TOL)
+    np.testing.assert_allclose(t2.grad.get(), g["mm_db"], **TOL)
+    x, ux = g["act_x"], g["act_up"]
+    for name, fn in (("relu", F.relu), ("sigmoid", F.sigmoid), ("tanh", F.tanh), ("gelu", F.gelu), ("silu", F.silu),
+                     ("gelu_tanh", lambda t: F.gelu(t, approximate=True)), ("softmax", lambda t: F.softmax(t, axis=-1)),
+                     ("softmax0", lambda t: F.softmax(t, axis=0))):
+        t = T(x, True)
+        out = fn(t)
+        out.backward(T(ux).data)
+        np.testing.assert_allclose(out.numpy(), g[f"{name}_out"], **TOL)
+        np.testing.assert_allclose(t.grad.get(), g[f"{name}_dx"], rtol=2e-5, atol=2e-6)
+    for red in ("mean", "sum"):
+        t = T(g["ce_z"], True)
+        loss = F.cross_entropy_loss(t, T(g["ce_t"]), reduction=red)
+        loss.backward()
+        np.testing.assert_allclose(loss.numpy(), g[f"ce_{red}_loss"], **TOL)
+        np.testing.assert_allclose(t.grad.get(), g[f"ce_{red}_dz"], rtol=1e-5, atol=1e-8)
+
+
+def test_layers_on_device():
+    from nfb200 import nn
+    from nfb200.core import set_default_device
+    g = load("layers")
+    set_default_device("cuda")
+    try:
+        x, up, w, b = g["norm_x"], g["norm_up"], g["norm_w"], g["norm_b"]
+        for key, layer in (("ln", nn.LayerNorm(16, eps=1e-5)), ("ln12", nn.LayerNorm(16, eps=1e-12)), ("rms", nn.RMSNorm(16, eps=1e-8))):
+            layer.weight.data = w.copy()
+            if layer.__dict__.get("bias") is not None:
+                layer.bias.data = b.copy()
+            t = T(x, True)
+            out = layer(t)
+            out.backward(T(up).data)
+            np.testing.assert_allclose(out.numpy(), g[f"{key}_out"], **TOL)
+            np.testing.assert_allclose(t.grad.get(), g[f"{key}_dx"], rtol=1e-4, atol=3e-6)
+            np.testing.assert_allclose(layer.weight.grad.get(), g[f"{key}_dw"], rtol=1e-5, atol=1e-5)
+            if key != "rms":
+                np.testing.assert_allclose(layer.bias.grad.get(), g[f"{key}_db"], rtol=1e-5, atol=1e-5)
+        for key, cls in (("lin", nn.Linear), ("slin", nn.StandardLinear)):
+            lin = cls(16, 8)
+            lin.weight.data, lin.bias.data = g[f"{key}_W"], g[f"{key}_b"]
+            t = T(g["lin_x"], True)
+            out = lin(t)
+            out.backward(T(g["lin_up"]).data)
+            np.testing.assert_allclose(out.numpy(), g[f"{key}_out"], **TOL)
+            np.testing.assert_allclose(t.grad.get(), g[f"{key}_dx"], **TOL)
+            np.testing.assert_allclose(lin.weight.grad.get(), g[f"{key}_dW"], **TOL)
+            np.testing.assert_allclose(lin.bias.grad.get(), g[f"{key}_db"], **TOL)
+        fused = nn.Linear(16, 8, activation="gelu")
+        fused.weight.data, fused.bias.data = g["lin_W"], g["lin_b"]
+        np.testing.assert_allclose(fused(T(g["lin_x"])).numpy(), g["lin_gelu_out"], rtol=1e-5, atol=2e-6)
+        emb = nn.Embedding(13, 8)
+        emb.weight.data = g["emb_W"]
+        out = emb(T(g["emb_idx"]))
+        assert np.array_equal(out.numpy(), g["emb_out"])                  # bit-exact gather
+        out.backward(T(g["emb_up"]).data)
+        assert np.array_equal(emb.weight.grad.get(), g["emb_dW"])         # bit-exact ordered scatter-add
+    finally:
+        set_default_device("cpu")
+
+
+@pytest.mark.parametrize("moments", ["float64", "float32"])
+def test_optimizers_on_device(moments):
+    from nfb200.core import Parameter
+    from nfb200.optim import SGD, Adam, AdamW
+    g = load("optim")
+    cases = (("adam", lambda p: Adam({"w": p}, lr=1e-3, moment_dtype=moments)), ("adam_wd", lambda p: Adam({"w": p}, lr=0.05, weight_decay=0.01, moment_dtype=moments)),
+             ("adamw", lambda p: AdamW({"w": p}, lr=5e-4, weight_decay=0.1, moment_dtype=moments)), ("adamw_default", lambda p: AdamW({"w": p}, moment_dtype=moments)),
+             ("sgd", lambda p: SGD({"w": p}, lr=0.1, momentum=0.9, weight_decay=1e-4, nesterov=True)))
+    tol = dict(rtol=1e-6, atol=1e-7) if moments == "float64" else dict(rtol=1e-5, atol=1e-6)
+    for key, make in cases:
+        p = Parameter(g["opt_p0"].copy(), device="cuda")
+        opt = make(p)
+        for i, gr in enumerate(g["opt_grads"]):
+            opt.zero_grad()
+            p.grad = gr.copy()
+            opt.step()
+            np.testing.assert_allclose(p.numpy(), g[f"{key}_traj"][i], err_msg=f"{key} step {i}", **tol)
+        if moments == "float64" and key != "sgd":
+            np.testing.assert_allclose(opt.state["w"]["exp_avg"].get(), g[f"{key}_m"], rtol=1e-12)
+            np.testing.assert_allclose(opt.state["w"]["exp_avg_sq"].get(), g[f"{key}_v"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", dict(rtol=1e-5, atol=3e-6)), ("bf16", dict(rtol=1e-2, atol=1e-2))])
+def test_seeded_gpt2_logits_match_reference_model(precision, tol):
+    """np.random.seed(0); GPT2(cfg) on the B200 == the reference's own GPT2(cfg) forward (golden logits)."""
+    from nfb200 import kernels as K
+    from nfb200.core import set_default_device
+    from nfb200.models import GPT2
+    g = load("gpt2")
+    cfg = {"vocab_size": 61, "n_positions": 32, "n_embd": 32, "n_layer": 2, "n_head": 2}
+    set_default_device("cuda")
+    K.set_precision(precision)
+    try:
+        np.random.seed(0)
+        model = GPT2(cfg)
+        assert np.array_equal(model.transformer.wte.weight.numpy()[:4], g["gpt2_wte_sample"])
+        logits = model(T(g["gpt2_ids"]))["logits"].numpy()
+        np.testing.assert_allclose(logits, g["gpt2_logits"], **tol)
+    finally:
+        K.set_precision("fp32")
+        set_default_device("cpu")

@@ -527,9 +527,9 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
 // x + part*part_stride + b*sb + s*ss + h*sh + d.
 template <typename T>
 __global__ void k_rope(T* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int n_parts, long long part_stride,
-                       int B, int S, int H, long long sb, long long ss, long long sh, int inverse) {
-  // one thread rotates 4 (d, d + D/2) pairs: 128-bit table loads, 64/128-bit data accesses
-  const int half = HD / 2, groups = half / 4;
+                       int B, int S, int H, int D, long long sb, long long ss, long long sh, int inverse) {
+  // one thread rotates 4 (d, d + D/2) pairs: 128-bit table loads, 64/128-bit data accesses (D % 8 == 0)
+  const int half = D / 2, groups = half / 4;
   long long total = (long long)n_parts * B * S * H * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int d = (int)(i % groups) * 4;
@@ -547,16 +547,41 @@ __global__ void k_rope(T* __restrict__ x, const float* __restrict__ cos_t, const
     st4<T>(p + d + half, {x2.x * c.x + x1.x * sn.x, x2.y * c.y + x1.y * sn.y, x2.z * c.z + x1.z * sn.z, x2.w * c.w + x1.w * sn.w});
   }
 }
+// any even head_dim / alignment: one pair per thread
+template <typename T>
+__global__ void k_rope_scalar(T* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int n_parts, long long part_stride,
+                              int B, int S, int H, int D, long long sb, long long ss, long long sh, int inverse) {
+  const int half = D / 2;
+  long long total = (long long)n_parts * B * S * H * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % half);
+    long long r = i / half;
+    int h = (int)(r % H); r /= H;
+    int s = (int)(r % S); r /= S;
+    int b = (int)(r % B);
+    int part = (int)(r / B);
+    float c = cos_t[s * half + d], sn = sin_t[s * half + d];
+    if (inverse) sn = -sn;
+    T* p = x + part * part_stride + b * sb + (long long)s * ss + (long long)h * sh;
+    float x1 = ld_f<T>(p, d), x2 = ld_f<T>(p, d + half);
+    st_f<T>(p, d, x1 * c - x2 * sn);
+    st_f<T>(p, d + half, x2 * c + x1 * sn);
+  }
+}
 NFB_API int nfb_rope(int dtype, void* x, const float* cos_t, const float* sin_t, int n_parts, int64_t part_stride, int B, int S, int H,
                      int head_dim, int64_t sb, int64_t ss, int64_t sh, int inverse) {
-  if (head_dim != HD) return NFB_FAIL("nfb_rope: head_dim %d unsupported", head_dim);
-  long long total = (long long)n_parts * B * S * H * (HD / 8);
+  if (head_dim <= 0 || head_dim % 2) return NFB_FAIL("nfb_rope: head_dim %d must be positive and even", head_dim);
+  int D = head_dim;
+  bool vec = (D % 8 == 0) && !(sb % 4 || ss % 4 || sh % 4 || part_stride % 4) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)cos_t % 16 == 0) && ((uintptr_t)sin_t % 16 == 0);
+  long long total = (long long)n_parts * B * S * H * (vec ? D / 8 : D / 2);
   if (total == 0) return 0;
-  if (sb % 4 || ss % 4 || sh % 4 || part_stride % 4 || ((uintptr_t)x % 16)) return NFB_FAIL("nfb_rope: strides/base must be 4-element / 16-byte aligned");
   int grid = nfb_grid_for(total, 256);
-  if (dtype == NFB_BF16) k_rope<__nv_bfloat16><<<grid, 256, 0, nfb_cur_stream()>>>((__nv_bfloat16*)x, cos_t, sin_t, n_parts, part_stride, B, S, H, sb, ss, sh, inverse);
-  else if (dtype == NFB_F32) k_rope<float><<<grid, 256, 0, nfb_cur_stream()>>>((float*)x, cos_t, sin_t, n_parts, part_stride, B, S, H, sb, ss, sh, inverse);
+  cudaStream_t st = nfb_cur_stream();
+#define RL(K, T) K<T><<<grid, 256, 0, st>>>((T*)x, cos_t, sin_t, n_parts, part_stride, B, S, H, D, sb, ss, sh, inverse)
+  if (dtype == NFB_BF16) { if (vec) RL(k_rope, __nv_bfloat16); else RL(k_rope_scalar, __nv_bfloat16); }
+  else if (dtype == NFB_F32) { if (vec) RL(k_rope, float); else RL(k_rope_scalar, float); }
   else return NFB_FAIL("nfb_rope: unsupported dtype %d", dtype);
+#undef RL
   NFB_LAUNCH_CHECK();
   return 0;
 }

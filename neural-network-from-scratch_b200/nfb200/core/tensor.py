@@ -279,7 +279,14 @@ class Tensor:
         if self._device.is_cpu:
             self._grad = value.get() if isinstance(value, B200Array) else np.asarray(value)
         else:
-            self._grad = value if isinstance(value, B200Array) else self._backend.from_numpy(np.asarray(value))
+            new = value if isinstance(value, B200Array) else self._backend.from_numpy(np.asarray(value, dtype=np.float32))
+            if self._grad_slot is not None and new is not self._grad_slot:
+                # arena-bound parameter (optimizer / DDP): the gradient must live in its slot of the flat buffer
+                self._grad_slot._assign(new if new.shape == self._grad_slot.shape else new.reshape(self._grad_slot.shape))
+                self._slot_zero = False
+                self._grad = self._grad_slot
+            else:
+                self._grad = new
 
     @property
     def grad_fn(self):

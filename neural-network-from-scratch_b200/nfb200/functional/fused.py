@@ -205,6 +205,14 @@ def embedding(weight: Tensor, indices, out_dtype=None) -> Tensor:
     return make_result(out, [weight], backward_host, "embedding")
 
 
+def to_float32(x: Tensor) -> Tensor:
+    """Differentiable up-cast of a bf16-stored activation (head dims the flash kernel does not cover fall back to the
+    unfused fp32 composition, which needs fp32 operands)."""
+    if _dev(x) and x.data.dtype is bfloat16:
+        return make_result(x.data.astype(np.float32), [x], lambda g: (g,), "to_float32")
+    return x
+
+
 # ====================================================================================== attention
 def _rope_tables_host(head_dim, seq_len, base=10000):
     inv_freq = 1.0 / (base ** (np.arange(0, head_dim, 2).astype(np.float32) / head_dim))
@@ -252,6 +260,7 @@ def scaled_dot_product_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, 
 
             return make_result(o, [q, k, v], backward, "flash_attention")
     # ---- composition from differentiable primitives (host tensors and the fp32 device path)
+    q, k, v = to_float32(q), to_float32(k), to_float32(v)
     from .activation import softmax
     from .arithmetic import add, matmul, mul
     from .shape import swapaxes
@@ -304,6 +313,7 @@ def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rop
 
             return make_result(out, [qkv], backward, "packed_qkv_attention")
     from .shape import getitem, reshape, transpose
+    qkv = to_float32(qkv)
     x5 = transpose(reshape(qkv, (B, S, 3, n_heads, D)), (2, 0, 3, 1, 4))
     q, k, v = getitem(x5, 0), getitem(x5, 1), getitem(x5, 2)
     if use_rope:

@@ -85,8 +85,9 @@ class SwiGLU(Module):
 
                 gu_fn.backward_fn = wrapped
             return self.w3(F.swiglu_packed(gu), residual=residual)
-        gate = F.silu(self.w1(x))
-        up = self.w2(x)
+        from ..functional.fused import to_float32
+        gate = F.silu(to_float32(self.w1(x)))   # unfused route (no flat arena yet, or host tensors): fp32 elementwise math
+        up = to_float32(self.w2(x))
         return self.w3(F.mul(gate, up), residual=residual)
 
 

@@ -1,2 +1,5 @@
 """Model zoo for the named configs: GPT-2 small/medium, BERT-base MLM, ViT-B/16, translation encoder-decoder."""
+from .bert import BERT, BERTConfig, BERTForMaskedLM, bert_base, bert_base_mlm
 from .gpt2 import GPT2, GPT2_CONFIGS, GPT2LMHead, GPT2Model, gpt2_large, gpt2_medium, gpt2_small, gpt2_xl
+from .translation import PositionalEncoding, TranslationTransformer
+from .vit import VisionTransformer, vit_b_16, vit_l_16

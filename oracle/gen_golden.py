@@ -185,6 +185,33 @@ def gen_gpt2_pieces(g):
     g["gpt2_cattn0_sample"] = model.transformer.h[0].attn.c_attn.weight.data[:2]
 
 
+def gen_bert_vit(g):
+    """Seeded BERT-MLM and ViT forwards of the reference model zoo (tiny configs): pins init order, wiring, the additive
+    attention mask, the fused tanh-GELU MLP and LayerNorm epsilons for the other two named model families."""
+    from neural_arch.core import Tensor
+    from neural_arch.optimization_config import configure
+    configure(enable_jit=False, enable_fusion=True)   # BERT/ViT MLPs use the fused Linear+GELU path (tanh form)
+    from neural_arch.models.language.bert import BERTConfig, BERTForMaskedLM
+    from neural_arch.models.vision.vision_transformer import VisionTransformer
+    rng = np.random.default_rng(500)
+    np.random.seed(0)
+    cfg = BERTConfig(vocab_size=97, hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64, max_position_embeddings=16)
+    bert = BERTForMaskedLM(cfg)
+    ids = rng.integers(0, 97, (2, 8))
+    mask = np.ones((2, 8), dtype=np.float32)
+    mask[1, 5:] = 0
+    out = bert(Tensor(ids), attention_mask=Tensor(mask))
+    g["bert_ids"], g["bert_mask"], g["bert_logits"] = ids, mask, out["logits"].data
+    g["bert_word_emb_sample"] = bert.bert.embeddings.word_embeddings.weight.data[:3]
+    g["bert_cls_w_sample"] = bert.cls.weight.data[:2]
+    np.random.seed(0)
+    vit = VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=32, depth=2, num_heads=2)
+    img = rng.standard_normal((2, 3, 32, 32)).astype(np.float32)
+    g["vit_img"], g["vit_logits"] = img, vit(Tensor(img)).data
+    g["vit_pos_sample"] = vit.pos_embed.data[0, :2]
+    configure(enable_jit=False, enable_fusion=False)
+
+
 def gen_sampler(g):
     from neural_arch.distributed.data_parallel import DistributedSampler
     for tag, kw in (("a", dict(dataset_size=10, num_replicas=4, rank=3, shuffle=False)), ("b", dict(dataset_size=23, num_replicas=3, rank=1, shuffle=True, seed=5)),
@@ -197,7 +224,8 @@ def gen_sampler(g):
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("sampler", gen_sampler)):
+    for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
+                     ("sampler", gen_sampler)):
         g = {}
         fn(g)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **{k: np.asarray(v) for k, v in g.items()})

@@ -147,3 +147,75 @@ def test_seeded_gpt2_logits_match_reference_model(precision, tol):
     finally:
         K.set_precision("fp32")
         set_default_device("cpu")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", dict(rtol=1e-5, atol=5e-6)), ("bf16", dict(rtol=1e-2, atol=2e-2))])
+def test_seeded_bert_and_vit_match_reference_models(precision, tol):
+    """BERT-MLM (additive key mask, LayerNorm eps 1e-12, fused tanh-GELU) and ViT (unmasked attention, cls token, pos
+    embed) on the B200 vs the reference model zoo's own forward (golden)."""
+    from nfb200 import kernels as K
+    from nfb200.core import set_default_device
+    from nfb200.models import BERTConfig, BERTForMaskedLM, VisionTransformer
+    g = load("bert_vit")
+    set_default_device("cuda")
+    K.set_precision(precision)
+    try:
+        np.random.seed(0)
+        bert = BERTForMaskedLM(BERTConfig(vocab_size=97, hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
+                                          max_position_embeddings=16))
+        out = bert(T(g["bert_ids"]), attention_mask=T(g["bert_mask"]))
+        np.testing.assert_allclose(out["logits"].numpy(), g["bert_logits"], **tol)
+        np.random.seed(0)
+        vit = VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=32, depth=2, num_heads=2)
+        np.testing.assert_allclose(vit(T(g["vit_img"])).numpy(), g["vit_logits"], **tol)
+    finally:
+        K.set_precision("fp32")
+        set_default_device("cpu")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bert_vit_train_step_real_head_dim(precision):
+    """hd = 64 so the fused flash kernels (key-mask and unmasked modes) run inside BERT / ViT; device step == host step."""
+    from nfb200 import kernels as K
+    from nfb200.core import Tensor, set_default_device
+    from nfb200.models import BERTConfig, BERTForMaskedLM, VisionTransformer
+    from nfb200.optim import AdamW
+    rng = np.random.default_rng(3)
+    ids = rng.integers(0, 211, (2, 24))
+    mask = np.ones((2, 24), np.float32)
+    mask[0, 20:] = 0
+    img = rng.standard_normal((2, 3, 32, 32)).astype(np.float32)
+    lab = np.array([3, 7])
+    res = {}
+    for dev in ("cpu", "cuda"):
+        set_default_device(dev)
+        K.set_precision(precision if dev == "cuda" else "fp32")
+        try:
+            np.random.seed(1)
+            bert = BERTForMaskedLM(BERTConfig(vocab_size=211, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                                              max_position_embeddings=32))
+            opt = AdamW(bert.parameters(), lr=1e-3, moment_dtype="float64")
+            losses = []
+            for _ in range(3):
+                opt.zero_grad()
+                l = bert(Tensor(ids, device=dev), attention_mask=Tensor(mask, device=dev), labels=Tensor(ids, device=dev))["loss"]
+                l.backward()
+                opt.step()
+                losses.append(float(l.item()))
+            np.random.seed(2)
+            vit = VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=128, depth=2, num_heads=2)
+            vopt = AdamW(vit.parameters(), lr=1e-3, moment_dtype="float64")
+            vl = []
+            for _ in range(3):
+                vopt.zero_grad()
+                l = vit(Tensor(img, device=dev), labels=Tensor(lab, device=dev))["loss"]
+                l.backward()
+                vopt.step()
+                vl.append(float(l.item()))
+            res[dev] = (losses, vl)
+        finally:
+            K.set_precision("fp32")
+            set_default_device("cpu")
+    tol = 5e-5 if precision == "fp32" else 1e-2
+    for a, b in zip(res["cuda"][0] + res["cuda"][1], res["cpu"][0] + res["cpu"][1]):
+        assert abs(a - b) <= tol * abs(b), f"{precision}: device {res['cuda']} vs host {res['cpu']}"

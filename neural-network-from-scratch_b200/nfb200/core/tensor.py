@@ -540,6 +540,14 @@ def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable],
     return out
 
 
+def _add_grads(a, b):
+    """Fan-in accumulation; bf16-stored gradients are summed in fp32."""
+    if isinstance(a, B200Array) and (a.dtype is bfloat16 or b.dtype is bfloat16):
+        a = a.astype(np.float32) if a.dtype is bfloat16 else a
+        b = b.astype(np.float32) if b.dtype is bfloat16 else b
+    return a + b
+
+
 def _ddp_targets(t):
     """Parameters tracked by a DistributedDataParallel wrapper that `t` stands for (itself, or the parameters a fused
     multi-parameter view aliases)."""
@@ -625,7 +633,7 @@ def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
                     if prev is None or (fn.fused_acc and i == 0):
                         pending[id(inp)] = gi
                     else:
-                        pending[id(inp)] = prev + gi
+                        pending[id(inp)] = _add_grads(prev, gi)
         for inp in fn.inputs:  # data-parallel: this consumer of the parameter is done -> maybe launch its bucket
             if isinstance(inp, Tensor) and inp._grad_fn is None:
                 for q in _ddp_targets(inp):

@@ -55,7 +55,12 @@ def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None,
             dW_out = weight.grad_buffer() if weight.requires_grad else None
             db_out = bias.grad_buffer() if (bias is not None and bias.requires_grad) else None
             clip = (get_grad_clip() or 0.0) if prec == "bf16" else 0.0
-            dx, _, _ = K.linear_backward(g, ctx, need_dx, dW_out, db_out, None, clip)
+            # dX comes back in the storage type of X: bf16 activations get bf16 gradients (they feed further GEMMs /
+            # the flash backward), fp32 activations (unfused elementwise neighbours) get fp32 gradients
+            dx_dt = None if x.data.dtype is bfloat16 else np.float32
+            dx, _, _ = K.linear_backward(g, ctx, need_dx, dW_out, db_out, dx_dt, clip)
+            if dx is not None and clip:
+                dx.clipped = True
             outs = [dx, ACCUMULATED]
             if bias is not None:
                 outs.append(ACCUMULATED)

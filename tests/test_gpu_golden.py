@@ -194,7 +194,7 @@ def test_bert_vit_train_step_real_head_dim(precision):
             np.random.seed(1)
             bert = BERTForMaskedLM(BERTConfig(vocab_size=211, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
                                               max_position_embeddings=32))
-            opt = AdamW(bert.parameters(), lr=1e-3, moment_dtype="float64")
+            opt = AdamW(bert.parameters(), lr=1e-4, moment_dtype="float64")
             losses = []
             for _ in range(3):
                 opt.zero_grad()
@@ -204,7 +204,7 @@ def test_bert_vit_train_step_real_head_dim(precision):
                 losses.append(float(l.item()))
             np.random.seed(2)
             vit = VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=128, depth=2, num_heads=2)
-            vopt = AdamW(vit.parameters(), lr=1e-3, moment_dtype="float64")
+            vopt = AdamW(vit.parameters(), lr=1e-4, moment_dtype="float64")
             vl = []
             for _ in range(3):
                 vopt.zero_grad()

@@ -121,6 +121,10 @@ int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, in
                   int64_t ldc, const float* bias, const float* residual, int64_t ldr, void* aux, int64_t ldaux, int epilogue, int accumulate,
                   int split_k, float clip);
 int nfb_gemm_bf16_force_tile(int block_n);           /* test hook: pin the N tile (0 = automatic) */
+int nfb_gemm_bf16_force_cta_group(int cg);           /* test hook: 1 = single-CTA tiles, 2 = cta_group::2 SM pairs, 0 = automatic */
+int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */
+int nfb_gemm_bf16_set_tma_store(int on);             /* test hook: 0 = register epilogue everywhere (default 1: TMA store when C rows are 16-byte addressable) */
+int nfb_set_pdl(int on);                             /* programmatic dependent launch of the GEMM kernels (default on; env NFB_PDL=0) */
 
 /* ---- attention: RoPE (models/language/gpt2.py:25-95) and the fused QK^T -> softmax -> V core of
  * models/language/gpt2.py:183-215, models/language/bert.py:155-231, models/vision/vision_transformer.py:100-134

@@ -15,9 +15,26 @@
 // elected lane), warps 2..9 = epilogue (two warps per 32-lane TMEM quarter 32*(warp%4) .. +31).
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), double-buffered TMEM accumulator
 // full/empty mbarriers (MMA <-> epilogue), static persistent tile schedule.
+//
+// CG = 2 (cta_group::2): two CTAs of a cluster (an SM pair) share one 256 x BLOCK_N tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile; the leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2, which reads both halves over the pair interconnect and writes rows
+// 0..127 of the accumulator into its own TMEM and rows 128..255 into the peer's.  Per CTA and
+// k-block the smem fill drops from 16 KB + BLOCK_N*128 B to 16 KB + BLOCK_N*64 B, which is what
+// lifts the kernel off the 64 B/clk/SM L2->smem port limit (a 128x256 single-CTA tile needs 768
+// clk of fill for 512 clk of MMA; the paired tile needs 512).  Barrier protocol in pair mode:
+// both producers' TMA loads complete_tx on the LEADER's full barrier; tcgen05.commit multicasts
+// the "slot free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive
+// on the leader's tmem_empty barrier through its shared::cluster address.
+//
+// Programmatic dependent launch: the kernel is launched with the programmatic-stream-serialization
+// attribute and executes griddepcontrol.wait after its prologue (barrier init, TMEM alloc,
+// tensor-map prefetch), so that prologue overlaps the tail of the preceding kernel in the stream.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -43,6 +60,8 @@ struct GemmParams {
   int accumulate;       // C += (fp32 only, red.global.add)
   float clip;           // > 0: clamp the result to [-clip, clip]
   int vec_ok;           // C / residual / aux pitches and bases allow 128-bit (fp32) / 64-bit (bf16) accesses
+  int tma_store;        // epilogue through shared memory + TMA store / reduce-add (C 16-byte aligned rows, no residual, no aux)
+  unsigned long long* timeline;  // debug: per-CTA clock64 stamps of the pipeline events (NULL in production)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -93,25 +112,92 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// ---- cluster (CTA pair) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]   (bf16 x bf16 -> fp32)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// shared::cluster address of `smem_addr` (a shared::cta address) in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair-mode TMA load: data lands in THIS CTA's smem, the bytes are counted on the barrier at `bar_cluster_addr`
+// (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-// mbarrier arrives once every previously issued tcgen05.mma has completed (implies fence::before_thread_sync)
+// TMA store / reduce-add of a shared-memory box into global memory (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// programmatic dependent launch
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (bf16 x bf16 -> fp32)
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// mbarrier arrives once every previously issued tcgen05.mma has completed (implies fence::before_thread_sync);
+// in pair mode the arrival is multicast to the barrier at the same offset in both CTAs
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -151,28 +237,51 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int m, int n)
   return d;
 }
 
+// explicit shared-space 128-bit accesses: the staging pointer is derived from an aligned uintptr_t, so plain C++
+// dereferences compile to GENERIC ld/st (LD.E/ST.E) instead of LDS/STS
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   float inner = 0.79788456080286535588f * (x + 0.044715f * x * x * x);
   return 0.5f * x * (1.f + tanhf(inner));
 }
 
-template <int BLOCK_N, int STAGES>
+// debug timeline: slot layout per CTA (64 x u64): 0 entry, 1 setup done, 2 first TMA issued, 3 end;
+// 8+4t first data landed (tile t), 9+4t last MMA issued, 10+4t accumulator ready, 11+4t epilogue done
+__device__ __forceinline__ void tl_stamp(const GemmParams& p, int slot) {
+  if (p.timeline && blockIdx.x < 8 && slot < 64) p.timeline[blockIdx.x * 64 + slot] = (unsigned long long)clock64();
+}
+
+template <int BLOCK_N, int STAGES, int CG>
 struct GemmSmem {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of A
+  static constexpr int B_ROWS = BLOCK_N / CG;             // pair mode: each CTA stages half of the B tile
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // per-epilogue-warp 32x32 fp32 transpose buffers (XOR swizzled)
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
+  static_assert(B_ROWS % 8 == 0, "B half-tile rows");
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = GemmSmem<BLOCK_N, STAGES>;
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+          const GemmParams p) {
+  using L = GemmSmem<BLOCK_N, STAGES, CG>;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024-B alignment
+  // SWIZZLE_128B needs 1024-B alignment; the dynamic-smem base offset is identical in both CTAs of a pair, so the
+  // aligned layout (and with it every UMMA descriptor / barrier offset) is identical too
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   float* staging = (float*)(smem + STAGES * L::STAGE_BYTES);
   uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + L::STAGING_BYTES);
@@ -182,65 +291,96 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_mn = p.num_m * p.num_n;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int cluster_id = (int)blockIdx.x / CG, num_clusters = (int)gridDim.x / CG;
+  const int tiles_mn = p.num_m * p.num_n;   // num_m counts (128*CG)-row tiles
   const int total_tiles = tiles_mn * p.split_k;
+  if (threadIdx.x == 0) tl_stamp(p, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8 * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the previous kernel's tail; its results are visible only after this point
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) tl_stamp(p, 1);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         int ks = tile / tiles_mn, mn = tile % tiles_mn;
         int m_blk = mn % p.num_m, n_blk = mn / p.num_m;
         int kb0 = ks * p.k_blocks_per_split;
         int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        const int m0 = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           int k0 = kb * BLOCK_K;
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m_blk * BLOCK_M);
-          } else {
+          if (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m_blk * BLOCK_M + j * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_blk * BLOCK_N);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n_blk * BLOCK_N + j * 64, k0);
+              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+            }
+          } else {
+            // the leader's barrier counts the bytes of BOTH CTAs (the peer's complete_tx may land before the
+            // leader's expect_tx: the phase cannot complete until the leader's own arrival)
+            const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CG * L::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_pair(sa, &tmA, lead_bar, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmA, lead_bar, m0 + j * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_pair(sb, &tmB, lead_bar, k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, lead_bar, n0 + j * 64, k0);
+            }
           }
+          if (tile == cluster_id && kb == kb0) tl_stamp(p, 2);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BLOCK_M, BLOCK_N);
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BLOCK_M * CG, BLOCK_N);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;  // bytes per UMMA_K
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         int ks = tile / tiles_mn;
         int kb0 = ks * p.k_blocks_per_split;
         int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -249,6 +389,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (kb == kb0) tl_stamp(p, 8 + 4 * tcount);
           tc_fence_after();
           uint32_t sa = smem_u32(stage_base + stage * L::STAGE_BYTES);
           uint32_t sb = sa + L::A_BYTES;
@@ -256,12 +397,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        umma_commit<CG>(&tmem_full[acc]);  // accumulator ready for the epilogue warps (of both CTAs)
+        tl_stamp(p, 9 + 4 * tcount);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -273,18 +415,128 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // activation / residual / clip -> 128-bit (fp32) or 64-bit (bf16) coalesced global stores.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float4* st4 = reinterpret_cast<float4*>(staging) + (warp - 2) * 256;
+    const uint32_t st4 = smem_u32(staging) + (uint32_t)(warp - 2) * 4096u;  // this warp's 32x32 fp32 transpose buffer (float4 slots of 16 B)
     const int g = lane & 7, rsub = lane >> 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int tcount = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
       int ks = tile / tiles_mn, mn = tile % tiles_mn;
       int m_blk = mn % p.num_m, n_blk = mn / p.num_m;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 2 && lane == 0) tl_stamp(p, 10 + 4 * tcount);
       tc_fence_after();
-      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
       const bool add_bias = p.bias != nullptr && ks == 0;
       const bool add_res = p.residual != nullptr && ks == 0;
+      if (p.tma_store) {
+        // ---- TMA-store epilogue.  tcgen05.ld leaves thread = row holding consecutive columns; the row segment is
+        // written straight into this warp's 32-row x 128-byte staging box in the SWIZZLE_128B pattern (16-byte slot c
+        // of row r at c ^ (r & 7): conflict-free STS.128) and ONE elected lane hands the box to the TMA unit, which
+        // writes (or reduce-adds, for split-K wgrad) full lines to global memory and clips the ragged M / N edges.
+        // No LDS, no per-thread global stores.  bf16: 64 columns per step, fp32: 32 columns per step.
+        const uint32_t sbox = smem_u32(staging) + (uint32_t)(warp - 2) * 4096u;
+        const uint32_t srow = sbox + (uint32_t)lane * 128u;
+        const int sw = lane & 7;
+        const int step = p.c_bf16 ? 64 : 32;
+#pragma unroll 1
+        for (int c0 = half * step; c0 < BLOCK_N; c0 += 2 * step) {
+          const int col0 = n_blk * BLOCK_N + c0;
+          if (col0 >= p.N) break;  // warp-uniform
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+          if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of shared memory
+          __syncwarp();
+          if (p.c_bf16) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr + (uint32_t)(hh * 32), r);
+              tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if (add_bias) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const int c = col0 + hh * 32 + j4 * 4;
+                  if (c + 3 < p.N) {
+                    float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                    v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (c + e < p.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
+                  }
+                }
+              }
+              if (p.epilogue == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+              } else if (p.epilogue == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (p.clip > 0.f) {
+                const float lo = -p.clip, hi = p.clip;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], lo), hi);
+              }
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {   // four 16-byte slots (8 bf16 each) per 32 columns
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * s + 2 * e], v[8 * s + 2 * e + 1]);
+                  w[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                const int slot = hh * 4 + s;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((slot ^ sw) * 16)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              }
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (add_bias) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = col0 + j4 * 4;
+                if (c + 3 < p.N) {
+                  float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                  v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) if (c + e < p.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
+                }
+              }
+            }
+            if (p.epilogue == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+            } else if (p.epilogue == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.clip > 0.f) {
+              const float lo = -p.clip, hi = p.clip;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], lo), hi);
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              sts128(srow + (uint32_t)((s ^ sw) * 16), v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+          }
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accumulate) tma_reduce_add_2d(&tmC, sbox, col0, row0);
+            else tma_store_2d(&tmC, sbox, col0, row0);
+            tma_store_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         const int col0 = n_blk * BLOCK_N + c0;
@@ -294,21 +546,89 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tmem_ld_wait();
 #pragma unroll
         for (int gg = 0; gg < 8; ++gg)
-          st4[lane * 8 + (gg ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]),
-                                                          __uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
+          sts128(st4 + (uint32_t)(lane * 8 + (gg ^ (lane & 7))) * 16u, __uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]),
+                 __uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
         __syncwarp();
         const int col = col0 + g * 4;
+        if (p.vec_ok && row0 + 32 <= p.M && col0 + 32 <= p.N) {
+          // ---- fast path: the whole 32x32 chunk is in bounds and 16-byte addressable.  Every stage is its own
+          // unrolled loop over the thread's 8 rows (conditions are kernel-uniform), so the 8 LDS / 8 residual LDG /
+          // 8 STG of a stage are in flight together instead of one row at a time.
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            t[i] = lds128(st4 + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16u);
+          }
+          const long long rbase = (long long)(row0 + rsub);
+          if (add_bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t[i].x += b4.x; t[i].y += b4.y; t[i].z += b4.z; t[i].w += b4.w; }
+          }
+          if (p.aux) {
+            __nv_bfloat16* ap = (__nv_bfloat16*)p.aux + rbase * p.ldaux + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(t[i].x, t[i].y), a1 = __floats2bfloat162_rn(t[i].z, t[i].w);
+              *reinterpret_cast<uint2*>(ap + (long long)i * 4 * p.ldaux) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+            }
+          }
+          if (p.epilogue == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t[i].x = gelu_tanh_f(t[i].x); t[i].y = gelu_tanh_f(t[i].y); t[i].z = gelu_tanh_f(t[i].z); t[i].w = gelu_tanh_f(t[i].w); }
+          } else if (p.epilogue == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t[i].x = fmaxf(t[i].x, 0.f); t[i].y = fmaxf(t[i].y, 0.f); t[i].z = fmaxf(t[i].z, 0.f); t[i].w = fmaxf(t[i].w, 0.f); }
+          }
+          if (add_res) {
+            const float* rp = p.residual + rbase * p.ldr + col;
+            float4 rv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (long long)i * 4 * p.ldr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t[i].x += rv[i].x; t[i].y += rv[i].y; t[i].z += rv[i].z; t[i].w += rv[i].w; }
+          }
+          if (p.clip > 0.f) {
+            const float lo = -p.clip, hi = p.clip;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              t[i].x = fminf(fmaxf(t[i].x, lo), hi); t[i].y = fminf(fmaxf(t[i].y, lo), hi);
+              t[i].z = fminf(fmaxf(t[i].z, lo), hi); t[i].w = fminf(fmaxf(t[i].w, lo), hi);
+            }
+          }
+          if (p.c_bf16) {
+            __nv_bfloat16* cp = (__nv_bfloat16*)p.C + rbase * p.ldc + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(t[i].x, t[i].y), a1 = __floats2bfloat162_rn(t[i].z, t[i].w);
+              *reinterpret_cast<uint2*>(cp + (long long)i * 4 * p.ldc) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+            }
+          } else if (p.accumulate) {
+            float* cp = (float*)p.C + rbase * p.ldc + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + (long long)i * 4 * p.ldc), "f"(t[i].x), "f"(t[i].y), "f"(t[i].z), "f"(t[i].w) : "memory");
+          } else {
+            float* cp = (float*)p.C + rbase * p.ldc + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(cp + (long long)i * 4 * p.ldc) = t[i];
+          }
+          __syncwarp();
+          continue;
+        }
+        // ---- generic path: ragged edges of M / N or unaligned pitches
         const bool full4 = (col + 3 < p.N) && p.vec_ok;
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (add_bias) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) if (col + e < p.N) bv[e] = p.bias[col + e];
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rsub;
           const int row = row0 + rr;
-          float4 t4 = st4[rr * 8 + (g ^ (rr & 7))];
+          float4 t4 = lds128(st4 + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16u);
           if (row < p.M && col < p.N) {
             float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
             if (full4) {
@@ -366,18 +686,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         __syncwarp();
       }
+      }  // !tma_store
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CG == 1 || cta_rank == 0) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // the leader's MMA warp owns the accumulator hand-off
+        if (warp == 2) tl_stamp(p, 11 + 4 * tcount);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
+  if (warp >= 2 && lane == 0 && p.tma_store) tma_store_wait_all();  // this warp's boxes have landed in global memory
   tc_fence_before();
-  __syncthreads();
+  if (threadIdx.x == 0) tl_stamp(p, 3);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair mode: neither CTA may exit while the other still reads its smem / signals its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -397,13 +724,15 @@ static int get_encode_fn() {
   return 0;
 }
 
-typedef std::tuple<const void*, long long, long long, long long, int, int> MapKey;
+typedef std::tuple<const void*, long long, long long, long long, int, int, int> MapKey;
 static std::map<MapKey, CUtensorMap> g_map_cache;
 static std::mutex g_map_mu;
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1, row pitch ld elements, box {box0, box1}, 128-B swizzle
-static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long dim1, long long ld, int box0, int box1) {
-  MapKey key(ptr, dim0, dim1, ld, box0, box1);
+static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long dim1, long long ld, int box0, int box1,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+  const int esz = (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32) ? 4 : 2;
+  MapKey key(ptr, dim0, dim1, ld, box0, box1, (int)dt);
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_map_cache.find(key);
@@ -411,12 +740,12 @@ static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long
   }
   if (get_encode_fn()) return -1;
   if (((uintptr_t)ptr & 15) != 0) return NFB_FAIL("gemm_bf16: operand base %p is not 16-byte aligned", ptr);
-  if ((ld * 2) % 16 != 0) return NFB_FAIL("gemm_bf16: operand leading dimension %lld must be a multiple of 8 elements", ld);
+  if ((ld * esz) % 16 != 0) return NFB_FAIL("gemm_bf16: leading dimension %lld is not a multiple of 16 bytes", ld);
   cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return NFB_FAIL("cuTensorMapEncodeTiled failed (%d) dims=(%lld,%lld) ld=%lld box=(%d,%d)", (int)r, dim0, dim1, ld, box0, box1);
@@ -426,21 +755,74 @@ static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long
   return 0;
 }
 
-template <int BLOCK_N, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid) {
-  using L = GemmSmem<BLOCK_N, STAGES>;
+static int g_pdl = -1;  // programmatic dependent launch: on unless NFB_PDL=0
+static bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("NFB_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+NFB_API int nfb_set_pdl(int on) { g_pdl = on ? 1 : 0; return 0; }
+
+template <int BLOCK_N, int STAGES, int CG>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid) {
+  using L = GemmSmem<BLOCK_N, STAGES, CG>;
   static bool configured = false;
   if (!configured) {
-    NFB_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  k_gemm_tc<BLOCK_N, STAGES><<<grid, GEMM_THREADS, L::TOTAL, nfb_cur_stream()>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = nfb_cur_stream();
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (CG == 2) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 2;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  NFB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, STAGES, CG>, tmA, tmB, tmC, p));
   NFB_LAUNCH_CHECK();
   return 0;
 }
 
-static int g_force_block_n = 0;
+static int g_force_block_n = 0, g_force_cg = 0, g_tma_store = 1;
+NFB_API int nfb_gemm_bf16_set_tma_store(int on) { g_tma_store = on ? 1 : 0; return 0; }  // test hook: 0 = register epilogue everywhere
+static unsigned long long* g_timeline = nullptr;
+// debug: device buffer of 8 x 64 u64 that the next launches fill with clock64 stamps (NULL = off)
+NFB_API int nfb_gemm_bf16_set_timeline(void* dev_buf) { g_timeline = (unsigned long long*)dev_buf; return 0; }
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
+NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }
+
+// Tile choice: a small cost model in SM clocks.  Per CTA and 64-deep k-block the MMA needs 2*BLOCK_N clk (tcgen05
+// floor, 128 x BLOCK_N x 16 per BLOCK_N/2 clk) and the smem fill needs (16 KB + BLOCK_N/CG * 128 B) / 64 B/clk
+// (the measured L2->smem port rate); a tile costs kblocks * max(of the two) and every launch pays a fixed
+// prologue + first-load + last-epilogue cost.  Whole-launch cost = waves * tile + fixed.
+struct TileChoice { int bn, cg, sk; double cost; };
+static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int sms) {
+  long long num_m = nfb_cdiv(M, BLOCK_M * cg), num_n = nfb_cdiv(N, bn);
+  long long units = sms / cg;                     // CTAs (or CTA pairs) running concurrently
+  long long work = num_m * num_n * sk;
+  long long waves = nfb_cdiv(work, units);
+  double kb = (double)nfb_cdiv(k_blocks, sk);
+  double mma = 2.0 * bn, fill = (16384.0 + (double)(bn / cg) * 128.0) / 64.0;
+  double per_kb = mma > fill ? mma : fill;
+  double epi = 150.0 * (bn / 32) / 2.0 + (sk > 1 ? 100.0 * (bn / 32) / 2.0 : 0.0);   // drain of the last tile; red.add is slower
+  return (double)waves * (kb * per_kb + 250.0) + epi + 2500.0;
+}
 
 // C (+)= epi(opA . opB + bias) + residual.  A, B bf16; C fp32 (c_dtype = NFB_F32) or bf16.
 // split_k: 0 = choose automatically (only used when accumulate != 0), >= 1 = explicit.
@@ -451,49 +833,51 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   if (K <= 0) return NFB_FAIL("gemm_bf16: K must be positive");
   if (c_dtype != NFB_F32 && c_dtype != NFB_BF16) return NFB_FAIL("gemm_bf16: C dtype %d", c_dtype);
   if (accumulate && c_dtype != NFB_F32) return NFB_FAIL("gemm_bf16: accumulate needs an fp32 C");
+  if (!accumulate && split_k > 1) return NFB_FAIL("gemm_bf16: split_k > 1 requires accumulate (C pre-initialised)");
+  if (split_k > 1 && epilogue != 0) return NFB_FAIL("gemm_bf16: split-K cannot be combined with an activation epilogue");
   const int sms = nfb_sm_count();
-  const int num_m = (int)nfb_cdiv(M, BLOCK_M);
-  // tile-N choice: best wave efficiency over {256, 192, 128, 64}, larger tile wins ties
-  int cand[4] = {256, 192, 128, 64};
-  int best_bn = 128;
-  double best_eff = -1.0;
-  for (int i = 0; i < 4; ++i) {
-    int bn = cand[i];
-    long long tiles = (long long)num_m * nfb_cdiv(N, bn);
-    long long waves = nfb_cdiv(tiles, sms);
-    double useful = (double)M * N / ((double)num_m * BLOCK_M * nfb_cdiv(N, bn) * bn);  // padding waste
-    double eff = (double)tiles / (double)(waves * sms) * useful * (bn >= 128 ? 1.0 : 0.8);
-    if (eff > best_eff + 0.03) { best_eff = eff; best_bn = bn; }
-  }
-  if (g_force_block_n) best_bn = g_force_block_n;
-  const int num_n = (int)nfb_cdiv(N, best_bn);
+  const int a_mn = transA ? 1 : 0, b_mn = transB ? 0 : 1;
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
-  int sk = 1;
-  if (accumulate) {
-    if (split_k >= 1) sk = split_k;
-    else {
-      long long tiles = (long long)num_m * num_n;
-      if (tiles < sms && k_blocks >= 8) {
-        sk = (int)(sms / tiles);
-        if (sk > k_blocks / 4) sk = k_blocks / 4;
-        if (sk < 1) sk = 1;
+
+  TileChoice best = {128, 1, 1, 1e30};
+  const int cand_bn[4] = {256, 192, 128, 64};
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (g_force_cg && cg != g_force_cg) continue;
+    if (cg == 2 && (sms % 2 != 0 || M <= BLOCK_M)) continue;
+    for (int i = 0; i < 4; ++i) {
+      int bn = cand_bn[i];
+      if (g_force_block_n && bn != g_force_block_n) continue;
+      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;   // MN-major B is staged in 64-column chunks
+      int sk_lo = 1, sk_hi = 1;
+      if (accumulate && epilogue == 0) {
+        if (split_k >= 1) sk_lo = sk_hi = split_k;
+        else sk_hi = k_blocks >= 8 ? (k_blocks / 4 < 16 ? k_blocks / 4 : 16) : 1;
+      }
+      for (int sk = sk_lo; sk <= sk_hi; ++sk) {
+        double c = tile_cost(M, N, k_blocks, bn, cg, sk, sms);
+        if (c < best.cost * 0.98) best = {bn, cg, sk, c};
       }
     }
-  } else if (split_k > 1) {
-    return NFB_FAIL("gemm_bf16: split_k > 1 requires accumulate (C pre-initialised)");
   }
-  if (sk > 1 && epilogue != 0) return NFB_FAIL("gemm_bf16: split-K cannot be combined with an activation epilogue");
+  if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
+    best = {g_force_block_n ? g_force_block_n : 128, 1, (accumulate && split_k >= 1) ? split_k : 1, 0.0};
+  }
+  const int best_bn = best.bn, cg = best.cg;
+  int sk = best.sk;
+  const int num_m = (int)nfb_cdiv(M, BLOCK_M * cg);
+  const int num_n = (int)nfb_cdiv(N, best_bn);
   int kbps = (int)nfb_cdiv(k_blocks, sk);
   sk = (int)nfb_cdiv(k_blocks, kbps);
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.a_mn = transA ? 1 : 0;
-  p.b_mn = transB ? 0 : 1;
+  p.a_mn = a_mn;
+  p.b_mn = b_mn;
   p.num_m = num_m; p.num_n = num_n; p.split_k = sk; p.k_blocks_per_split = kbps; p.k_blocks_total = k_blocks;
   p.C = C; p.c_bf16 = (c_dtype == NFB_BF16); p.ldc = ldc;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.aux = aux; p.ldaux = ldaux;
   p.epilogue = epilogue; p.accumulate = accumulate; p.clip = clip;
+  p.timeline = g_timeline;
   {
     bool ok = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
     if (residual) ok = ok && (ldr % 4 == 0) && ((uintptr_t)residual % 16 == 0);
@@ -501,19 +885,37 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
     p.vec_ok = ok ? 1 : 0;
   }
 
-  CUtensorMap tmA, tmB;
+  // TMA-store epilogue: C rows must be 16-byte addressable; residual / aux outputs keep the register epilogue
+  p.tma_store = (g_tma_store && !residual && !aux && ((uintptr_t)C % 16 == 0) && ((ldc * (p.c_bf16 ? 2 : 4)) % 16 == 0)) ? 1 : 0;
+  CUtensorMap tmA, tmB, tmC;
+  if (p.tma_store) {
+    if (make_map(&tmC, C, N, M, ldc, p.c_bf16 ? 64 : 32, 32, p.c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
+  } else {
+    memset(&tmC, 0, sizeof(tmC));
+  }
+  const int b_rows = best_bn / cg;
   if (!p.a_mn) { if (make_map(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M)) return -1; }
   else { if (make_map(&tmA, A, M, K, lda, 64, BLOCK_K)) return -1; }
-  if (!p.b_mn) { if (make_map(&tmB, B, K, N, ldb, BLOCK_K, best_bn)) return -1; }
+  if (!p.b_mn) { if (make_map(&tmB, B, K, N, ldb, BLOCK_K, b_rows)) return -1; }
   else { if (make_map(&tmB, B, N, K, ldb, 64, BLOCK_K)) return -1; }
 
   long long total = (long long)num_m * num_n * sk;
-  int grid = (int)(total < sms ? total : sms);
-  switch (best_bn) {
-    case 256: return launch_gemm<256, 4>(tmA, tmB, p, grid);
-    case 192: return launch_gemm<192, 4>(tmA, tmB, p, grid);
-    case 128: return launch_gemm<128, 6>(tmA, tmB, p, grid);
-    case 64: return launch_gemm<64, 8>(tmA, tmB, p, grid);
+  long long units = sms / cg;
+  int grid = (int)(total < units ? total : units) * cg;
+  if (cg == 1) {
+    switch (best_bn) {
+      case 256: return launch_gemm<256, 4, 1>(tmA, tmB, tmC, p, grid);
+      case 192: return launch_gemm<192, 4, 1>(tmA, tmB, tmC, p, grid);
+      case 128: return launch_gemm<128, 6, 1>(tmA, tmB, tmC, p, grid);
+      case 64: return launch_gemm<64, 8, 1>(tmA, tmB, tmC, p, grid);
+    }
+  } else {
+    switch (best_bn) {
+      case 256: return launch_gemm<256, 6, 2>(tmA, tmB, tmC, p, grid);
+      case 192: return launch_gemm<192, 6, 2>(tmA, tmB, tmC, p, grid);
+      case 128: return launch_gemm<128, 8, 2>(tmA, tmB, tmC, p, grid);
+      case 64: return launch_gemm<64, 8, 2>(tmA, tmB, tmC, p, grid);
+    }
   }
-  return NFB_FAIL("gemm_bf16: unsupported tile N %d", best_bn);
+  return NFB_FAIL("gemm_bf16: unsupported tile N %d (cta group %d)", best_bn, cg);
 }

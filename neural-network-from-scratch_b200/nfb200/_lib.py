@@ -96,6 +96,10 @@ _SIGNATURES = {
     "nfb_gemm_f32": [i32, i32, i32, i32, i32, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32, vp],
     "nfb_gemm_bf16": [i32, i32, i32, i32, i32, vp, i64, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, i32, i32, i32, f32],
     "nfb_gemm_bf16_force_tile": [i32],
+    "nfb_gemm_bf16_force_cta_group": [i32],
+    "nfb_set_pdl": [i32],
+    "nfb_gemm_bf16_set_tma_store": [i32],
+    "nfb_gemm_bf16_set_timeline": [vp],
     # attention
     "nfb_rope": [i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, i64, i64, i64, i32],
     "nfb_flash_attn_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, vp],

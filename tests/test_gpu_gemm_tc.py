@@ -26,9 +26,18 @@ def _ref(a, b, ta, tb):
 LAYOUTS = [(False, True), (False, False), (True, False), (True, True)]
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "cta1", "cta_pair"])
+def cta_group(request):
+    """0 = the library's own choice, 1 = single-CTA tiles, 2 = cta_group::2 SM-pair tiles (256 x BLOCK_N)."""
+    from nfb200 import _lib
+    _lib.call("nfb_gemm_bf16_force_cta_group", request.param)
+    yield request.param
+    _lib.call("nfb_gemm_bf16_force_cta_group", 0)
+
+
 @pytest.mark.parametrize("ta,tb", LAYOUTS)
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (512, 768, 768), (300, 200, 136), (129, 72, 72), (64, 40, 8), (4096, 2304, 768)])
-def test_gemm_layouts_and_ragged_shapes(be, ta, tb, M, N, K):
+def test_gemm_layouts_and_ragged_shapes(be, cta_group, ta, tb, M, N, K):
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(M + N + K)
     a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
@@ -40,7 +49,7 @@ def test_gemm_layouts_and_ragged_shapes(be, ta, tb, M, N, K):
 
 
 @pytest.mark.parametrize("bn", [64, 128, 192, 256])
-def test_every_tile_width(be, bn):
+def test_every_tile_width(be, cta_group, bn):
     from nfb200 import _lib, kernels as Kn
     rng = np.random.default_rng(bn)
     a = rng.standard_normal((384, 320)).astype(np.float32)
@@ -56,7 +65,7 @@ def test_every_tile_width(be, bn):
     np.testing.assert_allclose(got2, want, rtol=2e-5, atol=5e-4)
 
 
-def test_many_tiles_persistent_schedule(be):
+def test_many_tiles_persistent_schedule(be, cta_group):
     """More tiles than SMs: exercises smem-ring wrap-around and the double-buffered TMEM accumulator."""
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(1)
@@ -66,7 +75,7 @@ def test_many_tiles_persistent_schedule(be):
     np.testing.assert_allclose(got, _ref(a, b, False, True), rtol=2e-5, atol=5e-4)
 
 
-def test_unaligned_output_pitch_logits_shape(be):
+def test_unaligned_output_pitch_logits_shape(be, cta_group):
     """N = 50257-style odd row pitch: coalesced scalar stores, no alignment requirement on C."""
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(2)
@@ -76,7 +85,7 @@ def test_unaligned_output_pitch_logits_shape(be):
     np.testing.assert_allclose(got, _ref(x, w, False, True), rtol=2e-5, atol=4e-4)
 
 
-def test_epilogues_bias_gelu_relu_residual_bf16_out(be):
+def test_epilogues_bias_gelu_relu_residual_bf16_out(be, cta_group):
     from nfb200 import kernels as Kn
     from oracle import np_ops as O
     rng = np.random.default_rng(3)
@@ -99,8 +108,27 @@ def test_epilogues_bias_gelu_relu_residual_bf16_out(be):
     np.testing.assert_allclose(yc, np.clip(z, -0.5, 0.5), rtol=2e-5, atol=3e-4)
 
 
+@pytest.mark.parametrize("out_bf16", [False, True])
+@pytest.mark.parametrize("M,N,K", [(512, 768, 256), (300, 200, 136), (4096, 2304, 768)])
+def test_register_epilogue_without_tma_store(be, cta_group, M, N, K, out_bf16):
+    """The TMA-store epilogue is the default for 16-byte addressable C; this pins the register (LDS + STG) epilogue."""
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(M + N)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K)).astype(np.float32)
+    _lib.call("nfb_gemm_bf16_set_tma_store", 0)
+    try:
+        got = Kn.gemm_bf16(_to(be, a), _to(be, b), False, True, out_dtype=be.bfloat16 if out_bf16 else np.float32).get()
+    finally:
+        _lib.call("nfb_gemm_bf16_set_tma_store", 1)
+    if out_bf16:
+        np.testing.assert_allclose(got, _ref(a, b, False, True), rtol=1e-2, atol=1e-2 * np.sqrt(K / 64))
+    else:
+        np.testing.assert_allclose(got, _ref(a, b, False, True), rtol=2e-5, atol=2e-4 * np.sqrt(K / 64))
+
+
 @pytest.mark.parametrize("split_k", [0, 1, 3, 8])
-def test_wgrad_split_k_accumulate(be, split_k):
+def test_wgrad_split_k_accumulate(be, cta_group, split_k):
     """dW (+)= dY^T X with K = tokens: split-K partial sums land with red.global.add on a pre-initialised C."""
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(4)

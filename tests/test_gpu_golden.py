@@ -216,6 +216,8 @@ def test_bert_vit_train_step_real_head_dim(precision):
         finally:
             K.set_precision("fp32")
             set_default_device("cpu")
-    tol = 5e-5 if precision == "fp32" else 1e-2
+    # fp32 contract: 1e-5-class relative; bf16 contract (north_star): 1e-2 relative/abs on the loss trajectory -- the ViT loss
+    # reaches ~1e-2 after three steps on two images, where a purely relative bound on a near-zero loss is meaningless
+    rtol, atol = (5e-5, 1e-6) if precision == "fp32" else (1e-2, 1e-3)
     for a, b in zip(res["cuda"][0] + res["cuda"][1], res["cpu"][0] + res["cpu"][1]):
-        assert abs(a - b) <= tol * abs(b), f"{precision}: device {res['cuda']} vs host {res['cpu']}"
+        assert abs(a - b) <= rtol * abs(b) + atol, f"{precision}: device {res['cuda']} vs host {res['cpu']}"

@@ -105,6 +105,10 @@ int nfb_softmax_fwd(const float* x, float* y, int64_t rows, int cols);
 int nfb_softmax_bwd(const float* p, const float* g, float* dx, int64_t rows, int cols);
 int nfb_cross_entropy(const float* logits, const void* targets, int tgt_is_i64, float* loss, void* dlogits, int ddt, int64_t rows, int V,
                       int64_t ld, int64_t dld, float grad_scale);
+/* same with the logits dtype stated (NFB_F32 or NFB_BF16; bf16 logits need the wide-row kernel: 8192 <= V <= 53248) */
+int nfb_cross_entropy_set_bulk(int on);   /* test hook: 0 = bf16 logits through the register-resident kernel instead of the bulk-copy one */
+int nfb_cross_entropy_ex(int ldt, const void* logits, const void* targets, int tgt_is_i64, float* loss, void* dlogits, int ddt, int64_t rows,
+                         int V, int64_t ld, int64_t dld, float grad_scale);
 
 /* ---- embedding gather / bit-exact ordered scatter-add (nn/embedding.py:27-63) */
 int nfb_gather_rows(int idx_dtype, int wdt, int odt, const void* W, const void* idx, void* out, int64_t n, int d, int64_t V);

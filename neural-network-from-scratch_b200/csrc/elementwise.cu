@@ -698,50 +698,145 @@ NFB_API int nfb_arange(int dtype, void* p, int64_t n, double start, double step)
 // ------------------------------------------------------------------------------------------------
 // out = silu(gate) * up   (models/language/gpt2.py:119-139) ; gate/up are the two halves of one
 // (rows, 2*C) buffer when `packed`, else separate (rows, C) buffers.
+// sigmoid for the SwiGLU kernels: exact split form for fp32 storage (the 1e-5 contract); for bf16 storage the
+// 4-instruction form 1 / (1 + 2^(-x log2 e)) (ex2.approx + rcp.approx, ~2 ulp: invisible after bf16 rounding) -- the exact
+// form costs ~30 instructions per element and made these kernels issue-bound instead of HBM-bound
+template <typename T> __device__ __forceinline__ float swiglu_sigmoid(float x) { return sigmoid_t<float>(x); }
+template <> __device__ __forceinline__ float swiglu_sigmoid<__nv_bfloat16>(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// 16-byte vectors (4 fp32 / 8 bf16 per access), 32-bit index math, one (row, column-vector) per thread and iteration.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) { float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+  __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
 template <typename T>
-__global__ void k_swiglu_fwd(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out, int64_t rows, int64_t C, int64_t in_ld) {
-  int64_t n4 = rows * C / 4, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += stride) {
-    int64_t e = v * 4, r = e / C, c = e % C;
-    f4 g = ld4<T>(gate + r * in_ld + c), u = ld4<T>(up + r * in_ld + c);
-    f4 o = {g.x * sigmoid_t<float>(g.x) * u.x, g.y * sigmoid_t<float>(g.y) * u.y, g.z * sigmoid_t<float>(g.z) * u.z, g.w * sigmoid_t<float>(g.w) * u.w};
-    st4<T>(out + e, o);
+__global__ void k_swiglu_fwd(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out, int rows, int CV, int64_t C, int64_t in_ld) {
+  constexpr int N = Vec16<T>::N;
+  const unsigned total = (unsigned)rows * (unsigned)CV, stride = gridDim.x * blockDim.x;   // host checks rows * CV < 2^31
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int r = (int)(v / (unsigned)CV), c = (int)(v - (unsigned)r * (unsigned)CV) * N;
+    float g[N], u[N], o[N];
+    Vec16<T>::load(gate + r * in_ld + c, g);
+    Vec16<T>::load(up + r * in_ld + c, u);
+#pragma unroll
+    for (int k = 0; k < N; ++k) o[k] = g[k] * swiglu_sigmoid<T>(g[k]) * u[k];
+    Vec16<T>::store(out + (int64_t)r * C + c, o);
   }
 }
 // dgate = dout * up * silu'(gate) ; dup = dout * silu(gate)
 template <typename T>
 __global__ void k_swiglu_bwd(const T* __restrict__ gate, const T* __restrict__ up, const T* __restrict__ dout, T* __restrict__ dgate, T* __restrict__ dup,
-                             int64_t rows, int64_t C, int64_t in_ld) {
-  int64_t n4 = rows * C / 4, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += stride) {
-    int64_t e = v * 4, r = e / C, c = e % C;
-    f4 g = ld4<T>(gate + r * in_ld + c), u = ld4<T>(up + r * in_ld + c), d = ld4<T>(dout + e);
-    float gs[4] = {g.x, g.y, g.z, g.w}, us[4] = {u.x, u.y, u.z, u.w}, ds[4] = {d.x, d.y, d.z, d.w}, dg[4], du[4];
+                             int rows, int CV, int64_t C, int64_t in_ld) {
+  constexpr int N = Vec16<T>::N;
+  const unsigned total = (unsigned)rows * (unsigned)CV, stride = gridDim.x * blockDim.x;   // host checks rows * CV < 2^31
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int r = (int)(v / (unsigned)CV), c = (int)(v - (unsigned)r * (unsigned)CV) * N;
+    float g[N], u[N], d[N], dg[N], du[N];
+    Vec16<T>::load(gate + r * in_ld + c, g);
+    Vec16<T>::load(up + r * in_ld + c, u);
+    Vec16<T>::load(dout + (int64_t)r * C + c, d);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float sg = sigmoid_t<float>(gs[k]);
-      du[k] = ds[k] * gs[k] * sg;
-      dg[k] = ds[k] * us[k] * (sg * (1.f + gs[k] * (1.f - sg)));
+    for (int k = 0; k < N; ++k) {
+      float sg = swiglu_sigmoid<T>(g[k]);
+      du[k] = d[k] * g[k] * sg;
+      dg[k] = d[k] * u[k] * (sg * (1.f + g[k] * (1.f - sg)));
     }
-    st4<T>(dgate + r * in_ld + c, {dg[0], dg[1], dg[2], dg[3]});
-    st4<T>(dup + r * in_ld + c, {du[0], du[1], du[2], du[3]});
+    Vec16<T>::store(dgate + r * in_ld + c, dg);
+    Vec16<T>::store(dup + r * in_ld + c, du);
   }
 }
+// scalar fallbacks for shapes / pointers the 16-byte vectors cannot address
+template <typename T>
+__global__ void k_swiglu_fwd_scalar(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out, int64_t rows, int64_t C, int64_t in_ld) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * C; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C, c = i % C;
+    float g = ld_f<T>(gate, r * in_ld + c), u = ld_f<T>(up, r * in_ld + c);
+    st_f<T>(out, i, g * sigmoid_t<float>(g) * u);
+  }
+}
+template <typename T>
+__global__ void k_swiglu_bwd_scalar(const T* __restrict__ gate, const T* __restrict__ up, const T* __restrict__ dout, T* __restrict__ dgate,
+                                    T* __restrict__ dup, int64_t rows, int64_t C, int64_t in_ld) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * C; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C, c = i % C;
+    float g = ld_f<T>(gate, r * in_ld + c), u = ld_f<T>(up, r * in_ld + c), d = ld_f<T>(dout, i);
+    float sg = sigmoid_t<float>(g);
+    st_f<T>(dup, r * in_ld + c, d * g * sg);
+    st_f<T>(dgate, r * in_ld + c, d * u * (sg * (1.f + g * (1.f - sg))));
+  }
+}
+template <typename T>
+static bool swiglu_vec_ok(const void* a, const void* b, const void* c, const void* d, const void* e, int64_t rows, int64_t C, int64_t in_ld) {
+  constexpr int N = 16 / (int)sizeof(T);
+  return C % N == 0 && in_ld % N == 0 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & 15) == 0) && rows * (C / N) < (1LL << 31);
+}
+template <typename T>
+static int swiglu_check(const void* a, const void* b, const void* c, const void* d, const void* e, int64_t C, int64_t in_ld, const char* who) {
+  constexpr int N = 16 / (int)sizeof(T);
+  if (C % N || in_ld % N) return NFB_FAIL("%s: C and in_ld must be multiples of %d elements (16-byte vectors)", who, N);
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & 15) != 0) return NFB_FAIL("%s: buffers must be 16-byte aligned", who);
+  return 0;
+}
+static int swiglu_size_check(int64_t rows, int64_t CV, const char* who) {
+  if (rows * CV >= (1LL << 31)) return NFB_FAIL("%s: %lld x %lld vectors exceed the 32-bit index range", who, (long long)rows, (long long)CV);
+  return 0;
+}
 NFB_API int nfb_swiglu_fwd(int dtype, const void* gate, const void* up, void* out, int64_t rows, int64_t C, int64_t in_ld) {
-  if (C % 4 || in_ld % 4) return NFB_FAIL("nfb_swiglu_fwd: C and in_ld must be multiples of 4");
-  int grid = nfb_grid_for(rows * C / 4, 256);
-  if (dtype == NFB_F32) k_swiglu_fwd<float><<<grid, 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (float*)out, rows, C, in_ld);
-  else if (dtype == NFB_BF16) k_swiglu_fwd<__nv_bfloat16><<<grid, 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)out, rows, C, in_ld);
-  else return NFB_FAIL("nfb_swiglu_fwd: unsupported dtype %d", dtype);
+  if (rows == 0 || C == 0) return 0;
+  if (dtype == NFB_F32 && !swiglu_vec_ok<float>(gate, up, out, nullptr, nullptr, rows, C, in_ld)) {
+    k_swiglu_fwd_scalar<float><<<nfb_grid_for(rows * C, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (float*)out, rows, C, in_ld);
+  } else if (dtype == NFB_BF16 && !swiglu_vec_ok<__nv_bfloat16>(gate, up, out, nullptr, nullptr, rows, C, in_ld)) {
+    k_swiglu_fwd_scalar<__nv_bfloat16><<<nfb_grid_for(rows * C, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)out, rows, C, in_ld);
+  } else if (dtype == NFB_F32) {
+    if (swiglu_check<float>(gate, up, out, nullptr, nullptr, C, in_ld, "nfb_swiglu_fwd")) return -1;
+    int CV = (int)(C / 4);
+    if (swiglu_size_check(rows, CV, "nfb_swiglu_fwd")) return -1;
+    k_swiglu_fwd<float><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (float*)out, (int)rows, CV, C, in_ld);
+  } else if (dtype == NFB_BF16) {
+    if (swiglu_check<__nv_bfloat16>(gate, up, out, nullptr, nullptr, C, in_ld, "nfb_swiglu_fwd")) return -1;
+    int CV = (int)(C / 8);
+    if (swiglu_size_check(rows, CV, "nfb_swiglu_fwd")) return -1;
+    k_swiglu_fwd<__nv_bfloat16><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)out, (int)rows, CV, C, in_ld);
+  } else return NFB_FAIL("nfb_swiglu_fwd: unsupported dtype %d", dtype);
   NFB_LAUNCH_CHECK();
   return 0;
 }
 NFB_API int nfb_swiglu_bwd(int dtype, const void* gate, const void* up, const void* dout, void* dgate, void* dup, int64_t rows, int64_t C, int64_t in_ld) {
-  if (C % 4 || in_ld % 4) return NFB_FAIL("nfb_swiglu_bwd: C and in_ld must be multiples of 4");
-  int grid = nfb_grid_for(rows * C / 4, 256);
-  if (dtype == NFB_F32) k_swiglu_bwd<float><<<grid, 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (const float*)dout, (float*)dgate, (float*)dup, rows, C, in_ld);
-  else if (dtype == NFB_BF16) k_swiglu_bwd<__nv_bfloat16><<<grid, 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dgate, (__nv_bfloat16*)dup, rows, C, in_ld);
-  else return NFB_FAIL("nfb_swiglu_bwd: unsupported dtype %d", dtype);
+  if (rows == 0 || C == 0) return 0;
+  if (dtype == NFB_F32 && !swiglu_vec_ok<float>(gate, up, dout, dgate, dup, rows, C, in_ld)) {
+    k_swiglu_bwd_scalar<float><<<nfb_grid_for(rows * C, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (const float*)dout, (float*)dgate, (float*)dup, rows, C, in_ld);
+  } else if (dtype == NFB_BF16 && !swiglu_vec_ok<__nv_bfloat16>(gate, up, dout, dgate, dup, rows, C, in_ld)) {
+    k_swiglu_bwd_scalar<__nv_bfloat16><<<nfb_grid_for(rows * C, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dgate, (__nv_bfloat16*)dup, rows, C, in_ld);
+  } else if (dtype == NFB_F32) {
+    if (swiglu_check<float>(gate, up, dout, dgate, dup, C, in_ld, "nfb_swiglu_bwd")) return -1;
+    int CV = (int)(C / 4);
+    if (swiglu_size_check(rows, CV, "nfb_swiglu_bwd")) return -1;
+    k_swiglu_bwd<float><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (const float*)dout, (float*)dgate, (float*)dup, (int)rows, CV, C, in_ld);
+  } else if (dtype == NFB_BF16) {
+    if (swiglu_check<__nv_bfloat16>(gate, up, dout, dgate, dup, C, in_ld, "nfb_swiglu_bwd")) return -1;
+    int CV = (int)(C / 8);
+    if (swiglu_size_check(rows, CV, "nfb_swiglu_bwd")) return -1;
+    k_swiglu_bwd<__nv_bfloat16><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dgate, (__nv_bfloat16*)dup, (int)rows, CV, C, in_ld);
+  } else return NFB_FAIL("nfb_swiglu_bwd: unsupported dtype %d", dtype);
   NFB_LAUNCH_CHECK();
   return 0;
 }

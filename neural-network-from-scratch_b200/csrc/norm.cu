@@ -73,61 +73,77 @@ k_norm_fwd(const TX* __restrict__ x, const TX* __restrict__ res, TX* __restrict_
   }
 }
 
-// backward: each warp walks rows with a grid stride; its lanes own fixed columns, so dgamma/dbeta
-// partials accumulate in registers and are written once per block to `partial`
-// ([gridDim.x][2][cols]); k_norm_param_reduce then sums the blocks in a fixed order (deterministic).
+// backward: 8 warps per block, (at most) two blocks per SM, each warp walks rows with a grid stride.  Its lanes own
+// fixed columns, so dgamma / dbeta partials accumulate in registers over all of the warp's rows and are combined
+// through shared memory once per block into `partial` ([gridDim.x][NP][cols], NP = 1 for RMSNorm (no beta), 2 for
+// LayerNorm); k_norm_param_reduce then sums the block partials in a fixed order (deterministic, one launch).
+// The row is kept RAW in registers (x as loaded, dy packed as loaded) and x_hat / g*gamma are recomputed in the
+// second phase: that keeps the kernel at <= 128 registers so that 16 warps per SM have their rows in flight.
+#define BWD_WARPS 8
 template <int VPL, typename TX, typename TY, bool RMS>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(BWD_WARPS * 32, 2)
 k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
            const float* __restrict__ rstd_in, const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
            int64_t rows, int cols, float clip, __nv_bfloat16* __restrict__ dx_twin) {
-  __shared__ float sh[WARPS_PER_BLOCK][2][VPL * 128];
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + w;
-  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-  float inv_n = 1.f / (float)cols;
-  f4 dg[VPL], db[VPL];
-  float4 gm[VPL];
+  constexpr int NP = RMS ? 1 : 2;
+  __shared__ float sh[BWD_WARPS][VPL * 128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * BWD_WARPS + w;
+  const int64_t nwarps = (int64_t)gridDim.x * BWD_WARPS;
+  const float inv_n = 1.f / (float)cols;
+  f4 dg[VPL], db[RMS ? 1 : VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    dg[k] = {0.f, 0.f, 0.f, 0.f};
-    db[k] = {0.f, 0.f, 0.f, 0.f};
-    int c = k * 128 + lane * 4;
-    gm[k] = (gamma && c < cols) ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int k = 0; k < VPL; ++k) dg[k] = {0.f, 0.f, 0.f, 0.f};
+  if (!RMS) {
+#pragma unroll
+    for (int k = 0; k < (RMS ? 1 : VPL); ++k) db[k] = {0.f, 0.f, 0.f, 0.f};
   }
   for (int64_t row = warp_global; row < rows; row += nwarps) {
-    float mean = (RMS || !mean_in) ? 0.f : mean_in[row];
-    float rstd = rstd_in[row];
-    f4 xh[VPL], gh[VPL];
+    const float mean = (RMS || !mean_in) ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    f4 xv[VPL], gv[VPL];
+    if (dres) {   // the skip-connection gradient is only needed at the very end: start pulling its lines into L2 / L1 now
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = k * 128 + lane * 4;
+        if (c < cols) asm volatile("prefetch.global.L2 [%0];" ::"l"(dres + row * cols + c));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = k * 128 + lane * 4;
+      if (c < cols) {
+        xv[k] = ld4<TX>(x + row * cols + c);
+        gv[k] = ld4<TY>(dy + row * cols + c);
+      } else {
+        xv[k] = {mean, mean, mean, mean};
+        gv[k] = {0.f, 0.f, 0.f, 0.f};
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int c = k * 128 + lane * 4;
-      if (c < cols) {
-        f4 xv = ld4<TX>(x + row * cols + c);
-        f4 g = ld4<TY>(dy + row * cols + c);
-        xh[k] = {(xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd};
-        dg[k].x += g.x * xh[k].x; dg[k].y += g.y * xh[k].y; dg[k].z += g.z * xh[k].z; dg[k].w += g.w * xh[k].w;
-        db[k].x += g.x; db[k].y += g.y; db[k].z += g.z; db[k].w += g.w;
-        gh[k] = {g.x * gm[k].x, g.y * gm[k].y, g.z * gm[k].z, g.w * gm[k].w};
-        s1 += (gh[k].x + gh[k].y) + (gh[k].z + gh[k].w);
-        s2 += (gh[k].x * xh[k].x + gh[k].y * xh[k].y) + (gh[k].z * xh[k].z + gh[k].w * xh[k].w);
-      } else {
-        xh[k] = {0.f, 0.f, 0.f, 0.f};
-        gh[k] = {0.f, 0.f, 0.f, 0.f};
-      }
+      const int c = k * 128 + lane * 4;
+      const float4 gm = (gamma && c < cols) ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      // x_hat in place of x; g stays raw (dgamma / dbeta need it), g*gamma is formed on the fly
+      xv[k] = {(xv[k].x - mean) * rstd, (xv[k].y - mean) * rstd, (xv[k].z - mean) * rstd, (xv[k].w - mean) * rstd};
+      dg[k].x += gv[k].x * xv[k].x; dg[k].y += gv[k].y * xv[k].y; dg[k].z += gv[k].z * xv[k].z; dg[k].w += gv[k].w * xv[k].w;
+      if (!RMS) { db[k].x += gv[k].x; db[k].y += gv[k].y; db[k].z += gv[k].z; db[k].w += gv[k].w; }
+      gv[k] = {gv[k].x * gm.x, gv[k].y * gm.y, gv[k].z * gm.z, gv[k].w * gm.w};
+      s1 += (gv[k].x + gv[k].y) + (gv[k].z + gv[k].w);
+      s2 += (gv[k].x * xv[k].x + gv[k].y * xv[k].y) + (gv[k].z * xv[k].z + gv[k].w * xv[k].w);
     }
-    float m1 = RMS ? 0.f : warp_sum(s1) * inv_n;
-    float m2 = warp_sum(s2) * inv_n;
+    const float m1 = RMS ? 0.f : warp_sum(s1) * inv_n;
+    const float m2 = warp_sum(s2) * inv_n;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int c = k * 128 + lane * 4;
+      const int c = k * 128 + lane * 4;
       if (c < cols) {
         f4 o;
-        o.x = rstd * (gh[k].x - m1 - xh[k].x * m2);
-        o.y = rstd * (gh[k].y - m1 - xh[k].y * m2);
-        o.z = rstd * (gh[k].z - m1 - xh[k].z * m2);
-        o.w = rstd * (gh[k].w - m1 - xh[k].w * m2);
+        o.x = rstd * (gv[k].x - m1 - xv[k].x * m2);
+        o.y = rstd * (gv[k].y - m1 - xv[k].y * m2);
+        o.z = rstd * (gv[k].z - m1 - xv[k].z * m2);
+        o.w = rstd * (gv[k].w - m1 - xv[k].w * m2);
         if (dres) {
           f4 r = ld4<TX>(dres + row * cols + c);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -143,49 +159,47 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
   }
   if (!partial) return;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    int c = k * 128 + lane * 4;
-    *reinterpret_cast<float4*>(&sh[w][0][c]) = make_float4(dg[k].x, dg[k].y, dg[k].z, dg[k].w);
-    *reinterpret_cast<float4*>(&sh[w][1][c]) = make_float4(db[k].x, db[k].y, db[k].z, db[k].w);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
-    int which = i / cols, c = i % cols;
-    float a = 0.f;
+  for (int which = 0; which < NP; ++which) {
+    if (which) __syncthreads();
 #pragma unroll
-    for (int ww = 0; ww < WARPS_PER_BLOCK; ++ww) a += sh[ww][which][c];
-    partial[((int64_t)blockIdx.x * 2 + which) * cols + c] = a;
+    for (int k = 0; k < VPL; ++k) {
+      const f4 a = which == 0 ? dg[k] : db[RMS ? 0 : k];
+      *reinterpret_cast<float4*>(&sh[w][k * 128 + lane * 4]) = make_float4(a.x, a.y, a.z, a.w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < BWD_WARPS; ++ww) a += sh[ww][c];
+      partial[((int64_t)blockIdx.x * NP + which) * cols + c] = a;
+    }
   }
 }
 
-// partial is [nblocks][2][cols]; stage 1 sums row-chunks of it (grid = (col tiles of 32, chunks)), stage 2 sums the
-// chunks in a fixed order and writes / accumulates dgamma, dbeta: deterministic and parallel over blocks AND columns.
-__global__ void k_norm_param_stage1(const float* __restrict__ partial, int nblocks, int cols2, int chunk_len, float* __restrict__ tmp) {
-  __shared__ float red[8][33];
-  int col = blockIdx.x * 32 + threadIdx.x;
-  int lo = blockIdx.y * chunk_len, hi = min(lo + chunk_len, nblocks);
+// partial is [nblocks][NP][cols]: block (8, 32) owns 8 columns; threadIdx.y strides the row-blocks (<= 10 independent
+// loads per thread for 296 row-blocks, all in flight at once), then a fixed-order shared-memory sum over threadIdx.y and
+// a write / accumulate into dgamma (which = 0) or dbeta (which = 1).  Deterministic.
+__global__ void __launch_bounds__(256)
+k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int np, int cols, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int accumulate) {
+  __shared__ float red[32][9];
+  const int i = blockIdx.x * 8 + threadIdx.x;   // index into [np][cols]
+  const int total = np * cols;
   float a = 0.f;
-  if (col < cols2)
-    for (int b = lo + threadIdx.y; b < hi; b += 8) a += partial[(int64_t)b * cols2 + col];
+  if (i < total) {
+#pragma unroll 4
+    for (int b = threadIdx.y; b < nblocks; b += 32) a += __ldcg(partial + (int64_t)b * total + i);
+  }
   red[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
-  if (threadIdx.y == 0 && col < cols2) {
+  if (threadIdx.y == 0 && i < total) {
     float r = red[0][threadIdx.x];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) r += red[k][threadIdx.x];
-    tmp[(int64_t)blockIdx.y * cols2 + col] = r;
+    for (int k = 1; k < 32; ++k) r += red[k][threadIdx.x];
+    const int which = i / cols, c = i % cols;
+    float* dst = which == 0 ? dgamma : dbeta;
+    if (dst) dst[c] = accumulate ? dst[c] + r : r;
   }
-}
-__global__ void k_norm_param_stage2(const float* __restrict__ tmp, int chunks, int cols, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * cols) return;
-  int which = i / cols, c = i % cols;
-  float* dst = which == 0 ? dgamma : dbeta;
-  if (!dst) return;
-  float a = 0.f;
-  for (int b = 0; b < chunks; ++b) a += tmp[(int64_t)b * 2 * cols + i];
-  dst[c] = accumulate ? dst[c] + a : a;
 }
 
 // generic fallback (cols not a multiple of 4 or > 1024): one block per row, three passes.
@@ -285,16 +299,16 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
                       void* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int cols, float clip, void* dx_twin) {
   int vpl = pick_vpl(cols);
   cudaStream_t s = nfb_cur_stream();
-  // one row per warp while that keeps every SM busy: the kernel is latency-bound otherwise (was 4.7x off the HBM roofline)
-  int grid = nfb_grid_for(rows, WARPS_PER_BLOCK, 8);
+  // two 8-warp blocks per SM, every warp with a whole row (x, dy, dres) in flight; a warp handles several rows so the
+  // dgamma / dbeta partials amortise
+  int64_t want = nfb_cdiv(rows, BWD_WARPS);
+  int grid = (int)(want < 2LL * nfb_sm_count() ? want : 2LL * nfb_sm_count());
+  if (grid < 1) grid = 1;
+  constexpr int NP = RMS ? 1 : 2;
   float* partial = nullptr;
   bool need_params = dgamma || dbeta;
-  int chunks = grid >= 64 ? 16 : 1;
-  int chunk_len = (grid + chunks - 1) / chunks;
-  chunks = (grid + chunk_len - 1) / chunk_len;
-  size_t part_elems = 2 * (size_t)cols * grid;
-  if (need_params && nfb_malloc(sizeof(float) * (part_elems + 2 * (size_t)cols * chunks), (void**)&partial)) return -1;
-#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
+  if (need_params && nfb_malloc(sizeof(float) * (size_t)NP * cols * grid, (void**)&partial)) return -1;
+#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, BWD_WARPS * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
   switch (vpl) {
     case 1: LB(1); break;
     case 2: LB(2); break;
@@ -304,12 +318,9 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
     default: if (partial) nfb_free(partial); return NFB_FAIL("norm bwd: cols=%d needs the generic path", cols);
   }
 #undef LB
-  nfb_count_launch();
   if (need_params) {
-    float* tmp = partial + part_elems;
-    k_norm_param_stage1<<<dim3((2 * cols + 31) / 32, chunks), dim3(32, 8), 0, s>>>(partial, grid, 2 * cols, chunk_len, tmp);
     nfb_count_launch();
-    k_norm_param_stage2<<<(2 * cols + 255) / 256, 256, 0, s>>>(tmp, chunks, cols, dgamma, dbeta, accumulate);
+    k_norm_param_reduce<<<(NP * cols + 7) / 8, dim3(8, 32), 0, s>>>(partial, grid, NP, cols, dgamma, dbeta, accumulate);
     nfb_free(partial);
   }
   NFB_LAUNCH_CHECK();

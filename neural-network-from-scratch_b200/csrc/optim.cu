@@ -10,40 +10,95 @@
 //   * non-finite parameters are scrubbed with nan_to_num(nan=0, posinf=1, neginf=-1)
 #include "common.cuh"
 
+// per-launch scalars, computed once per block by thread 0 (two double pow() per THREAD cost more than the update itself)
+struct AdamScalars { double lr_eff, inv_bc1, inv_bc2; float gs; };
+__device__ __forceinline__ void adam_scalars(AdamScalars* sc, int variant, double lr, double beta1, double beta2, int step_host,
+                                             const int* step_dev, float gsign, const float* grad_scale) {
+  if (threadIdx.x == 0) {
+    // bias corrections from the step count: a host value, or a device counter so that a captured CUDA graph of the
+    // training step stays valid from one replay to the next
+    const int step = step_dev ? *step_dev : step_host;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    double lr_d;
+    if (variant == 0) lr_d = (lr <= 0.02 && lr > 0.0) ? lr * fmin(5.0, 0.1 / lr) : lr;
+    else lr_d = lr / bc1;
+    sc->lr_eff = lr_d; sc->inv_bc1 = 1.0 / bc1; sc->inv_bc2 = 1.0 / bc2;
+    sc->gs = (grad_scale ? *grad_scale : 1.f) * gsign;
+  }
+  __syncthreads();
+}
+
+template <typename MT>
+__device__ __forceinline__ float adam_one(int variant, float pi, float gi, MT& mi, MT& vi, MT beta1, MT beta2, MT eps, MT lr_eff,
+                                          MT inv_bc1, MT inv_bc2, float wd_factor, float wd_grad) {
+  if (variant == 0 && wd_grad != 0.f) gi = __fadd_rn(gi, __fmul_rn(wd_grad, pi));  // Adam: L2 term in the gradient (fp32)
+  MT gd = (MT)gi;
+  mi = beta1 * mi + (MT(1) - beta1) * gd;
+  vi = beta2 * vi + (MT(1) - beta2) * (gd * gd);
+  MT mhat = mi * inv_bc1;
+  MT vhat = vi * inv_bc2;
+  MT denom = sqrt(vhat + eps);
+  float upd = (float)(lr_eff * mhat / denom);
+  if (upd == upd) upd = fminf(fmaxf(upd, -10.f), 10.f);  // np.clip keeps NaN (scrubbed below)
+  float np_;
+  if (variant == 1 && wd_factor != 1.f) np_ = __fsub_rn(__fmul_rn(pi, wd_factor), upd);  // AdamW decoupled decay
+  else np_ = __fsub_rn(pi, upd);
+  if (!isfinite(np_)) np_ = (np_ != np_) ? 0.f : (np_ > 0.f ? 1.f : -1.f);
+  return np_;
+}
+
+// scalar variant (fp64 moments = the reference's exact state dtype; also the tail of the vector kernel)
 template <typename MT>
 __global__ void k_adam(int variant, float* __restrict__ p, const float* __restrict__ g, MT* __restrict__ m, MT* __restrict__ v,
-                       __nv_bfloat16* __restrict__ p_bf16, int64_t n, double lr, MT beta1, MT beta2, MT eps, float wd_factor, float wd_grad,
-                       int step_host, const int* __restrict__ step_dev, float gsign, const float* __restrict__ grad_scale) {
-  // bias corrections from the step count: a host value, or a device counter so that a captured CUDA graph of the
-  // training step stays valid from one replay to the next
-  const int step = step_dev ? *step_dev : step_host;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  double lr_d;
-  if (variant == 0) lr_d = (lr <= 0.02 && lr > 0.0) ? lr * fmin(5.0, 0.1 / lr) : lr;
-  else lr_d = lr / bc1;
-  const MT lr_eff = (MT)lr_d, inv_bc1 = (MT)(1.0 / bc1), inv_bc2 = (MT)(1.0 / bc2);
-  float gs = grad_scale ? *grad_scale : 1.f;
-  gs *= gsign;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float pi = p[i];
-    float gi = g[i] * gs;
-    if (variant == 0 && wd_grad != 0.f) gi = __fadd_rn(gi, __fmul_rn(wd_grad, pi));  // Adam: L2 term in the gradient (fp32)
-    MT gd = (MT)gi;
-    MT mi = beta1 * m[i] + (MT(1) - beta1) * gd;
-    MT vi = beta2 * v[i] + (MT(1) - beta2) * (gd * gd);
+                       __nv_bfloat16* __restrict__ p_bf16, int64_t n0, int64_t n, double lr, MT beta1, MT beta2, MT eps, float wd_factor, float wd_grad,
+                       int step_host, const int* step_dev, float gsign, const float* grad_scale) {
+  __shared__ AdamScalars sc;
+  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale);
+  const MT lr_eff = (MT)sc.lr_eff, inv_bc1 = (MT)sc.inv_bc1, inv_bc2 = (MT)sc.inv_bc2;
+  const float gs = sc.gs;
+  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    MT mi = m[i], vi = v[i];
+    float np_ = adam_one<MT>(variant, p[i], g[i] * gs, mi, vi, beta1, beta2, eps, lr_eff, inv_bc1, inv_bc2, wd_factor, wd_grad);
     m[i] = mi;
     v[i] = vi;
-    MT mhat = mi * inv_bc1;
-    MT vhat = vi * inv_bc2;
-    MT denom = sqrt(vhat + eps);
-    float upd = (float)(lr_eff * mhat / denom);
-    if (upd == upd) upd = fminf(fmaxf(upd, -10.f), 10.f);  // np.clip keeps NaN (scrubbed below)
-    float np_;
-    if (variant == 1 && wd_factor != 1.f) np_ = __fsub_rn(__fmul_rn(pi, wd_factor), upd);  // AdamW decoupled decay
-    else np_ = __fsub_rn(pi, upd);
-    if (!isfinite(np_)) np_ = (np_ != np_) ? 0.f : (np_ > 0.f ? 1.f : -1.f);
     p[i] = np_;
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(np_);
+  }
+}
+
+// fp32-moment variant, 128-bit accesses: 4 x LDG.128 + 3 x STG.128 + 1 x STG.64 per 4 parameters (30 B/param), two
+// independent vectors per thread and iteration so that 8 loads are in flight per thread
+__global__ void __launch_bounds__(256)
+k_adam_vec4(int variant, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+            uint2* __restrict__ p_bf16, int64_t n4, double lr, float beta1, float beta2, float eps, float wd_factor, float wd_grad,
+            int step_host, const int* step_dev, float gsign, const float* grad_scale) {
+  __shared__ AdamScalars sc;
+  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale);
+  const float lr_eff = (float)sc.lr_eff, inv_bc1 = (float)sc.inv_bc1, inv_bc2 = (float)sc.inv_bc2;
+  const float gs = sc.gs;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const int64_t i1 = i0 + stride;
+    const bool two = i1 < n4;
+    float4 pa = p[i0], ga = g[i0], ma = m[i0], va = v[i0];
+    float4 pb, gb, mb, vb;
+    if (two) { pb = p[i1]; gb = g[i1]; mb = m[i1]; vb = v[i1]; }
+#define ADAM_LANE(P, G, M, V) P = adam_one<float>(variant, P, G * gs, M, V, beta1, beta2, eps, lr_eff, inv_bc1, inv_bc2, wd_factor, wd_grad)
+    ADAM_LANE(pa.x, ga.x, ma.x, va.x); ADAM_LANE(pa.y, ga.y, ma.y, va.y); ADAM_LANE(pa.z, ga.z, ma.z, va.z); ADAM_LANE(pa.w, ga.w, ma.w, va.w);
+    m[i0] = ma; v[i0] = va; p[i0] = pa;
+    if (p_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pa.x, pa.y), hi = __floats2bfloat162_rn(pa.z, pa.w);
+      p_bf16[i0] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+    if (two) {
+      ADAM_LANE(pb.x, gb.x, mb.x, vb.x); ADAM_LANE(pb.y, gb.y, mb.y, vb.y); ADAM_LANE(pb.z, gb.z, mb.z, vb.z); ADAM_LANE(pb.w, gb.w, mb.w, vb.w);
+      m[i1] = mb; v[i1] = vb; p[i1] = pb;
+      if (p_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pb.x, pb.y), hi = __floats2bfloat162_rn(pb.z, pb.w);
+        p_bf16[i1] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+#undef ADAM_LANE
   }
 }
 
@@ -56,13 +111,20 @@ NFB_API int nfb_adam_step(int variant, int moment_dtype, float* p, const float* 
   float wd_factor = (variant == 1 && weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.f;
   float wd_grad = (variant == 0) ? (float)weight_decay : 0.f;
   float gsign = maximize ? -1.f : 1.f;
-  int grid = nfb_grid_for(n, 256, 8);
   cudaStream_t s = nfb_cur_stream();
-  if (moment_dtype == NFB_F64)
-    k_adam<double><<<grid, 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
-  else if (moment_dtype == NFB_F32)
-    k_adam<float><<<grid, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n, lr, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
-  else return NFB_FAIL("nfb_adam_step: moment dtype %d", moment_dtype);
+  if (moment_dtype == NFB_F64) {
+    k_adam<double><<<nfb_grid_for(n, 256, 8), 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, 0, n, lr, beta1, beta2, eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+  } else if (moment_dtype == NFB_F32) {
+    bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0) && ((uintptr_t)p_bf16 % 8 == 0);
+    int64_t n4 = vec ? n / 4 : 0;
+    if (n4 > 0) {
+      k_adam_vec4<<<nfb_grid_for(nfb_cdiv(n4, 2), 256, 8), 256, 0, s>>>(variant, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16, n4, lr,
+                                                                       (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+      if (n4 * 4 < n) nfb_count_launch();
+    }
+    if (n4 * 4 < n)
+      k_adam<float><<<1, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n4 * 4, n, lr, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+  } else return NFB_FAIL("nfb_adam_step: moment dtype %d", moment_dtype);
   NFB_LAUNCH_CHECK();
   return 0;
 }

@@ -234,8 +234,112 @@ __global__ void k_colsum_stage2(const float* __restrict__ tmp, int chunks, int C
   for (int b = 0; b < chunks; ++b) a += tmp[(int64_t)b * C + c];
   out[c] = accumulate ? out[c] + a : a;
 }
+// single-launch variant: 16-byte loads (8 bf16 / 4 fp32 columns per thread), block (32, 8) sums a row chunk of its
+// 32 x VEC columns, and the LAST block to finish a column strip (device counter, __threadfence) adds the chunk partials
+// in a fixed order -- deterministic, one kernel instead of two.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum_fused(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_len, float* __restrict__ tmp, unsigned* __restrict__ counters,
+               float* __restrict__ out, int accumulate) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  __shared__ float red[8][32 * VEC + 1];
+  __shared__ int s_last;
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int64_t lo = (int64_t)blockIdx.y * chunk_len, hi = lo + chunk_len < R ? lo + chunk_len : R;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (c0 < C) {
+    int64_t r = lo + threadIdx.y;
+    for (; r + 56 < hi; r += 64) {   // eight independent 16-byte loads in flight per thread
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = *reinterpret_cast<const uint4*>(x + (r + 8 * j) * ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (sizeof(T) == 4) {
+          const float* f = reinterpret_cast<const float*>(&u[j]);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] += f[k];
+        } else {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+#pragma unroll
+          for (int k = 0; k < VEC / 2; ++k) { float2 f = __bfloat1622float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+        }
+      }
+    }
+    for (; r < hi; r += 8) {
+      uint4 u0 = *reinterpret_cast<const uint4*>(x + r * ld + c0);
+      if (sizeof(T) == 4) {
+        const float* f = reinterpret_cast<const float*>(&u0);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += f[k];
+      } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u0);
+#pragma unroll
+        for (int k = 0; k < VEC / 2; ++k) { float2 f = __bfloat1622float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x * VEC + k] = acc[k];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int cc = tid; cc < 32 * VEC; cc += 256) {
+    const int col = blockIdx.x * 32 * VEC + cc;
+    if (col < C) {
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r += red[k][cc];
+      tmp[(int64_t)blockIdx.y * C + col] = r;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // fixed-order sum of the chunk partials (one column per thread, loads unrolled 8-deep so they are in flight together)
+  for (int cc = tid; cc < 32 * VEC; cc += 256) {
+    const int col = blockIdx.x * 32 * VEC + cc;
+    if (col < C) {
+      float a = 0.f;
+      const float* tp = tmp + col;
+#pragma unroll 8
+      for (unsigned b = 0; b < gridDim.y; ++b) a += __ldcg(tp + (int64_t)b * C);
+      out[col] = accumulate ? out[col] + a : a;
+    }
+  }
+  if (tid == 0) counters[blockIdx.x] = 0;   // ready for the next launch on this stream
+}
+
+static unsigned* g_colsum_counters = nullptr;   // 4096 strip counters, zero between launches
 NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, float* out, int accumulate) {
   if (C == 0) return 0;
+  cudaStream_t s = nfb_cur_stream();
+  const int esz = dtype == NFB_F32 ? 4 : 2, vec = 16 / esz;
+  if ((dtype == NFB_F32 || dtype == NFB_BF16) && C % vec == 0 && ld % vec == 0 && ((uintptr_t)x % 16 == 0) && R >= 64 && nfb_cdiv(C, 32 * vec) <= 4096) {
+    if (!g_colsum_counters) {
+      NFB_CUDA(cudaMalloc((void**)&g_colsum_counters, 4096 * sizeof(unsigned)));
+      NFB_CUDA(cudaMemset(g_colsum_counters, 0, 4096 * sizeof(unsigned)));
+    }
+    int strips = (int)nfb_cdiv(C, 32 * vec);
+    int chunks = (int)((2LL * nfb_sm_count() + strips - 1) / strips);
+    int64_t max_chunks = R / 64 > 0 ? R / 64 : 1;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t chunk_len = nfb_cdiv(R, chunks);
+    chunks = (int)nfb_cdiv(R, chunk_len);
+    float* tmp = nullptr;
+    if (nfb_malloc(sizeof(float) * (size_t)chunks * C, (void**)&tmp)) return -1;
+    dim3 grid(strips, chunks), block(32, 8);
+    if (dtype == NFB_F32) k_colsum_fused<float><<<grid, block, 0, s>>>((const float*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
+    else k_colsum_fused<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
+    nfb_free(tmp);
+    NFB_LAUNCH_CHECK();
+    return 0;
+  }
   int col_blocks = (C + 63) / 64;
   int chunks = (int)((4LL * nfb_sm_count() + col_blocks - 1) / col_blocks);
   int64_t max_chunks = R / 32 > 0 ? R / 32 : 1;
@@ -245,7 +349,6 @@ NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, f
   chunks = (int)nfb_cdiv(R > 0 ? R : 1, chunk_len);
   float* tmp = nullptr;
   if (nfb_malloc(sizeof(float) * (size_t)chunks * C, (void**)&tmp)) return -1;
-  cudaStream_t s = nfb_cur_stream();
   dim3 grid(col_blocks, chunks), block(32, 8);
   if (dtype == NFB_F32) k_colsum_stage1<float><<<grid, block, 0, s>>>((const float*)x, R, C, ld, chunk_len, tmp);
   else if (dtype == NFB_BF16) k_colsum_stage1<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp);

@@ -281,11 +281,27 @@ NFB_API int nfb_graph_destroy(void* exec) {
   return 0;
 }
 
-// L2 flush helper for benchmarks: writes a buffer larger than the 126 MB L2
+// L2 flush helper for benchmarks: writes a buffer larger than the 126 MB L2, then streams a second one through it with
+// loads, so that the cache is left full of CLEAN foreign lines (a write-only flush leaves 126 MB of dirty lines whose
+// write-back is then billed to the kernel under test)
 static void* g_flush = nullptr;
 static const size_t kFlushBytes = 256u << 20;
+__global__ void k_flush_read(const uint4* __restrict__ p, size_t n, unsigned* sink) {
+  unsigned acc = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 v = p[i];
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;   // never true for the zero-filled buffer; keeps the loads alive
+}
 NFB_API int nfb_flush_l2() {
-  if (!g_flush) NFB_CUDA(cudaMalloc(&g_flush, kFlushBytes));
+  if (!g_flush) {
+    NFB_CUDA(cudaMalloc(&g_flush, 2 * kFlushBytes + 256));
+    NFB_CUDA(cudaMemsetAsync(g_flush, 0, 2 * kFlushBytes + 256, g_stream));
+  }
   NFB_CUDA(cudaMemsetAsync(g_flush, 0, kFlushBytes, g_stream));
+  k_flush_read<<<nfb_sm_count() * 8, 256, 0, g_stream>>>((const uint4*)((char*)g_flush + kFlushBytes), kFlushBytes / 16,
+                                                        (unsigned*)((char*)g_flush + 2 * kFlushBytes));
+  NFB_CUDA(cudaGetLastError());
   return 0;
 }

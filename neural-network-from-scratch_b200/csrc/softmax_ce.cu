@@ -171,6 +171,188 @@ k_cross_entropy(const float* __restrict__ logits, const void* __restrict__ targe
   }
 }
 
+// exp(x - m) for x <= m as ONE FFMA + MUFU.EX2 (x * log2e - m * log2e); ~2 ulp, no overflow possible since the argument
+// is <= 0.  expf() costs ~10 instructions and made the wide-row kernels issue-bound (206 M exponentials per LM-head step).
+__device__ __forceinline__ float exp_sub_fast(float x, float m_log2e) { return exp2f(fmaf(x, 1.4426950408889634f, -m_log2e)); }
+
+// ---- register-resident variant for wide rows (the LM-head shapes: V = 50257, 30522).  One 1024-thread block per SM
+// keeps a whole logits row in registers (NV4 x 4 values per thread, element 4*(k*1024 + t) .. +3), so the row is read
+// from HBM exactly once, never touches shared memory, and the stores of row r overlap the loads of row r+1:
+// max -> block_max -> exp/sum -> block_sum -> scale/store.  Logits may be fp32 or bf16 (TL); dlogits fp32 or bf16 (TD)
+// and may alias the logits buffer.
+template <typename TL, typename TD, int NV4>
+__global__ void __launch_bounds__(1024, 1)
+k_cross_entropy_reg(const TL* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
+                    TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+  __shared__ float red[32];
+  const int t = threadIdx.x;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const TL* xr = logits + row * ld;
+    f4 x[NV4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const int c = (k * 1024 + t) * 4;
+      if (c < V) {   // the row pitch is padded to a multiple of 4 elements, the pad holds garbage: mask by column
+        x[k] = ld4<TL>(xr + c);
+        if (c + 1 >= V) x[k].y = -INFINITY;
+        if (c + 2 >= V) x[k].z = -INFINITY;
+        if (c + 3 >= V) x[k].w = -INFINITY;
+      } else {
+        x[k] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      }
+      m = fmaxf(m, fmaxf(fmaxf(x[k].x, x[k].y), fmaxf(x[k].z, x[k].w)));
+    }
+    int64_t tg = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
+    if (tg < 0) tg += V;  // numpy negative indexing
+    m = block_max(m, red);
+    const float ml2 = m * 1.4426950408889634f;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      x[k].x = exp_sub_fast(x[k].x, ml2); x[k].y = exp_sub_fast(x[k].y, ml2); x[k].z = exp_sub_fast(x[k].z, ml2); x[k].w = exp_sub_fast(x[k].w, ml2);
+      s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+    }
+    s = fmaxf(block_sum(s, red), 1e-8f);
+    const float inv = 1.f / s;
+    // the thread that owns the target column publishes its probability
+    {
+      const int tv = (int)(tg >> 2), tk = tv >> 10, tt = tv & 1023, te = (int)(tg & 3);
+      if (tt == t) {
+#pragma unroll
+        for (int k = 0; k < NV4; ++k)
+          if (k == tk) {
+            float e = te == 0 ? x[k].x : te == 1 ? x[k].y : te == 2 ? x[k].z : x[k].w;
+            loss[row] = -logf(e * inv + 1e-8f);
+            if (dlogits) {  // (p - onehot): subtract after scaling, below
+              if (te == 0) x[k].x -= s; else if (te == 1) x[k].y -= s; else if (te == 2) x[k].z -= s; else x[k].w -= s;
+            }
+          }
+      }
+    }
+    if (dlogits) {
+      TD* dr = dlogits + row * dld;
+      const float sc = inv * grad_scale;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int c = (k * 1024 + t) * 4;
+        if (c + 3 < V) {
+          st4<TD>(dr + c, {x[k].x * sc, x[k].y * sc, x[k].z * sc, x[k].w * sc});
+        } else if (c < V) {
+          st_f<TD>(dr, c, x[k].x * sc);
+          if (c + 1 < V) st_f<TD>(dr, c + 1, x[k].y * sc);
+          if (c + 2 < V) st_f<TD>(dr, c + 2, x[k].z * sc);
+        }
+      }
+    }
+  }
+}
+
+// ---- bf16 logits, wide rows: the row lives in SHARED memory as the raw bf16 it was loaded as (100 KB at V = 50257),
+// fetched by ONE bulk-async copy (cp.async.bulk global -> shared, mbarrier completion: no registers, no LSU issue), and
+// two 512-thread blocks share an SM so that one block's three shared-memory passes (max, sum of exp, scale + store)
+// overlap the other block's HBM load / store phases.  exp is evaluated twice per element; that is cheaper than a third
+// trip through memory.  dlogits may alias the logits buffer.
+__device__ __forceinline__ void ce_unpack8(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+template <typename TD>
+__global__ void __launch_bounds__(512, 2)
+k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
+                     TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+  extern __shared__ __align__(128) unsigned char ce_smem[];
+  __shared__ float red[32];
+  __shared__ __align__(8) unsigned long long bar;
+  const uint4* srow = reinterpret_cast<const uint4*>(ce_smem);
+  const int t = threadIdx.x;
+  const int nv = (V + 7) >> 3;                 // 16-byte vectors per row (the pitch is padded to a multiple of 8 elements)
+  const uint32_t row_bytes = (uint32_t)nv * 16u;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar), row_a = (uint32_t)__cvta_generic_to_shared(ce_smem);
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    if (t == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer vs this async write
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(row_a), "l"(logits + row * ld), "r"(row_bytes), "r"(bar_a) : "memory");
+    }
+    int64_t tg = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
+    if (tg < 0) tg += V;  // numpy negative indexing
+    {
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar_a), "r"(phase) : "memory");
+      }
+      phase ^= 1;
+    }
+    float m = -INFINITY;
+    for (int i = t; i < nv; i += 512) {
+      float v[8];
+      ce_unpack8(srow[i], v);
+      const int c = i * 8;
+      if (c + 8 > V) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (c + k >= V) v[k] = -INFINITY;   // the pad columns hold garbage
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m = fmaxf(m, v[k]);
+    }
+    m = block_max(m, red);
+    const float ml2 = m * 1.4426950408889634f;
+    float s = 0.f;
+    for (int i = t; i < nv; i += 512) {
+      float v[8];
+      ce_unpack8(srow[i], v);
+      const int c = i * 8;
+      if (c + 8 <= V) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += exp_sub_fast(v[k], ml2);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (c + k < V) ? exp_sub_fast(v[k], ml2) : 0.f;
+      }
+    }
+    s = fmaxf(block_sum(s, red), 1e-8f);
+    const float inv = 1.f / s;
+    if (t == 0) {
+      float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tg]);
+      loss[row] = -logf(exp_sub_fast(xt, ml2) * inv + 1e-8f);
+    }
+    if (dlogits) {
+      TD* dr = dlogits + row * dld;
+      const float sc = inv * grad_scale;
+      const int tvec = (int)(tg >> 3), te = (int)(tg & 7);
+      for (int i = t; i < nv; i += 512) {
+        float v[8];
+        ce_unpack8(srow[i], v);
+        const int c = i * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = exp_sub_fast(v[k], ml2) * sc;
+        if (i == tvec) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (k == te) v[k] -= grad_scale;
+        }
+        if (c + 8 <= V) {
+          st4<TD>(dr + c, {v[0], v[1], v[2], v[3]});
+          st4<TD>(dr + c + 4, {v[4], v[5], v[6], v[7]});
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (c + k < V) st_f<TD>(dr, c + k, v[k]);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with the row buffer before the next bulk copy overwrites it
+  }
+}
+
 template <typename TD>
 static int ce_launch(const float* logits, const void* targets, int tgt_is_i64, float* loss, TD* dlogits, int64_t rows, int V,
                      int64_t ld, int64_t dld, float grad_scale) {
@@ -195,12 +377,68 @@ static int ce_launch(const float* logits, const void* targets, int tgt_is_i64, f
   return 0;
 }
 
-// ddt: dtype of dlogits (NFB_F32 or NFB_BF16); dlogits may be NULL (forward only) and may alias logits (fp32, same ld).
-NFB_API int nfb_cross_entropy(const float* logits, const void* targets, int tgt_is_i64, float* loss, void* dlogits, int ddt,
-                              int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+// wide rows: the register-resident kernel (one block per SM)
+template <typename TL, typename TD>
+static int ce_launch_reg(const TL* logits, const void* targets, int tgt_is_i64, float* loss, TD* dlogits, int64_t rows, int V,
+                         int64_t ld, int64_t dld, float grad_scale) {
+  cudaStream_t s = nfb_cur_stream();
+  int nv4 = (int)nfb_cdiv(nfb_cdiv(V, 4), 1024);
+  int64_t grid = rows < nfb_sm_count() ? rows : nfb_sm_count();
+#define LR(NV) k_cross_entropy_reg<TL, TD, NV><<<(unsigned)grid, 1024, 0, s>>>(logits, targets, tgt_is_i64, loss, dlogits, rows, V, ld, dld, grad_scale)
+  if (nv4 <= 4) LR(4);
+  else if (nv4 <= 8) LR(8);
+  else if (nv4 <= 13) LR(13);
+  else return NFB_FAIL("cross entropy: V=%d exceeds the register-resident kernel", V);
+#undef LR
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int g_ce_bulk = 1;
+NFB_API int nfb_cross_entropy_set_bulk(int on) { g_ce_bulk = on ? 1 : 0; return 0; }  // test hook: 0 = register-resident kernel for bf16 logits too
+
+// ldt / ddt: dtypes of logits / dlogits (NFB_F32 or NFB_BF16); dlogits may be NULL (forward only) and may alias logits
+// (same dtype and pitch).
+NFB_API int nfb_cross_entropy_ex(int ldt, const void* logits, const void* targets, int tgt_is_i64, float* loss, void* dlogits, int ddt,
+                                 int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
   if (rows == 0) return 0;
   if (ld < V) return NFB_FAIL("nfb_cross_entropy: ld %lld < V %d", (long long)ld, V);
-  if (!dlogits || ddt == NFB_F32) return ce_launch<float>(logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
-  if (ddt == NFB_BF16) return ce_launch<__nv_bfloat16>(logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
-  return NFB_FAIL("nfb_cross_entropy: unsupported dlogits dtype %d", ddt);
+  if (ldt != NFB_F32 && ldt != NFB_BF16) return NFB_FAIL("nfb_cross_entropy: unsupported logits dtype %d", ldt);
+  if (dlogits && ddt != NFB_F32 && ddt != NFB_BF16) return NFB_FAIL("nfb_cross_entropy: unsupported dlogits dtype %d", ddt);
+  const int lsz = ldt == NFB_F32 ? 4 : 2, dsz = ddt == NFB_F32 ? 4 : 2;
+  // 4-element vectors: 16-byte (fp32) / 8-byte (bf16) aligned rows
+  bool vec = (ld % 4 == 0) && ((uintptr_t)logits % (4 * lsz) == 0) && (!dlogits || ((dld % 4 == 0) && ((uintptr_t)dlogits % (4 * dsz) == 0)));
+  if (vec && V >= 8192 && V <= 13 * 4096) {
+    if (ldt == NFB_F32) {
+      if (!dlogits || ddt == NFB_F32) return ce_launch_reg<float, float>((const float*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
+      return ce_launch_reg<float, __nv_bfloat16>((const float*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
+    }
+    // bf16 logits: shared-memory row + bulk-async copy, two blocks per SM (needs 16-byte aligned rows)
+    if (ld % 8 == 0 && (uintptr_t)logits % 16 == 0 && g_ce_bulk) {
+      const size_t smem = (size_t)((V + 7) / 8) * 16;
+      cudaStream_t s = nfb_cur_stream();
+      int64_t grid = 2LL * nfb_sm_count();
+      if (grid > rows) grid = rows;
+      if (!dlogits || ddt == NFB_BF16) {
+        NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cross_entropy_bulk<__nv_bfloat16><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
+      } else {
+        NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cross_entropy_bulk<float><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
+      }
+      NFB_LAUNCH_CHECK();
+      return 0;
+    }
+    if (!dlogits || ddt == NFB_BF16) return ce_launch_reg<__nv_bfloat16, __nv_bfloat16>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
+    return ce_launch_reg<__nv_bfloat16, float>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
+  }
+  if (ldt != NFB_F32) return NFB_FAIL("nfb_cross_entropy: bf16 logits need 8-byte aligned rows and 8192 <= V <= 53248 (V=%d, ld=%lld)", V, (long long)ld);
+  if (!dlogits || ddt == NFB_F32) return ce_launch<float>((const float*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
+  return ce_launch<__nv_bfloat16>((const float*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
+}
+
+// fp32 logits (the original entry point)
+NFB_API int nfb_cross_entropy(const float* logits, const void* targets, int tgt_is_i64, float* loss, void* dlogits, int ddt,
+                              int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+  return nfb_cross_entropy_ex(NFB_F32, logits, targets, tgt_is_i64, loss, dlogits, ddt, rows, V, ld, dld, grad_scale);
 }

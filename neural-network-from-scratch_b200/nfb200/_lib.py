@@ -81,6 +81,8 @@ _SIGNATURES = {
     "nfb_softmax_fwd": [vp, vp, i64, i32],
     "nfb_softmax_bwd": [vp, vp, vp, i64, i32],
     "nfb_cross_entropy": [vp, vp, i32, vp, vp, i32, i64, i32, i64, i64, f32],
+    "nfb_cross_entropy_set_bulk": [i32],
+    "nfb_cross_entropy_ex": [i32, vp, vp, i32, vp, vp, i32, i64, i32, i64, i64, f32],
     # embedding
     "nfb_gather_rows": [i32, i32, i32, vp, vp, vp, i64, i32, i64],
     "nfb_scatter_add_rows": [i32, i32, vp, vp, vp, i64, i32, i64, i32],

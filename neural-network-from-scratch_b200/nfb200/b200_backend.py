@@ -432,7 +432,10 @@ class B200Backend(Backend):
         if logits.ndim != 2:
             raise ValueError("cross_entropy expects 2-D logits (batch, classes)")
         rows, V = logits.shape
-        if logits.dtype != np.dtype(np.float32):
+        # bf16 logits (the bf16 tensor-core LM head) are consumed as they are when the wide-row kernel applies
+        ldv0 = logits.strides[0] if rows > 1 else max(V, 1)
+        keep_bf16 = (logits.dtype is bfloat16 and logits.strides[-1] == 1 and ldv0 >= V and ldv0 % 4 == 0 and 8192 <= V <= 13 * 4096)
+        if logits.dtype != np.dtype(np.float32) and not keep_bf16:
             logits = logits.astype(np.float32)
         if logits.strides[-1] != 1 or (logits.strides[0] < V):
             logits = logits.contiguous()
@@ -451,7 +454,7 @@ class B200Backend(Backend):
         if need_grad:
             dl = B200Array.empty((rows, dld), grad_dtype or np.float32)[:, :V]
         scale = 1.0 / rows if reduction == "mean" else 1.0
-        call("nfb_cross_entropy", logits.ptr, t.ptr, 1 if t.dtype == np.dtype(np.int64) else 0, per_row.ptr,
+        call("nfb_cross_entropy_ex", dtype_code(logits.dtype), logits.ptr, t.ptr, 1 if t.dtype == np.dtype(np.int64) else 0, per_row.ptr,
              dl.ptr if dl is not None else None, dtype_code(dl.dtype) if dl is not None else 0, rows, V, ldv, dld, float(scale))
         if reduction == "mean":
             loss = A.reduce("mean", per_row, None, False)

@@ -146,6 +146,49 @@ def test_cross_entropy_bf16_grad_and_onehot_targets(be):
     np.testing.assert_allclose(dl.get(), O.cross_entropy_bwd(np.float32(1), cache), rtol=1e-2, atol=1e-6)
 
 
+def _bf16_round(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+@pytest.mark.parametrize("rows,V", [(20, 50257), (300, 30522), (9, 8192), (5, 53248)])
+@pytest.mark.parametrize("mode", ["f32_reg", "bf16_bulk", "bf16_reg"])
+def test_cross_entropy_wide_rows_lm_head_layout(be, rows, V, mode):
+    """The LM-head layout: (T, V) logits with the row pitch padded to 8 elements (garbage in the pad), fp32 through the
+    register-resident kernel, bf16 through the bulk-copy shared-memory kernel and the register kernel; fp32 softmax math
+    either way (functional/loss.py:15-112).  bf16 logits are compared against the oracle ON the bf16-rounded logits."""
+    from nfb200 import _lib
+    from nfb200.array import B200Array
+    rng = np.random.default_rng(rows + V)
+    z = (rng.standard_normal((rows, V)) * 3).astype(np.float32)
+    t = rng.integers(0, V, rows)
+    t[0], t[-1] = V - 1, 0
+    ld = (V + 7) // 8 * 8
+    zp = np.full((rows, ld), np.nan, np.float32)   # NaN pad: a kernel that reads the pad poisons max / sum
+    zp[:, :V] = z
+    if mode == "f32_reg":
+        dev = _to(be, zp)[:, :V]
+        zin = z
+    else:
+        dev = be.astype(_to(be, zp), be.bfloat16)[:, :V]
+        zin = _bf16_round(z)
+    wl, cache = O.cross_entropy_fwd(zin, t, "mean")
+    wd = O.cross_entropy_bwd(np.float32(1.0), cache)
+    _lib.call("nfb_cross_entropy_set_bulk", 0 if mode == "bf16_reg" else 1)
+    try:
+        loss, dl = be.cross_entropy(dev, _to(be, t), "mean", grad_dtype=np.float32)
+        np.testing.assert_allclose(loss.get(), wl, rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(dl.get(), wd, rtol=1e-5, atol=1e-9)
+        loss2, dl2 = be.cross_entropy(dev, _to(be, t), "mean", grad_dtype=be.bfloat16)
+        np.testing.assert_allclose(loss2.get(), wl, rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(dl2.get(), wd, rtol=1e-2, atol=1e-7)
+        loss3, _ = be.cross_entropy(dev, _to(be, t.astype(np.int32)), "sum", need_grad=False)
+        np.testing.assert_allclose(loss3.get(), O.cross_entropy_fwd(zin, t, "sum")[0], rtol=2e-6)
+    finally:
+        _lib.call("nfb_cross_entropy_set_bulk", 1)
+
+
 def test_embedding_gather_known_and_bit_exact(be):
     """tests/test_layers.py:95-104 (identity gather) and tests/test_nn_embedding_95_coverage.py:133-181."""
     W = np.array([[1, 2], [3, 4], [5, 6]], np.float32)

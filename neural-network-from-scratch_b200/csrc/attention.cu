@@ -149,11 +149,13 @@ __device__ __forceinline__ float apply_mask(float s, int i, int j, const AttnPar
 
 // ================================================================== forward
 __global__ void __launch_bounds__(NTHREADS) k_flash_fwd(const AttnParams p) {
+  nfb_pdl_enter();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __nv_bfloat16* sQ = (__nv_bfloat16*)smem_raw;
   __nv_bfloat16* sK = sQ + BR * HD;          // 2 stages
   __nv_bfloat16* sV = sK + 2 * BC * HD;      // 2 stages
-  const int qb = blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  // causal: the last query blocks see the most keys -- schedule them first so the grid does not end on its longest CTAs
+  const int qb = (p.mask_mode & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* Q = p.q + b * p.q_sb + h * p.q_sh;
   const __nv_bfloat16* K = p.k + b * p.kv_sb + h * p.kv_sh;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_fwd(const AttnParams p) {
 
 // ================================================================== delta = rowsum(dO * O)
 __global__ void k_attn_delta(const AttnParams p, float* __restrict__ delta) {
+  nfb_pdl_enter();
   int lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over B*H*S
   long long total = (long long)p.B * p.H * p.S;
@@ -262,6 +265,7 @@ __global__ void k_attn_delta(const AttnParams p, float* __restrict__ delta) {
 // One CTA per 64-key block; warp w owns keys [16w, 16w+16).  Works on S^T so P^T / dS^T come out of
 // the tensor cores already in A-operand layout for the dV / dK products.
 __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dkv(const AttnParams p) {
+  nfb_pdl_enter();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __nv_bfloat16* sK = (__nv_bfloat16*)smem_raw;
   __nv_bfloat16* sV = sK + BC * HD;
@@ -381,12 +385,14 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dkv(const AttnParams p) 
 
 // ================================================================== backward: dQ
 __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dq(const AttnParams p) {
+  nfb_pdl_enter();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __nv_bfloat16* sQ = (__nv_bfloat16*)smem_raw;
   __nv_bfloat16* sdO = sQ + BR * HD;
   __nv_bfloat16* sK = sdO + BR * HD;        // 2 stages
   __nv_bfloat16* sV = sK + 2 * BC * HD;     // 2 stages
-  const int qb = blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  // causal: the last query blocks see the most keys -- schedule them first so the grid does not end on its longest CTAs
+  const int qb = (p.mask_mode & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* Q = p.q + b * p.q_sb + h * p.q_sh;
   const __nv_bfloat16* K = p.k + b * p.kv_sb + h * p.kv_sh;
@@ -462,6 +468,16 @@ static int check_attn(int head_dim, long long q_ss, long long kv_ss, long long o
   return 0;
 }
 
+// tcgen05 / TMEM / TMA forward (csrc/attention_tc.cu); the mma.sync kernel below stays as the path for layouts the
+// tensor maps cannot address (unaligned bases / strides)
+bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, const void* o, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh,
+                               int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_ss, int64_t o_sh, int64_t o_sb);
+int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
+                     int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
+                     const float* key_mask);
+static int g_attn_tc = 1;
+NFB_API int nfb_flash_attn_set_tc(int on) { g_attn_tc = on ? 1 : 0; return 0; }   // test hook: 0 = mma.sync kernels only
+
 // dtype must be NFB_BF16.  lse: (B,H,S) fp32 (may be NULL for inference).  key_mask: (B,Skv) fp32 or NULL.
 NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S,
                                int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh,
@@ -470,6 +486,8 @@ NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const vo
   if (B == 0 || H == 0 || S == 0) return 0;
   if (check_attn(head_dim, q_ss, kv_ss, o_ss)) return -1;
   if ((mask_mode & 2) && !key_mask) return NFB_FAIL("flash attention: mask_mode bit 1 set but key_mask is NULL");
+  if (g_attn_tc && nfb_flash_fwd_tc_eligible(q, k, v, o, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb))
+    return nfb_flash_fwd_tc(q, k, v, o, lse, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask);
   AttnParams p = {};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (__nv_bfloat16*)o; p.lse = lse;
   p.B = B; p.H = H; p.S = S; p.Skv = Skv;
@@ -477,7 +495,7 @@ NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const vo
   p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
   size_t smem = (size_t)(BR * HD + 4 * BC * HD) * 2;
   dim3 grid((unsigned)nfb_cdiv(S, BR), (unsigned)(B * H));
-  k_flash_fwd<<<grid, NTHREADS, smem, nfb_cur_stream()>>>(p);
+  nfb_launch_pdl(k_flash_fwd, grid, dim3(NTHREADS), smem, nfb_cur_stream(), p);
   NFB_LAUNCH_CHECK();
   return 0;
 }
@@ -501,7 +519,7 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
   p.delta = delta;
   cudaStream_t s = nfb_cur_stream();
   long long rows = (long long)B * H * S;
-  k_attn_delta<<<(unsigned)nfb_cdiv(rows, 8), 256, 0, s>>>(p, delta);
+  nfb_launch_pdl(k_attn_delta, dim3((unsigned)nfb_cdiv(rows, 8)), dim3(256), 0, s, p, delta);
   nfb_count_launch();
   size_t smem_dkv = (size_t)(2 * BC * HD + 4 * BR * HD) * 2 + 4 * BR * sizeof(float);
   static bool cfg = false;
@@ -510,10 +528,10 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
     cudaFuncSetAttribute(k_flash_bwd_dq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * BR * HD + 4 * BC * HD) * 2));
     cfg = true;
   }
-  k_flash_bwd_dkv<<<dim3((unsigned)nfb_cdiv(Skv, BC), (unsigned)(B * H)), NTHREADS, smem_dkv, s>>>(p);
+  nfb_launch_pdl(k_flash_bwd_dkv, dim3((unsigned)nfb_cdiv(Skv, BC), (unsigned)(B * H)), dim3(NTHREADS), smem_dkv, s, p);
   nfb_count_launch();
   size_t smem_dq = (size_t)(2 * BR * HD + 4 * BC * HD) * 2;
-  k_flash_bwd_dq<<<dim3((unsigned)nfb_cdiv(S, BR), (unsigned)(B * H)), NTHREADS, smem_dq, s>>>(p);
+  nfb_launch_pdl(k_flash_bwd_dq, dim3((unsigned)nfb_cdiv(S, BR), (unsigned)(B * H)), dim3(NTHREADS), smem_dq, s, p);
   nfb_free(delta);
   NFB_LAUNCH_CHECK();
   return 0;
@@ -525,32 +543,69 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
 // inverse=1 applies the transpose of the rotation (the backward).  Operates in place on n_parts consecutive
 // (B,S,H,D)-strided tensors (q and k of a packed qkv buffer): element (part, b, s, h, d) at
 // x + part*part_stride + b*sb + s*ss + h*sh + d.
+template <typename T> struct RopeVec;
+template <> struct RopeVec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) { float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+  __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct RopeVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+// one thread rotates N (d, d + D/2) pairs with 16-byte data accesses (N = 8 for bf16, 4 for fp32) and 16-byte table
+// loads; 32-bit index arithmetic (the launcher checks the element count)
 template <typename T>
 __global__ void k_rope(T* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int n_parts, long long part_stride,
                        int B, int S, int H, int D, long long sb, long long ss, long long sh, int inverse) {
-  // one thread rotates 4 (d, d + D/2) pairs: 128-bit table loads, 64/128-bit data accesses (D % 8 == 0)
-  const int half = D / 2, groups = half / 4;
-  long long total = (long long)n_parts * B * S * H * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int d = (int)(i % groups) * 4;
-    long long r = i / groups;
-    int h = (int)(r % H); r /= H;
-    int s = (int)(r % S); r /= S;
-    int b = (int)(r % B);
-    int part = (int)(r / B);
-    float4 c = *reinterpret_cast<const float4*>(cos_t + s * half + d);
-    float4 sn = *reinterpret_cast<const float4*>(sin_t + s * half + d);
-    if (inverse) { sn.x = -sn.x; sn.y = -sn.y; sn.z = -sn.z; sn.w = -sn.w; }
-    T* p = x + part * part_stride + b * sb + (long long)s * ss + (long long)h * sh;
-    f4 x1 = ld4<T>(p + d), x2 = ld4<T>(p + d + half);
-    st4<T>(p + d, {x1.x * c.x - x2.x * sn.x, x1.y * c.y - x2.y * sn.y, x1.z * c.z - x2.z * sn.z, x1.w * c.w - x2.w * sn.w});
-    st4<T>(p + d + half, {x2.x * c.x + x1.x * sn.x, x2.y * c.y + x1.y * sn.y, x2.z * c.z + x1.z * sn.z, x2.w * c.w + x1.w * sn.w});
+  nfb_pdl_enter();
+  constexpr int N = RopeVec<T>::N;
+  const unsigned half = D / 2, groups = half / N;
+  const unsigned total = (unsigned)n_parts * B * S * H * groups, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned d = (i % groups) * N;
+    unsigned r = i / groups;
+    const unsigned h = r % H; r /= H;
+    const unsigned sidx = r % S; r /= S;
+    const unsigned b = r % B;
+    const unsigned part = r / B;
+    float c[N], sn[N], x1[N], x2[N], y1[N], y2[N];
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+      float4 cv = __ldg(reinterpret_cast<const float4*>(cos_t + sidx * half + d + k)), sv = __ldg(reinterpret_cast<const float4*>(sin_t + sidx * half + d + k));
+      c[k] = cv.x; c[k + 1] = cv.y; c[k + 2] = cv.z; c[k + 3] = cv.w;
+      sn[k] = sv.x; sn[k + 1] = sv.y; sn[k + 2] = sv.z; sn[k + 3] = sv.w;
+    }
+    T* p = x + part * part_stride + b * sb + (long long)sidx * ss + (long long)h * sh;
+    RopeVec<T>::load(p + d, x1);
+    RopeVec<T>::load(p + d + half, x2);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float sk = inverse ? -sn[k] : sn[k];
+      y1[k] = x1[k] * c[k] - x2[k] * sk;
+      y2[k] = x2[k] * c[k] + x1[k] * sk;
+    }
+    RopeVec<T>::store(p + d, y1);
+    RopeVec<T>::store(p + d + half, y2);
   }
 }
 // any even head_dim / alignment: one pair per thread
 template <typename T>
 __global__ void k_rope_scalar(T* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int n_parts, long long part_stride,
                               int B, int S, int H, int D, long long sb, long long ss, long long sh, int inverse) {
+  nfb_pdl_enter();
   const int half = D / 2;
   long long total = (long long)n_parts * B * S * H * half;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -572,12 +627,14 @@ NFB_API int nfb_rope(int dtype, void* x, const float* cos_t, const float* sin_t,
                      int head_dim, int64_t sb, int64_t ss, int64_t sh, int inverse) {
   if (head_dim <= 0 || head_dim % 2) return NFB_FAIL("nfb_rope: head_dim %d must be positive and even", head_dim);
   int D = head_dim;
-  bool vec = (D % 8 == 0) && !(sb % 4 || ss % 4 || sh % 4 || part_stride % 4) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)cos_t % 16 == 0) && ((uintptr_t)sin_t % 16 == 0);
-  long long total = (long long)n_parts * B * S * H * (vec ? D / 8 : D / 2);
+  const int vn = dtype == NFB_BF16 ? 8 : 4;   // elements per 16-byte access
+  bool vec = ((D / 2) % vn == 0) && !(sb % vn || ss % vn || sh % vn || part_stride % vn) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)cos_t % 16 == 0) &&
+             ((uintptr_t)sin_t % 16 == 0) && ((long long)n_parts * B * S * H * (D / 2 / vn) < (1LL << 31));
+  long long total = (long long)n_parts * B * S * H * (vec ? D / 2 / vn : D / 2);
   if (total == 0) return 0;
   int grid = nfb_grid_for(total, 256);
   cudaStream_t st = nfb_cur_stream();
-#define RL(K, T) K<T><<<grid, 256, 0, st>>>((T*)x, cos_t, sin_t, n_parts, part_stride, B, S, H, D, sb, ss, sh, inverse)
+#define RL(K, T) nfb_launch_pdl(K<T>, dim3(grid), dim3(256), 0, st, (T*)x, cos_t, sin_t, n_parts, part_stride, B, S, H, D, sb, ss, sh, inverse)
   if (dtype == NFB_BF16) { if (vec) RL(k_rope, __nv_bfloat16); else RL(k_rope_scalar, __nv_bfloat16); }
   else if (dtype == NFB_F32) { if (vec) RL(k_rope, float); else RL(k_rope_scalar, float); }
   else return NFB_FAIL("nfb_rope: unsupported dtype %d", dtype);

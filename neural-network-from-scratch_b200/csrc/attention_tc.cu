@@ -1,0 +1,507 @@
+// Flash attention FORWARD on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by
+// TMA), head_dim 64.  Same semantics and (b, h, s, d)-strided layouts as csrc/attention.cu (SURVEY 8a row a6:
+// models/language/gpt2.py:183-215, models/language/bert.py:155-231, models/vision/vision_transformer.py:100-134):
+//   scores = q.k^T * scale ; causal: scores[j > i] REPLACED by -1e4 ; key mask: scores += mask[b, j] ; softmax ; . v
+//
+// One CTA per (batch, head, PAIR of 128-row query tiles) -- 320 threads:
+//   warps 0-3  softmax group 0 (query tile A: thread = one query row, TMEM lanes 32*warp ..)
+//   warps 4-7  softmax group 1 (query tile B)
+//   warp  8    TMA producer: Q tiles once, then K / V blocks of 128 keys through a 2-stage ring (4-D tensor maps over
+//              the strided (b, s, h, d) tensors: the packed qkv projection output is read in place)
+//   warp  9    MMA issuer (one elected lane): S_g = Q_g K^T (128x128x64) and O_g += P_g V (128x64x128) for g = 0, 1
+// The two query tiles ping-pong: while group g exponentiates S_g the tensor core works on the other group's
+// products, and both groups share every K / V block (half the K/V traffic of one tile per CTA).
+// TMEM (512 columns): S_0 [0,128) S_1 [128,256) O_0 [256,320) O_1 [320,384), fp32.
+// Softmax is online in the log2 domain with LAZY rescaling of the O accumulator (it lives in TMEM, so a rescale is a
+// tcgen05.ld / tcgen05.st round trip): the running maximum is only advanced when some row of the warp grew by more
+// than 2^8, otherwise the stale maximum is kept (exact: the final division by the row sum uses the same maximum).
+// P is rounded to bf16 and handed to the P.V product through shared memory in the K-major SWIZZLE_128B layout.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace {
+
+constexpr int ATC_THREADS = 320;
+constexpr int TILE_Q = 128, TILE_K = 128, HDIM = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnTcParams {
+  __nv_bfloat16* o;
+  float* lse;
+  int B, H, S, Skv;
+  long long o_sb, o_ss, o_sh;
+  float scale;
+  int mask_mode;
+  const float* key_mask;
+  unsigned long long* timeline;   // debug: clock64 stamps of CTA (0,0) (NULL in production)
+};
+
+// ---------------------------------------------------------------- PTX helpers (same conventions as gemm_tc.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 8000000u) {
+      printf("nfb attention_tc: mbarrier wait timed out (block %d,%d thread %d)\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {   // 2^x, one MUFU op (x <= ~8 here; -inf -> 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (see gemm_tc.cu)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 1u << 7;                       // a_format = BF16
+  d |= 1u << 10;                      // b_format = BF16
+  d |= (uint32_t)(a_mn & 1) << 15;
+  d |= (uint32_t)(b_mn & 1) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ void tl(const AttnTcParams& p, int slot) {
+  if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
+}
+
+// shared-memory carve-up (offsets from the 1024-byte aligned base)
+constexpr int KV_STAGES = 3;                     // K/V ring depth: block i+2 is requested while block i is being consumed
+constexpr int SM_Q = 0;                          // 2 x 16 KB   (query tiles A, B: [128 rows][64] K-major)
+constexpr int SM_K = 32768;                      // KV_STAGES x 16 KB ([128 keys][64] K-major)
+constexpr int SM_V = SM_K + KV_STAGES * 16384;   // KV_STAGES x 16 KB ([128 keys][64]: MN-major B operand, two 64-key chunks)
+constexpr int SM_P = SM_V + KV_STAGES * 16384;   // 2 groups x 32 KB ([128 rows][128 keys] bf16 as two 64-key K-major panels)
+constexpr int SM_BAR = SM_P + 65536;             // barriers + TMEM slot
+constexpr int SM_TOTAL = SM_BAR + 256 + 1024;    // + alignment slack
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+               const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + SM_BAR);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // KV_STAGES
+  uint64_t* kv_empty = bars + 5;      // KV_STAGES
+  uint64_t* s_full = bars + 9;        // 2 (per group)
+  uint64_t* p_full = bars + 11;       // 2 (per group, 128 arrivals)
+  uint64_t* pv_done = bars + 13;      // 2 (per group): P_g(i).V(i) has completed -> P_g buffer and O_g are safe to touch
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool causal = (p.mask_mode & 1) != 0;
+  // causal: the last tile pairs see the most keys -- schedule them first
+  const int pair = causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int q0A = pair * 2 * TILE_Q, q0B = q0A + TILE_Q;
+  const int nkv_all = (p.Skv + TILE_K - 1) / TILE_K;
+  const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
+  const int nB = (q0B < p.S) ? (causal ? min(nkv_all, q0B / TILE_K + 1) : nkv_all) : 0;
+  const int nMax = max(nA, nB);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  nfb_pdl_wait();      // everything above overlapped the previous kernel's tail
+  nfb_pdl_trigger();
+  if (threadIdx.x == 0) tl(p, 0);
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, nB > 0 ? 32768u : 16384u);
+      tma_load_4d(smem + SM_Q, &tmQ, q_full, 0, h, q0A, b);
+      if (nB > 0) tma_load_4d(smem + SM_Q + 16384, &tmQ, q_full, 0, h, q0B, b);
+      for (int i = 0; i < nMax; ++i) {
+        const int st = i % KV_STAGES;
+        mbar_wait(&kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 32768u);
+        tma_load_4d(smem + SM_K + st * 16384, &tmK, &kv_full[st], 0, h, i * TILE_K, b);
+        tma_load_4d(smem + SM_V + st * 16384, &tmV, &kv_full[st], 0, h, i * TILE_K, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(0, 0, TILE_Q, TILE_K);   // S = Q K^T : A, B K-major, N = 128
+      const uint32_t idesc_o = make_idesc(0, 1, TILE_Q, HDIM);     // O += P V  : A K-major, B MN-major, N = 64
+      const uint32_t sQ = smem_u32(smem + SM_Q), sK = smem_u32(smem + SM_K), sV = smem_u32(smem + SM_V), sP = smem_u32(smem + SM_P);
+      auto issue_s = [&](int g, int st) {
+#pragma unroll
+        for (int k = 0; k < HDIM / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(g * 128), make_smem_desc(sQ + g * 16384 + k * 32, 16, 1024),
+                    make_smem_desc(sK + st * 16384 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+      };
+      auto issue_pv = [&](int g, int st, bool acc) {
+#pragma unroll
+        for (int k = 0; k < TILE_K / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(256 + g * 64), make_smem_desc(sP + g * 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(sV + st * 16384 + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      if (nA > 0) { issue_s(0, 0); umma_commit(&s_full[0]); }
+      if (nB > 0) { issue_s(1, 0); umma_commit(&s_full[1]); }
+      for (int i = 0; i < nMax; ++i) {
+        const int st = i % KV_STAGES, stn = (i + 1) % KV_STAGES;
+        const bool more = (i + 1 < nMax);
+        if (more) { mbar_wait(&kv_full[stn], ((i + 1) / KV_STAGES) & 1); tc_fence_after(); }
+        // per group: once P_g(i) is in shared memory, S_g(i) has been consumed -> issue S_g(i+1) FIRST (the group's next
+        // softmax can start as soon as it lands), then the P_g(i).V(i) product
+        if (i < nA) {
+          mbar_wait(&p_full[0], i & 1);
+          tl(p, 16 + 4 * i);
+          tc_fence_after();
+          if (i + 1 < nA) { issue_s(0, stn); umma_commit(&s_full[0]); }
+          issue_pv(0, st, i > 0);
+          umma_commit(&pv_done[0]);
+        }
+        tl(p, 17 + 4 * i);
+        if (i < nB) {
+          mbar_wait(&p_full[1], i & 1);
+          tl(p, 18 + 4 * i);
+          tc_fence_after();
+          if (i + 1 < nB) { issue_s(1, stn); umma_commit(&s_full[1]); }
+          issue_pv(1, st, i > 0);
+          umma_commit(&pv_done[1]);
+        }
+        umma_commit(&kv_empty[st]);   // every product that reads K / V block i has been issued
+        tl(p, 19 + 4 * i);
+      }
+    }
+  } else {
+    // ===================== softmax groups (thread = query row) =====================
+    const int g = warp >> 2, quarter = warp & 3;
+    const int n = g == 0 ? nA : nB;
+    const int r = quarter * 32 + lane;
+    const int qi = (g == 0 ? q0A : q0B) + r;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sP_row = smem_u32(smem + SM_P) + (uint32_t)g * 32768u + (uint32_t)r * 128u;
+    const int sw = r & 7;
+    const float sl2 = p.scale * LOG2E;
+    const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
+    float m2 = -INFINITY, l = 0.f;    // running maximum (log2 domain) and row sum
+    for (int i = 0; i < n; ++i) {
+      mbar_wait(&s_full[g], i & 1);
+      if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i);
+      tc_fence_after();
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(g * 128 + c * 32), sr + c * 32);
+      tmem_ld_wait();
+      if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 1);
+      float t[128];
+      const int j0 = i * TILE_K;
+      const bool diag = causal && (j0 + TILE_K - 1 > (g == 0 ? q0A : q0B));   // some (row, key) of this block has key > row
+      const bool tail = j0 + TILE_K > p.Skv;
+      float bm;
+      if (!diag && !tail && !kmask) {
+        // eight independent running maxima: a single chain of 127 dependent FMNMX would cost ~500 clk of pure latency
+        // (there are only two softmax warps per scheduler to hide it)
+        float mx[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mx[a] = __uint_as_float(sr[a]);
+#pragma unroll
+        for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], __uint_as_float(sr[j]));
+        bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * sl2;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) t[j] = __uint_as_float(sr[j]) * sl2;
+      } else if (!tail && !kmask) {
+        // causal diagonal block: keys j0 + j > qi are REPLACED by -1e4 (two instructions per element)
+        const int lim = qi - j0;
+        const float neg = -1e4f * LOG2E;
+        float mx[8];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const float v = (j > lim) ? neg : __uint_as_float(sr[j]) * sl2;
+          t[j] = v;
+          if (j < 8) mx[j] = v; else mx[j & 7] = fmaxf(mx[j & 7], v);
+        }
+        bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      } else {
+        bm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const int kj = j0 + j;
+          float v = __uint_as_float(sr[j]) * sl2;
+          if (causal && kj > qi) v = -1e4f * LOG2E;          // the reference REPLACES masked scores by -1e4
+          if (kmask) v += (kj < p.Skv ? __ldg(kmask + kj) : 0.f) * LOG2E;
+          if (kj >= p.Skv) v = -INFINITY;
+          t[j] = v;
+          bm = fmaxf(bm, v);
+        }
+      }
+      // lazy rescale: advance the maximum only when some row of this warp grew by more than 2^8
+      const bool need = (bm - m2) > 8.f;   // also true on the first block (m2 = -inf)
+      const bool rescale = __any_sync(0xffffffffu, need);
+      if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 2);
+      float c = 1.f;
+      if (rescale) {
+        const float m_new = fmaxf(m2, bm);
+        c = (m2 == -INFINITY) ? 0.f : ex2(m2 - m_new);
+        l *= c;
+        m2 = m_new;
+      }
+      // S_g(i) was issued BEFORE P_g(i-1).V(i-1): wait for that product before overwriting its P operand (and before
+      // touching O_g); it has normally retired long before the row maximum above is known
+      if (i > 0) { mbar_wait(&pv_done[g], (i - 1) & 1); tc_fence_after(); }
+      float rsa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // P (bf16) -> shared memory, K-major SWIZZLE_128B: 16-byte slot c of row r at c ^ (r & 7), two 64-key panels
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = ex2(t[cc * 8 + 2 * e] - m2), p1 = ex2(t[cc * 8 + 2 * e + 1] - m2);
+          rsa[(2 * e) & 7] += p0;
+          rsa[(2 * e + 1) & 7] += p1;
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          w[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)(cc >> 3) * 16384u + (uint32_t)(((cc & 7) ^ sw) * 16)),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+      l += ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3])) + ((rsa[4] + rsa[5]) + (rsa[6] + rsa[7]));
+      if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 3);
+      // the (rare) rescale of O_g comes last, when the score registers are dead.  O_g holds the products of blocks < i,
+      // all complete (pv_done above); P.V of this block is only issued after the arrive below.
+      if (rescale && i > 0) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t orr[32];
+          tmem_ld32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * c);
+          tmem_st32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+      if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 4);
+    }
+    if (n > 0) {
+      mbar_wait(&pv_done[g], (n - 1) & 1);
+      tc_fence_after();
+      const float lc = fmaxf(l, 1e-8f);   // the reference's 1e-8 floor (functional/activation.py:95)
+      const float inv = 1.f / lc;
+      __nv_bfloat16* orow = p.o + b * p.o_sb + h * p.o_sh + (long long)qi * p.o_ss;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t orr[32];
+        tmem_ld32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
+        tmem_ld_wait();
+        if (qi < p.S) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(orr[c * 8 + 2 * e]) * inv, __uint_as_float(orr[c * 8 + 2 * e + 1]) * inv);
+              w[e] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            *reinterpret_cast<uint4*>(orow + cc * 32 + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (p.lse && qi < p.S) p.lse[(long long)bh * p.S + qi] = (m2 + log2f(lc)) * 0.6931471805599453f;
+    }
+  }
+
+  if (threadIdx.x == 0) tl(p, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int get_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return NFB_FAIL("cuTensorMapEncodeTiled entry point unavailable");
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+typedef std::tuple<const void*, int, int, int, long long, long long, long long> MapKey;
+std::map<MapKey, CUtensorMap> g_map_cache;
+std::mutex g_map_mu;
+
+// 4-D bf16 map over element (b, s, h, d) at base + b*sb + s*ss + h*sh + d: dims (d = 64, h, s, b), box (64, 1, 128, 1)
+int make_map_bshd(CUtensorMap* out, const void* base, int B, int S, int H, long long sb, long long ss, long long sh) {
+  MapKey key(base, B, S, H, sb, ss, sh);
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return 0; }
+  }
+  if (get_encode_fn()) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)HDIM, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
+  // a stride is irrelevant for an extent of 1 but must still be a legal (16-byte multiple, non-zero) value
+  cuuint64_t strides[3] = {(cuuint64_t)(H > 1 ? sh : HDIM) * 2, (cuuint64_t)(S > 1 ? ss : HDIM) * 2, (cuuint64_t)(B > 1 ? sb : HDIM) * 2};
+  cuuint32_t box[4] = {(cuuint32_t)HDIM, 1, (cuuint32_t)TILE_K, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return NFB_FAIL("attention_tc: cuTensorMapEncodeTiled failed (%d) B=%d S=%d H=%d strides=(%lld,%lld,%lld)", (int)r, B, S, H, sb, ss, sh);
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
+unsigned long long* g_attn_timeline = nullptr;
+}  // namespace
+
+NFB_API int nfb_flash_attn_set_timeline(void* dev_buf) { g_attn_timeline = (unsigned long long*)dev_buf; return 0; }   // debug: 256 x u64
+
+// true when the tcgen05 forward can take this problem (16-byte aligned bases and strides; head_dim 64)
+bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, const void* o, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh,
+                               int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_ss, int64_t o_sh, int64_t o_sb) {
+  if (head_dim != HDIM) return false;
+  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) != 0) return false;
+  if ((q_sb | q_ss | q_sh | kv_sb | kv_ss | kv_sh | o_ss | o_sh | o_sb) % 8 != 0) return false;
+  if (q_sb < 0 || q_ss <= 0 || q_sh < 0 || kv_sb < 0 || kv_ss <= 0 || kv_sh < 0) return false;
+  return true;
+}
+
+int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
+                     int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
+                     const float* key_mask) {
+  CUtensorMap tmQ, tmK, tmV;
+  if (make_map_bshd(&tmQ, q, B, S, H, q_sb, q_ss, q_sh)) return -1;
+  if (make_map_bshd(&tmK, k, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmV, v, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  AttnTcParams p = {};
+  p.o = (__nv_bfloat16*)o; p.lse = lse; p.B = B; p.H = H; p.S = S; p.Skv = Skv;
+  p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
+  p.timeline = g_attn_timeline;
+  static bool configured = false;
+  if (!configured) {
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    configured = true;
+  }
+  dim3 grid((unsigned)nfb_cdiv(S, 2 * TILE_Q), (unsigned)(B * H));
+  NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

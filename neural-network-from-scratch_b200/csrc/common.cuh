@@ -38,6 +38,29 @@ extern "C" int nfb_free(void* p);
 
 static inline int64_t nfb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL).  Kernels of the training step are launched with the programmatic stream
+// serialization attribute; each starts with nfb_pdl_wait() (= griddepcontrol.wait: blocks until the preceding kernel in
+// the stream has completed and its writes are visible) followed by nfb_pdl_trigger() (lets the NEXT kernel's blocks be
+// scheduled early, where they sit in their own nfb_pdl_wait()).  The launch latency and block ramp-up of kernel N+1 then
+// overlap the last wave of kernel N; with ~350 short launches per step that is a measurable share of the step.
+bool nfb_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t nfb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = nfb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // grid sizing for bandwidth-bound grid-stride kernels: a multiple of the SM count
 static inline int nfb_grid_for(int64_t work_items, int per_block, int waves_cap = 16) {
   int64_t blocks = nfb_cdiv(work_items, per_block);
@@ -49,6 +72,10 @@ static inline int nfb_grid_for(int64_t work_items, int per_block, int waves_cap 
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+__device__ __forceinline__ void nfb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void nfb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// both, at the top of a kernel that has no prologue worth overlapping
+__device__ __forceinline__ void nfb_pdl_enter() { nfb_pdl_wait(); nfb_pdl_trigger(); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -730,6 +730,7 @@ template <> struct Vec16<__nv_bfloat16> {
 
 template <typename T>
 __global__ void k_swiglu_fwd(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out, int rows, int CV, int64_t C, int64_t in_ld) {
+  nfb_pdl_enter();
   constexpr int N = Vec16<T>::N;
   const unsigned total = (unsigned)rows * (unsigned)CV, stride = gridDim.x * blockDim.x;   // host checks rows * CV < 2^31
   for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
@@ -746,6 +747,7 @@ __global__ void k_swiglu_fwd(const T* __restrict__ gate, const T* __restrict__ u
 template <typename T>
 __global__ void k_swiglu_bwd(const T* __restrict__ gate, const T* __restrict__ up, const T* __restrict__ dout, T* __restrict__ dgate, T* __restrict__ dup,
                              int rows, int CV, int64_t C, int64_t in_ld) {
+  nfb_pdl_enter();
   constexpr int N = Vec16<T>::N;
   const unsigned total = (unsigned)rows * (unsigned)CV, stride = gridDim.x * blockDim.x;   // host checks rows * CV < 2^31
   for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
@@ -810,12 +812,12 @@ NFB_API int nfb_swiglu_fwd(int dtype, const void* gate, const void* up, void* ou
     if (swiglu_check<float>(gate, up, out, nullptr, nullptr, C, in_ld, "nfb_swiglu_fwd")) return -1;
     int CV = (int)(C / 4);
     if (swiglu_size_check(rows, CV, "nfb_swiglu_fwd")) return -1;
-    k_swiglu_fwd<float><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (float*)out, (int)rows, CV, C, in_ld);
+    nfb_launch_pdl(k_swiglu_fwd<float>, dim3(nfb_grid_for(rows * CV, 256)), dim3(256), 0, nfb_cur_stream(), (const float*)gate, (const float*)up, (float*)out, (int)rows, CV, C, in_ld);
   } else if (dtype == NFB_BF16) {
     if (swiglu_check<__nv_bfloat16>(gate, up, out, nullptr, nullptr, C, in_ld, "nfb_swiglu_fwd")) return -1;
     int CV = (int)(C / 8);
     if (swiglu_size_check(rows, CV, "nfb_swiglu_fwd")) return -1;
-    k_swiglu_fwd<__nv_bfloat16><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)out, (int)rows, CV, C, in_ld);
+    nfb_launch_pdl(k_swiglu_fwd<__nv_bfloat16>, dim3(nfb_grid_for(rows * CV, 256)), dim3(256), 0, nfb_cur_stream(), (const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)out, (int)rows, CV, C, in_ld);
   } else return NFB_FAIL("nfb_swiglu_fwd: unsupported dtype %d", dtype);
   NFB_LAUNCH_CHECK();
   return 0;
@@ -830,12 +832,12 @@ NFB_API int nfb_swiglu_bwd(int dtype, const void* gate, const void* up, const vo
     if (swiglu_check<float>(gate, up, dout, dgate, dup, C, in_ld, "nfb_swiglu_bwd")) return -1;
     int CV = (int)(C / 4);
     if (swiglu_size_check(rows, CV, "nfb_swiglu_bwd")) return -1;
-    k_swiglu_bwd<float><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const float*)gate, (const float*)up, (const float*)dout, (float*)dgate, (float*)dup, (int)rows, CV, C, in_ld);
+    nfb_launch_pdl(k_swiglu_bwd<float>, dim3(nfb_grid_for(rows * CV, 256)), dim3(256), 0, nfb_cur_stream(), (const float*)gate, (const float*)up, (const float*)dout, (float*)dgate, (float*)dup, (int)rows, CV, C, in_ld);
   } else if (dtype == NFB_BF16) {
     if (swiglu_check<__nv_bfloat16>(gate, up, dout, dgate, dup, C, in_ld, "nfb_swiglu_bwd")) return -1;
     int CV = (int)(C / 8);
     if (swiglu_size_check(rows, CV, "nfb_swiglu_bwd")) return -1;
-    k_swiglu_bwd<__nv_bfloat16><<<nfb_grid_for(rows * CV, 256), 256, 0, nfb_cur_stream()>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dgate, (__nv_bfloat16*)dup, (int)rows, CV, C, in_ld);
+    nfb_launch_pdl(k_swiglu_bwd<__nv_bfloat16>, dim3(nfb_grid_for(rows * CV, 256)), dim3(256), 0, nfb_cur_stream(), (const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dgate, (__nv_bfloat16*)dup, (int)rows, CV, C, in_ld);
   } else return NFB_FAIL("nfb_swiglu_bwd: unsupported dtype %d", dtype);
   NFB_LAUNCH_CHECK();
   return 0;

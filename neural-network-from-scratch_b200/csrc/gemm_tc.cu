@@ -755,15 +755,6 @@ static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long
   return 0;
 }
 
-static int g_pdl = -1;  // programmatic dependent launch: on unless NFB_PDL=0
-static bool pdl_enabled() {
-  if (g_pdl < 0) {
-    const char* e = getenv("NFB_PDL");
-    g_pdl = (e && e[0] == '0') ? 0 : 1;
-  }
-  return g_pdl == 1;
-}
-NFB_API int nfb_set_pdl(int on) { g_pdl = on ? 1 : 0; return 0; }
 
 template <int BLOCK_N, int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid) {
@@ -787,7 +778,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attrs[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {
+  if (nfb_pdl_enabled()) {
     attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

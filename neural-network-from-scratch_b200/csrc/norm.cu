@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_norm_fwd(const TX* __restrict__ x, const TX* __restrict__ res, TX* __restrict__ sum_out, const float* __restrict__ gamma,
            const float* __restrict__ beta, TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
            int64_t rows, int cols, float eps) {
+  nfb_pdl_enter();
   int lane = threadIdx.x & 31;
   int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
 k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
            const float* __restrict__ rstd_in, const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
            int64_t rows, int cols, float clip, __nv_bfloat16* __restrict__ dx_twin) {
+  nfb_pdl_enter();
   constexpr int NP = RMS ? 1 : 2;
   __shared__ float sh[BWD_WARPS][VPL * 128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -182,6 +184,7 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
 __global__ void __launch_bounds__(256)
 k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int np, int cols, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int accumulate) {
+  nfb_pdl_enter();
   __shared__ float red[32][9];
   const int i = blockIdx.x * 8 + threadIdx.x;   // index into [np][cols]
   const int total = np * cols;
@@ -280,7 +283,7 @@ static int norm_fwd_t(const void* x, const void* res, void* sum_out, const float
   int vpl = pick_vpl(cols);
   cudaStream_t s = nfb_cur_stream();
   int grid = nfb_grid_for(rows, WARPS_PER_BLOCK, 8);
-#define LF(V) k_norm_fwd<V, TX, TY, RMS><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>((const TX*)x, (const TX*)res, (TX*)sum_out, gamma, beta, (TY*)y, mean, rstd, rows, cols, eps)
+#define LF(V) nfb_launch_pdl(k_norm_fwd<V, TX, TY, RMS>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, s, (const TX*)x, (const TX*)res, (TX*)sum_out, gamma, beta, (TY*)y, mean, rstd, rows, cols, eps)
   switch (vpl) {
     case 1: LF(1); break;
     case 2: LF(2); break;
@@ -308,7 +311,7 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   float* partial = nullptr;
   bool need_params = dgamma || dbeta;
   if (need_params && nfb_malloc(sizeof(float) * (size_t)NP * cols * grid, (void**)&partial)) return -1;
-#define LB(V) k_norm_bwd<V, TX, TY, RMS><<<grid, BWD_WARPS * 32, 0, s>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
+#define LB(V) nfb_launch_pdl(k_norm_bwd<V, TX, TY, RMS>, dim3(grid), dim3(BWD_WARPS * 32), 0, s, (const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
   switch (vpl) {
     case 1: LB(1); break;
     case 2: LB(2); break;
@@ -320,7 +323,7 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
 #undef LB
   if (need_params) {
     nfb_count_launch();
-    k_norm_param_reduce<<<(NP * cols + 7) / 8, dim3(8, 32), 0, s>>>(partial, grid, NP, cols, dgamma, dbeta, accumulate);
+    nfb_launch_pdl(k_norm_param_reduce, dim3((NP * cols + 7) / 8), dim3(8, 32), 0, s, partial, grid, NP, cols, dgamma, dbeta, accumulate);
     nfb_free(partial);
   }
   NFB_LAUNCH_CHECK();

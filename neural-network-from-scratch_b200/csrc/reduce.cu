@@ -241,6 +241,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_colsum_fused(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_len, float* __restrict__ tmp, unsigned* __restrict__ counters,
                float* __restrict__ out, int accumulate) {
+  nfb_pdl_enter();
   constexpr int VEC = 16 / (int)sizeof(T);
   __shared__ float red[8][32 * VEC + 1];
   __shared__ int s_last;
@@ -334,8 +335,8 @@ NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, f
     float* tmp = nullptr;
     if (nfb_malloc(sizeof(float) * (size_t)chunks * C, (void**)&tmp)) return -1;
     dim3 grid(strips, chunks), block(32, 8);
-    if (dtype == NFB_F32) k_colsum_fused<float><<<grid, block, 0, s>>>((const float*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
-    else k_colsum_fused<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
+    if (dtype == NFB_F32) nfb_launch_pdl(k_colsum_fused<float>, grid, block, 0, s, (const float*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
+    else nfb_launch_pdl(k_colsum_fused<__nv_bfloat16>, grid, block, 0, s, (const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
     nfb_free(tmp);
     NFB_LAUNCH_CHECK();
     return 0;

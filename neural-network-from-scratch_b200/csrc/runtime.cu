@@ -2,6 +2,7 @@
 // Replaces what the reference gets from CuPy in backends/cuda_backend.py:24-58 (device + memory pool)
 // and backends/cuda_kernels.py:490-526 (event timing).
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -280,6 +281,17 @@ NFB_API int nfb_graph_destroy(void* exec) {
   NFB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)exec));
   return 0;
 }
+
+// programmatic dependent launch switch (default on; env NFB_PDL=0 or nfb_set_pdl(0) turns it off)
+static int g_pdl = -1;
+bool nfb_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("NFB_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+NFB_API int nfb_set_pdl(int on) { g_pdl = on ? 1 : 0; return 0; }
 
 // L2 flush helper for benchmarks: writes a buffer larger than the 126 MB L2, then streams a second one through it with
 // loads, so that the cache is left full of CLEAN foreign lines (a write-only flush leaves 126 MB of dirty lines whose

@@ -25,9 +25,18 @@ def _close(got, want, tol=1e-2):
     assert err <= tol * scale + 1e-3 * tol, f"max err {err} vs scale {scale}"
 
 
-@pytest.mark.parametrize("B,H,S", [(2, 3, 128), (1, 2, 197), (2, 12, 512), (1, 1, 64), (1, 2, 70)])
+@pytest.fixture(params=[1, 0], ids=["tcgen05_fwd", "mma_sync"])
+def attn_impl(request):
+    """1 = tcgen05/TMEM/TMA forward (csrc/attention_tc.cu, the default), 0 = the mma.sync flash kernels only."""
+    from nfb200 import _lib
+    _lib.call("nfb_flash_attn_set_tc", request.param)
+    yield request.param
+    _lib.call("nfb_flash_attn_set_tc", 1)
+
+
+@pytest.mark.parametrize("B,H,S", [(2, 3, 128), (1, 2, 197), (2, 12, 512), (1, 1, 64), (1, 2, 70), (1, 2, 1024), (2, 2, 300)])
 @pytest.mark.parametrize("mode", ["none", "causal", "keymask", "causal+keymask"])
-def test_flash_forward_backward(be, B, H, S, mode):
+def test_flash_forward_backward(be, attn_impl, B, H, S, mode):
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(B * 1000 + S)
     D = 64
@@ -63,7 +72,7 @@ def test_flash_forward_backward(be, B, H, S, mode):
     _close(dk.get(), wdk)
 
 
-def test_flash_packed_qkv_layout_and_rope(be):
+def test_flash_packed_qkv_layout_and_rope(be, attn_impl):
     """The fused qkv projection output (B,S,3,H,D) is consumed in place; RoPE rotates q,k in place; the packed
     dqkv gradient buffer comes back ready for the dgrad GEMM (gpt2.py:228-262)."""
     from nfb200 import kernels as Kn

@@ -475,8 +475,11 @@ bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, cons
 int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
                      int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
                      const float* key_mask);
-static int g_attn_tc = 1;
-NFB_API int nfb_flash_attn_set_tc(int on) { g_attn_tc = on ? 1 : 0; return 0; }   // test hook: 0 = mma.sync kernels only
+int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                     int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
+                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask);
+static int g_attn_tc = 3;   // bit 0: tcgen05 forward, bit 1: tcgen05 backward
+NFB_API int nfb_flash_attn_set_tc(int on) { g_attn_tc = on; return 0; }   // test hook: 0 = mma.sync kernels only, 1 = tcgen05 forward only, 3 = both (default)
 
 // dtype must be NFB_BF16.  lse: (B,H,S) fp32 (may be NULL for inference).  key_mask: (B,Skv) fp32 or NULL.
 NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S,
@@ -486,7 +489,7 @@ NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const vo
   if (B == 0 || H == 0 || S == 0) return 0;
   if (check_attn(head_dim, q_ss, kv_ss, o_ss)) return -1;
   if ((mask_mode & 2) && !key_mask) return NFB_FAIL("flash attention: mask_mode bit 1 set but key_mask is NULL");
-  if (g_attn_tc && nfb_flash_fwd_tc_eligible(q, k, v, o, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb))
+  if ((g_attn_tc & 1) && nfb_flash_fwd_tc_eligible(q, k, v, o, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb))
     return nfb_flash_fwd_tc(q, k, v, o, lse, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask);
   AttnParams p = {};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (__nv_bfloat16*)o; p.lse = lse;
@@ -521,6 +524,12 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
   long long rows = (long long)B * H * S;
   nfb_launch_pdl(k_attn_delta, dim3((unsigned)nfb_cdiv(rows, 8)), dim3(256), 0, s, p, delta);
   nfb_count_launch();
+  if ((g_attn_tc & 2) && nfb_flash_fwd_tc_eligible(q, k, v, dout, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb) &&
+      ((((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)) {
+    int rc = nfb_flash_bwd_tc(q, k, v, dout, lse, delta, dq, dk, dv, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask);
+    nfb_free(delta);
+    return rc;
+  }
   size_t smem_dkv = (size_t)(2 * BC * HD + 4 * BR * HD) * 2 + 4 * BR * sizeof(float);
   static bool cfg = false;
   if (!cfg) {

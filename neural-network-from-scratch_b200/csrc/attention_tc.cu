@@ -147,6 +147,15 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int m, int n)
   return d;
 }
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// per-CTA (start, end) in globaltimer ns + SM id, slots 256.. (debug)
+__device__ __forceinline__ void tl_cta(const AttnTcParams& p, int which) {
+  if (!p.timeline) return;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (cta >= 256) return;
+  if (which == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.timeline[256 + 3 * cta + 2] = sm; }
+  p.timeline[256 + 3 * cta + which] = gtimer();
+}
 __device__ __forceinline__ void tl(const AttnTcParams& p, int slot) {
   if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
 }
@@ -184,6 +193,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
   const int nB = (q0B < p.S) ? (causal ? min(nkv_all, q0B / TILE_K + 1) : nkv_all) : 0;
   const int nMax = max(nA, nB);
+  if (threadIdx.x == 0) tl_cta(p, 0);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -425,6 +435,327 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  if (threadIdx.x == 0) tl_cta(p, 1);
+}
+
+
+// =====================================================================================================================
+// BACKWARD.  One CTA per (batch, head, 128-key block j) -- 192 threads: warps 0-3 = elementwise group (thread = one
+// query row of the current 128-query block i), warp 4 = TMA producer, warp 5 = MMA issuer.  For every query block i
+// (i >= j when causal) five tensor-core products run on tiles that TMA delivers as plain [128 rows][64] SWIZZLE_128B
+// boxes -- no transposed copy of anything is ever made, the transposes are expressed as MN-major UMMA operands:
+//     S   = Q_i K_j^T          (A = Q_i K-major,       B = K_j K-major,   128x128x64)   -> TMEM cols [0,128)
+//     dP  = dO_i V_j^T         (A = dO_i K-major,      B = V_j K-major,   128x128x64)   -> TMEM cols [128,256)
+//     dV += P^T dO_i           (A = P  MN-major (M=k), B = dO_i MN-major, 128x64x128)   -> TMEM cols [256,320)
+//     dK += dS^T Q_i           (A = dS MN-major (M=k), B = Q_i MN-major,  128x64x128)   -> TMEM cols [320,384)
+//     dQ_i = dS K_j            (A = dS K-major  (M=q), B = K_j MN-major,  128x64x128)   -> TMEM cols [384,448)
+// P = exp2(S*scale*log2e - LSE_i*log2e) and dS = P o (dP - delta_i) * scale are formed by the elementwise group
+// straight from TMEM (thread = row, so LSE_i / delta_i are per-thread scalars) and written as bf16 into ONE shared
+// memory layout ([two 64-key panels][128 query rows][128 B], SWIZZLE_128B) that serves both as the K-major operand
+// (M = queries) and, with LBO = 16 KB, as the MN-major operand (M = keys).  dK_j / dV_j accumulate in TMEM over the
+// whole query loop; the dQ_i partial of each (i, j) pair is drained TMEM -> registers -> shared memory and added into
+// an fp32 (B, H, S, 64) accumulation buffer by a TMA reduce-add (cp.reduce.async.bulk.tensor .add), which a small
+// kernel converts to the bf16 dq afterwards.  Masked scores carry P = 0, hence dS = 0 (the reference REPLACES them
+// by -1e4, models/language/gpt2.py:194-200, so no gradient flows through them).
+constexpr int BWD_THREADS = 192;
+constexpr int SB_K = 0;                 // K_j   16 KB
+constexpr int SB_V = 16384;             // V_j   16 KB
+constexpr int SB_Q = 32768;             // Q_i   2 stages x 16 KB
+constexpr int SB_DO = 65536;            // dO_i  2 stages x 16 KB
+constexpr int SB_P = 98304;             // P     32 KB
+constexpr int SB_DS = 131072;           // dS    32 KB
+constexpr int SB_DQ = 163840;           // dQ staging, fp32 [2 column halves][128 rows][128 B] = 32 KB
+constexpr int SB_BAR = 196608;
+constexpr int SB_TOTAL = SB_BAR + 256 + 1024;
+
+struct AttnBwdTcParams {
+  const float* lse;     // (B, H, S) natural log
+  const float* delta;   // (B, H, S)
+  __nv_bfloat16 *dk, *dv;
+  long long kv_sb, kv_ss, kv_sh;
+  int B, H, S, Skv;
+  float scale;
+  int mask_mode;
+  const float* key_mask;
+};
+
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+               const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ, const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + SB_BAR);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* q_full = bars + 1;       // 2 stages (Q_i + dO_i)
+  uint64_t* q_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;       // S ready
+  uint64_t* dp_full = bars + 6;      // dP ready
+  uint64_t* p_full = bars + 7;       // P in smem (128 arrivals)
+  uint64_t* ds_full = bars + 8;      // dS in smem (128 arrivals)
+  uint64_t* dq_full = bars + 9;      // dQ_i partial in TMEM; also: every product of block i has retired
+  uint64_t* dq_free = bars + 10;     // dQ TMEM columns drained (128 arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool causal = (p.mask_mode & 1) != 0;
+  const int jb = blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int k0 = jb * TILE_K;
+  const int nq = (p.S + TILE_Q - 1) / TILE_Q;
+  const int i0 = causal ? min(jb, nq) : 0;      // query blocks entirely above the diagonal see none of these keys
+  const int niter = nq - i0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 128); mbar_init(ds_full, 128); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  nfb_pdl_wait();
+  nfb_pdl_trigger();
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && niter > 0) {
+      mbar_expect_tx(kv_full, 32768u);
+      tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h, k0, b);
+      tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h, k0, b);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1;
+        mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 32768u);
+        tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, h, (i0 + it) * TILE_Q, b);
+        tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, h, (i0 + it) * TILE_Q, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && niter > 0) {
+      const uint32_t idesc_s = make_idesc(0, 0, 128, 128);    // S, dP : A K-major, B K-major, N = 128
+      const uint32_t idesc_kv = make_idesc(1, 1, 128, 64);    // dV, dK: A MN-major, B MN-major, N = 64
+      const uint32_t idesc_q = make_idesc(0, 1, 128, 64);     // dQ    : A K-major, B MN-major, N = 64
+      const uint32_t sK = smem_u32(smem + SB_K), sV = smem_u32(smem + SB_V), sQ = smem_u32(smem + SB_Q), sdO = smem_u32(smem + SB_DO);
+      const uint32_t sP = smem_u32(smem + SB_P), sdS = smem_u32(smem + SB_DS);
+      auto issue_s_dp = [&](int st) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + 0u, make_smem_desc(sQ + st * 16384 + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + 128u, make_smem_desc(sdO + st * 16384 + k * 32, 16, 1024), make_smem_desc(sV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1;
+        // dV += P^T dO_i : contraction over the 128 query rows (8 steps of 16 rows = 2048 B in both operands)
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 256u, make_smem_desc(sP + k * 2048, 16384, 1024), make_smem_desc(sdO + st * 16384 + k * 2048, 8192, 1024), idesc_kv,
+                    (it > 0 || k > 0) ? 1u : 0u);
+        // dK += dS^T Q_i ; dQ_i = dS K_j
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 320u, make_smem_desc(sdS + k * 2048, 16384, 1024), make_smem_desc(sQ + st * 16384 + k * 2048, 8192, 1024), idesc_kv,
+                    (it > 0 || k > 0) ? 1u : 0u);
+        if (it > 0) { mbar_wait(dq_free, (it - 1) & 1); tc_fence_after(); }   // the previous dQ partial has been drained
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 384u, make_smem_desc(sdS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), make_smem_desc(sK + k * 2048, 8192, 1024), idesc_q,
+                    k > 0 ? 1u : 0u);
+        umma_commit(dq_full);          // dQ_i ready; P / dS buffers and Q_i / dO_i stage are no longer read
+        umma_commit(&q_empty[st]);
+        if (it + 1 < niter) {
+          mbar_wait(&q_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s_dp(st ^ 1);          // S / dP columns were consumed when P / dS were written
+        }
+      }
+    }
+  } else {
+    // ===================== elementwise group: thread = query row =====================
+    const int r = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sP_row = smem_u32(smem + SB_P) + (uint32_t)r * 128u, sdS_row = smem_u32(smem + SB_DS) + (uint32_t)r * 128u;
+    const uint32_t sdQ_row = smem_u32(smem + SB_DQ) + (uint32_t)r * 128u;
+    const int sw = r & 7;
+    const float sl2 = p.scale * LOG2E;
+    const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
+    const bool tail = k0 + TILE_K > p.Skv;
+    for (int it = 0; it < niter; ++it) {
+      const int q0 = (i0 + it) * TILE_Q, qi = q0 + r;
+      const bool valid = qi < p.S;
+      // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
+      const float lse2 = valid ? p.lse[(long long)bh * p.S + qi] * LOG2E : INFINITY;
+      const float dlt = valid ? p.delta[(long long)bh * p.S + qi] : 0.f;
+      // ---- P = exp2(score - LSE)
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(c * 32), sr + c * 32);
+      tmem_ld_wait();
+      // (the products of block it-1 have retired -- their dq_full was awaited in the drain below -- so P / dS are free)
+      uint32_t pk[64];   // P as packed bf16 pairs (kept for dS)
+      const bool diag = causal && (k0 + TILE_K - 1 > q0);
+      if (!diag && !tail && !kmask) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      } else {
+        const float neg = -1e4f * LOG2E;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int kj = k0 + 2 * j + e;
+            float t = __uint_as_float(sr[2 * j + e]) * sl2;
+            if (causal && kj > qi) t = neg;                                   // REPLACED by -1e4
+            if (kmask) t += (kj < p.Skv ? __ldg(kmask + kj) : 0.f) * LOG2E;
+            v[e] = (kj < p.Skv) ? ex2(t - lse2) : 0.f;
+          }
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ sw) * 16)),
+                     "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- dS = P o (dP - delta) * scale
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(128 + c * 32), sr + c * 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[j]));
+        const float d0 = pf.x * (__uint_as_float(sr[2 * j]) - dlt) * p.scale, d1 = pf.y * (__uint_as_float(sr[2 * j + 1]) - dlt) * p.scale;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS_row + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ sw) * 16)),
+                     "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+      // ---- drain the dQ_i partial: TMEM -> registers -> shared memory (fp32, two 32-column SWIZZLE_128B boxes) -> TMA reduce-add
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous reduce has read the staging buffer
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t dq[32];
+        tmem_ld32(lane_addr + (uint32_t)(384 + cc * 32), dq);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)cc * 16384u + (uint32_t)((c ^ sw) * 16)),
+                       "r"(dq[4 * c]), "r"(dq[4 * c + 1]), "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3]) : "memory");
+      }
+      tc_fence_before();
+      mbar_arrive(dq_free);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0 && lane == 0) {
+        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ), 0, q0, bh);
+        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ) + 16384u, 32, q0, bh);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    // ---- epilogue: dK_j, dV_j (thread = key row)
+    const int kj = k0 + r;
+    if (niter > 0) {
+      // the last dq_full wait above already guarantees that every product has retired
+      __nv_bfloat16* dkrow = p.dk + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+      __nv_bfloat16* dvrow = p.dv + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t acc[32];
+          tmem_ld32(lane_addr + (uint32_t)((which == 0 ? 256 : 320) + cc * 32), acc);
+          tmem_ld_wait();
+          if (kj < p.Skv) {
+            __nv_bfloat16* dst = (which == 0 ? dvrow : dkrow) + cc * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(acc[c * 8 + 2 * e]), __uint_as_float(acc[c * 8 + 2 * e + 1]));
+                w[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+    } else if (kj < p.Skv) {
+      // no query block sees these keys (cannot happen for causal self-attention with S >= Skv, kept for safety)
+      __nv_bfloat16* dkrow = p.dk + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+      __nv_bfloat16* dvrow = p.dv + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        *reinterpret_cast<uint4*>(dkrow + c * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dvrow + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // dQ reductions have landed
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// dq (bf16, strided (b, s, h, d)) = fp32 accumulation buffer (B, H, S, 64)
+__global__ void k_dq_convert(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int S, long long sb, long long ss, long long sh) {
+  nfb_pdl_enter();
+  const unsigned total = (unsigned)B * H * S * 8, stride = gridDim.x * blockDim.x;   // 8 threads per row, 8 elements each
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned c = (i & 7) * 8, row = i >> 3;
+    const unsigned sidx = row % S, bhh = row / S, hh = bhh % H, bb = bhh / H;
+    const float4 a = *reinterpret_cast<const float4*>(acc + (size_t)row * 64 + c), bq = *reinterpret_cast<const float4*>(acc + (size_t)row * 64 + c + 4);
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(a.x, a.y), w1 = __floats2bfloat162_rn(a.z, a.w), w2 = __floats2bfloat162_rn(bq.x, bq.y), w3 = __floats2bfloat162_rn(bq.z, bq.w);
+    *reinterpret_cast<uint4*>(dq + bb * sb + (long long)sidx * ss + (long long)hh * sh + c) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&w0), *reinterpret_cast<uint32_t*>(&w1), *reinterpret_cast<uint32_t*>(&w2), *reinterpret_cast<uint32_t*>(&w3));
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -469,6 +800,19 @@ int make_map_bshd(CUtensorMap* out, const void* base, int B, int S, int H, long 
   return 0;
 }
 
+
+// 3-D fp32 map over the dQ accumulation buffer (B*H, S, 64): dims (64, S, B*H), box (32, 128, 1)
+int make_map_dq(CUtensorMap* out, const float* base, int BH, int S) {
+  if (get_encode_fn()) return -1;
+  cuuint64_t dims[3] = {64, (cuuint64_t)S, (cuuint64_t)BH};
+  cuuint64_t strides[2] = {64 * 4, (cuuint64_t)S * 64 * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return NFB_FAIL("attention_tc: cuTensorMapEncodeTiled (dQ) failed (%d) BH=%d S=%d", (int)r, BH, S);
+  return 0;
+}
 unsigned long long* g_attn_timeline = nullptr;
 }  // namespace
 
@@ -502,6 +846,40 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
   }
   dim3 grid((unsigned)nfb_cdiv(S, 2 * TILE_Q), (unsigned)(B * H));
   NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) is computed by the caller.  dq/dk/dv use the q / kv strides.
+int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                     int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
+                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask) {
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
+  if (make_map_bshd(&tmQ, q, B, S, H, q_sb, q_ss, q_sh)) return -1;
+  if (make_map_bshd(&tmK, k, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmV, v, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmdO, dout, B, S, H, o_sb, o_ss, o_sh)) return -1;
+  float* acc = nullptr;
+  const size_t acc_bytes = sizeof(float) * (size_t)B * H * S * 64;
+  if (nfb_malloc(acc_bytes, (void**)&acc)) return -1;
+  if (make_map_dq(&tmdQ, acc, B * H, S)) { nfb_free(acc); return -1; }
+  cudaStream_t st = nfb_cur_stream();
+  NFB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  AttnBwdTcParams p = {};
+  p.lse = lse; p.delta = delta; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.B = B; p.H = H; p.S = S; p.Skv = Skv; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
+  static bool configured = false;
+  if (!configured) {
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    configured = true;
+  }
+  dim3 grid((unsigned)nfb_cdiv(Skv, TILE_K), (unsigned)(B * H));
+  k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  nfb_count_launch();
+  const long long vecs = (long long)B * H * S * 8;
+  NFB_CUDA(nfb_launch_pdl(k_dq_convert, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const float*)acc, (__nv_bfloat16*)dq, B, H, S,
+                          (long long)q_sb, (long long)q_ss, (long long)q_sh));
+  nfb_free(acc);
   NFB_LAUNCH_CHECK();
   return 0;
 }

@@ -25,13 +25,14 @@ def _close(got, want, tol=1e-2):
     assert err <= tol * scale + 1e-3 * tol, f"max err {err} vs scale {scale}"
 
 
-@pytest.fixture(params=[1, 0], ids=["tcgen05_fwd", "mma_sync"])
+@pytest.fixture(params=[3, 1, 0], ids=["tcgen05", "tcgen05_fwd_only", "mma_sync"])
 def attn_impl(request):
-    """1 = tcgen05/TMEM/TMA forward (csrc/attention_tc.cu, the default), 0 = the mma.sync flash kernels only."""
+    """3 = tcgen05/TMEM/TMA forward and backward (csrc/attention_tc.cu, the default), 1 = tcgen05 forward with the
+    mma.sync backward, 0 = the mma.sync flash kernels only."""
     from nfb200 import _lib
     _lib.call("nfb_flash_attn_set_tc", request.param)
     yield request.param
-    _lib.call("nfb_flash_attn_set_tc", 1)
+    _lib.call("nfb_flash_attn_set_tc", 3)
 
 
 @pytest.mark.parametrize("B,H,S", [(2, 3, 128), (1, 2, 197), (2, 12, 512), (1, 1, 64), (1, 2, 70), (1, 2, 1024), (2, 2, 300)])

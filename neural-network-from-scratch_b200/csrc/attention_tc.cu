@@ -457,7 +457,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // an fp32 (B, H, S, 64) accumulation buffer by a TMA reduce-add (cp.reduce.async.bulk.tensor .add), which a small
 // kernel converts to the bf16 dq afterwards.  Masked scores carry P = 0, hence dS = 0 (the reference REPLACES them
 // by -1e4, models/language/gpt2.py:194-200, so no gradient flows through them).
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;        // warps 0-7 elementwise (two column halves x four lane quarters), warp 8 TMA, warp 9 MMA
 constexpr int SB_K = 0;                 // K_j   16 KB
 constexpr int SB_V = 16384;             // V_j   16 KB
 constexpr int SB_Q = 32768;             // Q_i   2 stages x 16 KB
@@ -477,13 +477,23 @@ struct AttnBwdTcParams {
   float scale;
   int mask_mode;
   const float* key_mask;
+  unsigned long long* timeline;
 };
+__device__ __forceinline__ void tlb(const AttnBwdTcParams& p, int slot) {
+  if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
+}
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// Issue order of the MMA thread (tensor-core products retire in issue order) and the matching order of the elementwise
+// warps; iteration `it` handles query block i0 + it:
+//   MMA :  S(0) dP(0) | loop it: [p_full(it)] dV(it) ; [ds_full(it)] S(it+1) ; dK(it) ; [dq_free(it-1)] dQ(it) ; dP(it+1)
+//   ELEM:  loop it: [s_full(it)] P(it) ; (it > 0: [dq_full(it-1)] drain dQ(it-1)) ; [dp_full(it)] dS(it)   ... final drain
+// S(it+1) is issued BEFORE dK(it) / dQ(it), so the exponentials of the next block run while those products and the
+// dQ drain of the previous block are in flight; the dS buffer of block it is only rewritten after dq_full(it).
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ, const AttnBwdTcParams p) {
@@ -493,12 +503,12 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* kv_full = bars;          // 1
   uint64_t* q_full = bars + 1;       // 2 stages (Q_i + dO_i)
   uint64_t* q_empty = bars + 3;      // 2
-  uint64_t* s_full = bars + 5;       // S ready
+  uint64_t* s_full = bars + 5;       // S ready (and: every product issued before it has retired)
   uint64_t* dp_full = bars + 6;      // dP ready
-  uint64_t* p_full = bars + 7;       // P in smem (128 arrivals)
-  uint64_t* ds_full = bars + 8;      // dS in smem (128 arrivals)
-  uint64_t* dq_full = bars + 9;      // dQ_i partial in TMEM; also: every product of block i has retired
-  uint64_t* dq_free = bars + 10;     // dQ TMEM columns drained (128 arrivals)
+  uint64_t* p_full = bars + 7;       // P in smem (256 arrivals)
+  uint64_t* ds_full = bars + 8;      // dS in smem (256 arrivals)
+  uint64_t* dq_full = bars + 9;      // dQ_i partial in TMEM; dK(it) / dQ(it) have retired -> dS buffer free
+  uint64_t* dq_free = bars + 10;     // dQ TMEM columns drained (256 arrivals)
   uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -509,14 +519,14 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int i0 = causal ? min(jb, nq) : 0;      // query blocks entirely above the diagonal see none of these keys
   const int niter = nq - i0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 128); mbar_init(ds_full, 128); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(dq_full, 1); mbar_init(dq_free, 256);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -526,8 +536,9 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   nfb_pdl_wait();
   nfb_pdl_trigger();
+  if (threadIdx.x == 0) tlb(p, 0);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0 && niter > 0) {
       mbar_expect_tx(kv_full, 32768u);
@@ -541,7 +552,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, h, (i0 + it) * TILE_Q, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0 && niter > 0) {
       const uint32_t idesc_s = make_idesc(0, 0, 128, 128);    // S, dP : A K-major, B K-major, N = 128
@@ -549,11 +560,13 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t idesc_q = make_idesc(0, 1, 128, 64);     // dQ    : A K-major, B MN-major, N = 64
       const uint32_t sK = smem_u32(smem + SB_K), sV = smem_u32(smem + SB_V), sQ = smem_u32(smem + SB_Q), sdO = smem_u32(smem + SB_DO);
       const uint32_t sP = smem_u32(smem + SB_P), sdS = smem_u32(smem + SB_DS);
-      auto issue_s_dp = [&](int st) {
+      auto issue_s = [&](int st) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base + 0u, make_smem_desc(sQ + st * 16384 + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+      };
+      auto issue_dp = [&](int st) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base + 128u, make_smem_desc(sdO + st * 16384 + k * 32, 16, 1024), make_smem_desc(sV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
@@ -562,9 +575,11 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
-      issue_s_dp(0);
+      issue_s(0);
+      issue_dp(0);
       for (int it = 0; it < niter; ++it) {
         const int st = it & 1;
+        const bool more = it + 1 < niter;
         // dV += P^T dO_i : contraction over the 128 query rows (8 steps of 16 rows = 2048 B in both operands)
         mbar_wait(p_full, it & 1);
         tc_fence_after();
@@ -572,9 +587,11 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 256u, make_smem_desc(sP + k * 2048, 16384, 1024), make_smem_desc(sdO + st * 16384 + k * 2048, 8192, 1024), idesc_kv,
                     (it > 0 || k > 0) ? 1u : 0u);
-        // dK += dS^T Q_i ; dQ_i = dS K_j
+        if (more) mbar_wait(&q_full[st ^ 1], ((it + 1) >> 1) & 1);
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
+        if (more) issue_s(st ^ 1);      // S columns were consumed when P(it) was written; its s_full also certifies dV(it)
+        // dK += dS^T Q_i ; dQ_i = dS K_j
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 320u, make_smem_desc(sdS + k * 2048, 16384, 1024), make_smem_desc(sQ + st * 16384 + k * 2048, 8192, 1024), idesc_kv,
@@ -584,25 +601,51 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 384u, make_smem_desc(sdS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), make_smem_desc(sK + k * 2048, 8192, 1024), idesc_q,
                     k > 0 ? 1u : 0u);
-        umma_commit(dq_full);          // dQ_i ready; P / dS buffers and Q_i / dO_i stage are no longer read
+        umma_commit(dq_full);          // dQ_i ready; dS buffer and the Q_i / dO_i stage are no longer read
         umma_commit(&q_empty[st]);
-        if (it + 1 < niter) {
-          mbar_wait(&q_full[st ^ 1], ((it + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s_dp(st ^ 1);          // S / dP columns were consumed when P / dS were written
-        }
+        if (more) issue_dp(st ^ 1);    // dP columns were consumed when dS(it) was written
       }
     }
   } else {
-    // ===================== elementwise group: thread = query row =====================
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t sP_row = smem_u32(smem + SB_P) + (uint32_t)r * 128u, sdS_row = smem_u32(smem + SB_DS) + (uint32_t)r * 128u;
-    const uint32_t sdQ_row = smem_u32(smem + SB_DQ) + (uint32_t)r * 128u;
+    // ===================== elementwise warps: thread = (query row, 64-key half) =====================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // this thread's 64 keys are one 64-key panel of the [panel][row][128 B] operand layout
+    const uint32_t sP_row = smem_u32(smem + SB_P) + (uint32_t)half * 16384u + (uint32_t)r * 128u;
+    const uint32_t sdS_row = smem_u32(smem + SB_DS) + (uint32_t)half * 16384u + (uint32_t)r * 128u;
+    const uint32_t sdQ_row = smem_u32(smem + SB_DQ) + (uint32_t)half * 16384u + (uint32_t)r * 128u;   // dQ columns [32*half, +32)
     const int sw = r & 7;
     const float sl2 = p.scale * LOG2E;
     const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
-    const bool tail = k0 + TILE_K > p.Skv;
+    const int kb0 = k0 + half * 64;                       // first key of this thread's half
+    const bool tail = kb0 + 64 > p.Skv;
+
+    auto drain_dq = [&](int it_d) {
+      // dQ partial of iteration it_d: TMEM -> registers -> shared memory (fp32, one 32-column SWIZZLE_128B box per half) -> TMA reduce-add
+      mbar_wait(dq_full, it_d & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous reduce has read the staging buffer
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t dq[32];
+      tmem_ld32(lane_addr + (uint32_t)(384 + half * 32), dq);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)((c ^ sw) * 16)),
+                     "r"(dq[4 * c]), "r"(dq[4 * c + 1]), "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3]) : "memory");
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        const int q0d = (i0 + it_d) * TILE_Q;
+        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ), 0, q0d, bh);
+        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ) + 16384u, 32, q0d, bh);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+
     for (int it = 0; it < niter; ++it) {
       const int q0 = (i0 + it) * TILE_Q, qi = q0 + r;
       const bool valid = qi < p.S;
@@ -611,29 +654,41 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float dlt = valid ? p.delta[(long long)bh * p.S + qi] : 0.f;
       // ---- P = exp2(score - LSE)
       mbar_wait(s_full, it & 1);
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it);
       tc_fence_after();
-      uint32_t sr[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(c * 32), sr + c * 32);
+      uint32_t sr[64];
+      tmem_ld32(lane_addr + (uint32_t)(half * 64), sr);
+      tmem_ld32(lane_addr + (uint32_t)(half * 64 + 32), sr + 32);
       tmem_ld_wait();
-      // (the products of block it-1 have retired -- their dq_full was awaited in the drain below -- so P / dS are free)
-      uint32_t pk[64];   // P as packed bf16 pairs (kept for dS)
-      const bool diag = causal && (k0 + TILE_K - 1 > q0);
+      uint32_t pk[32];   // P as packed bf16 pairs (kept for dS)
+      const bool diag = causal && (kb0 + 63 > q0);
       if (!diag && !tail && !kmask) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < 32; ++j) {
           const float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      } else if (!tail && !kmask) {
+        // causal diagonal: keys kb0 + j > qi are REPLACED by -1e4, whose exponential underflows to exactly 0
+        const int lim = qi - kb0;
+        const float pneg = ex2(-1e4f * LOG2E - lse2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
+          if (2 * j > lim) p0 = pneg;
+          if (2 * j + 1 > lim) p1 = pneg;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[j] = *reinterpret_cast<uint32_t*>(&b2);
         }
       } else {
         const float neg = -1e4f * LOG2E;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < 32; ++j) {
           float v[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int kj = k0 + 2 * j + e;
+            const int kj = kb0 + 2 * j + e;
             float t = __uint_as_float(sr[2 * j + e]) * sl2;
             if (causal && kj > qi) t = neg;                                   // REPLACED by -1e4
             if (kmask) t += (kj < p.Skv ? __ldg(kmask + kj) : 0.f) * LOG2E;
@@ -643,73 +698,56 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           pk[j] = *reinterpret_cast<uint32_t*>(&b2);
         }
       }
+      // (P buffer: dV(it-1) retired before s_full(it), which was committed after it)
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ sw) * 16)),
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)((c ^ sw) * 16)),
                      "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
-      // ---- dS = P o (dP - delta) * scale
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 1);
+      // ---- the dQ partial of the previous block (its products ran while the exponentials above were computed)
+      if (it > 0) drain_dq(it - 1);
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 2);
+      // ---- dS = P o (dP - delta) * scale   (dS buffer: dK(it-1), dQ(it-1) retired -- dq_full(it-1) awaited in the drain)
       mbar_wait(dp_full, it & 1);
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 3);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(128 + c * 32), sr + c * 32);
+      tmem_ld32(lane_addr + (uint32_t)(128 + half * 64), sr);
+      tmem_ld32(lane_addr + (uint32_t)(128 + half * 64 + 32), sr + 32);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
+      for (int j = 0; j < 32; ++j) {
         const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[j]));
         const float d0 = pf.x * (__uint_as_float(sr[2 * j]) - dlt) * p.scale, d1 = pf.y * (__uint_as_float(sr[2 * j + 1]) - dlt) * p.scale;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
         pk[j] = *reinterpret_cast<uint32_t*>(&b2);
       }
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS_row + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ sw) * 16)),
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS_row + (uint32_t)((c ^ sw) * 16)),
                      "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full);
-      // ---- drain the dQ_i partial: TMEM -> registers -> shared memory (fp32, two 32-column SWIZZLE_128B boxes) -> TMA reduce-add
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous reduce has read the staging buffer
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t dq[32];
-        tmem_ld32(lane_addr + (uint32_t)(384 + cc * 32), dq);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)cc * 16384u + (uint32_t)((c ^ sw) * 16)),
-                       "r"(dq[4 * c]), "r"(dq[4 * c + 1]), "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3]) : "memory");
-      }
-      tc_fence_before();
-      mbar_arrive(dq_free);
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 0 && lane == 0) {
-        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ), 0, q0, bh);
-        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ) + 16384u, 32, q0, bh);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 4);
     }
-    // ---- epilogue: dK_j, dV_j (thread = key row)
+    if (niter > 0) drain_dq(niter - 1);
+    if (threadIdx.x == 0) tlb(p, 1);
+    // ---- epilogue: dK_j, dV_j (thread = key row, 32 of the 64 columns); dq_full(niter-1) certifies every product
     const int kj = k0 + r;
-    if (niter > 0) {
-      // the last dq_full wait above already guarantees that every product has retired
-      __nv_bfloat16* dkrow = p.dk + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
-      __nv_bfloat16* dvrow = p.dv + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+    {
+      __nv_bfloat16* dkrow = p.dk + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss + half * 32;
+      __nv_bfloat16* dvrow = p.dv + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss + half * 32;
+      if (niter > 0) {
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int which = 0; which < 2; ++which) {
           uint32_t acc[32];
-          tmem_ld32(lane_addr + (uint32_t)((which == 0 ? 256 : 320) + cc * 32), acc);
+          tmem_ld32(lane_addr + (uint32_t)((which == 0 ? 256 : 320) + half * 32), acc);   // warp-collective: every lane executes it
           tmem_ld_wait();
           if (kj < p.Skv) {
-            __nv_bfloat16* dst = (which == 0 ? dvrow : dkrow) + cc * 32;
+            __nv_bfloat16* dst = which == 0 ? dvrow : dkrow;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t w[4];
@@ -722,23 +760,22 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
           }
         }
-      }
-    } else if (kj < p.Skv) {
-      // no query block sees these keys (cannot happen for causal self-attention with S >= Skv, kept for safety)
-      __nv_bfloat16* dkrow = p.dk + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
-      __nv_bfloat16* dvrow = p.dv + b * p.kv_sb + h * p.kv_sh + (long long)kj * p.kv_ss;
+      } else if (kj < p.Skv) {
+        // no query block sees these keys (cannot happen for causal self-attention with S >= Skv, kept for safety)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        *reinterpret_cast<uint4*>(dkrow + c * 8) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(dvrow + c * 8) = make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(dkrow + c * 8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dvrow + c * 8) = make_uint4(0, 0, 0, 0);
+        }
       }
     }
-    if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // dQ reductions have landed
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // dQ reductions have landed
+    if (threadIdx.x == 0) tlb(p, 2);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -868,6 +905,7 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* do
   AttnBwdTcParams p = {};
   p.lse = lse; p.delta = delta; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.B = B; p.H = H; p.S = S; p.Skv = Skv; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
+  p.timeline = g_attn_timeline;
   static bool configured = false;
   if (!configured) {
     NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));

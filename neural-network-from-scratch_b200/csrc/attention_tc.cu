@@ -480,7 +480,7 @@ struct AttnBwdTcParams {
   unsigned long long* timeline;
 };
 __device__ __forceinline__ void tlb(const AttnBwdTcParams& p, int slot) {
-  if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
+  if (p.timeline && blockIdx.x == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
 }
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
@@ -513,7 +513,9 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool causal = (p.mask_mode & 1) != 0;
-  const int jb = blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  // 1-D grid, key-block-major: with a causal mask key block 0 meets every query block -- all of those CTAs go first
+  const int nbh = p.B * p.H;
+  const int jb = (int)blockIdx.x / nbh, bh = (int)blockIdx.x % nbh, b = bh / p.H, h = bh % p.H;
   const int k0 = jb * TILE_K;
   const int nq = (p.S + TILE_Q - 1) / TILE_Q;
   const int i0 = causal ? min(jb, nq) : 0;      // query blocks entirely above the diagonal see none of these keys
@@ -769,7 +771,9 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // dQ reductions have landed
+    // the staging buffer must have been read before the CTA (and its shared memory) goes away; the reductions themselves
+    // complete at the latest with the grid
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (threadIdx.x == 0) tlb(p, 2);
   }
 
@@ -911,7 +915,7 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* do
     NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)nfb_cdiv(Skv, TILE_K), (unsigned)(B * H));
+  dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * H));
   k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   nfb_count_launch();
   const long long vecs = (long long)B * H * S * 8;

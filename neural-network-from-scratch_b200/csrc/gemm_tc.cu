@@ -698,7 +698,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   }
 
-  if (warp >= 2 && lane == 0 && p.tma_store) tma_store_wait_all();  // this warp's boxes have landed in global memory
+  // the staging boxes must have been read out before the CTA's shared memory goes away (the stores complete with the grid)
+  if (warp >= 2 && lane == 0 && p.tma_store) tma_store_wait_read();
   tc_fence_before();
   if (threadIdx.x == 0) tl_stamp(p, 3);
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair mode: neither CTA may exit while the other still reads its smem / signals its barriers

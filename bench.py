@@ -161,8 +161,9 @@ def run_b200(args):
         loss = fwd_model(ids_t, labels=labels_t)["loss"]
         loss.backward()
         if ddp is not None:
-            ddp.finish_gradient_sync()
-        opt.step()
+            ddp.step_optimizer(opt)   # bucket-pipelined: finish_gradient_sync() + opt.step()
+        else:
+            opt.step()
         return loss
 
     def barrier():

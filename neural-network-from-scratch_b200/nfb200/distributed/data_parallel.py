@@ -22,13 +22,14 @@ from .communication import ReduceOp
 
 
 class _Bucket:
-    __slots__ = ("lo", "hi", "params", "pending", "launched", "event")
+    __slots__ = ("lo", "hi", "params", "pending", "launched", "event", "seq")
 
     def __init__(self, lo, hi, params):
         self.lo, self.hi, self.params = lo, hi, params
         self.pending = 0
         self.launched = False
         self.event = None
+        self.seq = 0   # launch order of the all-reduce within the step
 
 
 class DistributedDataParallel(Module):
@@ -130,6 +131,8 @@ class DistributedDataParallel(Module):
         g.allreduce_buffer(self.arena.flat_g, b.hi - b.lo, ReduceOp.AVERAGE, g.comm_stream, offset=b.lo)
         b.event = Event(timing=False).record(g.comm_stream)
         b.launched = True
+        self._launch_seq = getattr(self, "_launch_seq", 0) + 1
+        b.seq = self._launch_seq
 
     def finish_gradient_sync(self):
         """Fence: launch what has not been launched (unused parameters, overlap off) and make the compute stream
@@ -150,6 +153,25 @@ class DistributedDataParallel(Module):
         for p in self._host_params:
             if p.grad is not None:
                 p.grad = self.group.all_reduce(Tensor(p.grad), ReduceOp.AVERAGE).data
+
+    def step_optimizer(self, optimizer):
+        """finish_gradient_sync() + optimizer.step() with the fused optimizer kernel pipelined behind the bucket
+        all-reduces: slice i of the arena is updated as soon as bucket i has arrived, while later buckets (the big
+        tied embedding gradient comes last) are still on the wire."""
+        if self.world_size == 1 or not self._require_sync or self.arena is None or self._host_params or \
+                getattr(optimizer, "arena", None) is None or optimizer.arena.flat_g is not self.arena.flat_g:
+            self.finish_gradient_sync()
+            optimizer.step()
+            return
+        for b in self.buckets:
+            if not b.launched:
+                self._launch_bucket(b)
+        for p in self.arena.params:   # every parameter will hold the averaged gradient (zeros if unused)
+            if p._grad is None:
+                p._grad = p._grad_slot
+            p._slot_zero = False
+        order = sorted(self.buckets, key=lambda b: getattr(b, "seq", 0))
+        optimizer.step(segments=[(b.lo, b.hi, b.event) for b in order])
 
     def sync_gradients(self):
         """Reference API (data_parallel.py:271-287): all-reduce(AVERAGE) every gradient after backward."""

@@ -79,7 +79,11 @@ class _AdamBase(Optimizer):
     def _update_learning_rate(self):
         pass
 
-    def step(self) -> None:
+    def step(self, segments=None) -> None:
+        """One optimizer step.  `segments` (optional, from DistributedDataParallel.step_optimizer): a list of
+        (lo, hi, event) slices of the gradient arena in the order their all-reduces were launched; the fused kernel
+        then runs slice by slice, each fenced only by ITS bucket's event, so the update of early buckets overlaps the
+        all-reduce of the late ones."""
         self.step_count += 1
         self._update_learning_rate()
         done = set()
@@ -106,6 +110,24 @@ class _AdamBase(Optimizer):
             mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
             msz = self.moment_dtype.itemsize
             a = self.arena
+            if segments is not None and len(steps) == 1 and len(next(iter(steps.values()))) == len(a.params):
+                from ..runtime import compute_stream_wait
+                (step, _ids), = steps.items()
+                for lo, hi, ev in segments:
+                    if ev is not None:
+                        compute_stream_wait(ev)
+                    call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + lo * 4, a.flat_g.ptr + lo * 4,
+                         a.moments[0].ptr + lo * msz, a.moments[1].ptr + lo * msz,
+                         (a.flat_bf16.ptr + lo * 2) if a.flat_bf16 is not None else None, hi - lo, float(self.lr), float(self.beta1),
+                         float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
+                         self.grad_scale.ptr if self.grad_scale is not None else None,
+                         self._step_dev.ptr if self._step_dev is not None else None)
+                steps = {}
+            elif segments is not None:
+                from ..runtime import compute_stream_wait
+                for _lo, _hi, ev in segments:
+                    if ev is not None:
+                        compute_stream_wait(ev)
             for step, ids in steps.items():
                 for off, n in a.runs(lambda q: id(q) in ids):
                     call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + off * 4, a.flat_g.ptr + off * 4,

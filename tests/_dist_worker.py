@@ -45,7 +45,7 @@ def ddp_train(out, device):
     opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, moment_dtype="float64")
     rng = np.random.default_rng(7)
     losses = []
-    for _ in range(2):
+    for step_i in range(2):
         GB = 4  # global batch, split evenly over the ranks
         ids = rng.integers(0, 101, (GB, 32))
         labels = np.concatenate([ids[:, 1:], np.zeros((GB, 1), dtype=ids.dtype)], axis=1)
@@ -54,8 +54,11 @@ def ddp_train(out, device):
         opt.zero_grad()
         loss = ddp(Tensor(ids[sl], device=device), labels=Tensor(labels[sl], device=device))["loss"]
         loss.backward()
-        ddp.finish_gradient_sync()
-        opt.step()
+        if step_i == 0:
+            ddp.finish_gradient_sync()   # the reference's two-call form (data_parallel.py:271-287)
+            opt.step()
+        else:
+            ddp.step_optimizer(opt)      # the optimizer kernel pipelined behind the bucket all-reduces
         losses.append(float(loss.item()))
     sd = {k: v.tolist() for k, v in list(model.state_dict().items())[:3]}
     json.dump({"losses": losses, "params": sd, "n_buckets": len(ddp.buckets)}, open(os.path.join(out, f"ddp_{rank}.json"), "w"))

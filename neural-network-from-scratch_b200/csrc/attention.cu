@@ -475,7 +475,7 @@ bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, cons
 int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
                      int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
                      const float* key_mask);
-int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
                      int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
                      int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask);
 static int g_attn_tc = 3;   // bit 0: tcgen05 forward, bit 1: tcgen05 backward
@@ -517,6 +517,10 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
   p.B = B; p.H = H; p.S = S; p.Skv = Skv;
   p.q_sb = q_sb; p.q_ss = q_ss; p.q_sh = q_sh; p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
+  if ((g_attn_tc & 2) && nfb_flash_fwd_tc_eligible(q, k, v, dout, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb) &&
+      ((((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)o) & 15) == 0))
+    return nfb_flash_bwd_tc(q, k, v, o, dout, lse, nullptr, dq, dk, dv, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale,
+                            mask_mode, key_mask);
   float* delta = nullptr;
   if (nfb_malloc(sizeof(float) * (size_t)B * H * S, (void**)&delta)) return -1;
   p.delta = delta;
@@ -524,12 +528,6 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
   long long rows = (long long)B * H * S;
   nfb_launch_pdl(k_attn_delta, dim3((unsigned)nfb_cdiv(rows, 8)), dim3(256), 0, s, p, delta);
   nfb_count_launch();
-  if ((g_attn_tc & 2) && nfb_flash_fwd_tc_eligible(q, k, v, dout, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb) &&
-      ((((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)) {
-    int rc = nfb_flash_bwd_tc(q, k, v, dout, lse, delta, dq, dk, dv, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask);
-    nfb_free(delta);
-    return rc;
-  }
   size_t smem_dkv = (size_t)(2 * BC * HD + 4 * BR * HD) * 2 + 4 * BR * sizeof(float);
   static bool cfg = false;
   if (!cfg) {

@@ -470,7 +470,9 @@ constexpr int SB_TOTAL = SB_BAR + 256 + 1024;
 
 struct AttnBwdTcParams {
   const float* lse;     // (B, H, S) natural log
-  const float* delta;   // (B, H, S)
+  const float* delta;   // (B, H, S) rowsum(dO o O), or NULL: computed in the kernel from `o` and the staged dO tile
+  const __nv_bfloat16* o;   // forward output, same (b, s, h, d) strides as dO
+  long long o_sb, o_ss, o_sh;
   __nv_bfloat16 *dk, *dv;
   long long kv_sb, kv_ss, kv_sh;
   int B, H, S, Skv;
@@ -648,12 +650,50 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     };
 
+    // delta_i = sum_d dO[i, d] * O[i, d] for the query block of iteration `itn` (when the caller passed no delta): the dO
+    // row comes from the TMA-staged (swizzled) tile, the O row straight from global memory (one 128-byte line per
+    // thread).  Called one iteration AHEAD, right after dS of the current block has been handed to the tensor core, so
+    // the global-load latency hides behind dK / dQ / the next S and dP products.
+    auto compute_delta = [&](int itn) -> float {
+      const int qin = (i0 + itn) * TILE_Q + r;
+      const bool validn = qin < p.S;
+      if (p.delta) return validn ? p.delta[(long long)bh * p.S + qin] : 0.f;
+      uint4 ov[8];
+      const __nv_bfloat16* orow = p.o + b * p.o_sb + h * p.o_sh + (long long)qin * p.o_ss;
+      if (validn) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ov[c] = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+      }
+      mbar_wait(&q_full[itn & 1], (itn >> 1) & 1);
+      float d = 0.f;
+      if (validn) {
+        const uint32_t dorow = smem_u32(smem + SB_DO) + (uint32_t)(itn & 1) * 16384u + (uint32_t)r * 128u;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 dv4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dv4.x), "=r"(dv4.y), "=r"(dv4.z), "=r"(dv4.w) : "r"(dorow + (uint32_t)((c ^ sw) * 16)));
+          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&dv4);
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&ov[c]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+            acc0 = fmaf(fa.x, fb.x, acc0);
+            acc1 = fmaf(fa.y, fb.y, acc1);
+          }
+        }
+        d = acc0 + acc1;
+      }
+      return d;
+    };
+    float dlt_next = niter > 0 ? compute_delta(0) : 0.f;
+
     for (int it = 0; it < niter; ++it) {
       const int q0 = (i0 + it) * TILE_Q, qi = q0 + r;
       const bool valid = qi < p.S;
       // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
       const float lse2 = valid ? p.lse[(long long)bh * p.S + qi] * LOG2E : INFINITY;
-      const float dlt = valid ? p.delta[(long long)bh * p.S + qi] : 0.f;
+      const float dlt = dlt_next;   // computed at the end of the previous iteration (see compute_delta)
       // ---- P = exp2(score - LSE)
       mbar_wait(s_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it);
@@ -734,6 +774,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(ds_full);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 4);
+      if (it + 1 < niter) dlt_next = compute_delta(it + 1);
     }
     if (niter > 0) drain_dq(niter - 1);
     if (threadIdx.x == 0) tlb(p, 1);
@@ -891,8 +932,8 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
   return 0;
 }
 
-// backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) is computed by the caller.  dq/dk/dv use the q / kv strides.
-int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+// backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) may be NULL (computed in the kernel from o and dO).  dq/dk/dv use the q / kv strides.
+int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
                      int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
                      int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask) {
   CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
@@ -907,7 +948,8 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* do
   cudaStream_t st = nfb_cur_stream();
   NFB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   AttnBwdTcParams p = {};
-  p.lse = lse; p.delta = delta; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.lse = lse; p.delta = delta; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
+  p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.B = B; p.H = H; p.S = S; p.Skv = Skv; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
   p.timeline = g_attn_timeline;
   static bool configured = false;

@@ -143,6 +143,7 @@ def run_b200(args):
         raise RuntimeError("bench.py: the b200 backend is unavailable (no libnfb200.so or no GPU); there is no CPU fallback")
     set_default_device(f"cuda:{local}")
     K.set_precision(args.precision)
+    K.set_wgrad_overlap(args.wgrad_overlap)
     np.random.seed(0)  # identical replicas on every rank (the reference relies on seeding too)
     model = GPT2(GPT2_SMALL)
     ddp = None
@@ -308,6 +309,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying a captured CUDA graph")
     ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
+    ap.add_argument("--no-wgrad-overlap", dest="wgrad_overlap", action="store_false", help="keep the weight-gradient GEMMs on the compute stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

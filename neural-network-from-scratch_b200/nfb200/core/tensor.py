@@ -575,6 +575,9 @@ def run_backward(root: Tensor, grad, unit_seed: bool = False) -> None:
         _run_backward(root, grad, unit_seed)
     finally:
         _UNIT_SEED = None
+        if isinstance(grad, B200Array):
+            from .. import kernels as _K
+            _K.join_side_stream()   # weight-gradient GEMMs issued on the side stream (kernels.set_wgrad_overlap)
 
 
 def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:

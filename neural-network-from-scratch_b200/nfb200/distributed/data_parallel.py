@@ -126,6 +126,8 @@ class DistributedDataParallel(Module):
             if p._grad is None and not p._slot_zero:
                 p._grad_slot.fill(0.0)
                 p._slot_zero = True
+        from .. import kernels as K
+        K.join_side_stream()                            # weight gradients computed on the side stream are part of the bucket
         ready = Event(timing=False).record()            # on the compute stream: gradients of this bucket are final
         g.comm_stream.wait_event(ready)
         g.allreduce_buffer(self.arena.flat_g, b.hi - b.lo, ReduceOp.AVERAGE, g.comm_stream, offset=b.lo)

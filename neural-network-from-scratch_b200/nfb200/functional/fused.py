@@ -194,6 +194,8 @@ def embedding(weight: Tensor, indices, out_dtype=None) -> Tensor:
         out = be.embedding_forward(weight.data, idx, out_dtype)
 
         def backward(g):
+            from .. import kernels as K
+            K.join_side_stream()   # a tied LM head's weight-gradient GEMM accumulates into the same buffer
             be.embedding_backward(g, idx, V, out=weight.grad_buffer(), accumulate=True)
             return (ACCUMULATED,)
 

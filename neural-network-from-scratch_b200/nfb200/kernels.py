@@ -177,6 +177,50 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
     return y.reshape(lead + (n_out,)), ctx
 
 
+# ---- weight-gradient GEMMs on a side stream ------------------------------------------------------------------------
+# dW (+)= dZ^T X depends on nothing downstream until the optimizer, while the layer GEMMs of GPT-2-small-sized models fill
+# only 0.65-2 waves of the 148 SMs.  With overlap on, every wgrad GEMM of the bf16 path is issued on a second stream
+# (a fork/join branch of the captured CUDA graph): its CTAs fill the SMs the dgrad / norm / attention kernels of the main
+# chain leave idle.  Operands are kept referenced until the join so the stream-ordered allocator cannot recycle them.
+_WGRAD_OVERLAP = False
+_side = None
+_side_dirty = False
+_held = []
+
+
+def set_wgrad_overlap(on: bool):
+    global _WGRAD_OVERLAP
+    join_side_stream()
+    _WGRAD_OVERLAP = bool(on)
+
+
+def join_side_stream():
+    """Make the compute stream wait for every weight-gradient GEMM issued on the side stream (no-op when none is pending).
+    Called at the end of backward(), before a DDP bucket is all-reduced and before the embedding scatter-add."""
+    global _side_dirty
+    if _side_dirty:
+        from .runtime import Event, compute_stream_wait
+        compute_stream_wait(Event(timing=False).record(_side))
+        _held.clear()
+        _side_dirty = False
+
+
+def _wgrad_on_side_stream(fn, *keep):
+    global _side, _side_dirty
+    from .runtime import Event, Stream, current_stream_handle
+    if _side is None:
+        _side = Stream()
+    _side.wait_event(Event(timing=False).record())   # operands are final on the compute stream
+    main = current_stream_handle()
+    call("nfb_set_stream", _side.handle)
+    try:
+        fn()
+    finally:
+        call("nfb_set_stream", main)
+    _held.append(keep)
+    _side_dirty = True
+
+
 def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, dx_dtype=None, clip=0.0):
     """Returns (dx, dW, db).  dW / db are ACCUMULATED into dW_out / db_out when given (gradient arena views),
     otherwise freshly allocated.  dX = dZ W ; dW = dZ^T X ; db = column sums of dZ."""
@@ -198,12 +242,17 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             odt = dx_dtype if dx_dtype is not None else bfloat16
             # dX (T,in) = dZ (T,out) . W(out,in): B operand is W stored (K=out, N=in) -> trans_b=False
             dx = gemm_bf16(dz, wb, False, not out_in, out_dtype=odt, clip=clip)
+        side = _WGRAD_OVERLAP and dW_out is not None
         if dW_out is None:
             dW_out = B200Array.full(W.shape, 0.0, np.float32)
         if out_in:   # dW (out,in) = dZ^T (out,T) . X (T,in)
-            gemm_bf16(dz, x2, True, False, out=dW_out, accumulate=True)
+            wg = lambda: gemm_bf16(dz, x2, True, False, out=dW_out, accumulate=True)
         else:        # dW (in,out) = X^T . dZ
-            gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
+            wg = lambda: gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
+        if side:
+            _wgrad_on_side_stream(wg, dz, x2, dW_out)
+        else:
+            wg()
         db = None
         if has_bias:
             db = _colsum(dz, db_out)

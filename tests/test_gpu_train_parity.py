@@ -40,15 +40,19 @@ def oracle_run():
     return _oracle(10, 5e-4, 0.1)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+wgrad_overlap"])
 def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
+    """bf16+wgrad_overlap: the weight-gradient GEMMs run on a side stream (kernels.set_wgrad_overlap), as bench.py does."""
     from nfb200 import kernels as K
     from nfb200.core import Tensor, set_default_device
     from nfb200.models import GPT2
     from nfb200.optim import AdamW
     want_losses, want_grads = oracle_run
     set_default_device("cuda")
+    overlap = precision.endswith("+wgrad_overlap")
+    precision = precision.split("+")[0]
     K.set_precision(precision)
+    K.set_wgrad_overlap(overlap)
     try:
         np.random.seed(0)
         model = GPT2(CFG)
@@ -80,11 +84,14 @@ def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
         for a, b in zip(losses, want_losses):
             assert abs(a - b) <= tol * abs(b), f"{precision} loss trajectory {losses} vs oracle {want_losses}"
     finally:
+        K.set_wgrad_overlap(False)
         K.set_precision("fp32")
         set_default_device("cpu")
 
 
-def test_cuda_graph_replay_equals_eager(be):
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_stream", "wgrad_side_stream"])
+def test_cuda_graph_replay_equals_eager(be, overlap):
+    """overlap=True: the captured graph has a fork/join branch for the weight-gradient GEMMs."""
     from nfb200 import kernels as K
     from nfb200.array import B200Array
     from nfb200.core import Tensor, set_default_device
@@ -93,6 +100,7 @@ def test_cuda_graph_replay_equals_eager(be):
     from nfb200.training import GraphedStep
     set_default_device("cuda")
     K.set_precision("bf16")
+    K.set_wgrad_overlap(overlap)
     try:
         batches = _batches(6, seed=5)
         results = []
@@ -134,6 +142,7 @@ def test_cuda_graph_replay_equals_eager(be):
         gs_losses = [x for x in graph[4:]]
         assert len(gs_losses) == 2 and all(l < 12.0 for l in gs_losses)
     finally:
+        K.set_wgrad_overlap(False)
         K.set_precision("fp32")
         set_default_device("cpu")
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > 8000000u) {
-      printf("nfb attention_tc: mbarrier wait timed out (block %d,%d thread %d)\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+      printf("nfb attention_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
   }
@@ -151,13 +151,13 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 // per-CTA (start, end) in globaltimer ns + SM id, slots 256.. (debug)
 __device__ __forceinline__ void tl_cta(const AttnTcParams& p, int which) {
   if (!p.timeline) return;
-  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int cta = blockIdx.x;
   if (cta >= 256) return;
   if (which == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.timeline[256 + 3 * cta + 2] = sm; }
   p.timeline[256 + 3 * cta + which] = gtimer();
 }
 __device__ __forceinline__ void tl(const AttnTcParams& p, int slot) {
-  if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
+  if (p.timeline && blockIdx.x == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
 }
 
 // shared-memory carve-up (offsets from the 1024-byte aligned base)
@@ -185,9 +185,11 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool causal = (p.mask_mode & 1) != 0;
-  // causal: the last tile pairs see the most keys -- schedule them first
-  const int pair = causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  // 1-D grid, tile-pair-major; causal: the last tile pairs see the most keys -- ALL of those CTAs are scheduled first
+  // (longest-processing-time order over the 148 single-CTA SMs)
+  const int nbh = p.B * p.H, npairs = (int)gridDim.x / nbh;
+  const int pidx = (int)blockIdx.x / nbh, bh = (int)blockIdx.x % nbh, b = bh / p.H, h = bh % p.H;
+  const int pair = causal ? (npairs - 1 - pidx) : pidx;
   const int q0A = pair * 2 * TILE_Q, q0B = q0A + TILE_Q;
   const int nkv_all = (p.Skv + TILE_K - 1) / TILE_K;
   const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
@@ -926,7 +928,7 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
     NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)nfb_cdiv(S, 2 * TILE_Q), (unsigned)(B * H));
+  dim3 grid((unsigned)(nfb_cdiv(S, 2 * TILE_Q) * B * H));
   NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   NFB_LAUNCH_CHECK();
   return 0;

@@ -3,6 +3,8 @@
 // gradient clipping. Semantics follow numpy_backend.py:138-160 of the reference (np.sum/mean/max/
 // min/argmax/argmin); NaNs propagate through max/min as in NumPy.
 #include "common.cuh"
+#include <map>
+#include <utility>
 #include <float.h>
 
 enum RedOp { R_SUM = 0, R_MEAN = 1, R_MAX = 2, R_MIN = 3, R_PROD = 4 };
@@ -315,16 +317,11 @@ k_colsum_fused(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t ch
   if (tid == 0) counters[blockIdx.x] = 0;   // ready for the next launch on this stream
 }
 
-static unsigned* g_colsum_counters = nullptr;   // 4096 strip counters, zero between launches
 NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, float* out, int accumulate) {
   if (C == 0) return 0;
   cudaStream_t s = nfb_cur_stream();
   const int esz = dtype == NFB_F32 ? 4 : 2, vec = 16 / esz;
   if ((dtype == NFB_F32 || dtype == NFB_BF16) && C % vec == 0 && ld % vec == 0 && ((uintptr_t)x % 16 == 0) && R >= 64 && nfb_cdiv(C, 32 * vec) <= 4096) {
-    if (!g_colsum_counters) {
-      NFB_CUDA(cudaMalloc((void**)&g_colsum_counters, 4096 * sizeof(unsigned)));
-      NFB_CUDA(cudaMemset(g_colsum_counters, 0, 4096 * sizeof(unsigned)));
-    }
     int strips = (int)nfb_cdiv(C, 32 * vec);
     int chunks = (int)((2LL * nfb_sm_count() + strips - 1) / strips);
     int64_t max_chunks = R / 64 > 0 ? R / 64 : 1;
@@ -332,12 +329,27 @@ NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, f
     if (chunks < 1) chunks = 1;
     int64_t chunk_len = nfb_cdiv(R, chunks);
     chunks = (int)nfb_cdiv(R, chunk_len);
-    float* tmp = nullptr;
-    if (nfb_malloc(sizeof(float) * (size_t)chunks * C, (void**)&tmp)) return -1;
+    // chunk partials live in a grow-only workspace PER STREAM (not in the stream-ordered caching allocator): bias gradients
+    // may be computed on the weight-gradient side stream, where an allocator block freed "in stream order" of the compute
+    // stream could be recycled while this kernel still runs
+    static std::map<cudaStream_t, std::pair<float*, size_t>> ws;
+    static std::map<cudaStream_t, unsigned*> ws_counters;
+    std::pair<float*, size_t>& w = ws[s];
+    const size_t need = (size_t)chunks * C;
+    if (w.second < need) {
+      if (w.first) NFB_CUDA(cudaFree(w.first));   // implicit device sync: earlier users have finished
+      NFB_CUDA(cudaMalloc((void**)&w.first, sizeof(float) * need));
+      w.second = need;
+    }
+    unsigned*& cnt = ws_counters[s];
+    if (!cnt) {
+      NFB_CUDA(cudaMalloc((void**)&cnt, 4096 * sizeof(unsigned)));
+      NFB_CUDA(cudaMemset(cnt, 0, 4096 * sizeof(unsigned)));
+    }
+    float* tmp = w.first;
     dim3 grid(strips, chunks), block(32, 8);
-    if (dtype == NFB_F32) nfb_launch_pdl(k_colsum_fused<float>, grid, block, 0, s, (const float*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
-    else nfb_launch_pdl(k_colsum_fused<__nv_bfloat16>, grid, block, 0, s, (const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, g_colsum_counters, out, accumulate);
-    nfb_free(tmp);
+    if (dtype == NFB_F32) nfb_launch_pdl(k_colsum_fused<float>, grid, block, 0, s, (const float*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate);
+    else nfb_launch_pdl(k_colsum_fused<__nv_bfloat16>, grid, block, 0, s, (const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate);
     NFB_LAUNCH_CHECK();
     return 0;
   }

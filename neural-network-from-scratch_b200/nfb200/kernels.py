@@ -249,12 +249,19 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             wg = lambda: gemm_bf16(dz, x2, True, False, out=dW_out, accumulate=True)
         else:        # dW (in,out) = X^T . dZ
             wg = lambda: gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
-        if side:
+        db = None
+        if side and has_bias and db_out is not None:
+            # the bias gradient (column sums of dZ) feeds only the optimizer too: same side stream
+            def wg_and_bias(wg=wg):
+                wg()
+                _colsum(dz, db_out)
+            _wgrad_on_side_stream(wg_and_bias, dz, x2, dW_out, db_out)
+            db = db_out
+        elif side:
             _wgrad_on_side_stream(wg, dz, x2, dW_out)
         else:
             wg()
-        db = None
-        if has_bias:
+        if has_bias and db is None:
             db = _colsum(dz, db_out)
         return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
     # ---- fp32 path

@@ -128,6 +128,7 @@ int nfb_gemm_bf16_force_tile(int block_n);           /* test hook: pin the N til
 int nfb_gemm_bf16_force_cta_group(int cg);           /* test hook: 1 = single-CTA tiles, 2 = cta_group::2 SM pairs, 0 = automatic */
 int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */
 int nfb_gemm_bf16_set_tma_store(int on);             /* test hook: 0 = register epilogue everywhere (default 1: TMA store when C rows are 16-byte addressable) */
+int nfb_set_aux_stream(void* stream);   /* side stream for optimizer-only work (norm-parameter reductions; the host also issues wgrad GEMMs / bias sums there); NULL = none */
 int nfb_set_pdl(int on);                             /* programmatic dependent launch of the GEMM kernels (default on; env NFB_PDL=0) */
 
 /* ---- attention: RoPE (models/language/gpt2.py:25-95) and the fused QK^T -> softmax -> V core of

@@ -31,6 +31,8 @@ int nfb_fail(const char* file, int line, const char* fmt, ...);
   } while (0)
 
 cudaStream_t nfb_cur_stream();
+cudaStream_t nfb_aux_stream();          // side stream for optimizer-only gradients (NULL = none)
+unsigned long long nfb_capture_epoch();  // bumps at graph-capture begin / end
 void nfb_count_launch();
 int nfb_sm_count();
 extern "C" int nfb_malloc(size_t nbytes, void** out);

@@ -310,7 +310,31 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   constexpr int NP = RMS ? 1 : 2;
   float* partial = nullptr;
   bool need_params = dgamma || dbeta;
-  if (need_params && nfb_malloc(sizeof(float) * (size_t)NP * cols * grid, (void**)&partial)) return -1;
+  // With an auxiliary stream the (tiny, optimizer-only) parameter reduction leaves the critical path: the block partials go
+  // to one of two grow-only workspaces instead of the stream-ordered allocator, the reduce kernel runs on the aux stream
+  // behind an event, and the workspace is fenced by the event of the reduce that last read it.
+  struct AuxWs { float* buf; size_t n; cudaEvent_t done; unsigned long long epoch; bool used; };
+  static AuxWs ws[2] = {};
+  static int ws_next = 0;
+  static cudaEvent_t ev_ready = nullptr;
+  cudaStream_t aux = need_params ? nfb_aux_stream() : nullptr;
+  if (aux == s) aux = nullptr;
+  AuxWs* w = nullptr;
+  const size_t part_elems = (size_t)NP * cols * grid;
+  if (aux) {
+    w = &ws[ws_next];
+    ws_next ^= 1;
+    if (!ev_ready) NFB_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    if (!w->done) NFB_CUDA(cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming));
+    if (w->n < part_elems) {
+      if (w->buf) NFB_CUDA(cudaFree(w->buf));   // implicit device sync
+      NFB_CUDA(cudaMalloc((void**)&w->buf, sizeof(float) * part_elems));
+      w->n = part_elems;
+      w->used = false;
+    }
+    if (w->used && w->epoch == nfb_capture_epoch()) NFB_CUDA(cudaStreamWaitEvent(s, w->done, 0));
+    partial = w->buf;
+  } else if (need_params && nfb_malloc(sizeof(float) * part_elems, (void**)&partial)) return -1;
 #define LB(V) nfb_launch_pdl(k_norm_bwd<V, TX, TY, RMS>, dim3(grid), dim3(BWD_WARPS * 32), 0, s, (const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
   switch (vpl) {
     case 1: LB(1); break;
@@ -318,13 +342,22 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
     case 4: LB(4); break;
     case 6: LB(6); break;
     case 8: LB(8); break;
-    default: if (partial) nfb_free(partial); return NFB_FAIL("norm bwd: cols=%d needs the generic path", cols);
+    default: if (partial && !aux) nfb_free(partial); return NFB_FAIL("norm bwd: cols=%d needs the generic path", cols);
   }
 #undef LB
   if (need_params) {
     nfb_count_launch();
-    nfb_launch_pdl(k_norm_param_reduce, dim3((NP * cols + 7) / 8), dim3(8, 32), 0, s, partial, grid, NP, cols, dgamma, dbeta, accumulate);
-    nfb_free(partial);
+    if (aux) {
+      NFB_CUDA(cudaEventRecord(ev_ready, s));
+      NFB_CUDA(cudaStreamWaitEvent(aux, ev_ready, 0));
+      k_norm_param_reduce<<<(NP * cols + 7) / 8, dim3(8, 32), 0, aux>>>(partial, grid, NP, cols, dgamma, dbeta, accumulate);
+      NFB_CUDA(cudaEventRecord(w->done, aux));
+      w->used = true;
+      w->epoch = nfb_capture_epoch();
+    } else {
+      nfb_launch_pdl(k_norm_param_reduce, dim3((NP * cols + 7) / 8), dim3(8, 32), 0, s, partial, grid, NP, cols, dgamma, dbeta, accumulate);
+      nfb_free(partial);
+    }
   }
   NFB_LAUNCH_CHECK();
   return 0;

@@ -213,6 +213,14 @@ NFB_API int nfb_stream_destroy(void* s) {
   return 0;
 }
 NFB_API void* nfb_get_stream() { return (void*)g_stream; }
+// auxiliary stream for work that only the optimizer consumes (weight / bias / norm-parameter gradients); NULL = none.
+// g_capture_epoch changes at every graph-capture boundary: cross-stream events recorded on one side of a boundary must
+// not be waited on from the other side.
+static cudaStream_t g_aux_stream = nullptr;
+static unsigned long long g_capture_epoch = 0;
+cudaStream_t nfb_aux_stream() { return g_aux_stream; }
+unsigned long long nfb_capture_epoch() { return g_capture_epoch; }
+NFB_API int nfb_set_aux_stream(void* s) { g_aux_stream = (cudaStream_t)s; return 0; }
 NFB_API int nfb_set_stream(void* s) {
   g_stream = (cudaStream_t)s;
   return 0;
@@ -260,10 +268,12 @@ NFB_API int nfb_stream_wait_event(void* stream, void* e) {
 
 // ---- CUDA graphs: capture the launch-bound steady-state step once, replay it ----
 NFB_API int nfb_graph_begin_capture() {
+  ++g_capture_epoch;
   NFB_CUDA(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeRelaxed));
   return 0;
 }
 NFB_API int nfb_graph_end_capture(void** out_exec) {
+  ++g_capture_epoch;
   cudaGraph_t g;
   NFB_CUDA(cudaStreamEndCapture(g_stream, &g));
   cudaGraphExec_t ex;

@@ -28,6 +28,7 @@ from . import _lib
 from . import array as A
 from ._lib import B200Error, call
 from .array import B200Array, bfloat16, dtype_code
+from . import kernels as K
 from .plugin import Backend, register_backend
 
 
@@ -420,6 +421,8 @@ class B200Backend(Backend):
              mean.ptr if mean is not None else None, rstd.ptr, dres.ptr if dres is not None else None, dx.ptr,
              dw.ptr if dw is not None else None, db.ptr if db is not None else None, 1 if accumulate else 0, rows, cols,
              float(clip or 0.0), twin.ptr if twin is not None else None)
+        if dw is not None or db is not None:
+            K.mark_side_stream_dirty()   # with an auxiliary stream set, the parameter reduction ran there
         if clip:
             dx.clipped = True
         dx.twin = twin

@@ -189,9 +189,22 @@ _held = []
 
 
 def set_wgrad_overlap(on: bool):
-    global _WGRAD_OVERLAP
+    """Weight / bias / norm-parameter gradients (everything only the optimizer consumes) on a side stream."""
+    global _WGRAD_OVERLAP, _side
     join_side_stream()
     _WGRAD_OVERLAP = bool(on)
+    if _WGRAD_OVERLAP and _side is None:
+        from .runtime import Stream
+        _side = Stream()
+    # the C side moves the norm-backward parameter reduction to this stream (csrc/norm.cu)
+    call("nfb_set_aux_stream", _side.handle if _WGRAD_OVERLAP else None)
+
+
+def mark_side_stream_dirty():
+    """The library issued optimizer-only work on the auxiliary stream: the next join must wait for it."""
+    global _side_dirty
+    if _WGRAD_OVERLAP:
+        _side_dirty = True
 
 
 def join_side_stream():

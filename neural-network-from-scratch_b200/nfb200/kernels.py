@@ -218,7 +218,9 @@ def join_side_stream():
         _side_dirty = False
 
 
-def _wgrad_on_side_stream(fn, *keep):
+def run_on_side_stream(fn, *keep):
+    """Issue `fn`'s kernels on the side stream, ordered after everything enqueued on the compute stream so far; `keep`
+    is held until the next join so the stream-ordered allocator cannot recycle those buffers."""
     global _side, _side_dirty
     from .runtime import Event, Stream, current_stream_handle
     if _side is None:
@@ -268,10 +270,10 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             def wg_and_bias(wg=wg):
                 wg()
                 _colsum(dz, db_out)
-            _wgrad_on_side_stream(wg_and_bias, dz, x2, dW_out, db_out)
+            run_on_side_stream(wg_and_bias, dz, x2, dW_out, db_out)
             db = db_out
         elif side:
-            _wgrad_on_side_stream(wg, dz, x2, dW_out)
+            run_on_side_stream(wg, dz, x2, dW_out)
         else:
             wg()
         if has_bias and db is None:

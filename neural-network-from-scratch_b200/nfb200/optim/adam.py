@@ -55,6 +55,7 @@ class _AdamBase(Optimizer):
         self.grad_scale = None  # optional device scalar multiplied into every gradient (global-norm clipping)
         self.capturable = False  # True: keep the step counter on the device (CUDA-graph capture of the training step)
         self._step_dev = None
+        self._sib = False        # step-in-backward mode (enable_step_in_backward)
         self.state: Dict[str, dict] = {}
         self.m, self.v = {}, {}
         dev_params = [p for p in self.parameters.values() if isinstance(p.data, B200Array)]
@@ -75,6 +76,112 @@ class _AdamBase(Optimizer):
             self.state[name] = {"step": 0, "exp_avg": ea, "exp_avg_sq": es}
             self.m[name], self.v[name] = ea, es
 
+    # ------------------------------------------------------------------ optimizer fused into backward
+    def enable_step_in_backward(self, min_run_elems: int = 1 << 21):
+        """Update every parameter as soon as its gradient is FINAL, from inside backward(): the autograd engine reports
+        when the last consumer of a parameter has run its backward (the data-parallel bucket machinery,
+        core/tensor.py), and contiguous runs of finished parameters get their fused Adam/AdamW launch on the side
+        stream (kernels.set_wgrad_overlap) right behind their weight-gradient GEMMs.  The HBM-bound optimizer pass
+        (30 B/param) then overlaps the tensor-core-bound backward of the earlier layers instead of trailing the step.
+        Same arithmetic and the same per-parameter update as step(); only valid when nothing needs ALL gradients
+        before the first update (global-norm clipping, gradient accumulation, DistributedDataParallel -- which has its
+        own bucket-pipelined step_optimizer).  step() must still be called after backward(): it updates whatever
+        is left (unused / host parameters) and closes the step."""
+        if self.arena is None:
+            return
+        for p in self.arena.params:
+            if "_ddp" in p.__dict__ and p._ddp is not self:
+                raise RuntimeError("enable_step_in_backward: parameters are wrapped by DistributedDataParallel (use ddp.step_optimizer)")
+        self._sib = True
+        self._sib_min = int(min_run_elems)
+        self._sib_names = {}
+        for name, p in self.parameters.items():
+            self._sib_names.setdefault(id(p), name)
+        for p in self.arena.params:
+            p._ddp = self
+        self._sib_reset()
+
+    def _sib_reset(self):
+        self._sib_begun = False
+        self._sib_ready = set()
+        self._sib_done = set()
+        for p in self.arena.params:
+            p._ddp_uses = 0
+
+    def _note_use(self, p):      # autograd: a graph node consumes parameter p (forward)
+        p._ddp_uses = getattr(p, "_ddp_uses", 0) + 1
+
+    def _note_grad_done(self, p):   # autograd: a consumer node of p has run its backward
+        if not self._sib:
+            return
+        p._ddp_uses -= 1
+        if p._ddp_uses == 0 and p._grad is not None and self.grad_scale is None:
+            self._sib_ready.add(id(p))
+            self._sib_flush(final=False)
+
+    def _sib_begin(self):
+        if self._sib_begun:
+            return
+        self._sib_begun = True
+        self.step_count += 1
+        self._update_learning_rate()
+        if self.capturable:
+            if self._step_dev is None:
+                self._step_dev = B200Array.full((1,), self.step_count - 1, np.int32)
+            call("nfb_add_i32", self._step_dev.ptr, 1)
+
+    def _sib_flush(self, final: bool):
+        """Launch the fused kernel for maximal contiguous runs of ready, not yet updated arena parameters."""
+        a = self.arena
+        from .arena import ALIGN
+
+        def padded(q):
+            return (q.size + ALIGN - 1) // ALIGN * ALIGN
+        runs, cur, prev_end = [], [], None
+        for p in a.params:
+            ok = id(p) in self._sib_ready and id(p) not in self._sib_done
+            o = a.offsets[id(p)]
+            if ok and cur and prev_end == o:
+                cur.append(p)
+            else:
+                if cur:
+                    runs.append(cur)
+                cur = [p] if ok else []
+            prev_end = o + padded(p)
+        if cur:
+            runs.append(cur)
+        launches = [rn for rn in runs if final or sum(padded(q) for q in rn) >= self._sib_min]
+        if not launches:
+            return
+        from .. import kernels as K
+        mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
+        msz = self.moment_dtype.itemsize
+        self._sib_begin()
+        for rn in launches:
+            steps = set()
+            for p in rn:
+                st = self.state[self._sib_names[id(p)]]
+                st["step"] += 1
+                steps.add(st["step"])
+                self._sib_done.add(id(p))
+                p._version += 1
+            if len(steps) != 1:
+                raise RuntimeError("enable_step_in_backward: parameters of one arena run have different step counts")
+            step = steps.pop()
+            lo = a.offsets[id(rn[0])]
+            hi = a.offsets[id(rn[-1])] + (rn[-1].size + ALIGN - 1) // ALIGN * ALIGN
+
+            def launch(lo=lo, hi=hi, step=step):
+                call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + lo * 4, a.flat_g.ptr + lo * 4,
+                     a.moments[0].ptr + lo * msz, a.moments[1].ptr + lo * msz,
+                     (a.flat_bf16.ptr + lo * 2) if a.flat_bf16 is not None else None, hi - lo, float(self.lr), float(self.beta1),
+                     float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
+                     None, self._step_dev.ptr if self._step_dev is not None else None)
+            if final or not K._WGRAD_OVERLAP:
+                launch()
+            else:
+                K.run_on_side_stream(launch)
+
     # ------------------------------------------------------------------ step
     def _update_learning_rate(self):
         pass
@@ -84,6 +191,23 @@ class _AdamBase(Optimizer):
         (lo, hi, event) slices of the gradient arena in the order their all-reduces were launched; the fused kernel
         then runs slice by slice, each fenced only by ITS bucket's event, so the update of early buckets overlaps the
         all-reduce of the late ones."""
+        if self._sib and self.arena is not None and self.grad_scale is None:
+            # step-in-backward: most (usually all) arena parameters were updated from inside backward()
+            from .. import kernels as K
+            K.join_side_stream()
+            for p in self.arena.params:
+                if p._grad is not None and id(p) not in self._sib_done:
+                    self._sib_ready.add(id(p))
+            self._sib_begin()
+            self._sib_flush(final=True)
+            done = set(self._sib_done)
+            self._sib_reset()
+            for name, p in self.parameters.items():
+                if id(p) in done or p.grad is None:
+                    continue
+                done.add(id(p))
+                self._host_step(name, p)
+            return
         self.step_count += 1
         self._update_learning_rate()
         done = set()
@@ -176,6 +300,8 @@ class _AdamBase(Optimizer):
     def zero_grad(self) -> None:
         if self.arena is not None:
             self.arena.zero_grad()
+            if self._sib:
+                self._sib_reset()
         for p in self.parameters.values():
             if self.arena is None or id(p) not in self.arena.offsets:
                 p.zero_grad()

@@ -40,7 +40,7 @@ def oracle_run():
     return _oracle(10, 5e-4, 0.1)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+wgrad_overlap"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+wgrad_overlap", "bf16+wgrad_overlap+step_in_backward", "fp32+step_in_backward"])
 def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
     """bf16+wgrad_overlap: the weight-gradient GEMMs run on a side stream (kernels.set_wgrad_overlap), as bench.py does."""
     from nfb200 import kernels as K
@@ -49,7 +49,8 @@ def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
     from nfb200.optim import AdamW
     want_losses, want_grads = oracle_run
     set_default_device("cuda")
-    overlap = precision.endswith("+wgrad_overlap")
+    overlap = "+wgrad_overlap" in precision
+    sib = "+step_in_backward" in precision   # AdamW launches from inside backward (optimizer.enable_step_in_backward)
     precision = precision.split("+")[0]
     K.set_precision(precision)
     K.set_wgrad_overlap(overlap)
@@ -57,6 +58,8 @@ def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
         np.random.seed(0)
         model = GPT2(CFG)
         opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float64" if precision == "fp32" else "float32")
+        if sib:
+            opt.enable_step_in_backward(min_run_elems=1 << 14)
         losses = []
         for i, (ids, labels) in enumerate(_batches(10)):
             opt.zero_grad()
@@ -89,7 +92,7 @@ def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
         set_default_device("cpu")
 
 
-@pytest.mark.parametrize("overlap", [False, True], ids=["one_stream", "wgrad_side_stream"])
+@pytest.mark.parametrize("overlap", [False, True, "sib"], ids=["one_stream", "wgrad_side_stream", "side_stream+step_in_backward"])
 def test_cuda_graph_replay_equals_eager(be, overlap):
     """overlap=True: the captured graph has a fork/join branch for the weight-gradient GEMMs."""
     from nfb200 import kernels as K
@@ -100,7 +103,7 @@ def test_cuda_graph_replay_equals_eager(be, overlap):
     from nfb200.training import GraphedStep
     set_default_device("cuda")
     K.set_precision("bf16")
-    K.set_wgrad_overlap(overlap)
+    K.set_wgrad_overlap(bool(overlap))
     try:
         batches = _batches(6, seed=5)
         results = []
@@ -108,6 +111,8 @@ def test_cuda_graph_replay_equals_eager(be, overlap):
             np.random.seed(0)
             model = GPT2(CFG)
             opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float32")
+            if overlap == "sib":
+                opt.enable_step_in_backward(min_run_elems=1 << 14)
             ids_t = Tensor(B200Array.empty((2, 128), np.int64))
             lab_t = Tensor(B200Array.empty((2, 128), np.int64))
 

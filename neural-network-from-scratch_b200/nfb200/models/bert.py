@@ -52,10 +52,19 @@ class BERTEmbeddings(Module):
     def forward(self, input_ids=None, token_type_ids=None, position_ids=None, inputs_embeds=None) -> Tensor:
         shape = input_ids.shape if input_ids is not None else inputs_embeds.shape[:-1]
         dev = self.word_embeddings.weight.device
+        # default position / segment ids are constants of the input shape: built once per (shape, device) and kept on the
+        # device, so a training step makes no host->device copy (and can be captured into a CUDA graph)
+        cache = self.__dict__.setdefault("_const_ids", {})
         if position_ids is None:
-            position_ids = Tensor(np.arange(shape[1], dtype=np.int64).reshape(1, -1), device=dev)
+            key = ("pos", int(shape[1]), str(dev))
+            if key not in cache:
+                cache[key] = Tensor(np.arange(shape[1], dtype=np.int64).reshape(1, -1), device=dev)
+            position_ids = cache[key]
         if token_type_ids is None:
-            token_type_ids = Tensor(np.zeros(shape, dtype=np.int64), device=dev)
+            key = ("seg", tuple(int(v) for v in shape), str(dev))
+            if key not in cache:
+                cache[key] = Tensor(np.zeros(shape, dtype=np.int64), device=dev)
+            token_type_ids = cache[key]
         if inputs_embeds is None:
             inputs_embeds = self.word_embeddings(input_ids)
         emb = inputs_embeds + self.token_type_embeddings(token_type_ids)

@@ -208,9 +208,45 @@ def run_b200(args):
     final_loss = float(loss.item())
     # ---- timed region 1b: the same steps with a CUDA-event pair around every tcgen05 GEMM launch (roofline numerator);
     # kept apart from region 1 so the ~200 extra event records per step do not perturb `value`
-    gemm_prof, ms_prof, prof_steps = None, None, max(1, min(args.steps, 5))
-    if args.profile_gemm and rank == 0:
-        K.GEMM_PROFILE = []
+    gemm_prof, ms_prof, prof_steps, prof_mode = None, None, max(1, min(args.steps, 5)), None
+    if args.profile_gemm and args.graph:
+        # the event pairs are CAPTURED with the step (event-record nodes of a second graph), so the per-launch durations
+        # are those of the replayed graph -- same kernels, same neighbours and cache state as in timed region 1 --
+        # rather than of an eager step whose launch gaps leave the GPU idle between kernels.  Every rank captures /
+        # replays (the graph contains the collectives); rank 0 reads the events of the last replay.
+        try:
+            from nfb200.training import GraphedStep
+            # single-stream capture for this pass: with the weight-gradient GEMMs on the side stream two kernels share
+            # the SMs and an event pair no longer brackets ONE kernel's own duration
+            K.set_wgrad_overlap(False)
+            step(ids_d, labels_d)   # warm the allocator in this mode
+            K.GEMM_PROFILE = []
+            gprof = GraphedStep(lambda: step(ids_d, labels_d), warmup=1, optimizers=[opt])
+            n_all = len(K.GEMM_PROFILE)
+            gemm_prof = K.GEMM_PROFILE[n_all // 2:]   # GraphedStep ran the step twice (eager warm-up, then the capture)
+            K.GEMM_PROFILE = None
+            K.set_wgrad_overlap(args.wgrad_overlap)
+            p0, p1 = R.Event(), R.Event()
+            gprof()
+            barrier()
+            p0.record()
+            for _ in range(prof_steps):
+                gprof()
+            p1.record()
+            p1.synchronize()
+            ms_prof = p0.elapsed_ms(p1) / prof_steps   # one step: the captured events hold the LAST replay
+            _ = sum(a.elapsed_ms(b) for a, b, _, _ in gemm_prof)   # raises if captured events cannot be read
+            prof_mode = "graph"
+            if rank != 0:
+                gemm_prof = None
+        except Exception as exc:  # noqa: BLE001 -- fall back to the eager measurement below
+            sys.stderr.write(f"bench.py: captured-event GEMM profile unavailable ({exc}); using the eager one\n")
+            K.GEMM_PROFILE = None
+            K.set_wgrad_overlap(args.wgrad_overlap)
+            gemm_prof = None
+    if args.profile_gemm and prof_mode is None:
+        if rank == 0:
+            K.GEMM_PROFILE = []
         p0, p1 = R.Event(), R.Event()
         p0.record()
         for _ in range(prof_steps):
@@ -220,9 +256,7 @@ def run_b200(args):
         ms_prof = p0.elapsed_ms(p1)
         gemm_prof = K.GEMM_PROFILE
         K.GEMM_PROFILE = None
-    elif args.profile_gemm:
-        for _ in range(prof_steps):
-            step(ids_d, labels_d)
+        prof_mode = "eager"
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -280,6 +314,8 @@ def run_b200(args):
                                   "(profiles/r01_ncu_gemm_full.txt): LM-head GEMMs 0.44 / 0.49 / 1.56 GB, layer GEMMs 8-41 MB; launch-weighted mean over the 147 launches of a step",
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "launches_timed": n, "avg_launch_ms": tot_ms / n, "avg_launch_gflop": tot_flop / n / 1e9, "share_of_step": tot_ms / ms_prof,
+                "timing": ("CUDA event pairs (external event nodes) captured into a single-stream graph of the same step around every GEMM launch; durations of the last replay" if prof_mode == "graph"
+                           else "CUDA event pairs around every GEMM launch of eager (un-graphed) steps"),
                 "algorithmic_flops": "2*M*N*K per launch (fwd, dgrad and wgrad GEMMs of every Linear + logits), summed over the launches of the timed steps"}
     line = {"metric": "training tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",

@@ -57,6 +57,7 @@ int nfb_event_create(void** out);
 int nfb_event_create_notiming(void** out);
 int nfb_event_destroy(void* e);
 int nfb_event_record(void* e, void* stream);
+int nfb_event_record_external(void* event, void* stream);   /* like nfb_event_record; inside a stream capture it becomes an external event node whose time of the last replay is readable */
 int nfb_event_sync(void* e);
 int nfb_event_elapsed_ms(void* a, void* b, float* ms);
 int nfb_stream_wait_event(void* stream, void* e);

@@ -20,7 +20,10 @@ int nfb_fail(const char* file, int line, const char* fmt, ...);
 #define NFB_CUDA(expr)                                                              \
   do {                                                                              \
     cudaError_t _e = (expr);                                                        \
-    if (_e != cudaSuccess) return NFB_FAIL("%s -> %s", #expr, cudaGetErrorString(_e)); \
+    if (_e != cudaSuccess) {                                                        \
+      (void)cudaGetLastError(); /* reported here: do not let it surface at the next launch check */ \
+      return NFB_FAIL("%s -> %s", #expr, cudaGetErrorString(_e));                   \
+    }                                                                               \
   } while (0)
 // after a kernel launch
 #define NFB_LAUNCH_CHECK()                                                          \

@@ -253,6 +253,16 @@ NFB_API int nfb_event_record(void* e, void* stream) {
   NFB_CUDA(cudaEventRecord((cudaEvent_t)e, stream ? (cudaStream_t)stream : g_stream));
   return 0;
 }
+// record as an EXTERNAL event node when the stream is being captured: such an event keeps its timestamp of the last
+// graph replay and can be read with nfb_event_elapsed_ms (a plainly captured event cannot)
+NFB_API int nfb_event_record_external(void* e, void* stream) {
+  cudaStream_t s = stream ? (cudaStream_t)stream : g_stream;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  NFB_CUDA(cudaStreamIsCapturing(s, &st));
+  if (st == cudaStreamCaptureStatusActive) NFB_CUDA(cudaEventRecordWithFlags((cudaEvent_t)e, s, cudaEventRecordExternal));
+  else NFB_CUDA(cudaEventRecord((cudaEvent_t)e, s));
+  return 0;
+}
 NFB_API int nfb_event_sync(void* e) {
   NFB_CUDA(cudaEventSynchronize((cudaEvent_t)e));
   return 0;

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "nfb_event_create_notiming": [C.POINTER(vp)],
     "nfb_event_destroy": [vp],
     "nfb_event_record": [vp, vp],
+    "nfb_event_record_external": [vp, vp],
     "nfb_event_sync": [vp],
     "nfb_event_elapsed_ms": [vp, vp, C.POINTER(C.c_float)],
     "nfb_stream_wait_event": [vp, vp],

@@ -99,12 +99,12 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
     prof = GEMM_PROFILE
     if prof is not None:
         from .runtime import Event
-        e0 = Event().record()
+        e0 = Event().record(external=True)
     call("nfb_gemm_bf16", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, a2.ptr, lda, b2.ptr, ldb, out.ptr,
          dtype_code(out.dtype), ldc_v, bias_ptr, res_ptr, ldr, aux_arr.ptr if aux_arr is not None else None, N, epi,
          1 if accumulate else 0, int(split_k), float(clip))
     if prof is not None:
-        prof.append((e0, Event().record(), 2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b))))
+        prof.append((e0, Event().record(external=True), 2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b))))
     return (out, aux_arr) if aux else out
 
 

@@ -14,8 +14,9 @@ class Event:
         call("nfb_event_create" if timing else "nfb_event_create_notiming", C.byref(h))
         self.handle = h.value
 
-    def record(self, stream=None):
-        call("nfb_event_record", self.handle, stream.handle if isinstance(stream, Stream) else stream)
+    def record(self, stream=None, external=False):
+        """external=True: when the stream is being captured, record as an external event node (readable after replays)."""
+        call("nfb_event_record_external" if external else "nfb_event_record", self.handle, stream.handle if isinstance(stream, Stream) else stream)
         return self
 
     def synchronize(self):

@@ -167,7 +167,8 @@ constexpr int SM_K = 32768;                      // KV_STAGES x 16 KB ([128 keys
 constexpr int SM_V = SM_K + KV_STAGES * 16384;   // KV_STAGES x 16 KB ([128 keys][64]: MN-major B operand, two 64-key chunks)
 constexpr int SM_P = SM_V + KV_STAGES * 16384;   // 2 groups x 32 KB ([128 rows][128 keys] bf16 as two 64-key K-major panels)
 constexpr int SM_BAR = SM_P + 65536;             // barriers + TMEM slot
-constexpr int SM_TOTAL = SM_BAR + 256 + 1024;    // + alignment slack
+constexpr int SM_MASK = SM_BAR + 256;            // KV_STAGES x 128 fp32: additive key mask (log2 domain) of the staged block; -inf beyond Skv
+constexpr int SM_TOTAL = SM_MASK + KV_STAGES * 512 + 1024;    // + alignment slack
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -226,15 +227,29 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (threadIdx.x == 0) tl(p, 0);
 
   if (warp == 8) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (lane 0) + key-mask staging (all lanes) =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, nB > 0 ? 32768u : 16384u);
       tma_load_4d(smem + SM_Q, &tmQ, q_full, 0, h, q0A, b);
       if (nB > 0) tma_load_4d(smem + SM_Q + 16384, &tmQ, q_full, 0, h, q0B, b);
-      for (int i = 0; i < nMax; ++i) {
-        const int st = i % KV_STAGES;
-        mbar_wait(&kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 32768u);
+    }
+    const float* kmask_p = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
+    float* smask = reinterpret_cast<float*>(smem + SM_MASK);
+    for (int i = 0; i < nMax; ++i) {
+      const int st = i % KV_STAGES;
+      mbar_wait(&kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
+      const int j0 = i * TILE_K;
+      if (kmask_p || j0 + TILE_K > p.Skv) {
+        // additive mask of this key block in the log2 domain; keys beyond Skv get -inf (their exponential is exactly 0)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kj = j0 + lane * 4 + e;
+          smask[st * 128 + lane * 4 + e] = kj < p.Skv ? (kmask_p ? __ldg(kmask_p + kj) * LOG2E : 0.f) : -INFINITY;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&kv_full[st], 32768u);   // release: the mask words above are visible to whoever acquires kv_full
         tma_load_4d(smem + SM_K + st * 16384, &tmK, &kv_full[st], 0, h, i * TILE_K, b);
         tma_load_4d(smem + SM_V + st * 16384, &tmV, &kv_full[st], 0, h, i * TILE_K, b);
       }
@@ -326,6 +341,25 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * sl2;
 #pragma unroll
         for (int j = 0; j < 128; ++j) t[j] = __uint_as_float(sr[j]) * sl2;
+      } else if (!diag) {
+        // key mask and / or ragged tail, no causal diagonal: one FFMA per element with the staged log2-domain mask
+        // (-inf beyond Skv); 16-byte broadcast reads of the mask row
+        mbar_wait(&kv_full[i % KV_STAGES], (i / KV_STAGES) & 1);   // acquire the producer's mask words (long complete: S(i) needed this stage)
+        const float4* sm4 = reinterpret_cast<const float4*>(smem + SM_MASK + (i % KV_STAGES) * 512);
+        float mx[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 32; ++j4) {
+          const float4 mk = sm4[j4];
+          t[4 * j4 + 0] = fmaf(__uint_as_float(sr[4 * j4 + 0]), sl2, mk.x);
+          t[4 * j4 + 1] = fmaf(__uint_as_float(sr[4 * j4 + 1]), sl2, mk.y);
+          t[4 * j4 + 2] = fmaf(__uint_as_float(sr[4 * j4 + 2]), sl2, mk.z);
+          t[4 * j4 + 3] = fmaf(__uint_as_float(sr[4 * j4 + 3]), sl2, mk.w);
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) mx[a] = t[a];
+#pragma unroll
+        for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], t[j]);
+        bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       } else if (!tail && !kmask) {
         // causal diagonal block: keys j0 + j > qi are REPLACED by -1e4 (two instructions per element)
         const int lim = qi - j0;
@@ -468,7 +502,8 @@ constexpr int SB_P = 98304;             // P     32 KB
 constexpr int SB_DS = 131072;           // dS    32 KB
 constexpr int SB_DQ = 163840;           // dQ staging, fp32 [2 column halves][128 rows][128 B] = 32 KB
 constexpr int SB_BAR = 196608;
-constexpr int SB_TOTAL = SB_BAR + 256 + 1024;
+constexpr int SB_MASK = SB_BAR + 256;   // 128 fp32: additive key mask of this CTA's key block (log2 domain), -inf beyond Skv
+constexpr int SB_TOTAL = SB_MASK + 512 + 1024;
 
 struct AttnBwdTcParams {
   const float* lse;     // (B, H, S) natural log
@@ -626,6 +661,16 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
     const int kb0 = k0 + half * 64;                       // first key of this thread's half
     const bool tail = kb0 + 64 > p.Skv;
+    // key mask / ragged tail: stage this CTA's 128 mask values once (log2 domain, -inf beyond Skv)
+    const bool use_smask = (kmask != nullptr) || (k0 + TILE_K > p.Skv);
+    const float* smask_h = reinterpret_cast<const float*>(smem + SB_MASK) + half * 64;
+    if (use_smask) {
+      if (threadIdx.x < 128) {
+        const int kj = k0 + (int)threadIdx.x;
+        reinterpret_cast<float*>(smem + SB_MASK)[threadIdx.x] = kj < p.Skv ? (kmask ? __ldg(kmask + kj) * LOG2E : 0.f) : -INFINITY;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 
     auto drain_dq = [&](int it_d) {
       // dQ partial of iteration it_d: TMEM -> registers -> shared memory (fp32, one 32-column SWIZZLE_128B box per half) -> TMA reduce-add
@@ -712,6 +757,18 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      } else if (!diag) {
+        // key mask and / or ragged tail, no causal diagonal: staged log2-domain mask (-inf beyond Skv), broadcast 16-byte reads
+        const float4* sm4 = reinterpret_cast<const float4*>(smask_h);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 mk = sm4[j4];
+          const float p0 = ex2(fmaf(__uint_as_float(sr[4 * j4 + 0]), sl2, mk.x) - lse2), p1 = ex2(fmaf(__uint_as_float(sr[4 * j4 + 1]), sl2, mk.y) - lse2);
+          const float p2 = ex2(fmaf(__uint_as_float(sr[4 * j4 + 2]), sl2, mk.z) - lse2), p3 = ex2(fmaf(__uint_as_float(sr[4 * j4 + 3]), sl2, mk.w) - lse2);
+          __nv_bfloat162 b01 = __floats2bfloat162_rn(p0, p1), b23 = __floats2bfloat162_rn(p2, p3);
+          pk[2 * j4] = *reinterpret_cast<uint32_t*>(&b01);
+          pk[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&b23);
         }
       } else if (!tail && !kmask) {
         // causal diagonal: keys kb0 + j > qi are REPLACED by -1e4, whose exponential underflows to exactly 0

@@ -80,12 +80,19 @@ __global__ void k_prep_keys(const TI* __restrict__ idx, int32_t* __restrict__ ke
 }
 
 // grid = (n candidate segment starts, ceil(d/128) column groups); 32 threads, one float4 column each.
+#define LONG_SEG 16
 template <typename TG>
 __global__ void k_scatter_add_sorted(const int32_t* __restrict__ keys, const int32_t* __restrict__ pos, const TG* __restrict__ grad,
-                                     float* __restrict__ dW, int64_t n, int d, int accumulate) {
+                                     float* __restrict__ dW, int64_t n, int d, int accumulate, int32_t* __restrict__ long_list) {
   int64_t i = blockIdx.x;
   int32_t key = keys[i];
   if (i > 0 && keys[i - 1] == key) return;  // not the first element of its segment
+  // long segments (an index repeated more than LONG_SEG times: BERT's position / segment-id tables) go to the
+  // cooperative kernel below -- this one-warp loop chases pos[j] -> grad row serially, ~1 us per row
+  if (long_list && i + LONG_SEG < n && keys[i + LONG_SEG] == key) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) long_list[1 + atomicAdd(long_list, 1)] = (int32_t)i;
+    return;
+  }
   int c = (blockIdx.y * 32 + threadIdx.x) * 4;
   if (c >= d) return;
   bool vec = (d % 4 == 0);
@@ -114,6 +121,76 @@ __global__ void k_scatter_add_sorted(const int32_t* __restrict__ keys, const int
   }
 }
 
+// Long segments, one block (128 threads) per (segment, 128-column group).  Still the reference's order -- row j of the
+// segment is added after row j-1, one fp32 add at a time (nn/embedding.py:54-55) -- but the memory side is parallel:
+// 64 gradient rows are fetched at once (16 independent 16-byte loads per thread) into shared memory, then every
+// thread walks ITS scalar column down the 64 staged rows.  long_list[0] = number of segments, long_list[1..] = starts.
+template <typename TG>
+__global__ void __launch_bounds__(128)
+k_scatter_add_long(const int32_t* __restrict__ keys, const int32_t* __restrict__ pos, const TG* __restrict__ grad, float* __restrict__ dW,
+                   int64_t n, int d, int accumulate, const int32_t* __restrict__ long_list) {
+  __shared__ float sbuf[64][128 + 4];
+  __shared__ int32_t spos[64];
+  __shared__ int64_t s_len;
+  if ((int)blockIdx.x >= long_list[0]) return;
+  const int64_t i = long_list[1 + blockIdx.x];
+  const int32_t key = keys[i];
+  const int t = threadIdx.x, c4 = t & 31, rg = t >> 5;
+  const int colbase = blockIdx.y * 128;
+  if (t == 0) {   // segment end: gallop, then bisect (keys are sorted)
+    int64_t lo = i, step = 1;
+    while (lo + step < n && keys[lo + step] == key) { lo += step; step <<= 1; }
+    int64_t hi = lo + step < n ? lo + step : n;   // keys[lo] == key, keys[hi] != key (or hi == n)
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] == key) lo = mid; else hi = mid;
+    }
+    s_len = hi - i;
+  }
+  __syncthreads();
+  const int64_t L = s_len;
+  const bool vec = (d % 4 == 0);
+  const int ncols = min(128, d - colbase);   // columns this block owns
+  float acc = 0.f;
+  for (int64_t base = 0; base < L; base += 64) {
+    const int rows = (int)min((int64_t)64, L - base);
+    if (t < rows) spos[t] = pos[i + base + t];
+    __syncthreads();
+    f4 v[16];
+    const int c = colbase + c4 * 4;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = rg * 16 + r;
+      v[r] = {0.f, 0.f, 0.f, 0.f};
+      if (row < rows && c < d) {
+        const TG* g = grad + (int64_t)spos[row] * d + c;
+        if (vec) v[r] = ld4<TG>(g);
+        else {
+          v[r].x = ld_f<TG>(g, 0);
+          if (c + 1 < d) v[r].y = ld_f<TG>(g, 1);
+          if (c + 2 < d) v[r].z = ld_f<TG>(g, 2);
+          if (c + 3 < d) v[r].w = ld_f<TG>(g, 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = rg * 16 + r;
+      sbuf[row][c4 * 4 + 0] = v[r].x; sbuf[row][c4 * 4 + 1] = v[r].y; sbuf[row][c4 * 4 + 2] = v[r].z; sbuf[row][c4 * 4 + 3] = v[r].w;
+    }
+    __syncthreads();
+    if (t < ncols) {
+#pragma unroll 8
+      for (int row = 0; row < rows; ++row) acc += sbuf[row][t];   // strictly in segment order
+    }
+    __syncthreads();
+  }
+  if (t < ncols) {
+    float* o = dW + (int64_t)key * d + colbase + t;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
 // dW[idx[i], :] (+)= sum over i in ascending order of grad[i, :].  Rows of dW that no index touches
 // are left alone: the caller zero-fills dW first when accumulate == 0.
 NFB_API int nfb_scatter_add_rows(int idx_dtype, int gdt, const void* grad, const void* idx, float* dW, int64_t n, int d, int64_t V, int accumulate) {
@@ -138,9 +215,22 @@ NFB_API int nfb_scatter_add_rows(int idx_dtype, int gdt, const void* grad, const
   nfb_count_launch();
   if (e != cudaSuccess) { nfb_free(tmp); nfb_free(buf); return NFB_FAIL("radix sort -> %s", cudaGetErrorString(e)); }
   dim3 grid((unsigned)n, (unsigned)nfb_cdiv(d, 128));
-  if (gdt == NFB_F32) k_scatter_add_sorted<float><<<grid, 32, 0, s>>>(keys_out, pos_out, (const float*)grad, dW, n, d, accumulate);
-  else if (gdt == NFB_BF16) k_scatter_add_sorted<__nv_bfloat16><<<grid, 32, 0, s>>>(keys_out, pos_out, (const __nv_bfloat16*)grad, dW, n, d, accumulate);
-  else { nfb_free(tmp); nfb_free(buf); return NFB_FAIL("nfb_scatter_add_rows: unsupported grad dtype %d", gdt); }
+  // segments longer than LONG_SEG are collected into a list and summed by the cooperative kernel
+  const int64_t max_long = n / (LONG_SEG + 1) + 1;
+  int32_t* long_list = nullptr;
+  if (nfb_malloc(sizeof(int32_t) * (size_t)(max_long + 1), (void**)&long_list)) { nfb_free(tmp); nfb_free(buf); return -1; }
+  NFB_CUDA(cudaMemsetAsync(long_list, 0, sizeof(int32_t), s));
+  dim3 grid_long((unsigned)max_long, (unsigned)nfb_cdiv(d, 128));
+  if (gdt == NFB_F32) {
+    k_scatter_add_sorted<float><<<grid, 32, 0, s>>>(keys_out, pos_out, (const float*)grad, dW, n, d, accumulate, long_list);
+    nfb_count_launch();
+    k_scatter_add_long<float><<<grid_long, 128, 0, s>>>(keys_out, pos_out, (const float*)grad, dW, n, d, accumulate, long_list);
+  } else if (gdt == NFB_BF16) {
+    k_scatter_add_sorted<__nv_bfloat16><<<grid, 32, 0, s>>>(keys_out, pos_out, (const __nv_bfloat16*)grad, dW, n, d, accumulate, long_list);
+    nfb_count_launch();
+    k_scatter_add_long<__nv_bfloat16><<<grid_long, 128, 0, s>>>(keys_out, pos_out, (const __nv_bfloat16*)grad, dW, n, d, accumulate, long_list);
+  } else { nfb_free(long_list); nfb_free(tmp); nfb_free(buf); return NFB_FAIL("nfb_scatter_add_rows: unsupported grad dtype %d", gdt); }
+  nfb_free(long_list);
   nfb_free(tmp);
   nfb_free(buf);
   NFB_LAUNCH_CHECK();

@@ -22,7 +22,7 @@ from .communication import ReduceOp
 
 
 class _Bucket:
-    __slots__ = ("lo", "hi", "params", "pending", "launched", "event", "seq")
+    __slots__ = ("lo", "hi", "params", "pending", "launched", "event", "seq", "pieces", "piece_events")
 
     def __init__(self, lo, hi, params):
         self.lo, self.hi, self.params = lo, hi, params
@@ -30,6 +30,8 @@ class _Bucket:
         self.launched = False
         self.event = None
         self.seq = 0   # launch order of the all-reduce within the step
+        self.pieces = [(lo, hi)]     # a bucket holding ONE oversized parameter is all-reduced in bucket-sized pieces
+        self.piece_events = []
 
 
 class DistributedDataParallel(Module):
@@ -75,6 +77,9 @@ class DistributedDataParallel(Module):
             cur.append(p)
         if cur:
             self.buckets.append(_Bucket(min(a.offsets[id(q)] for q in cur), cur_hi, cur))
+        for b in self.buckets:   # e.g. the 154 MB tied embedding gradient: pieces let the optimizer start on piece i while i+1 is on the wire
+            if b.hi - b.lo > 2 * cap:
+                b.pieces = [(o, min(o + cap, b.hi)) for o in range(b.lo, b.hi, cap)]
         self._bucket_of = {}
         for b in self.buckets:
             for p in b.params:
@@ -127,11 +132,16 @@ class DistributedDataParallel(Module):
                 p._grad_slot.fill(0.0)
                 p._slot_zero = True
         from .. import kernels as K
-        K.join_side_stream()                            # weight gradients computed on the side stream are part of the bucket
         ready = Event(timing=False).record()            # on the compute stream: gradients of this bucket are final
         g.comm_stream.wait_event(ready)
-        g.allreduce_buffer(self.arena.flat_g, b.hi - b.lo, ReduceOp.AVERAGE, g.comm_stream, offset=b.lo)
-        b.event = Event(timing=False).record(g.comm_stream)
+        side_ev = K.side_stream_event()                 # weight gradients computed on the side stream are part of the bucket:
+        if side_ev is not None:                         # the COMMUNICATION stream waits for them, the compute stream runs on
+            g.comm_stream.wait_event(side_ev)
+        b.piece_events = []
+        for lo, hi in b.pieces:
+            g.allreduce_buffer(self.arena.flat_g, hi - lo, ReduceOp.AVERAGE, g.comm_stream, offset=lo)
+            b.piece_events.append(Event(timing=False).record(g.comm_stream))
+        b.event = b.piece_events[-1]
         b.launched = True
         self._launch_seq = getattr(self, "_launch_seq", 0) + 1
         b.seq = self._launch_seq
@@ -173,7 +183,7 @@ class DistributedDataParallel(Module):
                 p._grad = p._grad_slot
             p._slot_zero = False
         order = sorted(self.buckets, key=lambda b: getattr(b, "seq", 0))
-        optimizer.step(segments=[(b.lo, b.hi, b.event) for b in order])
+        optimizer.step(segments=[(lo, hi, ev) for b in order for (lo, hi), ev in zip(b.pieces, b.piece_events)])
 
     def sync_gradients(self):
         """Reference API (data_parallel.py:271-287): all-reduce(AVERAGE) every gradient after backward."""

@@ -218,6 +218,15 @@ def join_side_stream():
         _side_dirty = False
 
 
+def side_stream_event():
+    """An event recorded on the side stream behind everything issued there so far, or None when nothing is pending.
+    Lets ANOTHER stream (the DDP communication stream) wait for the weight gradients without stalling the compute stream."""
+    if not _side_dirty:
+        return None
+    from .runtime import Event
+    return Event(timing=False).record(_side)
+
+
 def run_on_side_stream(fn, *keep):
     """Issue `fn`'s kernels on the side stream, ordered after everything enqueued on the compute stream so far; `keep`
     is held until the next join so the stream-ordered allocator cannot recycle those buffers."""

@@ -489,9 +489,10 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // straight from TMEM (thread = row, so LSE_i / delta_i are per-thread scalars) and written as bf16 into ONE shared
 // memory layout ([two 64-key panels][128 query rows][128 B], SWIZZLE_128B) that serves both as the K-major operand
 // (M = queries) and, with LBO = 16 KB, as the MN-major operand (M = keys).  dK_j / dV_j accumulate in TMEM over the
-// whole query loop; the dQ_i partial of each (i, j) pair is drained TMEM -> registers -> shared memory and added into
-// an fp32 (B, H, S, 64) accumulation buffer by a TMA reduce-add (cp.reduce.async.bulk.tensor .add), which a small
-// kernel converts to the bf16 dq afterwards.  Masked scores carry P = 0, hence dS = 0 (the reference REPLACES them
+// whole query loop; the dQ_i partial of each (i, j) pair is drained TMEM -> registers -> shared memory (bf16) and added
+// straight into the (zero-initialised, strided) bf16 dq tensor by a TMA reduce-add (cp.reduce.async.bulk.tensor .add):
+// the L2 reduction units turned out to be the limiter of this kernel (~0.75 TB/s of fp32 adds), bf16 partials halve
+// that traffic and remove the fp32 accumulation buffer and its conversion pass.  Masked scores carry P = 0, hence dS = 0 (the reference REPLACES them
 // by -1e4, models/language/gpt2.py:194-200, so no gradient flows through them).
 constexpr int BWD_THREADS = 320;        // warps 0-7 elementwise (two column halves x four lane quarters), warp 8 TMA, warp 9 MMA
 constexpr int SB_K = 0;                 // K_j   16 KB
@@ -500,10 +501,11 @@ constexpr int SB_Q = 32768;             // Q_i   2 stages x 16 KB
 constexpr int SB_DO = 65536;            // dO_i  2 stages x 16 KB
 constexpr int SB_P = 98304;             // P     32 KB
 constexpr int SB_DS = 131072;           // dS    32 KB
-constexpr int SB_DQ = 163840;           // dQ staging, fp32 [2 column halves][128 rows][128 B] = 32 KB
+constexpr int SB_DQ = 163840;           // dQ staging, bf16 [128 rows][128 B] = 16 KB (32 KB reserved)
 constexpr int SB_BAR = 196608;
 constexpr int SB_MASK = SB_BAR + 256;   // 128 fp32: additive key mask of this CTA's key block (log2 domain), -inf beyond Skv
-constexpr int SB_TOTAL = SB_MASK + 512 + 1024;
+constexpr int SB_DELTA = SB_MASK + 512; // 2 stages x 128 fp32: delta_i = rowsum(dO_i o O_i) of the staged query block
+constexpr int SB_TOTAL = SB_DELTA + 1024 + 1024;
 
 struct AttnBwdTcParams {
   const float* lse;     // (B, H, S) natural log
@@ -522,9 +524,9 @@ __device__ __forceinline__ void tlb(const AttnBwdTcParams& p, int slot) {
   if (p.timeline && blockIdx.x == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
 }
 
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 // Issue order of the MMA thread (tensor-core products retire in issue order) and the matching order of the elementwise
@@ -548,7 +550,8 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* ds_full = bars + 8;      // dS in smem (256 arrivals)
   uint64_t* dq_full = bars + 9;      // dQ_i partial in TMEM; dK(it) / dQ(it) have retired -> dS buffer free
   uint64_t* dq_free = bars + 10;     // dQ TMEM columns drained (256 arrivals)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  uint64_t* delta_full = bars + 11;  // 2 stages: delta_i of the staged query block is in shared memory
+  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool causal = (p.mask_mode & 1) != 0;
@@ -565,6 +568,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(dq_full, 1); mbar_init(dq_free, 256);
+    mbar_init(&delta_full[0], 1); mbar_init(&delta_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -580,17 +584,60 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (threadIdx.x == 0) tlb(p, 0);
 
   if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && niter > 0) {
-      mbar_expect_tx(kv_full, 32768u);
-      tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h, k0, b);
-      tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h, k0, b);
+    // ===================== TMA producer (lane 0) + delta (all lanes) =====================
+    // delta_i = sum_d dO[i, d] * O[i, d] of every staged query block (when the caller passed none): lane l owns rows
+    // 4l .. 4l+3 -- the O rows come straight from global memory (one 128-byte line each, 32 loads in flight per lane),
+    // the dO rows from the TMA-staged swizzled tile.  This warp runs a block ahead of the consumers and is otherwise
+    // idle, so the global-load latency never reaches the critical path.
+    if (niter > 0) {
+      if (lane == 0) {
+        mbar_expect_tx(kv_full, 32768u);
+        tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h, k0, b);
+        tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h, k0, b);
+      }
+      float* sdelta = reinterpret_cast<float*>(smem + SB_DELTA);
       for (int it = 0; it < niter; ++it) {
         const int st = it & 1;
+        const int q0 = (i0 + it) * TILE_Q;
         mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[st], 32768u);
-        tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, h, (i0 + it) * TILE_Q, b);
-        tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, h, (i0 + it) * TILE_Q, b);
+        if (lane == 0) {
+          mbar_expect_tx(&q_full[st], 32768u);
+          tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, h, q0, b);
+          tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, h, q0, b);
+        }
+        if (!p.delta) {
+          uint4 ov[4][8];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int qi = q0 + lane * 4 + rr;
+            const uint4* orow = reinterpret_cast<const uint4*>(p.o + b * p.o_sb + h * p.o_sh + (long long)qi * p.o_ss);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ov[rr][c] = qi < p.S ? __ldg(orow + c) : make_uint4(0, 0, 0, 0);
+          }
+          mbar_wait(&q_full[st], (it >> 1) & 1);   // the dO tile has landed
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int row = lane * 4 + rr;
+            const uint32_t dorow = smem_u32(smem + SB_DO) + (uint32_t)st * 16384u + (uint32_t)row * 128u;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint4 dv4;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dv4.x), "=r"(dv4.y), "=r"(dv4.z), "=r"(dv4.w) : "r"(dorow + (uint32_t)((c ^ (row & 7)) * 16)));
+              const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&dv4);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&ov[rr][c]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+                acc0 = fmaf(fa.x, fb.x, acc0);
+                acc1 = fmaf(fa.y, fb.y, acc1);
+              }
+            }
+            sdelta[st * 128 + row] = acc0 + acc1;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&delta_full[st]);
+        }
       }
     }
   } else if (warp == 9) {
@@ -655,7 +702,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // this thread's 64 keys are one 64-key panel of the [panel][row][128 B] operand layout
     const uint32_t sP_row = smem_u32(smem + SB_P) + (uint32_t)half * 16384u + (uint32_t)r * 128u;
     const uint32_t sdS_row = smem_u32(smem + SB_DS) + (uint32_t)half * 16384u + (uint32_t)r * 128u;
-    const uint32_t sdQ_row = smem_u32(smem + SB_DQ) + (uint32_t)half * 16384u + (uint32_t)r * 128u;   // dQ columns [32*half, +32)
+    const uint32_t sdQ_row = smem_u32(smem + SB_DQ) + (uint32_t)r * 128u;   // dQ staging row (bf16, 64 columns)
     const int sw = r & 7;
     const float sl2 = p.scale * LOG2E;
     const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
@@ -683,64 +730,31 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);
+      // bf16 staging box [128 rows][64 columns = 128 B], SWIZZLE_128B: this thread's 32 columns are 16-byte slots 4*half .. +3
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)((c ^ sw) * 16)),
-                     "r"(dq[4 * c]), "r"(dq[4 * c + 1]), "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3]) : "memory");
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(dq[c * 8 + 2 * e]), __uint_as_float(dq[c * 8 + 2 * e + 1]));
+          w[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)(((half * 4 + c) ^ sw) * 16)),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
-        const int q0d = (i0 + it_d) * TILE_Q;
-        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ), 0, q0d, bh);
-        tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ) + 16384u, 32, q0d, bh);
+        tma_reduce_add_4d(&tmdQ, smem_u32(smem + SB_DQ), 0, h, (i0 + it_d) * TILE_Q, b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
-
-    // delta_i = sum_d dO[i, d] * O[i, d] for the query block of iteration `itn` (when the caller passed no delta): the dO
-    // row comes from the TMA-staged (swizzled) tile, the O row straight from global memory (one 128-byte line per
-    // thread).  Called one iteration AHEAD, right after dS of the current block has been handed to the tensor core, so
-    // the global-load latency hides behind dK / dQ / the next S and dP products.
-    auto compute_delta = [&](int itn) -> float {
-      const int qin = (i0 + itn) * TILE_Q + r;
-      const bool validn = qin < p.S;
-      if (p.delta) return validn ? p.delta[(long long)bh * p.S + qin] : 0.f;
-      uint4 ov[8];
-      const __nv_bfloat16* orow = p.o + b * p.o_sb + h * p.o_sh + (long long)qin * p.o_ss;
-      if (validn) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ov[c] = __ldg(reinterpret_cast<const uint4*>(orow) + c);
-      }
-      mbar_wait(&q_full[itn & 1], (itn >> 1) & 1);
-      float d = 0.f;
-      if (validn) {
-        const uint32_t dorow = smem_u32(smem + SB_DO) + (uint32_t)(itn & 1) * 16384u + (uint32_t)r * 128u;
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 dv4;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dv4.x), "=r"(dv4.y), "=r"(dv4.z), "=r"(dv4.w) : "r"(dorow + (uint32_t)((c ^ sw) * 16)));
-          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&dv4);
-          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&ov[c]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-            acc0 = fmaf(fa.x, fb.x, acc0);
-            acc1 = fmaf(fa.y, fb.y, acc1);
-          }
-        }
-        d = acc0 + acc1;
-      }
-      return d;
-    };
-    float dlt_next = niter > 0 ? compute_delta(0) : 0.f;
 
     for (int it = 0; it < niter; ++it) {
       const int q0 = (i0 + it) * TILE_Q, qi = q0 + r;
       const bool valid = qi < p.S;
       // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
       const float lse2 = valid ? p.lse[(long long)bh * p.S + qi] * LOG2E : INFINITY;
-      const float dlt = dlt_next;   // computed at the end of the previous iteration (see compute_delta)
       // ---- P = exp2(score - LSE)
       mbar_wait(s_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it);
@@ -812,6 +826,13 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (it > 0) drain_dq(it - 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 2);
       // ---- dS = P o (dP - delta) * scale   (dS buffer: dK(it-1), dQ(it-1) retired -- dq_full(it-1) awaited in the drain)
+      float dlt;
+      if (p.delta) {
+        dlt = valid ? p.delta[(long long)bh * p.S + qi] : 0.f;
+      } else {
+        mbar_wait(&delta_full[it & 1], (it >> 1) & 1);   // written by the producer warp a block ahead
+        dlt = reinterpret_cast<const float*>(smem + SB_DELTA)[(it & 1) * 128 + r];
+      }
       mbar_wait(dp_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 3);
       tc_fence_after();
@@ -833,7 +854,6 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(ds_full);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 4);
-      if (it + 1 < niter) dlt_next = compute_delta(it + 1);
     }
     if (niter > 0) drain_dq(niter - 1);
     if (threadIdx.x == 0) tlb(p, 1);
@@ -885,20 +905,6 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// dq (bf16, strided (b, s, h, d)) = fp32 accumulation buffer (B, H, S, 64)
-__global__ void k_dq_convert(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int S, long long sb, long long ss, long long sh) {
-  nfb_pdl_enter();
-  const unsigned total = (unsigned)B * H * S * 8, stride = gridDim.x * blockDim.x;   // 8 threads per row, 8 elements each
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const unsigned c = (i & 7) * 8, row = i >> 3;
-    const unsigned sidx = row % S, bhh = row / S, hh = bhh % H, bb = bhh / H;
-    const float4 a = *reinterpret_cast<const float4*>(acc + (size_t)row * 64 + c), bq = *reinterpret_cast<const float4*>(acc + (size_t)row * 64 + c + 4);
-    __nv_bfloat162 w0 = __floats2bfloat162_rn(a.x, a.y), w1 = __floats2bfloat162_rn(a.z, a.w), w2 = __floats2bfloat162_rn(bq.x, bq.y), w3 = __floats2bfloat162_rn(bq.z, bq.w);
-    *reinterpret_cast<uint4*>(dq + bb * sb + (long long)sidx * ss + (long long)hh * sh + c) =
-        make_uint4(*reinterpret_cast<uint32_t*>(&w0), *reinterpret_cast<uint32_t*>(&w1), *reinterpret_cast<uint32_t*>(&w2), *reinterpret_cast<uint32_t*>(&w3));
-  }
-}
-
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -942,18 +948,6 @@ int make_map_bshd(CUtensorMap* out, const void* base, int B, int S, int H, long 
 }
 
 
-// 3-D fp32 map over the dQ accumulation buffer (B*H, S, 64): dims (64, S, B*H), box (32, 128, 1)
-int make_map_dq(CUtensorMap* out, const float* base, int BH, int S) {
-  if (get_encode_fn()) return -1;
-  cuuint64_t dims[3] = {64, (cuuint64_t)S, (cuuint64_t)BH};
-  cuuint64_t strides[2] = {64 * 4, (cuuint64_t)S * 64 * 4};
-  cuuint32_t box[3] = {32, 128, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return NFB_FAIL("attention_tc: cuTensorMapEncodeTiled (dQ) failed (%d) BH=%d S=%d", (int)r, BH, S);
-  return 0;
-}
 unsigned long long* g_attn_timeline = nullptr;
 }  // namespace
 
@@ -1000,12 +994,20 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   if (make_map_bshd(&tmK, k, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
   if (make_map_bshd(&tmV, v, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
   if (make_map_bshd(&tmdO, dout, B, S, H, o_sb, o_ss, o_sh)) return -1;
-  float* acc = nullptr;
-  const size_t acc_bytes = sizeof(float) * (size_t)B * H * S * 64;
-  if (nfb_malloc(acc_bytes, (void**)&acc)) return -1;
-  if (make_map_dq(&tmdQ, acc, B * H, S)) { nfb_free(acc); return -1; }
+  if (make_map_bshd(&tmdQ, dq, B, S, H, q_sb, q_ss, q_sh)) return -1;
   cudaStream_t st = nfb_cur_stream();
-  NFB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  // dq accumulates through reduce-adds: zero it first.  Its rows (b, s) hold H*64 contiguous elements at pitch q_ss when the
+  // heads are packed (q_sh == 64): one 2-D memset per batch entry; any other layout is cleared head by head.
+  if (q_sh == HDIM && (q_sb == (long long)S * q_ss || B == 1)) {   // the packed qkv layout: ONE strided clear of all B*S rows
+    NFB_CUDA(cudaMemset2DAsync(dq, (size_t)q_ss * 2, 0, (size_t)H * HDIM * 2, (size_t)B * S, st));
+  } else if (q_sh == HDIM) {
+    for (int bb = 0; bb < B; ++bb)
+      NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb, (size_t)q_ss * 2, 0, (size_t)H * HDIM * 2, (size_t)S, st));
+  } else {
+    for (int bb = 0; bb < B; ++bb)
+      for (int hh = 0; hh < H; ++hh)
+        NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb + (long long)hh * q_sh, (size_t)q_ss * 2, 0, (size_t)HDIM * 2, (size_t)S, st));
+  }
   AttnBwdTcParams p = {};
   p.lse = lse; p.delta = delta; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
@@ -1019,10 +1021,6 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * H));
   k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   nfb_count_launch();
-  const long long vecs = (long long)B * H * S * 8;
-  NFB_CUDA(nfb_launch_pdl(k_dq_convert, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const float*)acc, (__nv_bfloat16*)dq, B, H, S,
-                          (long long)q_sb, (long long)q_ss, (long long)q_sh));
-  nfb_free(acc);
   NFB_LAUNCH_CHECK();
   return 0;
 }

@@ -151,12 +151,22 @@ int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const void* v, c
  * and global-norm clipping (examples/translation/train_conversational.py:38-54; distributed/advanced.py:362-388). */
 int nfb_adam_step(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int step, int maximize, const float* grad_scale, const int* step_dev);
+/* lr_dev (device double, optional): the learning rate is read on the device, so the schedulers of optim/lr_scheduler.py:19-606
+ * keep acting on a training step that was captured into a CUDA graph. */
+int nfb_adam_step_ex(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, int step, int maximize, const float* grad_scale,
+                     const int* step_dev, const double* lr_dev);
 int nfb_add_i32(int* counter, int delta);
 int nfb_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
                  double weight_decay, int nesterov, int first_step, int maximize);
 int nfb_sumsq(const float* g, int64_t n, double* total, int accumulate);
 int nfb_clip_coef(const double* total, float max_norm, float eps, float* coef, float* norm_out);
 int nfb_scale_by_device_scalar(float* g, int64_t n, const float* coef);
+/* AdvancedGradScaler.unscale_ (optimization/grad_scaler.py:131-196): g /= scale per parameter, stop at the first parameter with a
+ * non-finite value (*first_bad, nseg if none), clip each parameter's own L2 norm to clip_threshold (0 = off).  chunks: nchunks
+ * records {int32 seg; int32 len; int64 start} cutting g into per-parameter pieces; norms2[nseg] = sum((g/scale)^2). */
+int nfb_grad_unscale(float* g, const void* chunks, int nchunks, int nseg, float scale, float clip_threshold, double* norms2,
+                     int* first_bad);
 
 /* ---- collectives: NCCL over NVLink 5 / NVSwitch (distributed/communication.py:115-347 NCCLBackend; ReduceOp :25-32;
  * call sites distributed/data_parallel.py:88-99,250-287).  op: 0 sum 1 average 2 max 3 min 4 product. */

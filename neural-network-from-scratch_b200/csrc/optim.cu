@@ -11,10 +11,17 @@
 #include "common.cuh"
 
 // per-launch scalars, computed once per block by thread 0 (two double pow() per THREAD cost more than the update itself)
-struct AdamScalars { double lr_eff, inv_bc1, inv_bc2; float gs; };
+struct AdamScalars { double lr_eff, inv_bc1, inv_bc2; float gs, wd_factor; };
 __device__ __forceinline__ void adam_scalars(AdamScalars* sc, int variant, double lr, double beta1, double beta2, int step_host,
-                                             const int* step_dev, float gsign, const float* grad_scale) {
+                                             const int* step_dev, float gsign, const float* grad_scale, float wd_factor,
+                                             const double* lr_dev, double weight_decay) {
   if (threadIdx.x == 0) {
+    // learning rate: a host value, or a device scalar a scheduler rewrites between replays of a captured step
+    if (lr_dev) {
+      lr = *lr_dev;
+      wd_factor = (variant == 1 && weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.f;
+    }
+    sc->wd_factor = wd_factor;
     // bias corrections from the step count: a host value, or a device counter so that a captured CUDA graph of the
     // training step stays valid from one replay to the next
     const int step = step_dev ? *step_dev : step_host;
@@ -51,9 +58,10 @@ __device__ __forceinline__ float adam_one(int variant, float pi, float gi, MT& m
 template <typename MT>
 __global__ void k_adam(int variant, float* __restrict__ p, const float* __restrict__ g, MT* __restrict__ m, MT* __restrict__ v,
                        __nv_bfloat16* __restrict__ p_bf16, int64_t n0, int64_t n, double lr, MT beta1, MT beta2, MT eps, float wd_factor, float wd_grad,
-                       int step_host, const int* step_dev, float gsign, const float* grad_scale) {
+                       int step_host, const int* step_dev, float gsign, const float* grad_scale, const double* lr_dev, double weight_decay) {
   __shared__ AdamScalars sc;
-  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale);
+  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale, wd_factor, lr_dev, weight_decay);
+  wd_factor = sc.wd_factor;
   const MT lr_eff = (MT)sc.lr_eff, inv_bc1 = (MT)sc.inv_bc1, inv_bc2 = (MT)sc.inv_bc2;
   const float gs = sc.gs;
   for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -71,9 +79,10 @@ __global__ void k_adam(int variant, float* __restrict__ p, const float* __restri
 __global__ void __launch_bounds__(256)
 k_adam_vec4(int variant, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             uint2* __restrict__ p_bf16, int64_t n4, double lr, float beta1, float beta2, float eps, float wd_factor, float wd_grad,
-            int step_host, const int* step_dev, float gsign, const float* grad_scale) {
+            int step_host, const int* step_dev, float gsign, const float* grad_scale, const double* lr_dev, double weight_decay) {
   __shared__ AdamScalars sc;
-  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale);
+  adam_scalars(&sc, variant, lr, (double)beta1, (double)beta2, step_host, step_dev, gsign, grad_scale, wd_factor, lr_dev, weight_decay);
+  wd_factor = sc.wd_factor;
   const float lr_eff = (float)sc.lr_eff, inv_bc1 = (float)sc.inv_bc1, inv_bc2 = (float)sc.inv_bc2;
   const float gs = sc.gs;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -104,29 +113,37 @@ k_adam_vec4(int variant, float4* __restrict__ p, const float4* __restrict__ g, f
 
 // variant: 0 = Adam, 1 = AdamW. moment_dtype: NFB_F32 or NFB_F64. step is 1-based (after increment); when step_dev
 // (a device int) is given it overrides `step`.
-NFB_API int nfb_adam_step(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n,
-                          double lr, double beta1, double beta2, double eps, double weight_decay, int step, int maximize,
-                          const float* grad_scale, const int* step_dev) {
+// lr_dev (a device double, optional) overrides `lr` the same way: learning-rate schedulers keep working across replays
+// of a captured training step.
+NFB_API int nfb_adam_step_ex(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n,
+                             double lr, double beta1, double beta2, double eps, double weight_decay, int step, int maximize,
+                             const float* grad_scale, const int* step_dev, const double* lr_dev) {
   if (n == 0) return 0;
   float wd_factor = (variant == 1 && weight_decay != 0.0) ? (float)(1.0 - lr * weight_decay) : 1.f;
   float wd_grad = (variant == 0) ? (float)weight_decay : 0.f;
   float gsign = maximize ? -1.f : 1.f;
   cudaStream_t s = nfb_cur_stream();
   if (moment_dtype == NFB_F64) {
-    k_adam<double><<<nfb_grid_for(n, 256, 8), 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, 0, n, lr, beta1, beta2, eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+    k_adam<double><<<nfb_grid_for(n, 256, 8), 256, 0, s>>>(variant, p, g, (double*)m, (double*)v, (__nv_bfloat16*)p_bf16, 0, n, lr, beta1, beta2, eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale, lr_dev, weight_decay);
   } else if (moment_dtype == NFB_F32) {
     bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0) && ((uintptr_t)p_bf16 % 8 == 0);
     int64_t n4 = vec ? n / 4 : 0;
     if (n4 > 0) {
       k_adam_vec4<<<nfb_grid_for(nfb_cdiv(n4, 2), 256, 8), 256, 0, s>>>(variant, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16, n4, lr,
-                                                                       (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+                                                                       (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale, lr_dev, weight_decay);
       if (n4 * 4 < n) nfb_count_launch();
     }
     if (n4 * 4 < n)
-      k_adam<float><<<1, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n4 * 4, n, lr, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale);
+      k_adam<float><<<1, 256, 0, s>>>(variant, p, g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n4 * 4, n, lr, (float)beta1, (float)beta2, (float)eps, wd_factor, wd_grad, step, step_dev, gsign, grad_scale, lr_dev, weight_decay);
   } else return NFB_FAIL("nfb_adam_step: moment dtype %d", moment_dtype);
   NFB_LAUNCH_CHECK();
   return 0;
+}
+
+NFB_API int nfb_adam_step(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n,
+                          double lr, double beta1, double beta2, double eps, double weight_decay, int step, int maximize,
+                          const float* grad_scale, const int* step_dev) {
+  return nfb_adam_step_ex(variant, moment_dtype, p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, maximize, grad_scale, step_dev, nullptr);
 }
 
 __global__ void k_add_i32(int* p, int delta) { *p += delta; }
@@ -237,6 +254,99 @@ NFB_API int nfb_scale_by_device_scalar(float* g, int64_t n, const float* coef) {
   bool vec = ((uintptr_t)g % 16 == 0);
   int64_t n4 = vec ? n / 4 : 0;
   k_scale_by<<<nfb_grid_for(vec && n4 ? n4 : n, 256), 256, 0, nfb_cur_stream()>>>(g, n4, n, coef);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- loss-scale unscaling with per-parameter norm clipping (optimization/grad_scaler.py:131-196) ----
+// The gradient buffer is cut into chunks of at most UNSCALE_CHUNK elements, none crossing a parameter boundary; the host
+// builds the chunk table (seg, start, len) once per parameter set.  Pass 1: per parameter, sum((g/scale)^2) in double and
+// the smallest parameter index holding a non-finite unscaled value.  Pass 2: g = g/scale * clip(param) for the
+// parameters in front of that index (the reference stops at the first bad parameter).
+struct UnscaleChunk { int seg; int len; int64_t start; };
+__global__ void __launch_bounds__(256)
+k_unscale_stats(const float* __restrict__ g, const UnscaleChunk* __restrict__ chunks, float scale, double* __restrict__ norms2,
+                int* __restrict__ first_bad) {
+  const UnscaleChunk c = chunks[blockIdx.x];
+  const float* p = g + c.start;
+  double acc = 0.0;
+  bool bad = false;
+  const int head = (int)(((16 - ((uintptr_t)p & 15)) & 15) >> 2);   // scalars in front of the first 16-byte boundary
+  const int h = head < c.len ? head : c.len;
+  const int n4 = (c.len - h) >> 2;
+  for (int i = threadIdx.x; i < h; i += blockDim.x) {
+    float u = __fdiv_rn(p[i], scale);
+    bad |= !isfinite(u);
+    acc += (double)u * (double)u;
+  }
+  const float4* p4 = reinterpret_cast<const float4*>(p + h);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 a = p4[i];
+    float u0 = __fdiv_rn(a.x, scale), u1 = __fdiv_rn(a.y, scale), u2 = __fdiv_rn(a.z, scale), u3 = __fdiv_rn(a.w, scale);
+    bad |= !(isfinite(u0) && isfinite(u1) && isfinite(u2) && isfinite(u3));
+    acc += (double)u0 * u0 + (double)u1 * u1 + (double)u2 * u2 + (double)u3 * u3;
+  }
+  for (int i = h + n4 * 4 + threadIdx.x; i < c.len; i += blockDim.x) {
+    float u = __fdiv_rn(p[i], scale);
+    bad |= !isfinite(u);
+    acc += (double)u * (double)u;
+  }
+  __shared__ double red[8];
+  __shared__ int any_bad;
+  if (threadIdx.x == 0) any_bad = 0;
+  __syncthreads();
+  if (bad) any_bad = 1;
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int k = 0; k < 8; ++k) r += red[k];
+    if (any_bad) atomicMin(first_bad, c.seg);
+    else atomicAdd(&norms2[c.seg], r);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_unscale_apply(float* __restrict__ g, const UnscaleChunk* __restrict__ chunks, float scale, float clip_threshold,
+                const double* __restrict__ norms2, const int* __restrict__ first_bad) {
+  const UnscaleChunk c = chunks[blockIdx.x];
+  if (c.seg >= *first_bad) return;
+  float coef = 1.f;
+  if (clip_threshold > 0.f) {
+    const float nrm = (float)sqrt(norms2[c.seg]);                 // np.linalg.norm of an fp32 array is an fp32 scalar
+    if (nrm > clip_threshold) coef = __fdiv_rn(clip_threshold, __fadd_rn(nrm, 1e-6f));
+  }
+  float* p = g + c.start;
+  const int head = (int)(((16 - ((uintptr_t)p & 15)) & 15) >> 2);
+  const int h = head < c.len ? head : c.len;
+  const int n4 = (c.len - h) >> 2;
+  for (int i = threadIdx.x; i < h; i += blockDim.x) p[i] = __fmul_rn(__fdiv_rn(p[i], scale), coef);
+  float4* p4 = reinterpret_cast<float4*>(p + h);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 a = p4[i];
+    a.x = __fmul_rn(__fdiv_rn(a.x, scale), coef); a.y = __fmul_rn(__fdiv_rn(a.y, scale), coef);
+    a.z = __fmul_rn(__fdiv_rn(a.z, scale), coef); a.w = __fmul_rn(__fdiv_rn(a.w, scale), coef);
+    p4[i] = a;
+  }
+  for (int i = h + n4 * 4 + threadIdx.x; i < c.len; i += blockDim.x) p[i] = __fmul_rn(__fdiv_rn(p[i], scale), coef);
+}
+__global__ void k_unscale_init(double* norms2, int nseg, int* first_bad) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += gridDim.x * blockDim.x) norms2[i] = 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *first_bad = nseg;
+}
+// chunks: device array of nchunks {int seg; int len; int64 start} records (16 bytes each).  norms2[nseg] receives
+// sum((g/scale)^2) per parameter, *first_bad the first parameter index with a non-finite value (nseg if none).
+NFB_API int nfb_grad_unscale(float* g, const void* chunks, int nchunks, int nseg, float scale, float clip_threshold, double* norms2,
+                             int* first_bad) {
+  if (nseg <= 0) return 0;
+  cudaStream_t s = nfb_cur_stream();
+  k_unscale_init<<<nfb_cdiv(nseg, 256), 256, 0, s>>>(norms2, nseg, first_bad);
+  if (nchunks > 0) {
+    nfb_count_launch();
+    k_unscale_stats<<<nchunks, 256, 0, s>>>(g, (const UnscaleChunk*)chunks, scale, norms2, first_bad);
+    nfb_count_launch();
+    k_unscale_apply<<<nchunks, 256, 0, s>>>(g, (const UnscaleChunk*)chunks, scale, clip_threshold, norms2, first_bad);
+  }
   NFB_LAUNCH_CHECK();
   return 0;
 }

@@ -24,6 +24,8 @@ class OptimizerError(ValueError):
 
 class _AdamBase(Optimizer):
     _variant = 0  # 0 Adam, 1 AdamW
+    _lr = None
+    _lr_dev = None
 
     def __init__(self, parameters, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-5, weight_decay=0.0, amsgrad=False, maximize=False,
                  betas: Optional[tuple] = None, moment_dtype: str = "float64"):
@@ -48,6 +50,8 @@ class _AdamBase(Optimizer):
             raise OptimizerError(f"Invalid weight decay: {weight_decay}")
         if amsgrad:
             raise NotImplementedError("amsgrad is not implemented on the b200 backend (not used by the named configs)")
+        self._lr_dev = None      # device copy of lr (capturable mode): schedulers act on replays of a captured step
+        self._replay_lag = 0     # replays of a captured step not yet reflected in the per-parameter "step" entries
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.weight_decay, self.amsgrad, self.maximize = weight_decay, amsgrad, maximize
         self.step_count = 0
@@ -75,6 +79,50 @@ class _AdamBase(Optimizer):
                 ea, es = np.zeros(p.shape, dtype=np.float64), np.zeros(p.shape, dtype=np.float64)
             self.state[name] = {"step": 0, "exp_avg": ea, "exp_avg_sq": es}
             self.m[name], self.v[name] = ea, es
+
+    # ------------------------------------------------------------------ learning rate (host value + device mirror)
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self._lr = value
+        if self._lr_dev is not None:
+            from ..runtime import is_capturing
+            if not is_capturing():   # inside a capture the write would be frozen into the graph
+                call("nfb_fill", C_F64, self._lr_dev.ptr, 1, float(value))
+
+    def _device_scalars(self):
+        """capturable mode: step counter and learning rate live on the device and are advanced / rewritten between
+        replays (GraphedStep), so one captured step stays valid for the whole run."""
+        if not self.capturable:
+            return
+        if self._step_dev is None:
+            self._step_dev = B200Array.full((1,), self.step_count - 1, np.int32)
+        if self._lr_dev is None:
+            self._lr_dev = B200Array.full((1,), float(self._lr), np.float64)
+        call("nfb_add_i32", self._step_dev.ptr, 1)
+
+    def _launch(self, lo, n, step, use_grad_scale=True):
+        a = self.arena
+        mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
+        msz = self.moment_dtype.itemsize
+        call("nfb_adam_step_ex", self._variant, mcode, a.flat_p.ptr + lo * 4, a.flat_g.ptr + lo * 4,
+             a.moments[0].ptr + lo * msz, a.moments[1].ptr + lo * msz,
+             (a.flat_bf16.ptr + lo * 2) if a.flat_bf16 is not None else None, n, float(self._lr), float(self.beta1),
+             float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
+             self.grad_scale.ptr if (use_grad_scale and self.grad_scale is not None) else None,
+             self._step_dev.ptr if self._step_dev is not None else None,
+             self._lr_dev.ptr if self._lr_dev is not None else None)
+
+    def _graph_replayed(self, before: bool):
+        """GraphedStep bookkeeping around one replay: the host-side step count advances and the built-in schedule (AdamW)
+        computes this step's learning rate BEFORE the replay reads it."""
+        if before:
+            self.step_count += 1
+            self._replay_lag += 1
+            self._update_learning_rate()
 
     # ------------------------------------------------------------------ optimizer fused into backward
     def enable_step_in_backward(self, min_run_elems: int = 1 << 21):
@@ -125,10 +173,7 @@ class _AdamBase(Optimizer):
         self._sib_begun = True
         self.step_count += 1
         self._update_learning_rate()
-        if self.capturable:
-            if self._step_dev is None:
-                self._step_dev = B200Array.full((1,), self.step_count - 1, np.int32)
-            call("nfb_add_i32", self._step_dev.ptr, 1)
+        self._device_scalars()
 
     def _sib_flush(self, final: bool):
         """Launch the fused kernel for maximal contiguous runs of ready, not yet updated arena parameters."""
@@ -154,8 +199,6 @@ class _AdamBase(Optimizer):
         if not launches:
             return
         from .. import kernels as K
-        mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
-        msz = self.moment_dtype.itemsize
         self._sib_begin()
         for rn in launches:
             steps = set()
@@ -172,11 +215,7 @@ class _AdamBase(Optimizer):
             hi = a.offsets[id(rn[-1])] + (rn[-1].size + ALIGN - 1) // ALIGN * ALIGN
 
             def launch(lo=lo, hi=hi, step=step):
-                call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + lo * 4, a.flat_g.ptr + lo * 4,
-                     a.moments[0].ptr + lo * msz, a.moments[1].ptr + lo * msz,
-                     (a.flat_bf16.ptr + lo * 2) if a.flat_bf16 is not None else None, hi - lo, float(self.lr), float(self.beta1),
-                     float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
-                     None, self._step_dev.ptr if self._step_dev is not None else None)
+                self._launch(lo, hi - lo, step, use_grad_scale=False)
             if final or not K._WGRAD_OVERLAP:
                 launch()
             else:
@@ -225,14 +264,9 @@ class _AdamBase(Optimizer):
                 st["step"] += 1
                 steps.setdefault(st["step"], set()).add(id(p))
                 done.add(id(p))
-            if self.capturable:
-                # graph-capturable mode: the step count lives on the device and is advanced by a kernel, so a captured
-                # step replays with the right bias corrections (all arena parameters share one count in this mode)
-                if self._step_dev is None:
-                    self._step_dev = B200Array.full((1,), self.step_count - 1, np.int32)
-                call("nfb_add_i32", self._step_dev.ptr, 1)
-            mcode = C_F64 if self.moment_dtype == np.dtype(np.float64) else C_F32
-            msz = self.moment_dtype.itemsize
+            # graph-capturable mode: the step count lives on the device and is advanced by a kernel, so a captured
+            # step replays with the right bias corrections (all arena parameters share one count in this mode)
+            self._device_scalars()
             a = self.arena
             if segments is not None and len(steps) == 1 and len(next(iter(steps.values()))) == len(a.params):
                 from ..runtime import compute_stream_wait
@@ -240,12 +274,7 @@ class _AdamBase(Optimizer):
                 for lo, hi, ev in segments:
                     if ev is not None:
                         compute_stream_wait(ev)
-                    call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + lo * 4, a.flat_g.ptr + lo * 4,
-                         a.moments[0].ptr + lo * msz, a.moments[1].ptr + lo * msz,
-                         (a.flat_bf16.ptr + lo * 2) if a.flat_bf16 is not None else None, hi - lo, float(self.lr), float(self.beta1),
-                         float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
-                         self.grad_scale.ptr if self.grad_scale is not None else None,
-                         self._step_dev.ptr if self._step_dev is not None else None)
+                    self._launch(lo, hi - lo, step)
                 steps = {}
             elif segments is not None:
                 from ..runtime import compute_stream_wait
@@ -254,12 +283,7 @@ class _AdamBase(Optimizer):
                         compute_stream_wait(ev)
             for step, ids in steps.items():
                 for off, n in a.runs(lambda q: id(q) in ids):
-                    call("nfb_adam_step", self._variant, mcode, a.flat_p.ptr + off * 4, a.flat_g.ptr + off * 4,
-                         a.moments[0].ptr + off * msz, a.moments[1].ptr + off * msz,
-                         (a.flat_bf16.ptr + off * 2) if a.flat_bf16 is not None else None, n, float(self.lr), float(self.beta1),
-                         float(self.beta2), float(self.eps), float(self.weight_decay), int(step), 1 if self.maximize else 0,
-                         self.grad_scale.ptr if self.grad_scale is not None else None,
-                         self._step_dev.ptr if self._step_dev is not None else None)
+                    self._launch(off, n, step)
             for p in a.params:
                 if id(p) in done:
                     p._version += 1
@@ -310,7 +334,8 @@ class _AdamBase(Optimizer):
     def get_state_dict(self) -> dict:
         def host(x):
             return x.get() if isinstance(x, B200Array) else np.asarray(x)
-        return {"state": {n: {"step": s["step"], "exp_avg": host(s["exp_avg"]).astype(np.float64),
+        lag = self._replay_lag
+        return {"state": {n: {"step": s["step"] + lag, "exp_avg": host(s["exp_avg"]).astype(np.float64),
                               "exp_avg_sq": host(s["exp_avg_sq"]).astype(np.float64)} for n, s in self.state.items()},
                 "param_groups": [{"lr": self.lr, "beta1": self.beta1, "beta2": self.beta2, "eps": self.eps,
                                   "weight_decay": self.weight_decay, "amsgrad": self.amsgrad, "maximize": self.maximize}],
@@ -334,6 +359,9 @@ class _AdamBase(Optimizer):
             if k in g:
                 setattr(self, k, g[k])
         self.step_count = sd.get("step_count", self.step_count)
+        self._replay_lag = 0
+        if self._step_dev is not None:   # capturable: the device counter follows the loaded state
+            call("nfb_fill", 2, self._step_dev.ptr, 1, float(self.step_count))  # 2 = NFB_I32
 
 
 class Adam(_AdamBase):

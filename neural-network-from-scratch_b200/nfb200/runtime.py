@@ -84,6 +84,14 @@ def empty_cache():
     call("nfb_empty_cache")
 
 
+_CAPTURING = 0
+
+
+def is_capturing() -> bool:
+    """True while a ``Graph`` is recording the compute stream (host code that must not be frozen into the graph checks it)."""
+    return _CAPTURING > 0
+
+
 class Graph:
     """Capture the kernels issued inside the ``with`` block on the compute stream; ``replay()`` relaunches them.
 
@@ -97,10 +105,14 @@ class Graph:
 
     def __enter__(self):
         _lib.ensure_init()
+        global _CAPTURING
         call("nfb_graph_begin_capture")
+        _CAPTURING += 1
         return self
 
     def __exit__(self, et, ev, tb):
+        global _CAPTURING
+        _CAPTURING = max(0, _CAPTURING - 1)
         h = C.c_void_p()
         if et is not None:
             try:

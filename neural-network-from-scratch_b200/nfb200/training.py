@@ -26,12 +26,24 @@ class GraphedStep:
             self.out = step_fn()
         R.synchronize()
         self.replays = 0
-        # the captured step already advanced host-side counters once without running on the device
         self._opts = list(optimizers)
+        # the captured step advanced the host-side counters (and a built-in schedule) once without running on the device
+        for opt in self._opts:
+            opt.step_count -= 1
+            if hasattr(opt, "state"):
+                for st in {id(s): s for s in opt.state.values()}.values():
+                    st["step"] -= 1
+            if hasattr(opt, "_update_learning_rate"):
+                opt._update_learning_rate()       # a built-in schedule was advanced by the capture call: back to this step's lr
 
     def __call__(self):
+        """One training step = one graph launch.  Learning rates are read on the device: whatever a scheduler (or the
+        optimizer's built-in schedule) wrote to ``opt.lr`` before this call is what the replayed AdamW kernels use."""
+        for opt in self._opts:
+            if hasattr(opt, "_graph_replayed"):
+                opt._graph_replayed(before=True)
+            else:
+                opt.step_count += 1
         self.graph.replay()
         self.replays += 1
-        for opt in self._opts:
-            opt.step_count += 1
         return self.out

@@ -221,11 +221,124 @@ def gen_sampler(g):
         g[f"sampler_{tag}"] = np.array(list(s))
 
 
+SCHEDULE_CASES = [  # (tag, class or factory name, kwargs, initial lr, epochs)
+    ("step", "StepLR", dict(step_size=3, gamma=0.5), 0.01, 12),
+    ("step_resume", "StepLR", dict(step_size=4, gamma=0.1, last_epoch=5), 0.2, 8),
+    ("exp", "ExponentialLR", dict(gamma=0.9), 5e-4, 10),
+    ("cosine", "CosineAnnealingLR", dict(T_max=8, eta_min=1e-5), 1e-3, 20),
+    ("linear", "LinearLR", dict(start_factor=0.25, end_factor=1.0, total_iters=6), 2e-3, 10),
+    ("warmup", "WarmupLR", dict(warmup_epochs=5, warmup_factor=0.2), 3e-4, 9),
+    ("poly", "PolynomialLR", dict(total_iters=9, power=2.0, end_lr=1e-6), 1e-3, 12),
+    ("lin_warm", "get_linear_schedule_with_warmup", dict(num_warmup_steps=4, num_training_steps=16), 5e-4, 20),
+    ("cos_warm", "get_cosine_schedule_with_warmup", dict(num_warmup_steps=3, num_training_steps=13), 1e-3, 16),
+]
+PLATEAU_CASES = [
+    ("plateau_min", dict(mode="min", factor=0.5, patience=2, threshold=1e-2, cooldown=1, min_lr=1e-5), 1e-2,
+     [1.0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5]),
+    ("plateau_max_abs", dict(mode="max", factor=0.1, patience=0, threshold=0.05, threshold_mode="abs"), 1.0,
+     [0.1, 0.2, 0.22, 0.3, 0.3, 0.31, 0.5]),
+]
+
+
+def gen_train_glue(g):
+    """Training-loop glue: learning-rate traces of every scheduler in optim/lr_scheduler.py driven through the
+    reference AdamW, and step-by-step traces of optimization/grad_scaler.py's AdvancedGradScaler (scale, skipped steps, the
+    unscaled + per-parameter-clipped gradients) over a gradient sequence with injected overflows."""
+    import json
+    from neural_arch.core import Parameter, Tensor
+    from neural_arch.optim import AdamW
+    from neural_arch.optim import lr_scheduler as S
+    from neural_arch.optimization import grad_scaler as GS
+
+    def opt_of(lr):
+        return AdamW({"w": Parameter(np.ones(3, dtype=np.float32))}, lr=lr)
+    for tag, name, kw, lr0, epochs in SCHEDULE_CASES:
+        opt = opt_of(lr0)
+        sch = getattr(S, name)(opt, **kw)
+        trace = [opt.lr]                      # the constructor already stepped once
+        for _ in range(epochs):
+            sch.step()
+            trace.append(opt.lr)
+        g[f"sched_{tag}"] = np.asarray(trace, dtype=np.float64)
+    for tag, kw, lr0, metrics in PLATEAU_CASES:
+        opt = opt_of(lr0)
+        sch = S.ReduceLROnPlateau(opt, **kw)
+        trace = []
+        for m in metrics:
+            sch.step(m)
+            trace.append(opt.lr)
+        g[f"sched_{tag}"] = np.asarray(trace, dtype=np.float64)
+    g["sched_cases"] = np.frombuffer(json.dumps({"sched": SCHEDULE_CASES, "plateau": PLATEAU_CASES}).encode(), dtype=np.uint8)
+
+    # --- AdvancedGradScaler: the reference reads `param.grad.data`, i.e. expects Tensor-valued grads (its tests assign Tensors)
+    class P:      # duck-typed parameter / optimizer: the scaler touches only .grad.data, .parameters and .step()
+        def __init__(self, shape):
+            self.grad, self.shape = None, shape
+
+    class O:
+        def __init__(self, params):
+            self.parameters, self.steps = params, 0
+
+        def step(self):
+            self.steps += 1
+    rng = np.random.default_rng(77)
+    shapes = [(5, 7), (11,), (3, 4, 2), (9,)]
+    nstep = 14
+    base = [[(rng.standard_normal(sh) * 10.0 ** rng.integers(-3, 1)).astype(np.float32) for sh in shapes] for _ in range(nstep)]
+    bad = {3: (1, np.inf), 4: (2, np.nan), 9: (0, -np.inf)}       # step -> (parameter index, value) injected overflow
+    for tag, cfg in (("dyn", dict(init_scale=1024.0, growth_interval=3, gradient_clip_threshold=1.0)),
+                     ("noclip", dict(init_scale=96.0, growth_interval=2, growth_factor=1.5, gradient_clip_threshold=0.0, max_loss_scale=200.0)),
+                     ("fixed", dict(init_scale=8.0, strategy=GS.ScalingStrategy.FIXED, gradient_clip_threshold=0.5)),
+                     ("conservative", dict(init_scale=4.0, strategy=GS.ScalingStrategy.CONSERVATIVE, consecutive_success_threshold=2,
+                                           overflow_cooldown=3, gradient_clip_threshold=1.0, min_loss_scale=2.0))):
+        sc = GS.AdvancedGradScaler(GS.ScalerConfig(**cfg))
+        params = {f"p{i}": P(sh) for i, sh in enumerate(shapes)}
+        opt = O(params)
+        scales, taken, scaled_in, outs = [], [], [], []
+        for t in range(nstep):
+            s_now = sc.get_scale()
+            ins = []
+            for i, p in enumerate(params.values()):
+                gr = (base[t][i] * np.float32(s_now)).astype(np.float32)   # what backward of the scaled loss would have produced
+                if t in bad and bad[t][0] == i:
+                    gr.flat[1] = bad[t][1]
+                ins.append(gr.copy())
+                p.grad = Tensor(gr)
+            ok = sc.step(opt)
+            scales.append(sc.get_scale())
+            taken.append(bool(ok))
+            scaled_in.append(np.concatenate([a.ravel() for a in ins]))
+            outs.append(np.concatenate([np.asarray(p.grad.data, dtype=np.float32).ravel() for p in params.values()]))
+        g[f"scaler_{tag}_scale"], g[f"scaler_{tag}_taken"] = np.asarray(scales, dtype=np.float64), np.asarray(taken)
+        g[f"scaler_{tag}_in"], g[f"scaler_{tag}_out"] = np.stack(scaled_in), np.stack(outs)
+        g[f"scaler_{tag}_optsteps"] = np.asarray(opt.steps)
+        st = sc.get_statistics()
+        g[f"scaler_{tag}_stats"] = np.asarray([st["total_overflows"], st["successful_steps"], st["growth_tracker"]], dtype=np.float64)
+        g[f"scaler_{tag}_norm_hist"] = np.asarray(sc._gradient_norms_history, dtype=np.float64)
+    g["scaler_shapes"] = np.frombuffer(json.dumps(shapes).encode(), dtype=np.uint8)
+    # loss scaling itself: scale(loss) multiplies the value (grad_scaler.py:90-129)
+    sc = GS.AdvancedGradScaler(GS.ScalerConfig(init_scale=512.0))
+    g["scaler_scaled_loss"] = np.asarray(sc.scale(Tensor(np.asarray(0.37, dtype=np.float32), requires_grad=True)).data)
+    # clip_gradients_by_norm / check_gradients_finite helpers (grad_scaler.py:501-597)
+    params = {f"p{i}": P(sh) for i, sh in enumerate(shapes)}
+    for i, p in enumerate(params.values()):
+        p.grad = Tensor(base[0][i] * np.float32(3.0))
+    opt = O(params)
+    fin, stats = GS.check_gradients_finite(opt)
+    g["helper_in"] = np.concatenate([np.asarray(p.grad.data).ravel() for p in params.values()])
+    g["helper_stats"] = np.asarray([float(fin), stats["params_with_grad"], stats["finite_grads"], stats["max_grad_norm"], stats["avg_grad_norm"]])
+    g["helper_total_norm"] = np.asarray(GS.clip_gradients_by_norm(opt, 0.75))
+    g["helper_clipped"] = np.concatenate([np.asarray(p.grad.data, dtype=np.float32).ravel() for p in params.values()])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue)):
+        if only and name not in only:
+            continue
         g = {}
         fn(g)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **{k: np.asarray(v) for k, v in g.items()})

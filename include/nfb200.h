@@ -137,6 +137,10 @@ int nfb_set_pdl(int on);                             /* programmatic dependent l
  * (CuPy precedent CudaBackend.flash_attention backends/cuda_backend.py:354-375).  mask_mode bit0 causal(-1e4), bit1 key mask. */
 int nfb_rope(int dtype, void* x, const float* cos_t, const float* sin_t, int n_parts, int64_t part_stride, int B, int S, int H, int head_dim,
              int64_t sb, int64_t ss, int64_t sh, int inverse);
+/* RotaryPositionalEmbedding.apply_rope (nn/positional.py:212-270): interleaved pairs (2j, 2j+1), tables (S, head_dim/2), in place on a
+ * (b, s, h, d)-strided tensor; inverse = 1 applies the transpose rotation (the gradient of the forward rotation). */
+int nfb_rope_interleaved(int dtype, void* x, const float* cos_t, const float* sin_t, int B, int S, int H, int head_dim, int64_t sb, int64_t ss,
+                         int64_t sh, int inverse);
 int nfb_flash_attn_set_timeline(void* dev_buf);   /* debug: 256 x u64 clock64 stamps of the tcgen05 forward (NULL = off) */
 int nfb_flash_attn_set_tc(int on);   /* test hook: 0 = mma.sync flash kernels only, 1 = tcgen05 forward only, 3 = tcgen05 forward + backward (default) when the layout is TMA-addressable */
 int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int head_dim,
@@ -146,6 +150,19 @@ int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const void* v, c
                        void* dk, void* dv, int B, int H, int S, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb,
                        int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale, int mask_mode,
                        const float* key_mask);
+
+/* Grouped-query / multi-query attention (nn/modern_attention.py:26-358: GroupedQueryAttention, MultiQueryAttention): q / o / lse / dq
+ * have H heads, k / v / dk / dv have Hkv heads, H % Hkv == 0.  Query head h reads key/value head h / (H / Hkv) in place (the
+ * repeat_kv copy of modern_attention.py:137-161 is never materialised); dk / dv come back already summed over each group. */
+int nfb_flash_attn_fwd_gqa(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv, int S, int head_dim,
+                           int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss,
+                           int64_t o_sh, int Skv, float scale, int mask_mode, const float* key_mask);
+int nfb_flash_attn_bwd_gqa(int dtype, const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
+                           void* dk, void* dv, int B, int H, int Hkv, int S, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh,
+                           int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale,
+                           int mask_mode, const float* key_mask);
+
+int nfb_flash_attn_set_dq_f32_blocks(int n); /* test hook: dQ partials of more than n key blocks are summed in fp32 (default 4) */
 
 /* ---- optimizers: Adam.step / AdamW.step / SGD.step (optim/adam.py:165-252, optim/adamw.py:278-372, optim/sgd.py:87-115)
  * and global-norm clipping (examples/translation/train_conversational.py:38-54; distributed/advanced.py:362-388). */

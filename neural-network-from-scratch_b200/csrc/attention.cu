@@ -35,6 +35,7 @@ struct AttnParams {
   int B, H, S, Skv;
   long long q_sb, q_ss, q_sh;      // q / dq strides (elements)
   long long kv_sb, kv_ss, kv_sh;   // k, v, dk, dv strides
+  int kv_group;                    // query heads per key/value head (grouped-query attention); k/v/dk/dv have H / kv_group heads
   long long o_sb, o_ss, o_sh;      // o / dout strides
   float scale;
   int mask_mode;
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_fwd(const AttnParams p) {
   const int qb = (p.mask_mode & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* Q = p.q + b * p.q_sb + h * p.q_sh;
-  const __nv_bfloat16* K = p.k + b * p.kv_sb + h * p.kv_sh;
-  const __nv_bfloat16* V = p.v + b * p.kv_sb + h * p.kv_sh;
+  const __nv_bfloat16* K = p.k + b * p.kv_sb + (h / p.kv_group) * p.kv_sh;
+  const __nv_bfloat16* V = p.v + b * p.kv_sb + (h / p.kv_group) * p.kv_sh;
   const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
   const int q0 = qb * BR;
   int nkv = (p.Skv + BC - 1) / BC;
@@ -273,31 +274,33 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dkv(const AttnParams p) 
   __nv_bfloat16* sdO = sQ + 2 * BR * HD;     // 2 stages
   float* sLse = (float*)(sdO + 2 * BR * HD); // 2 x 64
   float* sDelta = sLse + 2 * BR;             // 2 x 64
-  const int kb = blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  // blockIdx.y = (batch, KEY/VALUE head); with grouped-query attention the iterations run over the kv_group query heads
+  // that share this head, so dK / dV accumulate over the whole group in registers
+  const int Hkv = p.H / p.kv_group;
+  const int kb = blockIdx.x, b = blockIdx.y / Hkv, h = blockIdx.y % Hkv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const __nv_bfloat16* Q = p.q + b * p.q_sb + h * p.q_sh;
   const __nv_bfloat16* K = p.k + b * p.kv_sb + h * p.kv_sh;
   const __nv_bfloat16* V = p.v + b * p.kv_sb + h * p.kv_sh;
-  const __nv_bfloat16* dO = p.dout + b * p.o_sb + h * p.o_sh;
-  const float* LSE = p.lse + (long long)bh * p.S;
-  const float* DEL = p.delta + (long long)bh * p.S;
   const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
   const int k0 = kb * BC;
   const int nq = (p.S + BR - 1) / BR;
   const int qb_start = (p.mask_mode & 1) ? (k0 / BR) : 0;  // query blocks entirely above the diagonal see nothing
+  const int nqb = max(nq - qb_start, 0), niter = nqb * p.kv_group;
 
-  auto load_q_stage = [&](int stage, int qb) {
-    load_tile_async(sQ + stage * BR * HD, Q, p.q_ss, qb * BR, p.S);
-    load_tile_async(sdO + stage * BR * HD, dO, p.o_ss, qb * BR, p.S);
+  auto load_q_stage = [&](int stage, int it) {
+    const int hq = h * p.kv_group + it / nqb, qb = qb_start + it % nqb;
+    load_tile_async(sQ + stage * BR * HD, p.q + b * p.q_sb + hq * p.q_sh, p.q_ss, qb * BR, p.S);
+    load_tile_async(sdO + stage * BR * HD, p.dout + b * p.o_sb + hq * p.o_sh, p.o_ss, qb * BR, p.S);
     if (threadIdx.x < BR) {
       int r = qb * BR + threadIdx.x;
-      sLse[stage * BR + threadIdx.x] = r < p.S ? LSE[r] : 0.f;
-      sDelta[stage * BR + threadIdx.x] = r < p.S ? DEL[r] : 0.f;
+      const long long row0 = ((long long)b * p.H + hq) * p.S;
+      sLse[stage * BR + threadIdx.x] = r < p.S ? p.lse[row0 + r] : 0.f;
+      sDelta[stage * BR + threadIdx.x] = r < p.S ? p.delta[row0 + r] : 0.f;
     }
   };
   load_tile_async(sK, K, p.kv_ss, k0, p.Skv);
   load_tile_async(sV, V, p.kv_ss, k0, p.Skv);
-  if (qb_start < nq) load_q_stage(0, qb_start);
+  if (niter > 0) load_q_stage(0, 0);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -310,9 +313,9 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dkv(const AttnParams p) 
   const int key_a = k0 + warp * 16 + g, key_b = key_a + 8;
   const float km_a = (kmask && key_a < p.Skv) ? kmask[key_a] : 0.f, km_b = (kmask && key_b < p.Skv) ? kmask[key_b] : 0.f;
 
-  for (int qb = qb_start; qb < nq; ++qb) {
-    int st = (qb - qb_start) & 1;
-    if (qb + 1 < nq) { load_q_stage(st ^ 1, qb + 1); cp_async_commit(); }
+  for (int it = 0; it < niter; ++it) {
+    const int st = it & 1, qb = qb_start + it % nqb;
+    if (it + 1 < niter) { load_q_stage(st ^ 1, it + 1); cp_async_commit(); }
     __nv_bfloat16* tQ = sQ + st * BR * HD;
     __nv_bfloat16* tdO = sdO + st * BR * HD;
     // S^T (16 keys x 64 queries) = K . Q^T
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dkv(const AttnParams p) 
     c_to_a(pf, s);
     // dK += dS^T . Q
     mma_a_b(dk, pf, tQ, lane);
-    if (qb + 1 < nq) cp_async_wait<0>();
+    if (it + 1 < niter) cp_async_wait<0>();
     __syncthreads();
   }
   __nv_bfloat16* dK = p.dk + b * p.kv_sb + h * p.kv_sh;
@@ -395,8 +398,8 @@ __global__ void __launch_bounds__(NTHREADS) k_flash_bwd_dq(const AttnParams p) {
   const int qb = (p.mask_mode & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* Q = p.q + b * p.q_sb + h * p.q_sh;
-  const __nv_bfloat16* K = p.k + b * p.kv_sb + h * p.kv_sh;
-  const __nv_bfloat16* V = p.v + b * p.kv_sb + h * p.kv_sh;
+  const __nv_bfloat16* K = p.k + b * p.kv_sb + (h / p.kv_group) * p.kv_sh;
+  const __nv_bfloat16* V = p.v + b * p.kv_sb + (h / p.kv_group) * p.kv_sh;
   const __nv_bfloat16* dO = p.dout + b * p.o_sb + h * p.o_sh;
   const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
   const int q0 = qb * BR;
@@ -474,24 +477,33 @@ bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, cons
                                int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_ss, int64_t o_sh, int64_t o_sb);
 int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
                      int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
-                     const float* key_mask);
+                     const float* key_mask, int kv_group);
 int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
                      int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
-                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask);
+                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask, int kv_group);
 static int g_attn_tc = 3;   // bit 0: tcgen05 forward, bit 1: tcgen05 backward
 NFB_API int nfb_flash_attn_set_tc(int on) { g_attn_tc = on; return 0; }   // test hook: 0 = mma.sync kernels only, 1 = tcgen05 forward only, 3 = both (default)
 
+static int check_group(int H, int Hkv) {
+  if (Hkv <= 0 || H % Hkv) return NFB_FAIL("flash attention: %d query heads are not a multiple of %d key/value heads", H, Hkv);
+  return 0;
+}
 // dtype must be NFB_BF16.  lse: (B,H,S) fp32 (may be NULL for inference).  key_mask: (B,Skv) fp32 or NULL.
-NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S,
-                               int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh,
-                               int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale, int mask_mode, const float* key_mask) {
+// Grouped-query form: q / o / lse have H heads, k / v have Hkv heads (H % Hkv == 0); query head h reads key/value head
+// h / (H / Hkv) in place -- the repeated K/V of nn/modern_attention.py:137-161 never exists in memory.
+NFB_API int nfb_flash_attn_fwd_gqa(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv, int S,
+                                   int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh,
+                                   int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale, int mask_mode, const float* key_mask) {
   if (dtype != NFB_BF16) return NFB_FAIL("flash attention operands must be bf16");
   if (B == 0 || H == 0 || S == 0) return 0;
+  if (check_group(H, Hkv)) return -1;
+  const int kv_group = H / Hkv;
   if (check_attn(head_dim, q_ss, kv_ss, o_ss)) return -1;
   if ((mask_mode & 2) && !key_mask) return NFB_FAIL("flash attention: mask_mode bit 1 set but key_mask is NULL");
   if ((g_attn_tc & 1) && nfb_flash_fwd_tc_eligible(q, k, v, o, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb))
-    return nfb_flash_fwd_tc(q, k, v, o, lse, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask);
+    return nfb_flash_fwd_tc(q, k, v, o, lse, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale, mask_mode, key_mask, kv_group);
   AttnParams p = {};
+  p.kv_group = kv_group;
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (__nv_bfloat16*)o; p.lse = lse;
   p.B = B; p.H = H; p.S = S; p.Skv = Skv;
   p.q_sb = q_sb; p.q_ss = q_ss; p.q_sh = q_sh; p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
@@ -503,14 +515,26 @@ NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const vo
   return 0;
 }
 
-NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
-                               void* dq, void* dk, void* dv, int B, int H, int S, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh,
-                               int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale,
-                               int mask_mode, const float* key_mask) {
+NFB_API int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S,
+                               int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh,
+                               int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale, int mask_mode, const float* key_mask) {
+  return nfb_flash_attn_fwd_gqa(dtype, q, k, v, o, lse, B, H, H, S, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, Skv, scale,
+                                mask_mode, key_mask);
+}
+
+// dq has H heads; dk / dv have Hkv heads (k / v strides) and receive the SUM over the H / Hkv query heads of each group,
+// accumulated inside the kernels (TMEM / registers), not by a separate reduction.
+NFB_API int nfb_flash_attn_bwd_gqa(int dtype, const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                                   void* dq, void* dk, void* dv, int B, int H, int Hkv, int S, int head_dim, int64_t q_sb, int64_t q_ss,
+                                   int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv,
+                                   float scale, int mask_mode, const float* key_mask) {
   if (dtype != NFB_BF16) return NFB_FAIL("flash attention operands must be bf16");
   if (B == 0 || H == 0 || S == 0) return 0;
   if (check_attn(head_dim, q_ss, kv_ss, o_ss)) return -1;
+  if (check_group(H, Hkv)) return -1;
+  const int kv_group = H / Hkv;
   AttnParams p = {};
+  p.kv_group = kv_group;
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.o = (__nv_bfloat16*)const_cast<void*>(o);
   p.dout = (const __nv_bfloat16*)dout; p.lse = const_cast<float*>(lse);
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
@@ -520,7 +544,7 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
   if ((g_attn_tc & 2) && nfb_flash_fwd_tc_eligible(q, k, v, dout, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_ss, o_sh, o_sb) &&
       ((((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)o) & 15) == 0))
     return nfb_flash_bwd_tc(q, k, v, o, dout, lse, nullptr, dq, dk, dv, B, H, S, Skv, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss, o_sh, scale,
-                            mask_mode, key_mask);
+                            mask_mode, key_mask, kv_group);
   float* delta = nullptr;
   if (nfb_malloc(sizeof(float) * (size_t)B * H * S, (void**)&delta)) return -1;
   p.delta = delta;
@@ -535,13 +559,21 @@ NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const vo
     cudaFuncSetAttribute(k_flash_bwd_dq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * BR * HD + 4 * BC * HD) * 2));
     cfg = true;
   }
-  nfb_launch_pdl(k_flash_bwd_dkv, dim3((unsigned)nfb_cdiv(Skv, BC), (unsigned)(B * H)), dim3(NTHREADS), smem_dkv, s, p);
+  nfb_launch_pdl(k_flash_bwd_dkv, dim3((unsigned)nfb_cdiv(Skv, BC), (unsigned)(B * Hkv)), dim3(NTHREADS), smem_dkv, s, p);
   nfb_count_launch();
   size_t smem_dq = (size_t)(2 * BR * HD + 4 * BC * HD) * 2;
   nfb_launch_pdl(k_flash_bwd_dq, dim3((unsigned)nfb_cdiv(S, BR), (unsigned)(B * H)), dim3(NTHREADS), smem_dq, s, p);
   nfb_free(delta);
   NFB_LAUNCH_CHECK();
   return 0;
+}
+
+NFB_API int nfb_flash_attn_bwd(int dtype, const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                               void* dq, void* dk, void* dv, int B, int H, int S, int head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh,
+                               int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, int Skv, float scale,
+                               int mask_mode, const float* key_mask) {
+  return nfb_flash_attn_bwd_gqa(dtype, q, k, v, o, dout, lse, dq, dk, dv, B, H, H, S, head_dim, q_sb, q_ss, q_sh, kv_sb, kv_ss, kv_sh, o_sb, o_ss,
+                                o_sh, Skv, scale, mask_mode, key_mask);
 }
 
 // ================================================================== RoPE (models/language/gpt2.py:25-95)
@@ -629,6 +661,55 @@ __global__ void k_rope_scalar(T* __restrict__ x, const float* __restrict__ cos_t
     st_f<T>(p, d, x1 * c - x2 * sn);
     st_f<T>(p, d + half, x2 * c + x1 * sn);
   }
+}
+// Interleaved-pair rotary embedding of nn/positional.py:140-366 (RotaryPositionalEmbedding): pairs are (2j, 2j+1),
+//   y[2j] = x[2j] cos_j - x[2j+1] sin_j ;  y[2j+1] = x[2j+1] cos_j + x[2j] sin_j ;  tables (S, D/2).
+// One thread rotates the N/2 pairs of one 16-byte vector in place; inverse = transpose rotation (the gradient).
+template <typename T, bool VEC>
+__global__ void k_rope_pairs(T* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int B, int S, int H, int D,
+                             long long sb, long long ss, long long sh, int inverse) {
+  nfb_pdl_enter();
+  constexpr int N = VEC ? RopeVec<T>::N : 2;
+  const int half = D / 2, groups = D / N;
+  const long long total = (long long)B * S * H * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % groups) * N;
+    long long r = i / groups;
+    const int h = (int)(r % H); r /= H;
+    const int sidx = (int)(r % S);
+    const long long b = r / S;
+    T* p = x + b * sb + (long long)sidx * ss + (long long)h * sh + d;
+    float v[N], y[N];
+    if constexpr (VEC) RopeVec<T>::load(p, v);
+    else { v[0] = ld_f<T>(p, 0); v[1] = ld_f<T>(p, 1); }
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      const float c = __ldg(cos_t + (long long)sidx * half + d / 2 + j);
+      float sn = __ldg(sin_t + (long long)sidx * half + d / 2 + j);
+      if (inverse) sn = -sn;
+      y[2 * j] = v[2 * j] * c - v[2 * j + 1] * sn;
+      y[2 * j + 1] = v[2 * j + 1] * c + v[2 * j] * sn;
+    }
+    if constexpr (VEC) RopeVec<T>::store(p, y);
+    else { st_f<T>(p, 0, y[0]); st_f<T>(p, 1, y[1]); }
+  }
+}
+NFB_API int nfb_rope_interleaved(int dtype, void* x, const float* cos_t, const float* sin_t, int B, int S, int H, int head_dim, int64_t sb,
+                                 int64_t ss, int64_t sh, int inverse) {
+  if (head_dim <= 0 || head_dim % 2) return NFB_FAIL("nfb_rope_interleaved: head_dim %d must be positive and even", head_dim);
+  const int D = head_dim, vn = dtype == NFB_BF16 ? 8 : 4;
+  const bool vec = (D % vn == 0) && !(sb % vn || ss % vn || sh % vn) && ((uintptr_t)x % 16 == 0);
+  const long long total = (long long)B * S * H * (D / (vec ? vn : 2));
+  if (total == 0) return 0;
+  const int grid = nfb_grid_for(total, 256);
+  cudaStream_t st = nfb_cur_stream();
+#define RP(T, V) nfb_launch_pdl(k_rope_pairs<T, V>, dim3(grid), dim3(256), 0, st, (T*)x, cos_t, sin_t, B, S, H, D, sb, ss, sh, inverse)
+  if (dtype == NFB_BF16) { if (vec) RP(__nv_bfloat16, true); else RP(__nv_bfloat16, false); }
+  else if (dtype == NFB_F32) { if (vec) RP(float, true); else RP(float, false); }
+  else return NFB_FAIL("nfb_rope_interleaved: unsupported dtype %d", dtype);
+#undef RP
+  NFB_LAUNCH_CHECK();
+  return 0;
 }
 NFB_API int nfb_rope(int dtype, void* x, const float* cos_t, const float* sin_t, int n_parts, int64_t part_stride, int B, int S, int H,
                      int head_dim, int64_t sb, int64_t ss, int64_t sh, int inverse) {

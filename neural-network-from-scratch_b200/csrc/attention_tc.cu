@@ -38,6 +38,7 @@ struct AttnTcParams {
   int mask_mode;
   const float* key_mask;
   unsigned long long* timeline;   // debug: clock64 stamps of CTA (0,0) (NULL in production)
+  int kv_group;                   // query heads per key/value head (grouped-query attention): K/V maps have H / kv_group heads
 };
 
 // ---------------------------------------------------------------- PTX helpers (same conventions as gemm_tc.cu)
@@ -250,8 +251,8 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(&kv_full[st], 32768u);   // release: the mask words above are visible to whoever acquires kv_full
-        tma_load_4d(smem + SM_K + st * 16384, &tmK, &kv_full[st], 0, h, i * TILE_K, b);
-        tma_load_4d(smem + SM_V + st * 16384, &tmV, &kv_full[st], 0, h, i * TILE_K, b);
+        tma_load_4d(smem + SM_K + st * 16384, &tmK, &kv_full[st], 0, h / p.kv_group, i * TILE_K, b);
+        tma_load_4d(smem + SM_V + st * 16384, &tmV, &kv_full[st], 0, h / p.kv_group, i * TILE_K, b);
       }
     }
   } else if (warp == 9) {
@@ -519,11 +520,17 @@ struct AttnBwdTcParams {
   int mask_mode;
   const float* key_mask;
   unsigned long long* timeline;
+  int kv_group;   // query heads per key/value head: k / v / dk / dv have H / kv_group heads, the CTA loops over the group
+  int dq_f32;     // 1: tmdQ is the 3-D fp32 map of a (B*H, S, 64) accumulation buffer (long sequences), 0: the 4-D bf16 map of dq
 };
 __device__ __forceinline__ void tlb(const AttnBwdTcParams& p, int slot) {
   if (p.timeline && blockIdx.x == 0 && slot < 256) p.timeline[slot] = (unsigned long long)clock64();
 }
 
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -556,12 +563,19 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool causal = (p.mask_mode & 1) != 0;
   // 1-D grid, key-block-major: with a causal mask key block 0 meets every query block -- all of those CTAs go first
-  const int nbh = p.B * p.H;
-  const int jb = (int)blockIdx.x / nbh, bh = (int)blockIdx.x % nbh, b = bh / p.H, h = bh % p.H;
+  // CTA = (key block, batch, KEY/VALUE head h).  Its iterations run over the kv_group query heads sharing that head times
+  // the query blocks that see the key block, so dK / dV accumulate over the whole group in TMEM (grouped-query attention
+  // needs no separate reduction); iteration `it` -> query head hq_of(it), first query row q0_of(it).
+  const int Hkv = p.H / p.kv_group;
+  const int nbh = p.B * Hkv;
+  const int jb = (int)blockIdx.x / nbh, bh = (int)blockIdx.x % nbh, b = bh / Hkv, h = bh % Hkv;
   const int k0 = jb * TILE_K;
   const int nq = (p.S + TILE_Q - 1) / TILE_Q;
   const int i0 = causal ? min(jb, nq) : 0;      // query blocks entirely above the diagonal see none of these keys
-  const int niter = nq - i0;
+  const int nqb = nq - i0;
+  const int niter = nqb * p.kv_group;
+  auto hq_of = [&](int it) { return p.kv_group == 1 ? h : h * p.kv_group + it / nqb; };
+  auto q0_of = [&](int it) { return (i0 + (p.kv_group == 1 ? it : it % nqb)) * TILE_Q; };
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
@@ -598,19 +612,19 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float* sdelta = reinterpret_cast<float*>(smem + SB_DELTA);
       for (int it = 0; it < niter; ++it) {
         const int st = it & 1;
-        const int q0 = (i0 + it) * TILE_Q;
+        const int q0 = q0_of(it), hq = hq_of(it);
         mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1);
         if (lane == 0) {
           mbar_expect_tx(&q_full[st], 32768u);
-          tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, h, q0, b);
-          tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, h, q0, b);
+          tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, hq, q0, b);
+          tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, hq, q0, b);
         }
         if (!p.delta) {
           uint4 ov[4][8];
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
             const int qi = q0 + lane * 4 + rr;
-            const uint4* orow = reinterpret_cast<const uint4*>(p.o + b * p.o_sb + h * p.o_sh + (long long)qi * p.o_ss);
+            const uint4* orow = reinterpret_cast<const uint4*>(p.o + b * p.o_sb + hq * p.o_sh + (long long)qi * p.o_ss);
 #pragma unroll
             for (int c = 0; c < 8; ++c) ov[rr][c] = qi < p.S ? __ldg(orow + c) : make_uint4(0, 0, 0, 0);
           }
@@ -730,6 +744,14 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);
+      if (p.dq_f32) {
+        // fp32 staging: one [128 rows][32 columns = 128 B] SWIZZLE_128B box per column half, added into the fp32 buffer
+        const uint32_t row32 = smem_u32(smem + SB_DQ) + (uint32_t)half * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row32 + (uint32_t)((c ^ sw) * 16)),
+                       "r"(dq[4 * c]), "r"(dq[4 * c + 1]), "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3]) : "memory");
+      } else {
       // bf16 staging box [128 rows][64 columns = 128 B], SWIZZLE_128B: this thread's 32 columns are 16-byte slots 4*half .. +3
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -742,19 +764,27 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ_row + (uint32_t)(((half * 4 + c) ^ sw) * 16)),
                      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
       }
+      }
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
-        tma_reduce_add_4d(&tmdQ, smem_u32(smem + SB_DQ), 0, h, (i0 + it_d) * TILE_Q, b);
+        if (p.dq_f32) {
+          const int bhq = b * p.H + hq_of(it_d);
+          tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ), 0, q0_of(it_d), bhq);
+          tma_reduce_add_3d(&tmdQ, smem_u32(smem + SB_DQ) + 16384u, 32, q0_of(it_d), bhq);
+        } else {
+          tma_reduce_add_4d(&tmdQ, smem_u32(smem + SB_DQ), 0, hq_of(it_d), q0_of(it_d), b);
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
 
     for (int it = 0; it < niter; ++it) {
-      const int q0 = (i0 + it) * TILE_Q, qi = q0 + r;
+      const int q0 = q0_of(it), qi = q0 + r;
+      const long long row0 = ((long long)b * p.H + hq_of(it)) * p.S;   // (b, query head) row of lse / delta
       const bool valid = qi < p.S;
       // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
-      const float lse2 = valid ? p.lse[(long long)bh * p.S + qi] * LOG2E : INFINITY;
+      const float lse2 = valid ? p.lse[row0 + qi] * LOG2E : INFINITY;
       // ---- P = exp2(score - LSE)
       mbar_wait(s_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it);
@@ -828,7 +858,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- dS = P o (dP - delta) * scale   (dS buffer: dK(it-1), dQ(it-1) retired -- dq_full(it-1) awaited in the drain)
       float dlt;
       if (p.delta) {
-        dlt = valid ? p.delta[(long long)bh * p.S + qi] : 0.f;
+        dlt = valid ? p.delta[row0 + qi] : 0.f;
       } else {
         mbar_wait(&delta_full[it & 1], (it >> 1) & 1);   // written by the producer warp a block ahead
         dlt = reinterpret_cast<const float*>(smem + SB_DELTA)[(it & 1) * 128 + r];
@@ -905,6 +935,24 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// dq (bf16, strided (b, s, h, d)) = fp32 accumulation buffer (B, H, S, 64)   [long-sequence path]
+__global__ void k_dq_convert(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int S, long long sb, long long ss, long long sh) {
+  nfb_pdl_enter();
+  const long long total = (long long)B * H * S * 8;   // 8 threads per row, 8 elements each
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7) * 8;
+    const long long row = i >> 3;
+    const int sidx = (int)(row % S);
+    const long long bhh = row / S;
+    const int hh = (int)(bhh % H);
+    const long long bb = bhh / H;
+    const float4 a = *reinterpret_cast<const float4*>(acc + row * 64 + c), bq = *reinterpret_cast<const float4*>(acc + row * 64 + c + 4);
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(a.x, a.y), w1 = __floats2bfloat162_rn(a.z, a.w), w2 = __floats2bfloat162_rn(bq.x, bq.y), w3 = __floats2bfloat162_rn(bq.z, bq.w);
+    *reinterpret_cast<uint4*>(dq + bb * sb + (long long)sidx * ss + (long long)hh * sh + c) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&w0), *reinterpret_cast<uint32_t*>(&w1), *reinterpret_cast<uint32_t*>(&w2), *reinterpret_cast<uint32_t*>(&w3));
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -951,6 +999,20 @@ int make_map_bshd(CUtensorMap* out, const void* base, int B, int S, int H, long 
 unsigned long long* g_attn_timeline = nullptr;
 }  // namespace
 
+// 3-D fp32 map over the dQ accumulation buffer (B*H, S, 64): dims (64, S, B*H), box (32, 128, 1)
+int make_map_dq_f32(CUtensorMap* out, const float* base, int BH, int S) {
+  if (get_encode_fn()) return -1;
+  cuuint64_t dims[3] = {64, (cuuint64_t)S, (cuuint64_t)BH};
+  cuuint64_t strides[2] = {64 * 4, (cuuint64_t)S * 64 * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return NFB_FAIL("attention_tc: cuTensorMapEncodeTiled (dQ fp32) failed (%d) BH=%d S=%d", (int)r, BH, S);
+  return 0;
+}
+static int g_dq_f32_blocks = 4;   // more key blocks than this per query row -> fp32 dQ accumulation (bf16 partial sums lose ~2^-9 per add)
+NFB_API int nfb_flash_attn_set_dq_f32_blocks(int n) { g_dq_f32_blocks = n; return 0; }   // test hook: 0 = always fp32, large = always bf16
 NFB_API int nfb_flash_attn_set_timeline(void* dev_buf) { g_attn_timeline = (unsigned long long*)dev_buf; return 0; }   // debug: 256 x u64
 
 // true when the tcgen05 forward can take this problem (16-byte aligned bases and strides; head_dim 64)
@@ -965,12 +1027,13 @@ bool nfb_flash_fwd_tc_eligible(const void* q, const void* k, const void* v, cons
 
 int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss,
                      int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh, float scale, int mask_mode,
-                     const float* key_mask) {
+                     const float* key_mask, int kv_group) {
   CUtensorMap tmQ, tmK, tmV;
   if (make_map_bshd(&tmQ, q, B, S, H, q_sb, q_ss, q_sh)) return -1;
-  if (make_map_bshd(&tmK, k, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
-  if (make_map_bshd(&tmV, v, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmK, k, B, Skv, H / kv_group, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmV, v, B, Skv, H / kv_group, kv_sb, kv_ss, kv_sh)) return -1;
   AttnTcParams p = {};
+  p.kv_group = kv_group;
   p.o = (__nv_bfloat16*)o; p.lse = lse; p.B = B; p.H = H; p.S = S; p.Skv = Skv;
   p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
   p.timeline = g_attn_timeline;
@@ -988,14 +1051,24 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
 // backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) may be NULL (computed in the kernel from o and dO).  dq/dk/dv use the q / kv strides.
 int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
                      int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
-                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask) {
+                     int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask, int kv_group) {
   CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
   if (make_map_bshd(&tmQ, q, B, S, H, q_sb, q_ss, q_sh)) return -1;
-  if (make_map_bshd(&tmK, k, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
-  if (make_map_bshd(&tmV, v, B, Skv, H, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmK, k, B, Skv, H / kv_group, kv_sb, kv_ss, kv_sh)) return -1;
+  if (make_map_bshd(&tmV, v, B, Skv, H / kv_group, kv_sb, kv_ss, kv_sh)) return -1;
   if (make_map_bshd(&tmdO, dout, B, S, H, o_sb, o_ss, o_sh)) return -1;
-  if (make_map_bshd(&tmdQ, dq, B, S, H, q_sb, q_ss, q_sh)) return -1;
   cudaStream_t st = nfb_cur_stream();
+  // dQ partials (one per key block) are summed by L2 reduce-adds: straight into the bf16 dq for short key ranges, into an
+  // fp32 (B*H, S, 64) buffer converted afterwards when more than g_dq_f32_blocks partials meet in one element
+  const bool dq_f32 = nfb_cdiv(Skv, TILE_K) > g_dq_f32_blocks;
+  float* acc = nullptr;
+  if (dq_f32) {
+    const size_t acc_bytes = sizeof(float) * (size_t)B * H * S * 64;
+    if (nfb_malloc(acc_bytes, (void**)&acc)) return -1;
+    if (make_map_dq_f32(&tmdQ, acc, B * H, S)) { nfb_free(acc); return -1; }
+    NFB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  } else {
+  if (make_map_bshd(&tmdQ, dq, B, S, H, q_sb, q_ss, q_sh)) return -1;
   // dq accumulates through reduce-adds: zero it first.  Its rows (b, s) hold H*64 contiguous elements at pitch q_ss when the
   // heads are packed (q_sh == 64): one 2-D memset per batch entry; any other layout is cleared head by head.
   if (q_sh == HDIM && (q_sb == (long long)S * q_ss || B == 1)) {   // the packed qkv layout: ONE strided clear of all B*S rows
@@ -1008,19 +1081,28 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
       for (int hh = 0; hh < H; ++hh)
         NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb + (long long)hh * q_sh, (size_t)q_ss * 2, 0, (size_t)HDIM * 2, (size_t)S, st));
   }
+  }
   AttnBwdTcParams p = {};
   p.lse = lse; p.delta = delta; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.B = B; p.H = H; p.S = S; p.Skv = Skv; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
   p.timeline = g_attn_timeline;
+  p.kv_group = kv_group;
+  p.dq_f32 = dq_f32 ? 1 : 0;
   static bool configured = false;
   if (!configured) {
     NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * H));
+  dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * (H / kv_group)));
   k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
-  nfb_count_launch();
+  if (dq_f32) {
+    const long long vecs = (long long)B * H * S * 8;
+    nfb_launch_pdl(k_dq_convert, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const float*)acc, (__nv_bfloat16*)dq, B, H, S,
+                   (long long)q_sb, (long long)q_ss, (long long)q_sh);
+    nfb_count_launch();
+    nfb_free(acc);
+  }
   NFB_LAUNCH_CHECK();
   return 0;
 }

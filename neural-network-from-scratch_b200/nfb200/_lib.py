@@ -113,6 +113,11 @@ _SIGNATURES = {
     "nfb_flash_attn_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, vp],
     "nfb_flash_attn_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64,
                            i32, f32, i32, vp],
+    "nfb_flash_attn_set_dq_f32_blocks": [i32],
+    "nfb_rope_interleaved": [i32, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i32],
+    "nfb_flash_attn_fwd_gqa": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, vp],
+    "nfb_flash_attn_bwd_gqa": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64,
+                               i32, f32, i32, vp],
     # collectives
     "nfb_comm_load": [C.c_char_p],
     "nfb_comm_unique_id": [C.c_char_p, i32],

@@ -5,5 +5,5 @@ from .fused import (embedding, layer_norm, linear, packed_qkv_attention, rms_nor
                     swiglu_packed)
 from .loss import cross_entropy_loss, mse_loss
 from .reduction import mean, sum  # noqa: A004
-from .shape import concatenate, getitem, reshape, swapaxes, transpose
+from .shape import concatenate, getitem, repeat_kv, reshape, swapaxes, transpose
 from .utils import reduce_gradient

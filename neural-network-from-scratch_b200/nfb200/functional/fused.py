@@ -253,12 +253,18 @@ def rope(x: Tensor, base: int = 10000) -> Tensor:
 
 
 def scaled_dot_product_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, causal: bool = False, mask=None) -> Tensor:
-    """softmax(q k^T * scale [causal -1e4 replace] [+ additive mask]) v for (B,H,S,D) tensors.
-    cuda + bf16 precision: the fused flash kernels; otherwise the unfused fp32 composition (1e-5 path)."""
+    """softmax(q k^T * scale [causal -1e4 replace] [+ additive mask]) v for (B,H,S,D) tensors; k / v may carry fewer heads
+    (grouped-query / multi-query attention: query head h uses key/value head h // (H // Hkv)).
+    cuda + bf16 precision: the fused flash kernels (grouped K/V read in place, per-key additive masks); otherwise the
+    unfused fp32 composition (1e-5 path, any broadcastable additive mask)."""
     mk = mask.data if isinstance(mask, Tensor) else mask
+    H, Hkv = q.shape[1], k.shape[1]
+    if Hkv <= 0 or H % Hkv:
+        raise ValueError(f"{H} query heads are not a multiple of {Hkv} key/value heads")
     if _dev(q):
         from .. import kernels as K
-        if K.get_precision() == "bf16" and q.shape[-1] == 64:
+        per_key = mk is None or int(np.prod(mk.shape)) in (k.shape[2], q.shape[0] * k.shape[2])
+        if K.get_precision() == "bf16" and q.shape[-1] == 64 and per_key:
             qd, kd, vd = K.to_bf16(q.data), K.to_bf16(k.data), K.to_bf16(v.data)
             o, lse = K.attention_forward(qd, kd, vd, scale, causal, mk)
 
@@ -270,7 +276,8 @@ def scaled_dot_product_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, 
     q, k, v = to_float32(q), to_float32(k), to_float32(v)
     from .activation import softmax
     from .arithmetic import add, matmul, mul
-    from .shape import swapaxes
+    from .shape import repeat_kv, swapaxes
+    k, v = repeat_kv(k, H // Hkv), repeat_kv(v, H // Hkv)
     s = mul(matmul(q, swapaxes(k, -1, -2)), float(scale))
     if causal:
         S, Skv = s.shape[-2], s.shape[-1]

@@ -29,6 +29,28 @@ def swapaxes(x: Tensor, a: int, b: int) -> Tensor:
     return transpose(x, ax)
 
 
+def repeat_kv(x: Tensor, n_rep: int) -> Tensor:
+    """(B, Hkv, S, D) -> (B, Hkv * n_rep, S, D), head h of the result = head h // n_rep of x -- the explicit key/value
+    repetition of grouped-query attention (nn/modern_attention.py:137-161; there on the (B,S,Hkv,D) layout).  Backward sums
+    each group.  Only the unfused attention composition needs it: the flash kernels read grouped K/V in place."""
+    if n_rep == 1:
+        return x
+    B, Hkv, S, D = x.shape
+    xd = x.data
+    if isinstance(xd, B200Array):
+        out = xd.reshape(B, Hkv, 1, S, D).broadcast_to((B, Hkv, n_rep, S, D)).contiguous().reshape(B, Hkv * n_rep, S, D)
+
+        def backward(g):
+            g32 = g if g.dtype == np.dtype(np.float32) else g.astype(np.float32)
+            return (g32.reshape(B, Hkv, n_rep, S, D).sum(axis=2),)
+    else:
+        out = np.repeat(xd, n_rep, axis=1)
+
+        def backward(g):
+            return (g.reshape(B, Hkv, n_rep, S, D).sum(axis=2),)
+    return make_result(out, [x], backward, "repeat_kv")
+
+
 def _zeros_like_data(x: Tensor):
     if isinstance(x.data, B200Array):
         return x.backend.zeros(x.shape, np.float32)

@@ -349,6 +349,21 @@ def _bhsd_strides(x: B200Array):
     return x.strides[0], x.strides[2], x.strides[1]
 
 
+def rope_interleaved_inplace(x: B200Array, cos_t: B200Array, sin_t: B200Array, inverse=False):
+    """Interleaved-pair rotary embedding (nn/positional.py:212-270) in place on a logical (B,H,S,D) or (B,S,D) array;
+    cos_t / sin_t: device fp32 (S, D/2) tables of the positions of these S rows."""
+    if x.ndim == 3:
+        Bn, S, D = x.shape
+        H, sb, ss, sh = 1, x.strides[0], x.strides[1], 0
+        if x.strides[2] != 1:
+            raise ValueError("rope: the last dimension must be contiguous")
+    else:
+        Bn, H, S, D = x.shape
+        sb, ss, sh = _bhsd_strides(x)
+    call("nfb_rope_interleaved", dtype_code(x.dtype), x.ptr, cos_t.ptr, sin_t.ptr, Bn, S, H, D, sb, ss, sh, 1 if inverse else 0)
+    return x
+
+
 def rope_inplace(x: B200Array, inverse=False, base=10000):
     """Rotate a logical (B,H,S,D) array (any strides) in place."""
     Bn, H, S, D = x.shape
@@ -382,10 +397,12 @@ def _key_mask(mask, Bn, Skv):
 
 def attention_forward(q: B200Array, k: B200Array, v: B200Array, scale: float, causal=False, mask=None, need_lse=True):
     """Fused softmax(q k^T * scale [masks]) v.  q,k,v logical (B,H,S,D), bf16 (fp32 inputs are cast), D == 64.
+    k / v may have fewer heads than q (grouped-query / multi-query attention, nn/modern_attention.py:26-358): query head h
+    then reads key/value head h // (H // Hkv) in place.
     Returns (o, lse): o logical (B,H,S,D) stored as (B,S,H,D) so o.transpose(0,2,1,3).reshape(B,S,H*D) is free."""
     q, k, v = to_bf16(q), to_bf16(k), to_bf16(v)
     Bn, H, S, D = q.shape
-    Skv = k.shape[2]
+    Hkv, Skv = k.shape[1], k.shape[2]
     o_store = B200Array.empty((Bn, S, H, D), bfloat16)
     lse = B200Array.empty((Bn, H, S), np.float32) if need_lse else None
     km = _key_mask(mask, Bn, Skv)
@@ -395,17 +412,18 @@ def attention_forward(q: B200Array, k: B200Array, v: B200Array, scale: float, ca
         k = k.contiguous()
         ks_ = _bhsd_strides(k)
     mode = (1 if causal else 0) | (2 if km is not None else 0)
-    call("nfb_flash_attn_fwd", _lib.BF16, q.ptr, k.ptr, v.ptr, o_store.ptr, lse.ptr if lse is not None else None, Bn, H, S, D,
+    call("nfb_flash_attn_fwd_gqa", _lib.BF16, q.ptr, k.ptr, v.ptr, o_store.ptr, lse.ptr if lse is not None else None, Bn, H, Hkv, S, D,
          qs[0], qs[1], qs[2], ks_[0], ks_[1], ks_[2], S * H * D, H * D, D, Skv, float(scale), mode, km.ptr if km is not None else None)
     return o_store.transpose(0, 2, 1, 3), lse
 
 
 def attention_backward(dout: B200Array, q, k, v, o, lse, scale, causal=False, mask=None, packed=False):
-    """Returns (dq, dk, dv) as logical (B,H,S,D) bf16 arrays.  With packed=True the three live in ONE
-    (B,S,3,H,D) buffer (returned as a 4th value) laid out like a fused qkv projection output."""
+    """Returns (dq, dk, dv) as logical (B,H,S,D) bf16 arrays (dk / dv with k's head count: grouped-query gradients are
+    summed over each group inside the kernel).  With packed=True the three live in ONE (B,S,3,H,D) buffer (returned
+    as a 4th value) laid out like a fused qkv projection output."""
     q, k, v = to_bf16(q), to_bf16(k), to_bf16(v)
     Bn, H, S, D = q.shape
-    Skv = k.shape[2]
+    Hkv, Skv = k.shape[1], k.shape[2]
     dout = to_bf16(dout)
     os_ = _bhsd_strides(o)
     if _bhsd_strides(dout) != os_:
@@ -423,8 +441,8 @@ def attention_backward(dout: B200Array, q, k, v, o, lse, scale, causal=False, ma
     km = _key_mask(mask, Bn, Skv)
     mode = (1 if causal else 0) | (2 if km is not None else 0)
     if packed:
-        if S != Skv:
-            raise ValueError("packed dqkv needs S == S_kv")
+        if S != Skv or H != Hkv:
+            raise ValueError("packed dqkv needs S == S_kv and as many key/value heads as query heads")
         buf = B200Array.empty((Bn, S, 3, H, D), bfloat16)
         dq = buf[:, :, 0].transpose(0, 2, 1, 3)
         dk = buf[:, :, 1].transpose(0, 2, 1, 3)
@@ -432,8 +450,8 @@ def attention_backward(dout: B200Array, q, k, v, o, lse, scale, causal=False, ma
     else:
         buf = None
         dq = B200Array.empty((Bn, S, H, D), bfloat16).transpose(0, 2, 1, 3)
-        dk = B200Array.empty((Bn, Skv, H, D), bfloat16).transpose(0, 2, 1, 3)
-        dv = B200Array.empty((Bn, Skv, H, D), bfloat16).transpose(0, 2, 1, 3)
+        dk = B200Array.empty((Bn, Skv, Hkv, D), bfloat16).transpose(0, 2, 1, 3)
+        dv = B200Array.empty((Bn, Skv, Hkv, D), bfloat16).transpose(0, 2, 1, 3)
     # the kernels address dq with q's strides and dk/dv with k's strides: make operand layouts agree
     if _bhsd_strides(dq) != qs:
         q = _relayout_like(q, dq)
@@ -442,7 +460,7 @@ def attention_backward(dout: B200Array, q, k, v, o, lse, scale, causal=False, ma
         k = _relayout_like(k, dk)
         v = _relayout_like(v, dv)
         ks_ = _bhsd_strides(k)
-    call("nfb_flash_attn_bwd", _lib.BF16, q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr, dq.ptr, dk.ptr, dv.ptr, Bn, H, S, D,
+    call("nfb_flash_attn_bwd_gqa", _lib.BF16, q.ptr, k.ptr, v.ptr, o.ptr, dout.ptr, lse.ptr, dq.ptr, dk.ptr, dv.ptr, Bn, H, Hkv, S, D,
          qs[0], qs[1], qs[2], ks_[0], ks_[1], ks_[2], os_[0], os_[1], os_[2], Skv, float(scale), mode, km.ptr if km is not None else None)
     return (dq, dk, dv, buf) if packed else (dq, dk, dv)
 

@@ -4,3 +4,6 @@ from .layers import (GELU, Dropout, Embedding, LayerError, LayerNorm, ModuleList
                      Tanh)
 from .linear import Linear, OptimizedLinear, StandardLinear
 from .transformer import MultiHeadAttention, TransformerBlock, TransformerDecoderBlock
+from .modern_attention import FlashAttentionConcept, GroupedQueryAttention, MultiQueryAttention
+from .positional import (LearnedPE, LearnedPositionalEmbedding, RoPE, RotaryPositionalEmbedding, SinusoidalPE,
+                         SinusoidalPositionalEncoding, create_rope, create_sinusoidal_pe)

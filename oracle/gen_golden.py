@@ -331,12 +331,72 @@ def gen_train_glue(g):
     g["helper_clipped"] = np.concatenate([np.asarray(p.grad.data, dtype=np.float32).ravel() for p in params.values()])
 
 
+def gen_modern(g):
+    """Zoo blocks on the same kernels: nn/modern_attention.py GroupedQueryAttention / MultiQueryAttention forwards
+    (weights stored, so the fixtures do not depend on RNG call order) and nn/positional.py forwards (+ the learned table's
+    gradients; the reference's GQA and RoPE backwards are placeholders / wrong -- PARITY.md #17, #18 -- and are not pinned)."""
+    from neural_arch.core import Tensor
+    from neural_arch.nn.modern_attention import GroupedQueryAttention, MultiQueryAttention
+    from neural_arch.nn.positional import LearnedPositionalEmbedding, RotaryPositionalEmbedding, SinusoidalPositionalEncoding
+    rng = np.random.default_rng(500)
+    for tag, kw, B, S, mask_kind in (("gqa", dict(d_model=64, n_heads=4, n_kv_heads=2), 2, 9, None),
+                                     ("gqa_bias_keymask", dict(d_model=96, n_heads=6, n_kv_heads=3, bias=True), 3, 7, "key"),
+                                     ("gqa_full_mask", dict(d_model=64, n_heads=4, n_kv_heads=1), 2, 6, "causal"),
+                                     ("mha", dict(d_model=32, n_heads=2), 1, 5, None)):
+        np.random.seed(7)
+        m = GroupedQueryAttention(**kw)
+        for n in ("b_q", "b_k", "b_v", "b_o"):
+            if getattr(m, n) is not None:
+                getattr(m, n).data = (rng.standard_normal(getattr(m, n).shape) * 0.1).astype(np.float32)
+        x = rng.standard_normal((B, S, kw["d_model"])).astype(np.float32)
+        mask = None
+        if mask_kind == "key":
+            mask = np.where(rng.random((B, 1, 1, S)) < 0.3, -1e4, 0.0).astype(np.float32)
+            mask[..., 0] = 0.0
+        elif mask_kind == "causal":
+            mask = np.triu(np.full((S, S), -1e9, dtype=np.float32), k=1)
+        out = m(Tensor(x), None if mask is None else Tensor(mask))
+        g[f"{tag}_x"], g[f"{tag}_out"] = x, np.asarray(out.data)
+        if mask is not None:
+            g[f"{tag}_mask"] = mask
+        for n in ("W_q", "W_k", "W_v", "W_o", "b_q", "b_k", "b_v", "b_o"):
+            if getattr(m, n) is not None:
+                g[f"{tag}_{n}"] = np.asarray(getattr(m, n).data)
+    np.random.seed(8)
+    mq = MultiQueryAttention(d_model=64, n_heads=4)
+    x = rng.standard_normal((2, 5, 64)).astype(np.float32)
+    g["mqa_x"], g["mqa_out"] = x, np.asarray(mq(Tensor(x)).data)
+    for n in ("W_q", "W_k", "W_v", "W_o"):
+        g[f"mqa_{n}"] = np.asarray(getattr(mq.gqa, n).data)
+    kv = rng.standard_normal((2, 3, 2, 4)).astype(np.float32)
+    g["repeat_in"], g["repeat_out"] = kv, GroupedQueryAttention(d_model=32, n_heads=8, n_kv_heads=2).repeat_kv(kv)
+    # positional
+    x = rng.standard_normal((2, 7, 16)).astype(np.float32)
+    g["pos_x"] = x
+    g["sin_out"] = np.asarray(SinusoidalPositionalEncoding(16, max_len=64)(Tensor(x), start_pos=3).data)
+    g["sin_out_base"] = np.asarray(SinusoidalPositionalEncoding(16, max_len=32, base=500.0)(Tensor(x)).data)
+    q4, k4 = rng.standard_normal((2, 3, 7, 16)).astype(np.float32), rng.standard_normal((2, 3, 7, 16)).astype(np.float32)
+    rope = RotaryPositionalEmbedding(16, max_seq_len=32)
+    rq, rk = rope(Tensor(q4), Tensor(k4), start_pos=5)
+    g["rope_q"], g["rope_k"], g["rope_q_out"], g["rope_k_out"] = q4, k4, np.asarray(rq.data), np.asarray(rk.data)
+    r3q, _ = RotaryPositionalEmbedding(16, max_seq_len=8, base=100.0)(Tensor(x), Tensor(x), start_pos=4)   # grows its tables
+    g["rope3_out"] = np.asarray(r3q.data)
+    np.random.seed(9)
+    lpe = LearnedPositionalEmbedding(12, 16)
+    xt = Tensor(x, requires_grad=True)
+    out = lpe(xt, start_pos=2)
+    up = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(up)
+    g["lpe_table"], g["lpe_out"], g["lpe_up"] = np.asarray(lpe.embedding.data), np.asarray(out.data), up
+    g["lpe_dx"], g["lpe_dtable"] = np.asarray(xt.grad), np.asarray(lpe.embedding.grad)
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern)):
         if only and name not in only:
             continue
         g = {}

@@ -521,6 +521,7 @@ struct AttnBwdTcParams {
   const float* key_mask;
   unsigned long long* timeline;
   int kv_group;   // query heads per key/value head: k / v / dk / dv have H / kv_group heads, the CTA loops over the group
+  int kv_split;   // CTAs per key/value head (few-kv-head grids): CTA head h reads K/V head h / kv_split and writes dk/dv slice h
   int dq_f32;     // 1: tmdQ is the 3-D fp32 map of a (B*H, S, 64) accumulation buffer (long sequences), 0: the 4-D bf16 map of dq
 };
 __device__ __forceinline__ void tlb(const AttnBwdTcParams& p, int slot) {
@@ -606,8 +607,8 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (niter > 0) {
       if (lane == 0) {
         mbar_expect_tx(kv_full, 32768u);
-        tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h, k0, b);
-        tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h, k0, b);
+        tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h / p.kv_split, k0, b);
+        tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h / p.kv_split, k0, b);
       }
       float* sdelta = reinterpret_cast<float*>(smem + SB_DELTA);
       for (int it = 0; it < niter; ++it) {
@@ -953,6 +954,32 @@ __global__ void k_dq_convert(const float* __restrict__ acc, __nv_bfloat16* __res
   }
 }
 
+// dk / dv (bf16, k / v strides, Hkv heads) = sum over the `split` partial heads of a contiguous (B, Skv, Hkv*split, 64) bf16 buffer
+__global__ void k_kv_split_sum(const __nv_bfloat16* __restrict__ part, __nv_bfloat16* __restrict__ out, int B, int Skv, int Hkv, int split,
+                               long long sb, long long ss, long long sh) {
+  nfb_pdl_enter();
+  const long long total = (long long)B * Skv * Hkv * 8;   // 8 threads per (b, s, head) row, 8 elements each
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7) * 8;
+    long long r = i >> 3;
+    const int hk = (int)(r % Hkv); r /= Hkv;
+    const int sidx = (int)(r % Skv);
+    const long long bb = r / Skv;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* src = part + ((bb * Skv + sidx) * (long long)(Hkv * split) + (long long)hk * split) * 64 + c;
+    for (int j = 0; j < split; ++j) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + (long long)j * 64);
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(v2[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+    }
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(acc[0], acc[1]), w1 = __floats2bfloat162_rn(acc[2], acc[3]), w2 = __floats2bfloat162_rn(acc[4], acc[5]),
+                   w3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + bb * sb + (long long)sidx * ss + (long long)hk * sh + c) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&w0), *reinterpret_cast<uint32_t*>(&w1), *reinterpret_cast<uint32_t*>(&w2), *reinterpret_cast<uint32_t*>(&w3));
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1082,20 +1109,54 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
         NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb + (long long)hh * q_sh, (size_t)q_ss * 2, 0, (size_t)HDIM * 2, (size_t)S, st));
   }
   }
+  // grouped-query grids with few key/value heads (multi-query attention: one) would leave most SMs idle: split each
+  // group over kv_split CTAs, each writing its partial dK / dV into a slice of a scratch buffer summed afterwards
+  const int Hkv = H / kv_group;
+  const long long kv_sb_out = kv_sb, kv_ss_out = kv_ss, kv_sh_out = kv_sh;
+  int kv_split = 1;
+  {
+    const long long base = (long long)nfb_cdiv(Skv, TILE_K) * B * Hkv;
+    for (int sdiv = 1; sdiv <= kv_group; ++sdiv) {
+      if (kv_group % sdiv) continue;
+      kv_split = sdiv;
+      if (base * sdiv >= 148) break;
+    }
+  }
+  __nv_bfloat16* part = nullptr;
+  if (kv_split > 1) {
+    if (nfb_malloc(sizeof(__nv_bfloat16) * 2 * (size_t)B * Skv * Hkv * kv_split * HDIM, (void**)&part)) { if (acc) nfb_free(acc); return -1; }
+  }
   AttnBwdTcParams p = {};
   p.lse = lse; p.delta = delta; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  if (part) {   // partial dK | dV: two contiguous (B, Skv, Hkv * kv_split, 64) halves
+    const long long hp = (long long)Hkv * kv_split;
+    p.dk = part; p.dv = part + (size_t)B * Skv * hp * HDIM;
+    kv_sb = (long long)Skv * hp * HDIM; kv_ss = hp * HDIM; kv_sh = HDIM;
+  }
+  p.kv_split = kv_split;
   p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.B = B; p.H = H; p.S = S; p.Skv = Skv; p.scale = scale; p.mask_mode = mask_mode; p.key_mask = key_mask;
   p.timeline = g_attn_timeline;
-  p.kv_group = kv_group;
+  p.kv_group = kv_group / kv_split;
   p.dq_f32 = dq_f32 ? 1 : 0;
   static bool configured = false;
   if (!configured) {
     NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * (H / kv_group)));
+  dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * Hkv * kv_split));
   k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  if (part) {
+    const long long vecs = (long long)B * Skv * Hkv * 8;
+    const long long half_elems = (long long)B * Skv * Hkv * kv_split * HDIM;
+    nfb_launch_pdl(k_kv_split_sum, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const __nv_bfloat16*)part, (__nv_bfloat16*)dk, B, Skv, Hkv,
+                   kv_split, kv_sb_out, kv_ss_out, kv_sh_out);
+    nfb_count_launch();
+    nfb_launch_pdl(k_kv_split_sum, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const __nv_bfloat16*)(part + half_elems), (__nv_bfloat16*)dv, B,
+                   Skv, Hkv, kv_split, kv_sb_out, kv_ss_out, kv_sh_out);
+    nfb_count_launch();
+    nfb_free(part);
+  }
   if (dq_f32) {
     const long long vecs = (long long)B * H * S * 8;
     nfb_launch_pdl(k_dq_convert, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const float*)acc, (__nv_bfloat16*)dq, B, H, S,

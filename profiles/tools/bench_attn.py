@@ -24,7 +24,7 @@ for B, H, S, causal in cfgs:
         def fwd():
             for q, k, v, _ in sets: Kn.attention_forward(q, k, v, scale, causal=causal)
         def bwd():
-            for (q, k, v, go), (o, lse) in zip(sets, outs): Kn.attention_backward(go, q, k, v, o, lse, scale, causal=causal)
+            for (q, k, v, go), (o, lse) in zip(sets, outs): Kn.attention_backward(go, q, k, v, o, lse, scale, causal=causal, packed=True)
         res = []
         for name, fn, fl in (("fwd", fwd, flop_fwd), ("bwd", bwd, 2.5 * flop_fwd)):
             fn(); R.synchronize()
@@ -35,3 +35,26 @@ for B, H, S, causal in cfgs:
             res.append(f"{name} {ms*1e3:7.1f} us {fl/ms/1e9:6.0f} TF/s")
         print(f"B={B} H={H} S={S} causal={causal} impl={'tcgen05' if impl else 'mma.sync'}: " + " | ".join(res), flush=True)
 _lib.call("nfb_flash_attn_set_tc", 3)
+# ---- grouped-query attention: K/V heads read in place; same algorithmic flops as MHA with H query heads
+for B, H, Hkv, S, causal in [(8, 12, 12, 512, True), (8, 12, 4, 512, True), (8, 12, 1, 512, True), (8, 16, 4, 1024, True), (8, 32, 8, 2048, True)]:
+    D = 64
+    sets = []
+    for _ in range(3):
+        q = bf(B, S, H, D).transpose(0, 2, 1, 3); k = bf(B, S, Hkv, D).transpose(0, 2, 1, 3); v = bf(B, S, Hkv, D).transpose(0, 2, 1, 3)
+        go = bf(B, S, H, D).transpose(0, 2, 1, 3)
+        sets.append((q, k, v, go))
+    flop_fwd = 4.0 * B * H * S * S * D * 0.5
+    outs = [Kn.attention_forward(q, k, v, 0.125, causal=causal) for q, k, v, _ in sets]
+    def fwd():
+        for q, k, v, _ in sets: Kn.attention_forward(q, k, v, 0.125, causal=causal)
+    def bwd():
+        for (q, k, v, go), (o, lse) in zip(sets, outs): Kn.attention_backward(go, q, k, v, o, lse, 0.125, causal=causal)
+    res = []
+    for name, fn, fl in (("fwd", fwd, flop_fwd), ("bwd", bwd, 2.5 * flop_fwd)):
+        fn(); R.synchronize()
+        g = R.Graph()
+        with g: fn()
+        R.synchronize()
+        ms = R.time_ms(g.replay, iters=10, warmup=2) / len(sets)
+        res.append(f"{name} {ms*1e3:7.1f} us {fl/ms/1e9:6.0f} TF/s")
+    print(f"GQA B={B} H={H} Hkv={Hkv} S={S} causal: " + " | ".join(res), flush=True)

@@ -76,4 +76,26 @@ W = f32(V, d, scale=0.02); ids = B200Array.from_numpy(rng.integers(0, V, (T,)).a
 report("embedding gather (T rows of 768)", T*d*(4+4), lambda: be.embedding_forward(W, ids))
 qkv = bf(8, 512, 3, 12, 64)
 report("rope q,k in place (packed qkv)", 8*512*2*12*64*2*2, lambda: Kn.rope_packed_qk_inplace(qkv, 12))
+# ---- loss-scaler unscale + finite check + per-parameter norm clip over a 109.4 M-element gradient arena cut like GPT-2 small
+# (two passes: statistics reads g once, apply reads and writes it: 12 B / element)
+from nfb200.core import Parameter
+from nfb200.optim import SGD
+from nfb200.optimization import AdvancedGradScaler, ScalerConfig
+shapes = [(V, d)] + [s_ for _ in range(12) for s_ in ((d,), (2304, d), (d, d), (d,), (3072, d), (d, 1536))] + [(d,)]
+params = {f"p{i}": Parameter(B200Array.full(s_, 0.01, np.float32)) for i, s_ in enumerate(shapes)}
+sgd = SGD(params, lr=0.0)
+for p_ in params.values():
+    p_.grad = B200Array.full(p_.shape, 1e-3, np.float32)
+sc = AdvancedGradScaler(ScalerConfig(init_scale=1.0, gradient_clip_threshold=1e9))
+sc.unscale_(sgd)
+tab = sc._arena_table(sgd.arena, list(params.values()))
+ntot = sum(int(np.prod(s_)) for s_ in shapes)
+report("grad unscale+check+clip (arena)", ntot*12, lambda: call("nfb_grad_unscale", sgd.arena.flat_g.ptr, tab[0].ptr, tab[1], len(shapes), 1.0, 1e9, tab[2].ptr, tab[3].ptr))
+del params, sgd
+# ---- interleaved-pair RoPE (nn/positional.py) in place on bf16 (8, 12, 512, 64)
+from nfb200.nn import RotaryPositionalEmbedding
+rp = RotaryPositionalEmbedding(64, 512)
+xq = bf(8, 512, 12, 64).transpose(0, 2, 1, 3)
+ct, st_ = B200Array.from_numpy(rp.cos_cached), B200Array.from_numpy(rp.sin_cached)
+report("rope interleaved in place bf16", 8*512*12*64*2*2, lambda: Kn.rope_interleaved_inplace(xq, ct, st_))
 json.dump([{"kernel": n, "bytes": b_, "ms": ms, "gbs": gb, "frac": gb / PEAK} for n, b_, ms, gb in rows], open("gpurun_out/bw_kernels.json", "w"), indent=1)

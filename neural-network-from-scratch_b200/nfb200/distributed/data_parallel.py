@@ -9,6 +9,8 @@ transfer overlaps the rest of backward; finish_gradient_sync() fences the comput
 """
 from __future__ import annotations
 
+import os
+
 from contextlib import contextmanager
 from typing import List, Optional
 
@@ -19,6 +21,9 @@ from ..core import Module, Tensor
 from ..optim.arena import ALIGN, ParamArena
 from . import communication as comm
 from .communication import ReduceOp
+
+
+_DEBUG_SKIP_ALLREDUCE = bool(int(os.environ.get("NFB_DDP_DEBUG_SKIP_ALLREDUCE", "0")))
 
 
 class _Bucket:
@@ -139,7 +144,8 @@ class DistributedDataParallel(Module):
             g.comm_stream.wait_event(side_ev)
         b.piece_events = []
         for lo, hi in b.pieces:
-            g.allreduce_buffer(self.arena.flat_g, hi - lo, ReduceOp.AVERAGE, g.comm_stream, offset=lo)
+            if not _DEBUG_SKIP_ALLREDUCE:   # measurement aid: same streams / events / optimizer pipeline, no NCCL kernel
+                g.allreduce_buffer(self.arena.flat_g, hi - lo, ReduceOp.AVERAGE, g.comm_stream, offset=lo)
             b.piece_events.append(Event(timing=False).record(g.comm_stream))
         b.event = b.piece_events[-1]
         b.launched = True

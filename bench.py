@@ -322,6 +322,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step (fwd + CE + bwd + AdamW)",
                        "per_gpu_batch": BATCH, "seq_len": SEQ, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       **({"gradient_buckets": f"{args.bucket_mb:g} MB NCCL all-reduce (ncclAvg) overlapped with backward, AdamW pipelined behind them"} if world > 1 else {}),
                        "precision": "bf16 tensor-core GEMM/attention operands, fp32 accumulate / residual stream / master weights / Adam moments" if args.precision == "bf16" else "fp32",
                        "l2": "no explicit flush: each step streams ~3 GB of weights/optimizer state and ~5 GB of activations, far above the 126 MB L2",
                        "grad_clip": "reference +-10 clip on fp32 gradients and in the dgrad GEMM epilogues"},

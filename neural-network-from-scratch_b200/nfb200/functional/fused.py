@@ -52,8 +52,14 @@ def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None,
         def backward(g):
             from ..core.tensor import get_grad_clip
             need_dx = x.requires_grad
-            dW_out = weight.grad_buffer() if weight.requires_grad else None
-            db_out = bias.grad_buffer() if (bias is not None and bias.requires_grad) else None
+            # leaf parameters: the wgrad GEMM / column sum accumulate straight into the gradient slot.  A weight or bias that is
+            # itself a graph node (e.g. a concatenation of several parameters) gets a fresh buffer that is handed on.
+            w_leaf = weight._grad_fn is None
+            b_leaf = bias is None or bias._grad_fn is None
+            dW_out = (weight.grad_buffer() if w_leaf else B200Array.full(weight.shape, 0.0, np.float32)) if weight.requires_grad else None
+            db_out = None
+            if bias is not None and bias.requires_grad:
+                db_out = bias.grad_buffer() if b_leaf else B200Array.full(bias.shape, 0.0, np.float32)
             clip = (get_grad_clip() or 0.0) if prec == "bf16" else 0.0
             # dX comes back in the storage type of X: bf16 activations get bf16 gradients (they feed further GEMMs /
             # the flash backward), fp32 activations (unfused elementwise neighbours) get fp32 gradients
@@ -61,9 +67,11 @@ def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None,
             dx, _, _ = K.linear_backward(g, ctx, need_dx, dW_out, db_out, dx_dt, clip)
             if dx is not None and clip:
                 dx.clipped = True
-            outs = [dx, ACCUMULATED]
+            if not (w_leaf and b_leaf):
+                K.join_side_stream()   # the handed-on buffers may have been written on the wgrad side stream
+            outs = [dx, ACCUMULATED if (w_leaf or dW_out is None) else dW_out]
             if bias is not None:
-                outs.append(ACCUMULATED)
+                outs.append(ACCUMULATED if (b_leaf or db_out is None) else db_out)
             if residual is not None:
                 outs.append(g if g.dtype == F32 else g.astype(np.float32))
             return tuple(outs)

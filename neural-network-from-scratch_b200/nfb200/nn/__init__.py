@@ -7,3 +7,5 @@ from .transformer import MultiHeadAttention, TransformerBlock, TransformerDecode
 from .modern_attention import FlashAttentionConcept, GroupedQueryAttention, MultiQueryAttention
 from .positional import (LearnedPE, LearnedPositionalEmbedding, RoPE, RotaryPositionalEmbedding, SinusoidalPE,
                          SinusoidalPositionalEncoding, create_rope, create_sinusoidal_pe)
+from .modern_activations import GeGLU, SiLU, SwiGLU, Swish
+from .differential_attention import DifferentialAttention, DifferentialTransformer, DifferentialTransformerBlock

@@ -26,7 +26,7 @@ from .. import functional as F
 from ..array import B200Array, bfloat16
 from ..core import Module, Parameter, Tensor
 from .layers import LayerError
-from .linear import Linear
+from .linear import StandardLinear as Linear   # the reference imports nn/linear.py here (xavier_uniform, (in, out) weight)
 
 
 def _act_dtype(x: Tensor):

@@ -389,6 +389,64 @@ def gen_modern(g):
     out.backward(up)
     g["lpe_table"], g["lpe_out"], g["lpe_up"] = np.asarray(lpe.embedding.data), np.asarray(out.data), up
     g["lpe_dx"], g["lpe_dtable"] = np.asarray(xt.grad), np.asarray(lpe.embedding.grad)
+    # gated feed-forward blocks (nn/modern_activations.py): the reference's SwiGLU has a complete backward -> gradients pinned too
+    from neural_arch.nn.modern_activations import GeGLU, SwiGLU, Swish
+    np.random.seed(21)
+    ff = SwiGLU(24, 40)
+    for n in ("b_gate", "b_up", "b_down"):
+        getattr(ff, n).data = (rng.standard_normal(getattr(ff, n).shape) * 0.1).astype(np.float32)
+    x = rng.standard_normal((2, 5, 24)).astype(np.float32)
+    up = (rng.standard_normal((2, 5, 24)) * 0.1).astype(np.float32)
+    xt = Tensor(x, requires_grad=True)
+    out = ff(xt)
+    out.backward(up)
+    g["swiglu_x"], g["swiglu_up"], g["swiglu_out"], g["swiglu_dx"] = x, up, np.asarray(out.data), np.asarray(xt.grad)
+    for n in ("W_gate", "W_up", "W_down", "b_gate", "b_up", "b_down"):
+        g[f"swiglu_{n}"], g[f"swiglu_d{n}"] = np.asarray(getattr(ff, n).data), np.asarray(getattr(ff, n).grad)
+    g["swiglu_default_hidden"] = np.asarray(SwiGLU(30).hidden_dim)
+    np.random.seed(22)
+    ge = GeGLU(24, 40, bias=False)
+    g["geglu_out"] = np.asarray(ge(Tensor(x)).data)
+    for n in ("W_gate", "W_up", "W_down"):
+        g[f"geglu_{n}"] = np.asarray(getattr(ge, n).data)
+    xt = Tensor(x, requires_grad=True)
+    sw = Swish()(xt)
+    sw.backward(up)
+    g["swish_out"], g["swish_dx"] = np.asarray(sw.data), np.asarray(xt.grad)
+    # differential attention (nn/differential_attention.py): forwards only (its backward is a placeholder)
+    from neural_arch.nn.differential_attention import DifferentialAttention, DifferentialTransformer, DifferentialTransformerBlock
+    for tag, kw, B, S, mask_kind in (("diff", dict(d_model=64, n_heads=4), 2, 9, None),
+                                     ("diff_bias_keymask", dict(d_model=48, n_heads=6, bias=True, lambda_init=0.8), 2, 7, "key"),
+                                     ("diff_full_mask", dict(d_model=32, n_heads=2, lambda_init=0.3), 1, 6, "causal")):
+        np.random.seed(23)
+        m = DifferentialAttention(**kw)
+        m.lambda_param.data = (m.lambda_param.data + rng.standard_normal(m.lambda_param.shape).astype(np.float32) * 0.1).astype(np.float32)
+        names = ["lambda_param", "W_q1", "W_k1", "W_v1", "W_q2", "W_k2", "W_v2", "W_o"]
+        if kw.get("bias"):
+            names += ["b_q1", "b_k1", "b_v1", "b_q2", "b_k2", "b_v2", "b_o"]
+            for n in names[8:]:
+                getattr(m, n).data = (rng.standard_normal(getattr(m, n).shape) * 0.1).astype(np.float32)
+        x = rng.standard_normal((B, S, kw["d_model"])).astype(np.float32)
+        mask = None
+        if mask_kind == "key":
+            mask = np.where(rng.random((B, 1, 1, S)) < 0.3, -1e4, 0.0).astype(np.float32)
+            mask[..., 0] = 0.0
+        elif mask_kind == "causal":
+            mask = np.triu(np.full((S, S), -1e9, dtype=np.float32), k=1)
+        out, (a1, a2) = m(Tensor(x), None if mask is None else Tensor(mask), return_attention_weights=True)
+        g[f"{tag}_x"], g[f"{tag}_out"], g[f"{tag}_a1"], g[f"{tag}_a2"] = x, np.asarray(out.data), a1, a2
+        if mask is not None:
+            g[f"{tag}_mask"] = mask
+        for n in names:
+            g[f"{tag}_{n}"] = np.asarray(getattr(m, n).data)
+    np.random.seed(24)
+    blk = DifferentialTransformerBlock(d_model=32, n_heads=4, d_ff=48)
+    x = rng.standard_normal((2, 6, 32)).astype(np.float32)
+    g["diffblock_x"], g["diffblock_out"] = x, np.asarray(blk(Tensor(x)).data)
+    np.random.seed(25)
+    net = DifferentialTransformer(n_layers=2, d_model=32, n_heads=4, d_ff=48, vocab_size=50, max_seq_len=16)
+    ids = rng.integers(0, 50, (2, 7))
+    g["diffnet_ids"], g["diffnet_logits"] = ids, np.asarray(net(Tensor(ids)).data)
 
 
 def main():

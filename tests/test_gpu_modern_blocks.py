@@ -151,3 +151,73 @@ def test_gqa_module_bf16_flash_vs_fp32(be, n_kv, masked):
         assert float(np.abs(got - want).max()) <= 2e-2 * scale, (name, float(np.abs(got - want).max()), scale)
         l2 = float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30))
         assert l2 <= 2e-2, (name, l2)   # a chain of four bf16 kernels (each held to 1e-2 in isolation); measured 0.3-1.0e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def test_swiglu_module_fp32_matches_reference_device(be):
+    from nfb200.core import Tensor
+    from test_modern_blocks import load_swiglu
+    ff = load_swiglu("cuda")
+    xt = Tensor(G["swiglu_x"], device="cuda", requires_grad=True)
+    out = ff(xt)
+    np.testing.assert_allclose(out.data.get(), G["swiglu_out"], rtol=2e-5, atol=5e-6)
+    out.backward(be.from_numpy(G["swiglu_up"]))
+    np.testing.assert_allclose(xt.grad.get(), G["swiglu_dx"], rtol=1e-4, atol=5e-6)
+    for n in ("W_gate", "W_up", "W_down", "b_gate", "b_up", "b_down"):     # gradients reach each parameter THROUGH the concatenation
+        np.testing.assert_allclose(getattr(ff, n).grad.get(), G[f"swiglu_d{n}"], rtol=1e-4, atol=5e-6, err_msg=n)
+
+
+@pytest.mark.parametrize("tag", ["diff", "diff_bias_keymask", "diff_full_mask"])
+def test_differential_attention_fp32_matches_reference_device(be, tag):
+    from nfb200.core import Tensor
+    from test_modern_blocks import load_diff
+    m, x, mask, want = load_diff(tag, "cuda")
+    out, (a1, a2) = m(Tensor(x, device="cuda"), None if mask is None else Tensor(mask, device="cuda"), return_attention_weights=True)
+    np.testing.assert_allclose(out.data.get(), want, rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(a1, G[f"{tag}_a1"], rtol=1e-4, atol=1e-6)
+
+
+def test_differential_model_fp32_matches_reference_device(be):
+    from nfb200.core import Tensor
+    from nfb200.nn import DifferentialTransformer
+    np.random.seed(25)
+    net = DifferentialTransformer(n_layers=2, d_model=32, n_heads=4, d_ff=48, vocab_size=50, max_seq_len=16).to("cuda")
+    out = net(Tensor(G["diffnet_ids"], device="cuda"))
+    np.testing.assert_allclose(out.data.get(), G["diffnet_logits"], rtol=5e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_stream", "wgrad_side_stream"])
+def test_differential_block_bf16_flash_vs_fp32(be, overlap):
+    """head_dim 64: one concatenated-projection GEMM -> packed flash attention for both maps -> lambda combination -> SwiGLU FFN
+    with its concatenated [up|gate] GEMM; output and EVERY parameter gradient (through the differentiable concatenations, with
+    the weight-gradient GEMMs on the side stream in the second variant) against the fp32 composition."""
+    from nfb200 import kernels as K
+    from nfb200.core import Tensor
+    from nfb200.nn import DifferentialTransformerBlock
+    rng = np.random.default_rng(17)
+    B, S, d, H = 2, 160, 256, 4
+    x = rng.standard_normal((B, S, d)).astype(np.float32)
+    up = (rng.standard_normal((B, S, d)) * 1e-2).astype(np.float32)
+    res = {}
+    try:
+        for prec in ("fp32", "bf16"):
+            K.set_precision(prec)
+            K.set_wgrad_overlap(bool(overlap) and prec == "bf16")
+            np.random.seed(13)
+            blk = DifferentialTransformerBlock(d_model=d, n_heads=H, d_ff=384, lambda_init=0.6).to("cuda")
+            xt = Tensor(x, device="cuda", requires_grad=True)
+            out = blk(xt)
+            out.backward(be.from_numpy(up))
+            res[prec] = {"out": out.data.get().astype(np.float32), "dx": xt.grad.get().astype(np.float32),
+                         **{n: p.grad.get().astype(np.float32) for n, p in blk.named_parameters()}}
+    finally:
+        K.set_wgrad_overlap(False)
+        K.set_precision("fp32")
+    assert {"attention.lambda_param", "attention.W_k2", "ffn.W_gate", "ffn.b_up", "norm1.weight"} <= set(res["bf16"])
+    for name, want in res["fp32"].items():
+        got = res["bf16"][name]
+        scale = float(np.abs(want).max())
+        assert scale > 0, name
+        assert float(np.abs(got - want).max()) <= 3e-2 * scale, (name, float(np.abs(got - want).max()), scale)
+        l2 = float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30))
+        assert l2 <= 2.5e-2, (name, l2)   # whole-block chain of bf16 kernels (each 1e-2 in isolation)

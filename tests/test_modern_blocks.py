@@ -155,3 +155,115 @@ def test_positional_validation_errors():
         RotaryPositionalEmbedding(8)(x, Tensor(np.zeros((1, 4, 8), dtype=np.float32)))
     with pytest.raises(LayerError):
         RotaryPositionalEmbedding(16)(x, x)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# gated feed-forward blocks (nn/modern_activations.py) and differential attention (nn/differential_attention.py)
+DIFF_CASES = {"diff": dict(d_model=64, n_heads=4), "diff_bias_keymask": dict(d_model=48, n_heads=6, bias=True, lambda_init=0.8),
+              "diff_full_mask": dict(d_model=32, n_heads=2, lambda_init=0.3)}
+
+
+def load_swiglu(device=None):
+    from nfb200.nn import SwiGLU
+    ff = SwiGLU(24, 40)
+    for n in ("W_gate", "W_up", "W_down", "b_gate", "b_up", "b_down"):
+        getattr(ff, n).data = G[f"swiglu_{n}"].copy()
+    return ff.to(device) if device else ff
+
+
+def load_diff(tag, device=None):
+    from nfb200.nn import DifferentialAttention
+    m = DifferentialAttention(**DIFF_CASES[tag])
+    for n in ("lambda_param", "W_q1", "W_k1", "W_v1", "W_q2", "W_k2", "W_v2", "W_o", "b_q1", "b_k1", "b_v1", "b_q2", "b_k2", "b_v2", "b_o"):
+        if f"{tag}_{n}" in G:
+            getattr(m, n).data = G[f"{tag}_{n}"].copy()
+    if device:
+        m.to(device)
+    return m, G[f"{tag}_x"], (G[f"{tag}_mask"] if f"{tag}_mask" in G else None), G[f"{tag}_out"]
+
+
+def test_swiglu_forward_and_gradients_match_reference_host():
+    from nfb200.nn import GeGLU, SwiGLU, Swish
+    np.random.seed(21)
+    fresh = SwiGLU(24, 40)
+    np.testing.assert_array_equal(np.asarray(fresh.W_up.data), G["swiglu_W_up"])          # init order: W_gate, W_up, W_down
+    assert SwiGLU(30).hidden_dim == int(G["swiglu_default_hidden"])
+    ff = load_swiglu()
+    xt = Tensor(G["swiglu_x"], requires_grad=True)
+    out = ff(xt)
+    np.testing.assert_allclose(np.asarray(out.data), G["swiglu_out"], rtol=1e-5, atol=2e-6)
+    out.backward(G["swiglu_up"])
+    np.testing.assert_allclose(np.asarray(xt.grad), G["swiglu_dx"], rtol=1e-4, atol=2e-6)
+    for n in ("W_gate", "W_up", "W_down", "b_gate", "b_up", "b_down"):
+        np.testing.assert_allclose(np.asarray(getattr(ff, n).grad), G[f"swiglu_d{n}"], rtol=1e-4, atol=2e-6, err_msg=n)
+    np.random.seed(22)
+    ge = GeGLU(24, 40, bias=False)
+    np.testing.assert_array_equal(np.asarray(ge.W_down.data), G["geglu_W_down"])
+    np.testing.assert_allclose(np.asarray(ge(Tensor(G["swiglu_x"])).data), G["geglu_out"], rtol=1e-5, atol=2e-6)
+    xt = Tensor(G["swiglu_x"], requires_grad=True)
+    sw = Swish()(xt)
+    np.testing.assert_allclose(np.asarray(sw.data), G["swish_out"], rtol=1e-6, atol=1e-7)
+    sw.backward(G["swiglu_up"])
+    np.testing.assert_allclose(np.asarray(xt.grad), G["swish_dx"], rtol=1e-5, atol=1e-7)
+    with pytest.raises(LayerError):
+        SwiGLU(0)
+    with pytest.raises(LayerError):
+        ff(Tensor(np.zeros((2, 23), dtype=np.float32)))
+
+
+@pytest.mark.parametrize("tag", list(DIFF_CASES))
+def test_differential_attention_forward_matches_reference_host(tag):
+    m, x, mask, want = load_diff(tag)
+    out, (a1, a2) = m(Tensor(x), None if mask is None else Tensor(mask), return_attention_weights=True)
+    np.testing.assert_allclose(np.asarray(out.data), want, rtol=1e-5, atol=3e-6)
+    np.testing.assert_allclose(a1, G[f"{tag}_a1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(a2, G[f"{tag}_a2"], rtol=1e-5, atol=1e-6)
+    st = m.get_attention_stats()
+    assert abs(st["lambda_mean"] - float(np.mean(G[f"{tag}_lambda_param"]))) < 1e-6
+
+
+def test_differential_block_and_model_match_reference_host():
+    """No weights stored for these two: they also pin the RNG call order of every sub-module constructor."""
+    from nfb200.nn import DifferentialAttention, DifferentialTransformer, DifferentialTransformerBlock
+    np.random.seed(24)
+    blk = DifferentialTransformerBlock(d_model=32, n_heads=4, d_ff=48)
+    np.testing.assert_allclose(np.asarray(blk(Tensor(G["diffblock_x"])).data), G["diffblock_out"], rtol=1e-5, atol=3e-6)
+    np.random.seed(25)
+    net = DifferentialTransformer(n_layers=2, d_model=32, n_heads=4, d_ff=48, vocab_size=50, max_seq_len=16)
+    np.testing.assert_allclose(np.asarray(net(Tensor(G["diffnet_ids"])).data), G["diffnet_logits"], rtol=1e-5, atol=3e-6)
+    assert set(net.get_all_lambda_stats()) == {"layer_0", "layer_1", "global"}
+    names = [n for n, _ in net.named_parameters()]
+    assert "block_0.attention.lambda_param" in names and "block_1.ffn.W_down" in names and "output_proj.weight" in names
+    with pytest.raises(LayerError):
+        DifferentialAttention(d_model=30, n_heads=4)
+    with pytest.raises(LayerError):
+        DifferentialAttention(d_model=30, n_heads=3)
+
+
+def test_differential_attention_true_gradients_host():
+    """Finite differences on x, lambda and one projection of each group (the reference's backward is a placeholder)."""
+    from nfb200.nn import DifferentialAttention
+    rng = np.random.default_rng(4)
+    np.random.seed(5)
+    m = DifferentialAttention(d_model=16, n_heads=4, bias=True, lambda_init=0.4)
+    x = rng.standard_normal((2, 5, 16)).astype(np.float32)
+    up = (rng.standard_normal((2, 5, 16)) * 1e-2).astype(np.float32)
+    xt = Tensor(x, requires_grad=True)
+    m(xt).backward(up)
+
+    def loss():
+        return float((np.asarray(m(Tensor(x)).data, dtype=np.float64) * up).sum())
+    eps = 1e-2
+    for p, idxs in ((m.lambda_param, [(0,), (1,)]), (m.W_k2, [(0, 0), (9, 5)]), (m.W_q1, [(3, 2)]), (m.W_v1, [(7, 7)]), (m.b_q2, [(4,)])):
+        base = np.asarray(p.data).copy()
+        for idx in idxs:
+            hi, lo = base.copy(), base.copy()
+            hi[idx] += eps
+            lo[idx] -= eps
+            p.data = hi
+            fp = loss()
+            p.data = lo
+            fm = loss()
+            p.data = base
+            fd = (fp - fm) / (2 * eps)
+            assert abs(np.asarray(p.grad)[idx] - fd) <= 3e-2 * abs(fd) + 2e-5, (p.name, idx, np.asarray(p.grad)[idx], fd)

@@ -3,3 +3,5 @@ from .bert import BERT, BERTConfig, BERTForMaskedLM, bert_base, bert_base_mlm
 from .gpt2 import GPT2, GPT2_CONFIGS, GPT2LMHead, GPT2Model, gpt2_large, gpt2_medium, gpt2_small, gpt2_xl
 from .translation import PositionalEncoding, TranslationTransformer
 from .vit import VisionTransformer, vit_b_16, vit_l_16
+from .roberta import (ROBERTA_CONFIGS, RoBERTa, RoBERTaConfig, RoBERTaForMaskedLM, RoBERTaForSequenceClassification, roberta_base,
+                      roberta_large)

@@ -449,12 +449,43 @@ def gen_modern(g):
     g["diffnet_ids"], g["diffnet_logits"] = ids, np.asarray(net(Tensor(ids)).data)
 
 
+ROBERTA_TINY = dict(vocab_size=97, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, intermediate_size=64, max_position_embeddings=20)
+
+
+def gen_roberta(g):
+    """Seeded forwards of models/language/roberta.py (tiny config): masked-LM logits + loss with a padding mask, the sequence
+    classifier's logits + loss; pins the position-id offset, the one-row token-type table and the init quirk (LayerNorm gains
+    redrawn from N(0, 0.02^2))."""
+    from neural_arch.core import Tensor
+    from neural_arch.models.language.roberta import RoBERTaForMaskedLM, RoBERTaForSequenceClassification
+    from neural_arch.optimization_config import configure
+    configure(enable_jit=False, enable_fusion=False)
+    rng = np.random.default_rng(600)
+    ids = rng.integers(3, 97, (3, 11))
+    mask = np.ones((3, 11), dtype=np.float32)
+    mask[0, 8:] = 0
+    mask[2, 5:] = 0
+    ids[mask == 0] = 1
+    labels = rng.integers(0, 97, (3, 11))
+    np.random.seed(31)
+    m = RoBERTaForMaskedLM(**ROBERTA_TINY)
+    out = m(Tensor(ids), attention_mask=Tensor(mask), labels=Tensor(labels))
+    g["ids"], g["mask"], g["labels"] = ids, mask, labels
+    g["mlm_logits"], g["mlm_loss"] = np.asarray(out["logits"].data), np.asarray(out["loss"].data)
+    g["ln_gain_first"] = np.asarray(m.roberta.embeddings.LayerNorm.weight.data)
+    np.random.seed(32)
+    c = RoBERTaForSequenceClassification(num_labels=3, **ROBERTA_TINY)
+    cl = rng.integers(0, 3, (3,))
+    out = c(Tensor(ids), attention_mask=Tensor(mask), labels=Tensor(cl))
+    g["cls_labels"], g["cls_logits"], g["cls_loss"] = cl, np.asarray(out["logits"].data), np.asarray(out["loss"].data)
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta)):
         if only and name not in only:
             continue
         g = {}

@@ -5,3 +5,4 @@ from .translation import PositionalEncoding, TranslationTransformer
 from .vit import VisionTransformer, vit_b_16, vit_l_16
 from .roberta import (ROBERTA_CONFIGS, RoBERTa, RoBERTaConfig, RoBERTaForMaskedLM, RoBERTaForSequenceClassification, roberta_base,
                       roberta_large)
+from .clip import CLIP, CLIP_CONFIGS, CLIPModel, CLIPTextTransformer, CLIPVisionTransformer, clip_base, clip_large

@@ -480,12 +480,35 @@ def gen_roberta(g):
     g["cls_labels"], g["cls_logits"], g["cls_loss"] = cl, np.asarray(out["logits"].data), np.asarray(out["loss"].data)
 
 
+CLIP_TINY = dict(embed_dim=24, image_resolution=16, vision_layers=2, vision_width=64, vision_patch_size=8, context_length=9, vocab_size=50,
+                 transformer_width=32, transformer_heads=4, transformer_layers=2)
+
+
+def gen_clip(g):
+    """Seeded forward of models/multimodal/clip.py (tiny config): normalised image / text embeddings, logits and the symmetric
+    contrastive loss."""
+    from neural_arch.core import Tensor
+    from neural_arch.models.multimodal.clip import CLIP
+    from neural_arch.optimization_config import configure
+    configure(enable_jit=False, enable_fusion=False)
+    rng = np.random.default_rng(700)
+    img = rng.standard_normal((3, 3, 16, 16)).astype(np.float32)
+    txt = rng.integers(0, 50, (3, 9))
+    np.random.seed(41)
+    m = CLIP(**CLIP_TINY)
+    out = m(Tensor(img), Tensor(txt))
+    g["img"], g["txt"] = img, txt
+    g["image_embeds"], g["text_embeds"] = np.asarray(out["image_embeds"].data), np.asarray(out["text_embeds"].data)
+    g["logits_per_image"], g["loss"] = np.asarray(out["logits_per_image"].data), np.asarray(out["loss"].data)
+    g["pos_emb_sample"] = np.asarray(m.transformer.positional_embedding.data)[:2]
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip)):
         if only and name not in only:
             continue
         g = {}

@@ -345,8 +345,9 @@ def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rop
 
 
 # ====================================================================================== SwiGLU
-def swiglu_packed(gu: Tensor) -> Tensor:
-    """silu(gu[..., :C]) * gu[..., C:] for the fused [w1 | w2] projection output (models/language/gpt2.py:119-139)."""
+def swiglu_packed(gu: Tensor, gate_last: bool = False) -> Tensor:
+    """silu(gate) * up on a packed projection output: [gate | up] (models/language/gpt2.py:119-139), or with
+    ``gate_last`` [up | gate] -- the layout of functional.swiglu (functional/activation.py:512-572: x, gate = split(x))."""
     C = gu.shape[-1] // 2
     if _dev(gu):
         from .._lib import call
@@ -356,23 +357,24 @@ def swiglu_packed(gu: Tensor) -> Tensor:
         g2 = gd.reshape(rows, 2 * C)
         out = B200Array.empty((rows, C), gd.dtype)
         isz = gd.itemsize
-        call("nfb_swiglu_fwd", dtype_code(gd.dtype), g2.ptr, g2.ptr + C * isz, out.ptr, rows, C, 2 * C)
+        og, ou = (C * isz, 0) if gate_last else (0, C * isz)          # byte offsets of the gate / up halves inside a row
+        call("nfb_swiglu_fwd", dtype_code(gd.dtype), g2.ptr + og, g2.ptr + ou, out.ptr, rows, C, 2 * C)
 
         def backward(g):
             gg = g if (g.dtype == gd.dtype or g.dtype is gd.dtype) else g.astype(gd.dtype)
             gg = gg.contiguous().reshape(rows, C)
             dgu = B200Array.empty((rows, 2 * C), gd.dtype)
-            call("nfb_swiglu_bwd", dtype_code(gd.dtype), g2.ptr, g2.ptr + C * isz, gg.ptr, dgu.ptr, dgu.ptr + C * isz, rows, C, 2 * C)
+            call("nfb_swiglu_bwd", dtype_code(gd.dtype), g2.ptr + og, g2.ptr + ou, gg.ptr, dgu.ptr + og, dgu.ptr + ou, rows, C, 2 * C)
             return (dgu.reshape(gu.shape),)
 
         return make_result(out.reshape(gu.shape[:-1] + (C,)), [gu], backward, "swiglu")
     gd = gu.data
-    gate, up = gd[..., :C], gd[..., C:]
+    gate, up = (gd[..., C:], gd[..., :C]) if gate_last else (gd[..., :C], gd[..., C:])
     sg = 1.0 / (1.0 + np.exp(-gate))
 
     def backward_host(g):
         dgate = g * up * (sg * (1.0 + gate * (1.0 - sg)))
         dup = g * gate * sg
-        return (np.concatenate((dgate, dup), axis=-1).astype(gd.dtype),)
+        return (np.concatenate((dup, dgate) if gate_last else (dgate, dup), axis=-1).astype(gd.dtype),)
 
     return make_result((gate * sg * up).astype(gd.dtype), [gu], backward_host, "swiglu")

@@ -6,3 +6,5 @@ from .vit import VisionTransformer, vit_b_16, vit_l_16
 from .roberta import (ROBERTA_CONFIGS, RoBERTa, RoBERTaConfig, RoBERTaForMaskedLM, RoBERTaForSequenceClassification, roberta_base,
                       roberta_large)
 from .clip import CLIP, CLIP_CONFIGS, CLIPModel, CLIPTextTransformer, CLIPVisionTransformer, clip_base, clip_large
+from .modern_transformer import (ModelError, ModernTransformer, PreNormTransformer, PreNormTransformerConfig, RoPETransformer,
+                                 prenorm_transformer_base, prenorm_transformer_large, prenorm_transformer_small)

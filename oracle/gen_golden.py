@@ -503,12 +503,41 @@ def gen_clip(g):
     g["pos_emb_sample"] = np.asarray(m.transformer.positional_embedding.data)[:2]
 
 
+PRENORM_CASES = {
+    "gelu_ln": dict(d_model=32, num_layers=2, num_heads=4, d_ff=64, max_seq_len=16, vocab_size=60),
+    "swiglu_rms_untied": dict(d_model=32, num_layers=2, num_heads=2, d_ff=48, max_seq_len=16, vocab_size=60, activation="swiglu",
+                              normalization="rmsnorm", tie_embeddings=False, scale_embeddings=False, rope_base=500.0),
+    "relu_norope": dict(d_model=24, num_layers=1, num_heads=3, d_ff=40, max_seq_len=16, vocab_size=60, activation="relu", use_rope=False),
+}
+
+
+def gen_prenorm(g):
+    """Seeded forwards of models/language/modern_transformer.py (tiny configs covering gelu/swiglu/relu, LayerNorm/RMSNorm, tied and
+    untied heads, RoPE on/off), with and without a padding mask."""
+    from neural_arch.core import Tensor
+    from neural_arch.models.language.modern_transformer import PreNormTransformer
+    from neural_arch.optimization_config import configure
+    configure(enable_jit=False, enable_fusion=False)
+    rng = np.random.default_rng(800)
+    ids = rng.integers(0, 60, (3, 10))
+    mask = np.ones((3, 10), dtype=np.int64)
+    mask[0, 7:] = 0
+    mask[2, 4:] = 0
+    g["ids"], g["mask"] = ids, mask
+    for i, (tag, kw) in enumerate(PRENORM_CASES.items()):
+        np.random.seed(50 + i)
+        m = PreNormTransformer(**kw)
+        g[f"{tag}_logits"] = np.asarray(m(Tensor(ids))["logits"].data)
+        g[f"{tag}_logits_masked"] = np.asarray(m(Tensor(ids), attention_mask=Tensor(mask))["logits"].data)
+        g[f"{tag}_logits_pos3"] = np.asarray(m(Tensor(ids[:, :5]), start_pos=3)["logits"].data)
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip), ("prenorm", gen_prenorm)):
         if only and name not in only:
             continue
         g = {}

@@ -185,7 +185,11 @@ class CLIP(Module):
             B = image.shape[0]
             labels = np.arange(B, dtype=np.int64)
             if isinstance(logits.data, B200Array):
-                labels = B200Array.from_numpy(labels)
+                # a constant of the batch size: uploaded once and kept, so a training step does no host->device copy (graph-capturable)
+                cache = self.__dict__.setdefault("_diag_labels", {})
+                if B not in cache:
+                    cache[B] = B200Array.from_numpy(labels)
+                labels = cache[B]
             li = F.cross_entropy_loss(out["logits_per_image"], labels)
             lt = F.cross_entropy_loss(out["logits_per_text"], labels)
             out["loss"] = F.mul(F.add(li, lt), 0.5)

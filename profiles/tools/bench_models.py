@@ -55,3 +55,38 @@ if which in ("all", "gpt2m"):
         lab = np.concatenate([ids[:, 1:], np.zeros((8, 1), dtype=ids.dtype)], axis=1)
         return (Tensor(ids, device="cuda"),), dict(labels=Tensor(lab, device="cuda"))
     run("GPT-2 medium B8xS1024 (per-GPU shard of config 5)", gpt2_medium, mk, 8 * 1024, "tokens")
+if which in ("all", "zoo", "prenorm"):
+    from nfb200.models import PreNormTransformer
+    def mk():
+        ids = rng.integers(0, 30000, (8, 512))
+        return (Tensor(ids, device="cuda"),), dict(labels=Tensor(ids, device="cuda"))
+    run("PreNormTransformer base (d768 L12 H12, swiglu+rmsnorm, interleaved RoPE) B8xS512",
+        lambda: PreNormTransformer(d_model=768, num_layers=12, num_heads=12, d_ff=3072, max_seq_len=512, vocab_size=30000, activation="swiglu",
+                                   normalization="rmsnorm"), mk, 8 * 512, "tokens")
+if which in ("all", "zoo", "roberta"):
+    from nfb200.models import RoBERTaForMaskedLM
+    def mk():
+        ids = rng.integers(3, 50265, (32, 512))
+        return (Tensor(ids, device="cuda"),), dict(attention_mask=Tensor(np.ones((32, 512), np.float32), device="cuda"), labels=Tensor(ids, device="cuda"))
+    run("RoBERTa-base MLM B32xS512", lambda: RoBERTaForMaskedLM(), mk, 32 * 512, "tokens")
+if which in ("all", "zoo", "clip"):
+    from nfb200.models import clip_base
+    def mk():
+        img = rng.standard_normal((64, 3, 224, 224)).astype(np.float32)
+        txt = rng.integers(0, 49408, (64, 77))
+        return (Tensor(img, device="cuda"), Tensor(txt, device="cuda")), {}
+    run("CLIP base (ViT-B/32 + 12-layer text tower) B64", clip_base, mk, 64, "pairs")
+if which in ("all", "zoo", "diff"):
+    from nfb200.nn import DifferentialTransformer
+    from nfb200 import functional as Fn
+    class _LM:
+        def __init__(self): self.net = DifferentialTransformer(n_layers=12, d_model=768, n_heads=12, d_ff=2048, vocab_size=50257, max_seq_len=512)
+        def parameters(self): return self.net.parameters()
+        def __call__(self, ids, labels):
+            lg = self.net(ids)
+            B, S, V = lg.shape
+            return {"loss": Fn.cross_entropy_loss(Fn.reshape(lg, (B * S, V)), labels.data.reshape(-1))}
+    def mk():
+        ids = rng.integers(0, 50257, (8, 512))
+        return (Tensor(ids, device="cuda"),), dict(labels=Tensor(ids, device="cuda"))
+    run("DifferentialTransformer (d768 L12 H12) B8xS512", _LM, mk, 8 * 512, "tokens")

@@ -346,8 +346,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bucket-mb", type=float, default=50.0,
-                    help="gradient all-reduce bucket size (the reference's default is 25; 50 measured 2.5 %% faster at 4 GPUs, profiles/r01_ddp_explore.txt)")
+    ap.add_argument("--bucket-mb", type=float, default=100.0,
+                    help="gradient all-reduce bucket size (the reference's default is 25; 100 measured 2.5 %% faster at 4 GPUs and 3.5 %% at 8, profiles/r01_ddp_explore.txt)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying a captured CUDA graph")
     ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
     ap.add_argument("--step-in-backward", dest="step_in_backward", action="store_true",

@@ -430,6 +430,23 @@ class Tensor:
             shape = tuple(shape[0])
         return reshape(self, shape)
 
+    def squeeze(self, axis=None) -> "Tensor":
+        """Drop size-1 dimensions (models/language/deberta.py:518 chains ``.squeeze(-2).unsqueeze(-1)`` on a mask Tensor)."""
+        shp = self.shape
+        if axis is None:
+            new = tuple(d for d in shp if d != 1)
+        else:
+            ax = axis + len(shp) if axis < 0 else axis
+            if shp[ax] != 1:
+                return self
+            new = shp[:ax] + shp[ax + 1:]
+        return self.reshape(new)
+
+    def unsqueeze(self, axis: int) -> "Tensor":
+        shp = self.shape
+        ax = axis + len(shp) + 1 if axis < 0 else axis
+        return self.reshape(shp[:ax] + (1,) + shp[ax:])
+
     def flatten(self):
         """Flat view of the DATA (nn/embedding.py:49 iterates it as row indices)."""
         return self._data.flatten() if not isinstance(self._data, B200Array) else self._data.reshape(-1)

@@ -173,6 +173,9 @@ int nfb_adam_step(int variant, int moment_dtype, float* p, const float* g, void*
 int nfb_adam_step_ex(int variant, int moment_dtype, float* p, const float* g, void* m, void* v, void* p_bf16, int64_t n, double lr,
                      double beta1, double beta2, double eps, double weight_decay, int step, int maximize, const float* grad_scale,
                      const int* step_dev, const double* lr_dev);
+/* Lion.step (optim/lion.py:129-175): sign-of-interpolation update clipped to +-1, decoupled lr*wd*p term, EMA momentum. */
+int nfb_lion_step(int moment_dtype, float* p, const float* g, void* m, void* p_bf16, int64_t n, double lr, double beta1, double beta2,
+                  double weight_decay, int maximize, const float* grad_scale, const double* lr_dev);
 int nfb_add_i32(int* counter, int delta);
 int nfb_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
                  double weight_decay, int nesterov, int first_step, int maximize);

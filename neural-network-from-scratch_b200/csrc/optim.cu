@@ -350,3 +350,76 @@ NFB_API int nfb_grad_unscale(float* g, const void* chunks, int nchunks, int nseg
   NFB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- Lion (optim/lion.py:129-175): c = b1*m + (1-b1)*g ; p -= clip(fp32(lr*sign(c) + lr*wd*p), +-1) ; m = b2*m + (1-b2)*g ----
+// The interpolation / update are formed in the moment dtype (fp64 = the reference's arithmetic, fp32 = throughput mode), the
+// parameter subtraction in fp32 as NumPy does it; non-finite parameters are scrubbed (nan -> 0, +-inf -> +-1).
+template <typename MT>
+__device__ __forceinline__ float lion_one(float pi, float gi, MT& mi, MT beta1, MT beta2, double lr, double lr_wd) {
+  const MT gd = (MT)gi;
+  const MT c = beta1 * mi + (MT(1) - beta1) * gd;
+  const double sgn = (c > MT(0)) ? 1.0 : ((c < MT(0)) ? -1.0 : ((c == c) ? 0.0 : (double)c));   // np.sign keeps NaN
+  float upd = (float)(lr * sgn + lr_wd * (double)pi);
+  if (upd == upd) upd = fminf(fmaxf(upd, -1.f), 1.f);
+  mi = beta2 * mi + (MT(1) - beta2) * gd;
+  float np_ = __fsub_rn(pi, upd);
+  if (!isfinite(np_)) np_ = (np_ != np_) ? 0.f : (np_ > 0.f ? 1.f : -1.f);
+  return np_;
+}
+template <typename MT>
+__global__ void k_lion(float* __restrict__ p, const float* __restrict__ g, MT* __restrict__ m, __nv_bfloat16* __restrict__ p_bf16, int64_t n0,
+                       int64_t n, double lr, MT beta1, MT beta2, double wd, float gsign, const float* grad_scale, const double* lr_dev) {
+  if (lr_dev) lr = *lr_dev;
+  const double lr_wd = lr * wd;
+  const float gs = (grad_scale ? *grad_scale : 1.f) * gsign;
+  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    MT mi = m[i];
+    const float np_ = lion_one<MT>(p[i], g[i] * gs, mi, beta1, beta2, lr, lr_wd);
+    m[i] = mi;
+    p[i] = np_;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(np_);
+  }
+}
+// fp32 momentum, 128-bit accesses: 3 x LDG.128 + 2 x STG.128 + 1 x STG.64 per 4 parameters (22 B/param)
+__global__ void __launch_bounds__(256)
+k_lion_vec4(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, uint2* __restrict__ p_bf16, int64_t n4, double lr,
+            float beta1, float beta2, double wd, float gsign, const float* grad_scale, const double* lr_dev) {
+  if (lr_dev) lr = *lr_dev;
+  const double lr_wd = lr * wd;
+  const float gs = (grad_scale ? *grad_scale : 1.f) * gsign;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pa = p[i], ga = g[i], ma = m[i];
+    pa.x = lion_one<float>(pa.x, ga.x * gs, ma.x, beta1, beta2, lr, lr_wd);
+    pa.y = lion_one<float>(pa.y, ga.y * gs, ma.y, beta1, beta2, lr, lr_wd);
+    pa.z = lion_one<float>(pa.z, ga.z * gs, ma.z, beta1, beta2, lr, lr_wd);
+    pa.w = lion_one<float>(pa.w, ga.w * gs, ma.w, beta1, beta2, lr, lr_wd);
+    m[i] = ma;
+    p[i] = pa;
+    if (p_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pa.x, pa.y), hi = __floats2bfloat162_rn(pa.z, pa.w);
+      p_bf16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+// moment_dtype: NFB_F32 or NFB_F64.  grad_scale (device float) and lr_dev (device double) are optional, as in nfb_adam_step_ex.
+NFB_API int nfb_lion_step(int moment_dtype, float* p, const float* g, void* m, void* p_bf16, int64_t n, double lr, double beta1, double beta2,
+                          double weight_decay, int maximize, const float* grad_scale, const double* lr_dev) {
+  if (n == 0) return 0;
+  const float gsign = maximize ? -1.f : 1.f;
+  cudaStream_t s = nfb_cur_stream();
+  if (moment_dtype == NFB_F64) {
+    k_lion<double><<<nfb_grid_for(n, 256, 8), 256, 0, s>>>(p, g, (double*)m, (__nv_bfloat16*)p_bf16, 0, n, lr, beta1, beta2, weight_decay, gsign, grad_scale, lr_dev);
+  } else if (moment_dtype == NFB_F32) {
+    const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m) % 16 == 0) && ((uintptr_t)p_bf16 % 8 == 0);
+    const int64_t n4 = vec ? n / 4 : 0;
+    if (n4 > 0) {
+      k_lion_vec4<<<nfb_grid_for(n4, 256, 8), 256, 0, s>>>((float4*)p, (const float4*)g, (float4*)m, (uint2*)p_bf16, n4, lr, (float)beta1, (float)beta2,
+                                                          weight_decay, gsign, grad_scale, lr_dev);
+      if (n4 * 4 < n) nfb_count_launch();
+    }
+    if (n4 * 4 < n)
+      k_lion<float><<<1, 256, 0, s>>>(p, g, (float*)m, (__nv_bfloat16*)p_bf16, n4 * 4, n, lr, (float)beta1, (float)beta2, weight_decay, gsign, grad_scale, lr_dev);
+  } else return NFB_FAIL("nfb_lion_step: moment dtype %d", moment_dtype);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

@@ -91,6 +91,7 @@ _SIGNATURES = {
     # optimizers
     "nfb_adam_step": [i32, i32, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, i32, vp, vp],
     "nfb_adam_step_ex": [i32, i32, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, i32, vp, vp, vp],
+    "nfb_lion_step": [i32, vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, vp, vp],
     "nfb_grad_unscale": [vp, vp, i32, i32, f32, f32, vp, vp],
     "nfb_add_i32": [vp, i32],
     "nfb_sgd_step": [vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, i32, i32],

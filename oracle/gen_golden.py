@@ -532,12 +532,34 @@ def gen_prenorm(g):
         g[f"{tag}_logits_pos3"] = np.asarray(m(Tensor(ids[:, :5]), start_pos=3)["logits"].data)
 
 
+def gen_lion(g):
+    """optim/lion.py trajectories: plain, with weight decay + maximize, and a gradient sequence containing exact zeros and a NaN."""
+    from neural_arch.core import Parameter
+    from neural_arch.optim.lion import Lion
+    rng = np.random.default_rng(900)
+    p0 = rng.standard_normal((6, 9)).astype(np.float32)
+    grads = [(rng.standard_normal((6, 9)) * (10.0 ** rng.integers(-3, 1))).astype(np.float32) for _ in range(7)]
+    grads[2][0, :3] = 0.0
+    grads[0][1, 1] = 0.0            # c = 0 on the very first step -> sign 0 -> no update of that element
+    grads[4][2, 2] = np.nan
+    g["p0"], g["grads"] = p0, np.stack(grads)
+    for name, kw in (("plain", dict(lr=1e-2)), ("wd_max", dict(lr=3e-3, weight_decay=0.1, maximize=True, betas=(0.8, 0.95))), ("biglr", dict(lr=2.5, beta1=0.5))):
+        p = Parameter(p0.copy())
+        opt = Lion({"w": p}, **kw)
+        traj = []
+        for gr in grads:
+            p.grad = gr.copy()
+            opt.step()
+            traj.append(np.asarray(p.data).copy())
+        g[f"{name}_traj"], g[f"{name}_m"] = np.stack(traj), np.asarray(opt.state["w"]["momentum_buffer"])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip), ("prenorm", gen_prenorm)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip), ("prenorm", gen_prenorm), ("lion", gen_lion)):
         if only and name not in only:
             continue
         g = {}

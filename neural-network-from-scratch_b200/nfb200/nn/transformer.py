@@ -65,3 +65,50 @@ class TransformerDecoderBlock(Module):
         x = self.self_attn(self.norm1(x), mask=tgt_mask, residual=x)
         x = self.cross_attn(self.norm2(x), residual=x)
         return self.ffn2(self.ffn1(self.norm3(x)), residual=x)
+
+
+class TransformerEncoder(Module):
+    """Stack of TransformerBlocks + final LayerNorm (nn/transformer.py:119-183).  As in the reference the blocks live in a plain
+    list and ``parameters()`` is overridden to expose them as ``layer{i}_{name}`` / ``final_norm_{name}``."""
+
+    def __init__(self, d_model: int, num_layers: int = 6, num_heads: int = 8, d_ff: int = 2048, dropout: float = 0.1):
+        super().__init__()
+        self.d_model, self.num_layers = d_model, num_layers
+        self.layers = []
+        for _ in range(num_layers):
+            self.layers.append(TransformerBlock(d_model, num_heads, d_ff, dropout))
+        self.norm = LayerNorm(d_model)
+
+    def forward(self, x: Tensor, mask=None) -> Tensor:
+        for layer in self.layers:
+            x = layer(x, mask=mask)
+        return self.norm(x)
+
+    def parameters(self, recurse: bool = True):
+        from collections import OrderedDict
+        from ..core.base import ParameterView
+        params = OrderedDict()
+        for i, layer in enumerate(self.layers):
+            # the reference block exposes attn_* / ffn1_* / ffn2_* / norm1_* / norm2_* (nn/transformer.py:95-116)
+            for prefix, sub in (("attn", layer.self_attn), ("ffn1", layer.ffn1), ("ffn2", layer.ffn2), ("norm1", layer.norm1), ("norm2", layer.norm2)):
+                for name, p in sub.parameters().items():
+                    params[f"layer{i}_{prefix}_{name}"] = p
+        for name, p in self.norm.parameters().items():
+            params[f"final_norm_{name}"] = p
+        return ParameterView(params)
+
+    def to(self, device):
+        for layer in self.layers:
+            layer.to(device)
+        return super().to(device)
+
+
+class SelfAttention(Module):
+    """Identity placeholder, as in the reference (nn/attention.py:83-92)."""
+
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.d_model = d_model
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x

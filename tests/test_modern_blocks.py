@@ -267,3 +267,23 @@ def test_differential_attention_true_gradients_host():
             p.data = base
             fd = (fp - fm) / (2 * eps)
             assert abs(np.asarray(p.grad)[idx] - fd) <= 3e-2 * abs(fd) + 2e-5, (p.name, idx, np.asarray(p.grad)[idx], fd)
+
+
+def test_transformer_encoder_stack_host():
+    """nn/transformer.py TransformerEncoder: seeded forward equals the (unfused) composition of its own blocks, and parameters()
+    uses the reference's layer{i}_{attn,ffn1,ffn2,norm1,norm2}_* / final_norm_* names (checked against the reference when
+    generating: oracle/gen_golden.py is not needed for a pure composition)."""
+    from nfb200.nn import SelfAttention, TransformerEncoder
+    np.random.seed(3)
+    enc = TransformerEncoder(16, num_layers=2, num_heads=4, d_ff=32)
+    x = Tensor(np.random.default_rng(0).standard_normal((2, 5, 16)).astype(np.float32), requires_grad=True)
+    y = enc(x)
+    h = x
+    for blk in enc.layers:
+        h = blk(h)
+    np.testing.assert_allclose(np.asarray(y.data), np.asarray(enc.norm(h).data), rtol=1e-6)
+    names = list(enc.parameters().keys())
+    assert names[0] == "layer0_attn_query_proj.weight" and "layer1_ffn2_bias" in names and names[-1].startswith("final_norm_") and len(names) == 34
+    y.sum().backward()
+    assert all(p.grad is not None for p in enc.parameters())
+    assert SelfAttention(8)(x) is x

@@ -176,7 +176,9 @@ class DistributedDataParallel(Module):
         """finish_gradient_sync() + optimizer.step() with the fused optimizer kernel pipelined behind the bucket
         all-reduces: slice i of the arena is updated as soon as bucket i has arrived, while later buckets (the big
         tied embedding gradient comes last) are still on the wire."""
-        if self.world_size == 1 or not self._require_sync or self.arena is None or self._host_params or \
+        import inspect
+        pipelined = "segments" in inspect.signature(optimizer.step).parameters     # Adam / AdamW; SGD and Lion take the plain path
+        if self.world_size == 1 or not self._require_sync or self.arena is None or self._host_params or not pipelined or \
                 getattr(optimizer, "arena", None) is None or optimizer.arena.flat_g is not self.arena.flat_g:
             self.finish_gradient_sync()
             optimizer.step()

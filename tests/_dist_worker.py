@@ -42,7 +42,15 @@ def ddp_train(out, device):
     np.random.seed(0)
     model = GPT2(cfg)
     ddp = dist.DistributedDataParallel(model, bucket_size_mb=0.25)
-    opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, moment_dtype="float64")
+    which = os.environ.get("NFB200_TEST_OPT", "adamw")
+    if which == "lion":
+        from nfb200.optim import Lion
+        opt = Lion(model.parameters(), lr=1e-4, weight_decay=0.01)
+    elif which == "sgd":
+        from nfb200.optim import SGD
+        opt = SGD(model.parameters(), lr=1e-2, momentum=0.9)
+    else:
+        opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, moment_dtype="float64")
     rng = np.random.default_rng(7)
     losses = []
     for step_i in range(2):

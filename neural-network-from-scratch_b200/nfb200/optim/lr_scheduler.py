@@ -7,7 +7,7 @@ arguments, validation errors and -- epoch by epoch -- the same learning rates, q
 * ``ChainedScheduler`` forwards the GLOBAL epoch to the active scheduler (no offset by the milestone, lr_scheduler.py:528-545).
 
 Everything here is host-side scalar arithmetic in Python floats, evaluated in the reference's operation order so the
-values agree bit for bit (tests/test_oracle_golden.py pins them against traces of the unmodified reference).  The only
+values agree bit for bit (tests/test_train_glue.py pins them against traces of the unmodified reference).  The only
 B200-specific part is where the number goes: ``optimizer.lr`` is a property whose setter also refreshes the device
 scalar the fused Adam/AdamW kernel reads (optim/adam.py), so a scheduler keeps working when the training step is
 replayed from a CUDA graph (training.GraphedStep): call ``scheduler.step()`` between replays as in an eager loop.

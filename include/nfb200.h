@@ -179,6 +179,8 @@ int nfb_lion_step(int moment_dtype, float* p, const float* g, void* m, void* p_b
 int nfb_add_i32(int* counter, int delta);
 int nfb_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
                  double weight_decay, int nesterov, int first_step, int maximize);
+int nfb_sgd_step_ex(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
+                    double weight_decay, int nesterov, int first_step, int maximize, const double* lr_dev);   /* lr_dev: as nfb_adam_step_ex */
 int nfb_sumsq(const float* g, int64_t n, double* total, int accumulate);
 int nfb_clip_coef(const double* total, float max_norm, float eps, float* coef, float* norm_out);
 int nfb_scale_by_device_scalar(float* g, int64_t n, const float* coef);

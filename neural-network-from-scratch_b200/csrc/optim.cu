@@ -156,7 +156,8 @@ NFB_API int nfb_add_i32(int* counter, int delta) {
 
 // SGD with momentum / dampening / nesterov / L2 (optim/sgd.py:87-115)
 __global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, __nv_bfloat16* __restrict__ p_bf16, int64_t n,
-                      float lr, float momentum, float dampening, float wd, int nesterov, int first_step, float gsign) {
+                      float lr, float momentum, float dampening, float wd, int nesterov, int first_step, float gsign, const double* lr_dev) {
+  if (lr_dev) lr = (float)*lr_dev;     // device-side learning rate: schedulers act on replays of a captured step
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], gi = g[i] * gsign;
     if (wd != 0.f) gi = __fadd_rn(gi, __fmul_rn(wd, pi));
@@ -170,13 +171,17 @@ __global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float*
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(np_);
   }
 }
-NFB_API int nfb_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
-                         double weight_decay, int nesterov, int first_step, int maximize) {
+NFB_API int nfb_sgd_step_ex(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
+                            double weight_decay, int nesterov, int first_step, int maximize, const double* lr_dev) {
   if (n == 0) return 0;
   k_sgd<<<nfb_grid_for(n, 256, 8), 256, 0, nfb_cur_stream()>>>(p, g, buf, (__nv_bfloat16*)p_bf16, n, (float)lr, (float)momentum, (float)dampening,
-                                                                 (float)weight_decay, nesterov, first_step, maximize ? -1.f : 1.f);
+                                                                 (float)weight_decay, nesterov, first_step, maximize ? -1.f : 1.f, lr_dev);
   NFB_LAUNCH_CHECK();
   return 0;
+}
+NFB_API int nfb_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, double lr, double momentum, double dampening,
+                         double weight_decay, int nesterov, int first_step, int maximize) {
+  return nfb_sgd_step_ex(p, g, buf, p_bf16, n, lr, momentum, dampening, weight_decay, nesterov, first_step, maximize, nullptr);
 }
 
 // ---- global-norm clipping: sumsq accumulates sum(g^2) over one or more buffers in double ----

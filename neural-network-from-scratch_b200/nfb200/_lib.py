@@ -95,6 +95,7 @@ _SIGNATURES = {
     "nfb_grad_unscale": [vp, vp, i32, i32, f32, f32, vp, vp],
     "nfb_add_i32": [vp, i32],
     "nfb_sgd_step": [vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, i32, i32],
+    "nfb_sgd_step_ex": [vp, vp, vp, vp, i64, f64, f64, f64, f64, i32, i32, i32, vp],
     "nfb_sumsq": [vp, i64, vp, i32],
     "nfb_clip_coef": [vp, f32, f32, vp, vp],
     "nfb_scale_by_device_scalar": [vp, i64, vp],

@@ -11,8 +11,8 @@ values agree bit for bit (tests/test_train_glue.py pins them against traces of t
 B200-specific part is where the number goes: ``optimizer.lr`` is a property whose setter also refreshes the device
 scalar the fused Adam/AdamW kernel reads (optim/adam.py), so a scheduler keeps working when the training step is
 replayed from a CUDA graph (training.GraphedStep): call ``scheduler.step()`` between replays as in an eager loop.
-(Adam, AdamW and Lion read the device scalar; SGD's kernel takes the learning rate as a launch argument, so a captured SGD
-step keeps the value it was captured with -- re-capture after changing it.)
+(Adam, AdamW, Lion and SGD all read the device scalar in capturable mode: nfb_adam_step_ex, nfb_lion_step, nfb_sgd_step_ex;
+tests/test_gpu_train_glue.py replays captured steps under StepLR / cosine / plateau schedules.)
 """
 from __future__ import annotations
 

@@ -10,6 +10,22 @@ from .arena import ParamArena
 
 
 class SGD(Optimizer):
+    _lr = None
+    _lr_dev = None
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        """Host value + device mirror (capturable mode), as in optim/adam.py: schedulers act on CUDA-graph replays."""
+        self._lr = value
+        if self._lr_dev is not None:
+            from ..runtime import is_capturing
+            if not is_capturing():
+                call("nfb_fill", 1, self._lr_dev.ptr, 1, float(value))   # 1 = NFB_F64
+
     def __init__(self, parameters, lr: float = 0.01, momentum: float = 0.0, weight_decay: float = 0.0, dampening: float = 0.0,
                  nesterov: bool = False, maximize: bool = False):
         if hasattr(parameters, "items"):
@@ -19,6 +35,7 @@ class SGD(Optimizer):
         super().__init__(param_dict, lr=lr)
         self.lr, self.momentum, self.weight_decay, self.dampening, self.nesterov, self.maximize = lr, momentum, weight_decay, dampening, nesterov, maximize
         self.step_count = 0
+        self.capturable = False
         dev = [p for p in self.parameters.values() if isinstance(p.data, B200Array)]
         self.arena = None
         if dev:
@@ -38,13 +55,15 @@ class SGD(Optimizer):
         done = set()
         if self.arena is not None:
             a = self.arena
+            if self.capturable and self._lr_dev is None:
+                self._lr_dev = B200Array.full((1,), float(self._lr), np.float64)
             for first in (True, False):
                 ids = {id(p) for p in a.params if p.grad is not None and ((id(p) not in self._started) == first)}
                 for off, n in a.runs(lambda q: id(q) in ids):
-                    call("nfb_sgd_step", a.flat_p.ptr + off * 4, a.flat_g.ptr + off * 4, a.moments[0].ptr + off * 4,
+                    call("nfb_sgd_step_ex", a.flat_p.ptr + off * 4, a.flat_g.ptr + off * 4, a.moments[0].ptr + off * 4,
                          (a.flat_bf16.ptr + off * 2) if a.flat_bf16 is not None else None, n, float(self.lr), float(self.momentum),
                          float(self.dampening), float(self.weight_decay), 1 if self.nesterov else 0, 1 if first else 0,
-                         1 if self.maximize else 0)
+                         1 if self.maximize else 0, self._lr_dev.ptr if self._lr_dev is not None else None)
                 done |= ids
             self._started |= done
             for p in a.params:

@@ -151,3 +151,60 @@ def test_lr_schedule_acts_on_graph_replays(be, schedule):
     finally:
         K.set_precision("fp32")
         set_default_device("cpu")
+
+
+def test_sgd_lr_schedule_acts_on_graph_replays(be):
+    """SGD (optim/sgd.py:87-115) with momentum under a StepLR schedule: steps 3.. replayed from one captured graph must
+    follow the eager trajectory (the kernel reads the learning rate from device memory, nfb_sgd_step_ex), and a graphed
+    run whose scheduler is never stepped must not."""
+    from nfb200 import kernels as K
+    from nfb200.core import Tensor, set_default_device
+    from nfb200.models import GPT2
+    from nfb200.optim import SGD
+    from nfb200.optim import lr_scheduler as S
+    from nfb200.training import GraphedStep
+    set_default_device("cuda")
+    K.set_precision("bf16")
+    rng = np.random.default_rng(12)
+    ids = rng.integers(0, CFG["vocab_size"], (2, 128))
+    labels = np.concatenate([ids[:, 1:], np.zeros((2, 1), dtype=ids.dtype)], axis=1)
+    nsteps = 8
+
+    def run(graphed, use_schedule=True):
+        np.random.seed(0)
+        model = GPT2(CFG)
+        opt = SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True)
+        sch = S.StepLR(opt, step_size=2, gamma=0.3) if use_schedule else None
+        ids_t, lab_t = Tensor(ids, device="cuda"), Tensor(labels, device="cuda")
+
+        def step():
+            opt.zero_grad()
+            loss = model(ids_t, labels=lab_t)["loss"]
+            loss.backward()
+            opt.step()
+            return loss
+        lrs, losses, gs = [], [], None
+        for i in range(nsteps):
+            lrs.append(opt.lr)
+            if graphed and i == 2:
+                gs = GraphedStep(step, warmup=1, optimizers=[opt])
+                loss = None
+            else:
+                loss = gs() if gs is not None else step()
+            losses.append(float(loss.item()) if loss is not None else None)
+            if sch is not None:
+                sch.step()
+        assert opt.step_count == nsteps
+        return lrs, losses
+
+    try:
+        e_lr, e_loss = run(False)
+        g_lr, g_loss = run(True)
+        c_lr, c_loss = run(True, use_schedule=False)
+        assert e_lr == g_lr and len(set(e_lr)) > 2, (e_lr, g_lr)
+        keep = [i for i, x in enumerate(g_loss) if x is not None]
+        np.testing.assert_allclose([g_loss[i] for i in keep], [e_loss[i] for i in keep], rtol=2e-4)
+        assert abs(c_loss[-1] - e_loss[-1]) > 1e-3 * abs(e_loss[-1]), (c_loss, e_loss)
+    finally:
+        K.set_precision("fp32")
+        set_default_device("cpu")

@@ -131,7 +131,7 @@ def run_b200(args):
     import nfb200
     from nfb200 import _lib, kernels as K, runtime as R
     from nfb200.array import B200Array
-    from nfb200.core import Tensor, set_default_device, set_grad_clip
+    from nfb200.core import Tensor, set_default_device
     from nfb200.models import GPT2
     from nfb200.optim import AdamW
 

@@ -7,6 +7,7 @@
 // Optional fusions: `res` (forward: s = x + res is normalised and written back to `sum_out`) and
 // `dres` (backward: dx += dres, the gradient arriving over the skip connection).
 #include "common.cuh"
+#include <stdlib.h>
 
 #define WARPS_PER_BLOCK 4
 
@@ -283,6 +284,10 @@ static int norm_fwd_t(const void* x, const void* res, void* sum_out, const float
   int vpl = pick_vpl(cols);
   cudaStream_t s = nfb_cur_stream();
   int grid = nfb_grid_for(rows, WARPS_PER_BLOCK, 8);
+  if (const char* e = getenv("NFB_NORM_FWD_GRID")) {   // measurement hook (profiles/tools/sweep_norm.py)
+    int g = atoi(e);
+    if (g > 0 && g < grid) grid = g;
+  }
 #define LF(V) nfb_launch_pdl(k_norm_fwd<V, TX, TY, RMS>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, s, (const TX*)x, (const TX*)res, (TX*)sum_out, gamma, beta, (TY*)y, mean, rstd, rows, cols, eps)
   switch (vpl) {
     case 1: LF(1); break;
@@ -305,7 +310,14 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   // two 8-warp blocks per SM, every warp with a whole row (x, dy, dres) in flight; a warp handles several rows so the
   // dgamma / dbeta partials amortise
   int64_t want = nfb_cdiv(rows, BWD_WARPS);
-  int grid = (int)(want < 2LL * nfb_sm_count() ? want : 2LL * nfb_sm_count());
+  // equal work per warp: with r = ceil(want / resident blocks) rows per warp, cdiv(want, r) blocks leave no warp a row short
+  // (T = 4096: 256 blocks x 2 rows instead of 296 blocks x 1.73 -> 15.5 -> 13.5 us, profiles/r01_norm_grid_sweep.txt)
+  const int64_t cap = 2LL * nfb_sm_count();
+  int grid = (int)(want <= cap ? want : nfb_cdiv(want, nfb_cdiv(want, cap)));
+  if (const char* e = getenv("NFB_NORM_BWD_GRID")) {   // measurement hook (profiles/tools/sweep_norm.py)
+    int g = atoi(e);
+    if (g > 0 && g <= want) grid = g;
+  }
   if (grid < 1) grid = 1;
   constexpr int NP = RMS ? 1 : 2;
   float* partial = nullptr;

@@ -17,16 +17,13 @@ embedding forward+backward, Adam/AdamW).
 """
 from __future__ import annotations
 
-import ctypes as C
-import math
 import numbers
-import re
 
 import numpy as np
 
 from . import _lib
 from . import array as A
-from ._lib import B200Error, call
+from ._lib import call
 from .array import B200Array, bfloat16, dtype_code
 from . import kernels as K
 from .plugin import Backend, register_backend

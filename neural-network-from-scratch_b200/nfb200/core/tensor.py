@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import itertools
 import logging
-import numbers
 from contextlib import contextmanager
 from typing import Any, Callable, Optional, Sequence, Tuple, Union
 

@@ -19,7 +19,6 @@ import os
 import pickle
 import socket
 import struct
-import threading
 import time
 from enum import Enum
 from typing import List, Optional

@@ -14,7 +14,6 @@ import numpy as np
 
 from ..array import B200Array, bfloat16
 from ..core.tensor import ACCUMULATED, Tensor, make_result
-from .utils import reduce_gradient
 
 F32 = np.dtype(np.float32)
 

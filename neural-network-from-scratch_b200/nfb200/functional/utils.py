@@ -5,7 +5,6 @@ import numbers
 
 import numpy as np
 
-from ..array import B200Array
 from ..core.tensor import Tensor
 
 

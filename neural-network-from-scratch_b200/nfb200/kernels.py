@@ -9,7 +9,6 @@ compute mode of the backend):
 """
 from __future__ import annotations
 
-import math
 
 import numpy as np
 

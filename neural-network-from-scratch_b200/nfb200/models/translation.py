@@ -6,7 +6,6 @@ from __future__ import annotations
 
 import numpy as np
 
-from .. import functional as F
 from ..array import B200Array
 from ..core import Module, Tensor
 from ..nn import Embedding, Linear, ModuleList, TransformerBlock, TransformerDecoderBlock

@@ -11,7 +11,7 @@ import numpy as np
 from .. import functional as F
 from ..array import B200Array, bfloat16
 from ..core import Module, Parameter, Tensor
-from ..nn import Dropout, LayerNorm, Linear, ModuleList
+from ..nn import LayerNorm, Linear, ModuleList
 
 
 def _act_dtype(x: Tensor):

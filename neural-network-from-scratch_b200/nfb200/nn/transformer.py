@@ -8,7 +8,6 @@ from __future__ import annotations
 import math
 from typing import Optional
 
-from .. import functional as F
 from ..core import Module, Tensor
 from .layers import Dropout, LayerNorm
 from .linear import StandardLinear

@@ -11,7 +11,6 @@ Tied parameters are de-duplicated by identity.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, List
 
 import numpy as np

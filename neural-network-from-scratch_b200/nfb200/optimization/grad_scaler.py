@@ -17,7 +17,6 @@ product in a fresh Tensor, which severs the graph (backward through the scaled l
 """
 from __future__ import annotations
 
-import ctypes as C
 import logging
 import time
 from dataclasses import dataclass

@@ -15,7 +15,7 @@ tensors to it.
 from __future__ import annotations
 
 import abc
-from typing import Any, Dict, List, Optional
+from typing import Dict, List, Optional
 
 # The abstract surface, grouped as in SURVEY 8(b).  name -> one-line contract.
 _ABSTRACT_PROPERTIES = ("name", "is_available", "supports_gradients")
@@ -162,7 +162,7 @@ def install_into_reference() -> bool:
         from neural_arch.backends import backend as ref_backend  # type: ignore
     except Exception:
         return False
-    from .b200_backend import B200Backend, make_reference_subclass
+    from .b200_backend import make_reference_subclass
 
     cls = make_reference_subclass(ref_backend.Backend)
     ref_backend.register_backend("b200", cls)

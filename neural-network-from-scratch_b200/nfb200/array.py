@@ -791,7 +791,8 @@ def reduce(op: str, x: B200Array, axis=None, keepdims=False) -> B200Array:
     if x.size == 0 or _prod([x.shape[i] for i in axes]) == 0:
         if op in ("max", "min") and _prod([x.shape[i] for i in axes]) == 0:
             raise ValueError("zero-size array to reduction operation which has no identity")
-        return B200Array.full(out_shape, {"sum": 0, "prod": 1, "mean": float("nan")}[op], dt)
+        # (max / min over a NON-empty axis of an empty array: an empty result, the fill value is never used)
+        return B200Array.full(out_shape, {"sum": 0, "prod": 1, "mean": float("nan"), "max": 0, "min": 0}[op], dt)
     xc, outer, R, inner = _reduce_layout(x, axes)
     out = B200Array.empty(out_shape, dt)
     call("nfb_reduce", RED[op], dtype_code(dt), xc.ptr, out.ptr, outer, R, inner)

@@ -48,6 +48,7 @@ struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;       // operand major-ness (1 = MN-major)
   int num_m, num_n, split_k, k_blocks_per_split, k_blocks_total;
+  int n_fast;           // tile order inside a k-split: 0 = m fastest (concurrent tiles share a B panel), 1 = n fastest (share an A panel)
   void* C;
   int c_bf16;
   long long ldc;
@@ -322,7 +323,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         int ks = tile / tiles_mn, mn = tile % tiles_mn;
-        int m_blk = mn % p.num_m, n_blk = mn / p.num_m;
+        int m_blk = p.n_fast ? mn / p.num_n : mn % p.num_m, n_blk = p.n_fast ? mn % p.num_n : mn / p.num_m;
         int kb0 = ks * p.k_blocks_per_split;
         int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         const int m0 = (m_blk * CG + (int)cta_rank) * BLOCK_M;
@@ -422,7 +423,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int tcount = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
       int ks = tile / tiles_mn, mn = tile % tiles_mn;
-      int m_blk = mn % p.num_m, n_blk = mn / p.num_m;
+      int m_blk = p.n_fast ? mn / p.num_n : mn % p.num_m, n_blk = p.n_fast ? mn % p.num_n : mn / p.num_m;
       mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 2 && lane == 0) tl_stamp(p, 10 + 4 * tcount);
       tc_fence_after();
@@ -791,13 +792,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
-static int g_force_block_n = 0, g_force_cg = 0, g_tma_store = 1;
+static int g_force_block_n = 0, g_force_cg = 0, g_tma_store = 1, g_force_raster = 0;
 NFB_API int nfb_gemm_bf16_set_tma_store(int on) { g_tma_store = on ? 1 : 0; return 0; }  // test hook: 0 = register epilogue everywhere
 static unsigned long long* g_timeline = nullptr;
 // debug: device buffer of 8 x 64 u64 that the next launches fill with clock64 stamps (NULL = off)
 NFB_API int nfb_gemm_bf16_set_timeline(void* dev_buf) { g_timeline = (unsigned long long*)dev_buf; return 0; }
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
 NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }
+NFB_API int nfb_gemm_bf16_force_raster(int order) { g_force_raster = order; return 0; }   // test hook: 0 = auto, 1 = m fastest, 2 = n fastest
 
 // Tile choice: a small cost model in SM clocks.  Per CTA and 64-deep k-block the MMA needs 2*BLOCK_N clk (tcgen05
 // floor, 128 x BLOCK_N x 16 per BLOCK_N/2 clk) and the smem fill needs (16 KB + BLOCK_N/CG * 128 B) / 64 B/clk
@@ -866,6 +868,17 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   p.a_mn = a_mn;
   p.b_mn = b_mn;
   p.num_m = num_m; p.num_n = num_n; p.split_k = sk; p.k_blocks_per_split = kbps; p.k_blocks_total = k_blocks;
+  {
+    // Tile order for L2 reuse.  The tiles of one wave run concurrently and walk K roughly in lockstep, so a panel they
+    // share is fetched from HBM once; a panel they do not share is fetched again for every tile that needs it unless the
+    // whole operand stays in L2.  m fastest: a wave shares B panels, A is read num_n times if it does not fit; n fastest:
+    // the other way round.  Only the LM-head weight gradient (A = dlogits^T, 412 MB, num_n = 3) cares: 1.56 -> 0.73 GB.
+    const double l2_keep = 48e6;   // what an operand may occupy and still survive in the 126 MB L2 next to the other traffic
+    const double a_bytes = 2.0 * (double)M * K, b_bytes = 2.0 * (double)N * K;
+    const double m_fast_cost = (a_bytes > l2_keep ? num_n * a_bytes : a_bytes) + b_bytes;
+    const double n_fast_cost = a_bytes + (b_bytes > l2_keep ? num_m * b_bytes : b_bytes);
+    p.n_fast = g_force_raster ? (g_force_raster == 2) : (n_fast_cost < m_fast_cost);
+  }
   p.C = C; p.c_bf16 = (c_dtype == NFB_BF16); p.ldc = ldc;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.aux = aux; p.ldaux = ldaux;
   p.epilogue = epilogue; p.accumulate = accumulate; p.clip = clip;

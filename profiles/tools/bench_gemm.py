@@ -27,6 +27,7 @@ shapes = [
 only = sys.argv[1] if len(sys.argv) > 1 else None
 tiles = [int(t) for t in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 64, 128, 192, 256]
 cgs = [int(t) for t in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2]
+if len(sys.argv) > 4: _lib.call("nfb_gemm_bf16_force_raster", int(sys.argv[4]))   # 1 = m fastest, 2 = n fastest tile order
 rng = np.random.default_rng(0)
 def rand_bf16(shape):
     x = B200Array.from_numpy((rng.standard_normal(shape) * 0.5).astype(np.float32))

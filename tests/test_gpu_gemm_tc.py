@@ -142,6 +142,30 @@ def test_wgrad_split_k_accumulate(be, cta_group, split_k):
     np.testing.assert_allclose(out.get(), want, rtol=3e-5, atol=2e-3)
 
 
+@pytest.mark.parametrize("raster", [1, 2], ids=["m_fastest", "n_fastest"])
+def test_tile_order_for_l2_reuse(be, cta_group, raster):
+    """Both tile orders of the persistent scheduler (m fastest / n fastest; the library picks by an L2-reuse estimate, which
+    only flips for operands larger than L2, e.g. the LM-head weight gradient) on shapes with several ragged m AND n tiles:
+    a forward, and a split-K weight gradient accumulating into C."""
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal((1100, 200)).astype(np.float32)
+    b = rng.standard_normal((900, 200)).astype(np.float32)
+    T, dout, din = 2048, 1100, 600
+    dy = (rng.standard_normal((T, dout)) * 0.1).astype(np.float32)
+    x = rng.standard_normal((T, din)).astype(np.float32)
+    base = rng.standard_normal((dout, din)).astype(np.float32)
+    out = _to(be, base.copy())
+    _lib.call("nfb_gemm_bf16_force_raster", raster)
+    try:
+        got = Kn.gemm_bf16(_to(be, a), _to(be, b), False, True).get()
+        Kn.gemm_bf16(_to(be, dy), _to(be, x), True, False, out=out, accumulate=True, split_k=3)
+    finally:
+        _lib.call("nfb_gemm_bf16_force_raster", 0)
+    np.testing.assert_allclose(got, _ref(a, b, False, True), rtol=2e-5, atol=5e-4)
+    np.testing.assert_allclose(out.get(), base + _ref(dy, x, True, False), rtol=3e-5, atol=2e-3)
+
+
 def test_gemm_f32_wrapper(be):
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(5)

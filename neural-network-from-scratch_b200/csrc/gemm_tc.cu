@@ -800,6 +800,9 @@ NFB_API int nfb_gemm_bf16_set_timeline(void* dev_buf) { g_timeline = (unsigned l
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
 NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }
 NFB_API int nfb_gemm_bf16_force_raster(int order) { g_force_raster = order; return 0; }   // test hook: 0 = auto, 1 = m fastest, 2 = n fastest
+static int g_auto_split = 1;
+// internal split-K of non-accumulating launches: 0 = off, 1 = automatic (cost model), 2 = whenever eligible (test hook)
+NFB_API int nfb_gemm_bf16_set_auto_split(int mode) { g_auto_split = mode; return 0; }
 
 // Tile choice: a small cost model in SM clocks.  Per CTA and 64-deep k-block the MMA needs 2*BLOCK_N clk (tcgen05
 // floor, 128 x BLOCK_N x 16 per BLOCK_N/2 clk) and the smem fill needs (16 KB + BLOCK_N/CG * 128 B) / 64 B/clk
@@ -818,6 +821,51 @@ static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int 
   return (double)waves * (kb * per_kb + 250.0) + epi + 2500.0;
 }
 
+// Best (tile N, CTA group, split-K) for a launch.  may_split: the caller accumulates into a pre-initialised fp32 C, so K may
+// be cut (split_k >= 1 pins the factor, 0 lets the model choose).
+static TileChoice choose_tiles(int M, int N, int k_blocks, int b_mn, bool may_split, int split_k, int sms) {
+  TileChoice best = {128, 1, 1, 1e30};
+  const int cand_bn[4] = {256, 192, 128, 64};
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (g_force_cg && cg != g_force_cg) continue;
+    if (cg == 2 && (sms % 2 != 0 || M <= BLOCK_M)) continue;
+    for (int i = 0; i < 4; ++i) {
+      int bn = cand_bn[i];
+      if (g_force_block_n && bn != g_force_block_n) continue;
+      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;   // MN-major B is staged in 64-column chunks
+      int sk_lo = 1, sk_hi = 1;
+      if (may_split) {
+        if (split_k >= 1) sk_lo = sk_hi = split_k;
+        else sk_hi = k_blocks >= 8 ? (k_blocks / 4 < 16 ? k_blocks / 4 : 16) : 1;
+      }
+      for (int sk = sk_lo; sk <= sk_hi; ++sk) {
+        double c = tile_cost(M, N, k_blocks, bn, cg, sk, sms);
+        if (c < best.cost * 0.98) best = {bn, cg, sk, c};
+      }
+    }
+  }
+  return best;
+}
+
+// finishing pass of an internal split-K: C = clip(workspace), cast to C's type (4 elements per thread, 64-bit indexing)
+template <typename TC>
+__global__ void __launch_bounds__(256)
+k_splitk_finish(const float* __restrict__ ws, TC* __restrict__ C, int64_t M, int N, int64_t ldc, float clip) {
+  nfb_pdl_enter();
+  const int nv = N >> 2;
+  const int64_t total = M * nv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nv;
+    const int c = (int)(i - r * nv) << 2;
+    f4 v = ld4<float>(ws + r * N + c);
+    if (clip > 0.f) {
+      v.x = fminf(fmaxf(v.x, -clip), clip); v.y = fminf(fmaxf(v.y, -clip), clip);
+      v.z = fminf(fmaxf(v.z, -clip), clip); v.w = fminf(fmaxf(v.w, -clip), clip);
+    }
+    st4<TC>(C + r * ldc + c, v);
+  }
+}
+
 // C (+)= epi(opA . opB + bias) + residual.  A, B bf16; C fp32 (c_dtype = NFB_F32) or bf16.
 // split_k: 0 = choose automatically (only used when accumulate != 0), >= 1 = explicit.
 NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -833,26 +881,35 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   const int a_mn = transA ? 1 : 0, b_mn = transB ? 0 : 1;
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
 
-  TileChoice best = {128, 1, 1, 1e30};
-  const int cand_bn[4] = {256, 192, 128, 64};
-  for (int cg = 1; cg <= 2; ++cg) {
-    if (g_force_cg && cg != g_force_cg) continue;
-    if (cg == 2 && (sms % 2 != 0 || M <= BLOCK_M)) continue;
-    for (int i = 0; i < 4; ++i) {
-      int bn = cand_bn[i];
-      if (g_force_block_n && bn != g_force_block_n) continue;
-      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;   // MN-major B is staged in 64-column chunks
-      int sk_lo = 1, sk_hi = 1;
-      if (accumulate && epilogue == 0) {
-        if (split_k >= 1) sk_lo = sk_hi = split_k;
-        else sk_hi = k_blocks >= 8 ? (k_blocks / 4 < 16 ? k_blocks / 4 : 16) : 1;
+  // ---- internal split-K: a launch whose tiles fill well under one wave and whose K is long (the LM-head input gradient:
+  // 48 tile pairs on 74 SM pairs, 786 k-blocks each) is split along K into a zeroed fp32 workspace (TMA reduce-add, the
+  // weight-gradient path) and finished by one clip / cast pass.  Three launches instead of one; taken only when the cost
+  // model sees a clear win, never on the side stream (the workspace comes from the stream-ordered allocator).
+  if (!accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_auto_split && k_blocks >= 16 && N % 4 == 0 &&
+      ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream())) {
+    const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
+    const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
+    // memset + finishing pass: two launches and 14 B per output element at ~3400 B/clk of HBM
+    const double overhead = 6000.0 + (double)M * (double)N * 14.0 / 3400.0;
+    if (many.sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) {
+      float* ws = nullptr;
+      if (nfb_malloc(sizeof(float) * (size_t)M * N, (void**)&ws)) return -1;
+      NFB_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)M * N, nfb_cur_stream()));
+      int rc = nfb_gemm_bf16(transA, transB, M, N, K, A, lda, B, ldb, ws, NFB_F32, N, nullptr, nullptr, 0, nullptr, 0, 0, 1, many.sk, 0.f);
+      if (rc == 0) {
+        const int64_t vecs = (int64_t)M * (N / 4);
+        const int grid = nfb_grid_for(vecs, 256, 8);
+        if (c_dtype == NFB_BF16) nfb_launch_pdl(k_splitk_finish<__nv_bfloat16>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, (__nv_bfloat16*)C, (int64_t)M, N, (int64_t)ldc, clip);
+        else nfb_launch_pdl(k_splitk_finish<float>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, (float*)C, (int64_t)M, N, (int64_t)ldc, clip);
       }
-      for (int sk = sk_lo; sk <= sk_hi; ++sk) {
-        double c = tile_cost(M, N, k_blocks, bn, cg, sk, sms);
-        if (c < best.cost * 0.98) best = {bn, cg, sk, c};
-      }
+      nfb_free(ws);
+      if (rc) return rc;
+      NFB_LAUNCH_CHECK();
+      return 0;
     }
   }
+
+  TileChoice best = choose_tiles(M, N, k_blocks, b_mn, accumulate && epilogue == 0, split_k, sms);
   if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
     best = {g_force_block_n ? g_force_block_n : 128, 1, (accumulate && split_k >= 1) ? split_k : 1, 0.0};
   }

@@ -166,6 +166,62 @@ def test_tile_order_for_l2_reuse(be, cta_group, raster):
     np.testing.assert_allclose(out.get(), base + _ref(dy, x, True, False), rtol=3e-5, atol=2e-3)
 
 
+@pytest.mark.parametrize("ta,tb", LAYOUTS)
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+def test_internal_split_k_forced(be, cta_group, ta, tb, out_dtype):
+    """Non-accumulating launches split along K into a zeroed fp32 workspace + finishing clip / cast pass (taken automatically
+    only for under-filled long-K launches such as the LM-head input gradient; forced here on small ragged shapes)."""
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(8)
+    M, N, K = 300, 200, 2000
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    odt = be.bfloat16 if out_dtype == "bf16" else np.float32
+    a_d, b_d = Kn.to_bf16(_to(be, a)), Kn.to_bf16(_to(be, b))
+    n0 = _lib.launch_count()
+    _lib.call("nfb_gemm_bf16_set_auto_split", 2)
+    try:
+        got = Kn.gemm_bf16(a_d, b_d, ta, tb, out_dtype=odt, clip=30.0)
+    finally:
+        _lib.call("nfb_gemm_bf16_set_auto_split", 1)
+    launches = _lib.launch_count() - n0
+    got = got.get()
+    want = np.clip(_ref(a, b, ta, tb), -30.0, 30.0)
+    assert np.abs(want).max() == 30.0                                  # the clip is active
+    if out_dtype == "bf16":
+        np.testing.assert_allclose(got, want, rtol=1e-2, atol=1e-2 * np.sqrt(K / 64))
+    else:
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-4 * np.sqrt(K / 64))
+    assert launches >= 2, launches                                      # GEMM + finishing pass (+ a pitch-aligning operand copy)
+
+
+def test_internal_split_k_lm_head_dgrad(be):
+    """The shape the cost model splits on its own: dX (4096, 768) = dlogits (4096, 50257) . wte (50257, 768).  Same result as
+    the single launch (fp32 accumulation either way, one rounding to bf16) and two launches where there was one."""
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(9)
+    T, V, d = 4096, 50257, 768
+    ldv = (V + 7) // 8 * 8
+    dl = Kn.to_bf16(_to(be, (rng.standard_normal((T, ldv)) * 1e-2).astype(np.float32)))[:, :V]
+    w = Kn.to_bf16(_to(be, (rng.standard_normal((V, d)) * 0.02).astype(np.float32)))
+    _lib.call("nfb_gemm_bf16_set_auto_split", 0)
+    try:
+        n0 = _lib.launch_count()
+        one = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
+        n1 = _lib.launch_count()
+    finally:
+        _lib.call("nfb_gemm_bf16_set_auto_split", 1)
+    split = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
+    n2 = _lib.launch_count()
+    assert n1 - n0 == 1 and n2 - n1 == 2, (n1 - n0, n2 - n1)
+    a, b = one.get(), split.get()
+    assert np.isfinite(b).all()
+    np.testing.assert_allclose(b, a, rtol=8e-3, atol=8e-3 * float(np.abs(a).max()))   # one bf16 ulp of the larger values
+    # against fp64 on a slice of rows
+    ref = dl[:64].get().astype(np.float64) @ w.get().astype(np.float64)
+    np.testing.assert_allclose(b[:64], ref, rtol=1e-2, atol=1e-2 * float(np.abs(ref).max()))
+
+
 def test_gemm_f32_wrapper(be):
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(5)

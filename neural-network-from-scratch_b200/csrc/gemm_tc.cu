@@ -48,6 +48,7 @@ struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;       // operand major-ness (1 = MN-major)
   int num_m, num_n, split_k, k_blocks_per_split, k_blocks_total;
+  int slice_rows;       // > 0: k-split ks stores (no add) its partial product at row offset ks * slice_rows of C (deterministic split-K)
   int n_fast;           // tile order inside a k-split: 0 = m fastest (concurrent tiles share a B panel), 1 = n fastest (share an A panel)
   void* C;
   int c_bf16;
@@ -533,7 +534,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           __syncwarp();
           if (lane == 0) {
             if (p.accumulate) tma_reduce_add_2d(&tmC, sbox, col0, row0);
-            else tma_store_2d(&tmC, sbox, col0, row0);
+            else tma_store_2d(&tmC, sbox, col0, row0 + ks * p.slice_rows);
             tma_store_commit();
           }
         }
@@ -847,17 +848,23 @@ static TileChoice choose_tiles(int M, int N, int k_blocks, int b_mn, bool may_sp
   return best;
 }
 
-// finishing pass of an internal split-K: C = clip(workspace), cast to C's type (4 elements per thread, 64-bit indexing)
+// finishing pass of an internal split-K: C = clip(slice 0 + slice 1 + ... in that fixed order), cast to C's type
+// (4 elements per thread, 64-bit indexing; the slices are (slice_rows, N) fp32, stacked)
 template <typename TC>
 __global__ void __launch_bounds__(256)
-k_splitk_finish(const float* __restrict__ ws, TC* __restrict__ C, int64_t M, int N, int64_t ldc, float clip) {
+k_splitk_finish(const float* __restrict__ ws, int slices, int64_t slice_elems, TC* __restrict__ C, int64_t M, int N, int64_t ldc, float clip) {
   nfb_pdl_enter();
   const int nv = N >> 2;
   const int64_t total = M * nv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nv;
     const int c = (int)(i - r * nv) << 2;
-    f4 v = ld4<float>(ws + r * N + c);
+    const float* src = ws + r * N + c;
+    f4 v = ld4<float>(src);
+    for (int k = 1; k < slices; ++k) {
+      const f4 u = ld4<float>(src + k * slice_elems);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     if (clip > 0.f) {
       v.x = fminf(fmaxf(v.x, -clip), clip); v.y = fminf(fmaxf(v.y, -clip), clip);
       v.z = fminf(fmaxf(v.z, -clip), clip); v.w = fminf(fmaxf(v.w, -clip), clip);
@@ -868,9 +875,11 @@ k_splitk_finish(const float* __restrict__ ws, TC* __restrict__ C, int64_t M, int
 
 // C (+)= epi(opA . opB + bias) + residual.  A, B bf16; C fp32 (c_dtype = NFB_F32) or bf16.
 // split_k: 0 = choose automatically (only used when accumulate != 0), >= 1 = explicit.
-NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+// slice_split > 1 (internal): C is a stack of slice_split (slice_rows, N) fp32 slices; k-split ks STORES its partial product
+// into slice ks (no pre-zeroing, no atomics); the caller sums the slices in a fixed order.
+static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
                           void* C, int c_dtype, int64_t ldc, const float* bias, const float* residual, int64_t ldr, void* aux,
-                          int64_t ldaux, int epilogue, int accumulate, int split_k, float clip) {
+                          int64_t ldaux, int epilogue, int accumulate, int split_k, float clip, int slice_split, int slice_rows) {
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) return NFB_FAIL("gemm_bf16: K must be positive");
   if (c_dtype != NFB_F32 && c_dtype != NFB_BF16) return NFB_FAIL("gemm_bf16: C dtype %d", c_dtype);
@@ -882,25 +891,26 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
 
   // ---- internal split-K: a launch whose tiles fill well under one wave and whose K is long (the LM-head input gradient:
-  // 48 tile pairs on 74 SM pairs, 786 k-blocks each) is split along K into a zeroed fp32 workspace (TMA reduce-add, the
-  // weight-gradient path) and finished by one clip / cast pass.  Three launches instead of one; taken only when the cost
-  // model sees a clear win, never on the side stream (the workspace comes from the stream-ordered allocator).
-  if (!accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_auto_split && k_blocks >= 16 && N % 4 == 0 &&
-      ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream())) {
+  // 48 tile pairs on 74 SM pairs, 786 k-blocks each) is cut along K; every k-split stores its partial product into its own
+  // fp32 slice of a workspace and one finishing pass sums the slices in a fixed order, clips and casts -- deterministic,
+  // unlike a reduce-add.  Two launches instead of one; taken only when the cost model sees a clear win, never on the side
+  // stream (the workspace comes from the stream-ordered allocator).
+  if (!slice_split && !accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_auto_split && g_tma_store &&
+      k_blocks >= 16 && N % 4 == 0 && ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream())) {
     const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
     const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
-    // memset + finishing pass: two launches and 14 B per output element at ~3400 B/clk of HBM
-    const double overhead = 6000.0 + (double)M * (double)N * 14.0 / 3400.0;
-    if (many.sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) {
+    const int sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, many.sk));   // the factor after rounding the k-blocks per split
+    // the extra launch + the slices written once and read once + C written, at ~3400 B/clk of HBM
+    const double overhead = 3000.0 + (double)M * (double)N * (8.0 * sk + 2.0) / 3400.0;
+    if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) {
+      const int64_t rows = nfb_cdiv(M, 2 * BLOCK_M) * 2 * BLOCK_M;           // whole tiles: an edge tile never reaches the next slice
       float* ws = nullptr;
-      if (nfb_malloc(sizeof(float) * (size_t)M * N, (void**)&ws)) return -1;
-      NFB_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)M * N, nfb_cur_stream()));
-      int rc = nfb_gemm_bf16(transA, transB, M, N, K, A, lda, B, ldb, ws, NFB_F32, N, nullptr, nullptr, 0, nullptr, 0, 0, 1, many.sk, 0.f);
+      if (nfb_malloc(sizeof(float) * (size_t)sk * rows * N, (void**)&ws)) return -1;
+      int rc = gemm_bf16_impl(transA, transB, M, N, K, A, lda, B, ldb, ws, NFB_F32, N, nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, 0.f, sk, (int)rows);
       if (rc == 0) {
-        const int64_t vecs = (int64_t)M * (N / 4);
-        const int grid = nfb_grid_for(vecs, 256, 8);
-        if (c_dtype == NFB_BF16) nfb_launch_pdl(k_splitk_finish<__nv_bfloat16>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, (__nv_bfloat16*)C, (int64_t)M, N, (int64_t)ldc, clip);
-        else nfb_launch_pdl(k_splitk_finish<float>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, (float*)C, (int64_t)M, N, (int64_t)ldc, clip);
+        const int grid = nfb_grid_for((int64_t)M * (N / 4), 256, 8);
+        if (c_dtype == NFB_BF16) nfb_launch_pdl(k_splitk_finish<__nv_bfloat16>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (__nv_bfloat16*)C, (int64_t)M, N, (int64_t)ldc, clip);
+        else nfb_launch_pdl(k_splitk_finish<float>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (float*)C, (int64_t)M, N, (int64_t)ldc, clip);
       }
       nfb_free(ws);
       if (rc) return rc;
@@ -909,22 +919,25 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
     }
   }
 
-  TileChoice best = choose_tiles(M, N, k_blocks, b_mn, accumulate && epilogue == 0, split_k, sms);
+  TileChoice best = slice_split > 1 ? choose_tiles(M, N, k_blocks, b_mn, true, slice_split, sms)
+                                    : choose_tiles(M, N, k_blocks, b_mn, accumulate && epilogue == 0, split_k, sms);
   if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
-    best = {g_force_block_n ? g_force_block_n : 128, 1, (accumulate && split_k >= 1) ? split_k : 1, 0.0};
+    best = {g_force_block_n ? g_force_block_n : 128, 1, slice_split > 1 ? slice_split : ((accumulate && split_k >= 1) ? split_k : 1), 0.0};
   }
   const int best_bn = best.bn, cg = best.cg;
   int sk = best.sk;
   const int num_m = (int)nfb_cdiv(M, BLOCK_M * cg);
   const int num_n = (int)nfb_cdiv(N, best_bn);
   int kbps = (int)nfb_cdiv(k_blocks, sk);
-  sk = (int)nfb_cdiv(k_blocks, kbps);
+  if (slice_split <= 1) sk = (int)nfb_cdiv(k_blocks, kbps);   // (slice mode: the caller already passes the rounded factor, every split is non-empty)
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.a_mn = a_mn;
   p.b_mn = b_mn;
   p.num_m = num_m; p.num_n = num_n; p.split_k = sk; p.k_blocks_per_split = kbps; p.k_blocks_total = k_blocks;
+  p.slice_rows = slice_split > 1 ? slice_rows : 0;
+  if (slice_split > 1 && (sk != slice_split || (long long)(sk - 1) * kbps >= k_blocks)) return NFB_FAIL("gemm_bf16: internal split-K factor %d does not fit %d k-blocks", slice_split, k_blocks);
   {
     // Tile order for L2 reuse.  The tiles of one wave run concurrently and walk K roughly in lockstep, so a panel they
     // share is fetched from HBM once; a panel they do not share is fetched again for every tile that needs it unless the
@@ -951,8 +964,10 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
   p.tma_store = (g_tma_store && !residual && !aux && ((uintptr_t)C % 16 == 0) && ((ldc * (p.c_bf16 ? 2 : 4)) % 16 == 0)) ? 1 : 0;
   CUtensorMap tmA, tmB, tmC;
   if (p.tma_store) {
-    if (make_map(&tmC, C, N, M, ldc, p.c_bf16 ? 64 : 32, 32, p.c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
+    const long long c_rows = slice_split > 1 ? (long long)slice_split * slice_rows : M;
+    if (make_map(&tmC, C, N, c_rows, ldc, p.c_bf16 ? 64 : 32, 32, p.c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
   } else {
+    if (slice_split > 1) return NFB_FAIL("gemm_bf16: the internal split-K needs the TMA-store epilogue");
     memset(&tmC, 0, sizeof(tmC));
   }
   const int b_rows = best_bn / cg;
@@ -980,4 +995,11 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
     }
   }
   return NFB_FAIL("gemm_bf16: unsupported tile N %d (cta group %d)", best_bn, cg);
+}
+
+NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                          void* C, int c_dtype, int64_t ldc, const float* bias, const float* residual, int64_t ldr, void* aux,
+                          int64_t ldaux, int epilogue, int accumulate, int split_k, float clip) {
+  return gemm_bf16_impl(transA, transB, M, N, K, A, lda, B, ldb, C, c_dtype, ldc, bias, residual, ldr, aux, ldaux, epilogue, accumulate,
+                        split_k, clip, 0, 0);
 }

@@ -169,8 +169,9 @@ def test_tile_order_for_l2_reuse(be, cta_group, raster):
 @pytest.mark.parametrize("ta,tb", LAYOUTS)
 @pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
 def test_internal_split_k_forced(be, cta_group, ta, tb, out_dtype):
-    """Non-accumulating launches split along K into a zeroed fp32 workspace + finishing clip / cast pass (taken automatically
-    only for under-filled long-K launches such as the LM-head input gradient; forced here on small ragged shapes)."""
+    """Non-accumulating launches cut along K: every k-split stores its partial product into its own fp32 slice and a finishing
+    pass sums the slices in a fixed order, clips and casts (taken automatically only for under-filled long-K launches such
+    as the LM-head input gradient; forced here on small ragged shapes)."""
     from nfb200 import _lib, kernels as Kn
     rng = np.random.default_rng(8)
     M, N, K = 300, 200, 2000
@@ -216,6 +217,8 @@ def test_internal_split_k_lm_head_dgrad(be):
     assert n1 - n0 == 1 and n2 - n1 == 2, (n1 - n0, n2 - n1)
     a, b = one.get(), split.get()
     assert np.isfinite(b).all()
+    again = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
+    assert np.array_equal(again, b)                                      # slices summed in a fixed order: run-to-run bit-identical
     np.testing.assert_allclose(b, a, rtol=8e-3, atol=8e-3 * float(np.abs(a).max()))   # one bf16 ulp of the larger values
     # against fp64 on a slice of rows
     ref = dl[:64].get().astype(np.float64) @ w.get().astype(np.float64)

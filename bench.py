@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 GPT2_SMALL = {"vocab_size": 50257, "n_positions": 1024, "n_embd": 768, "n_layer": 12, "n_head": 12}
 BATCH, SEQ = 8, 512
 TRAIN_FLOP_PER_TOKEN = 712.88e6  # SURVEY App. C (GEMM + logits + attention, x3 for training)
-GEMM_DRAM_BYTES_PER_LAUNCH = 38.7e6  # measured, see roofline.traffic_source
+GEMM_DRAM_BYTES_PER_LAUNCH = 34.3e6  # measured, see roofline.traffic_source
 
 
 def peaks():
@@ -311,7 +311,8 @@ def run_b200(args):
         roof = {"bound": "tensor", "kernel": "k_gemm_tc (tcgen05/TMEM bf16 GEMM)", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "traffic": GEMM_DRAM_BYTES_PER_LAUNCH,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per k_gemm_tc launch, ncu --set full capture of this command "
-                                  "(profiles/r01_ncu_gemm_full.txt): LM-head GEMMs 0.44 / 0.49 / 1.56 GB, layer GEMMs 8-41 MB; launch-weighted mean over the 147 launches of a step",
+                                  "(profiles/r01_ncu_gemm_full.txt, LM-head backward re-captured in profiles/r01_ncu_gemm_lmhead_full.txt after the tile-order / split-K change): "
+                                  "LM-head GEMMs 0.44 / 0.66 / 0.74 GB (0.44 / 0.49 / 1.56 before), layer GEMMs 8-41 MB; launch-weighted mean over the 147 launches of a step",
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "launches_timed": n, "avg_launch_ms": tot_ms / n, "avg_launch_gflop": tot_flop / n / 1e9, "share_of_step": tot_ms / ms_prof,
                 "timing": ("CUDA event pairs (external event nodes) captured into a single-stream graph of the same step around every GEMM launch; durations of the last replay" if prof_mode == "graph"

@@ -129,6 +129,9 @@ int nfb_gemm_bf16_force_tile(int block_n);           /* test hook: pin the N til
 int nfb_gemm_bf16_force_cta_group(int cg);           /* test hook: 1 = single-CTA tiles, 2 = cta_group::2 SM pairs, 0 = automatic */
 int nfb_gemm_bf16_force_raster(int order);           /* test hook: tile order 1 = m fastest, 2 = n fastest, 0 = automatic (L2-reuse estimate) */
 int nfb_gemm_bf16_set_auto_split(int mode);          /* internal split-K of under-filled non-accumulating launches: 0 = off, 1 = automatic, 2 = whenever eligible (test hook) */
+/* What nfb_gemm_bf16 would do with a launch of this shape on `sms` SMs (aligned operands, no bias / residual / aux):
+   out[5] = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices}.  Host logic only, no device needed. */
+int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epilogue, int split_k, int sms, int* out);
 int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */
 int nfb_gemm_bf16_set_tma_store(int on);             /* test hook: 0 = register epilogue everywhere (default 1: TMA store when C rows are 16-byte addressable) */
 int nfb_set_aux_stream(void* stream);   /* side stream for optimizer-only work (norm-parameter reductions; the host also issues wgrad GEMMs / bias sums there); NULL = none */

@@ -848,6 +848,54 @@ static TileChoice choose_tiles(int M, int N, int k_blocks, int b_mn, bool may_sp
   return best;
 }
 
+// Everything the host decides about a launch, in one place (also what nfb_gemm_bf16_plan reports to the CPU tests).
+struct GemmPlan {
+  int bn, cg, sk;        // tile N, CTA group, k-splits of the (possibly accumulating) launch
+  int n_fast;            // tile order (see below)
+  int internal_split;    // > 1: cut K into this many slices through the fp32 workspace + finishing pass instead
+};
+// may_split / split_k as in choose_tiles.  split_eligible: the launch does not accumulate, has no fused epilogue operands and
+// an aligned C, so an under-filled grid may be traded for an internal split-K.
+static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int split_k, bool split_eligible, int sms) {
+  const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
+  GemmPlan g = {128, 1, 1, 0, 0};
+  if (split_eligible && g_auto_split && k_blocks >= 16 && N % 4 == 0) {
+    const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
+    const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
+    const int sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, many.sk));   // the factor after rounding the k-blocks per split
+    // the extra launch + the slices written once and read once + C written, at ~3400 B/clk of HBM
+    const double overhead = 3000.0 + (double)M * (double)N * (8.0 * sk + 2.0) / 3400.0;
+    if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) g.internal_split = sk;
+  }
+  const bool slices = g.internal_split > 1;
+  TileChoice best = slices ? choose_tiles(M, N, k_blocks, b_mn, true, g.internal_split, sms) : choose_tiles(M, N, k_blocks, b_mn, may_split, split_k, sms);
+  if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
+    best = {g_force_block_n ? g_force_block_n : 128, 1, slices ? g.internal_split : ((may_split && split_k >= 1) ? split_k : 1), 0.0};
+  }
+  g.bn = best.bn; g.cg = best.cg; g.sk = best.sk;
+  if (!slices) g.sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, g.sk));   // (slices: already the rounded factor, every split non-empty)
+  // Tile order for L2 reuse.  The tiles of one wave run concurrently and walk K roughly in lockstep, so a panel they
+  // share is fetched from HBM once; a panel they do not share is fetched again for every tile that needs it unless the
+  // whole operand stays in L2.  m fastest: a wave shares B panels, A is read num_n times if it does not fit; n fastest:
+  // the other way round.  Only the LM-head weight gradient (A = dlogits^T, 412 MB, num_n = 3) cares: 1.56 -> 0.74 GB.
+  const double num_m = (double)nfb_cdiv(M, BLOCK_M * g.cg), num_n = (double)nfb_cdiv(N, g.bn);
+  const double l2_keep = 48e6;   // what an operand may occupy and still survive in the 126 MB L2 next to the other traffic
+  const double a_bytes = 2.0 * (double)M * K, b_bytes = 2.0 * (double)N * K;
+  const double m_fast_cost = (a_bytes > l2_keep ? num_n * a_bytes : a_bytes) + b_bytes;
+  const double n_fast_cost = a_bytes + (b_bytes > l2_keep ? num_m * b_bytes : b_bytes);
+  g.n_fast = g_force_raster ? (g_force_raster == 2) : (n_fast_cost < m_fast_cost);
+  return g;
+}
+// What nfb_gemm_bf16 would do with a launch of this shape on `sms` SMs (aligned operands, no bias / residual / aux):
+// out = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices}.  Host logic only, no device needed.
+NFB_API int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epilogue, int split_k, int sms, int* out) {
+  if (M <= 0 || N <= 0 || K <= 0 || sms <= 0 || !out) return NFB_FAIL("gemm_bf16_plan: bad arguments");
+  const bool eligible = !accumulate && split_k <= 1 && epilogue == 0 && g_tma_store;
+  const GemmPlan g = plan_gemm(M, N, K, transB ? 0 : 1, accumulate && epilogue == 0, split_k, eligible, sms);
+  out[0] = g.bn; out[1] = g.cg; out[2] = g.sk; out[3] = g.n_fast; out[4] = g.internal_split;
+  return 0;
+}
+
 // finishing pass of an internal split-K: C = clip(slice 0 + slice 1 + ... in that fixed order), cast to C's type
 // (4 elements per thread, 64-bit indexing; the slices are (slice_rows, N) fp32, stacked)
 template <typename TC>
@@ -895,41 +943,32 @@ static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const voi
   // fp32 slice of a workspace and one finishing pass sums the slices in a fixed order, clips and casts -- deterministic,
   // unlike a reduce-add.  Two launches instead of one; taken only when the cost model sees a clear win, never on the side
   // stream (the workspace comes from the stream-ordered allocator).
-  if (!slice_split && !accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_auto_split && g_tma_store &&
-      k_blocks >= 16 && N % 4 == 0 && ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream())) {
-    const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
-    const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
-    const int sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, many.sk));   // the factor after rounding the k-blocks per split
-    // the extra launch + the slices written once and read once + C written, at ~3400 B/clk of HBM
-    const double overhead = 3000.0 + (double)M * (double)N * (8.0 * sk + 2.0) / 3400.0;
-    if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) {
-      const int64_t rows = nfb_cdiv(M, 2 * BLOCK_M) * 2 * BLOCK_M;           // whole tiles: an edge tile never reaches the next slice
-      float* ws = nullptr;
-      if (nfb_malloc(sizeof(float) * (size_t)sk * rows * N, (void**)&ws)) return -1;
-      int rc = gemm_bf16_impl(transA, transB, M, N, K, A, lda, B, ldb, ws, NFB_F32, N, nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, 0.f, sk, (int)rows);
-      if (rc == 0) {
-        const int grid = nfb_grid_for((int64_t)M * (N / 4), 256, 8);
-        if (c_dtype == NFB_BF16) nfb_launch_pdl(k_splitk_finish<__nv_bfloat16>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (__nv_bfloat16*)C, (int64_t)M, N, (int64_t)ldc, clip);
-        else nfb_launch_pdl(k_splitk_finish<float>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (float*)C, (int64_t)M, N, (int64_t)ldc, clip);
-      }
-      nfb_free(ws);
-      if (rc) return rc;
-      NFB_LAUNCH_CHECK();
-      return 0;
+  const bool eligible = !slice_split && !accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_tma_store &&
+                        ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream());
+  const GemmPlan plan = slice_split > 1 ? plan_gemm(M, N, K, b_mn, true, slice_split, false, sms)
+                                        : plan_gemm(M, N, K, b_mn, accumulate && epilogue == 0, split_k, eligible, sms);
+  if (plan.internal_split > 1) {
+    const int sk = plan.internal_split;
+    const int64_t rows = nfb_cdiv(M, 2 * BLOCK_M) * 2 * BLOCK_M;           // whole tiles: an edge tile never reaches the next slice
+    float* ws = nullptr;
+    if (nfb_malloc(sizeof(float) * (size_t)sk * rows * N, (void**)&ws)) return -1;
+    int rc = gemm_bf16_impl(transA, transB, M, N, K, A, lda, B, ldb, ws, NFB_F32, N, nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, 0.f, sk, (int)rows);
+    if (rc == 0) {
+      const int grid = nfb_grid_for((int64_t)M * (N / 4), 256, 8);
+      if (c_dtype == NFB_BF16) nfb_launch_pdl(k_splitk_finish<__nv_bfloat16>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (__nv_bfloat16*)C, (int64_t)M, N, (int64_t)ldc, clip);
+      else nfb_launch_pdl(k_splitk_finish<float>, dim3(grid), dim3(256), 0, nfb_cur_stream(), (const float*)ws, sk, rows * (int64_t)N, (float*)C, (int64_t)M, N, (int64_t)ldc, clip);
     }
+    nfb_free(ws);
+    if (rc) return rc;
+    NFB_LAUNCH_CHECK();
+    return 0;
   }
 
-  TileChoice best = slice_split > 1 ? choose_tiles(M, N, k_blocks, b_mn, true, slice_split, sms)
-                                    : choose_tiles(M, N, k_blocks, b_mn, accumulate && epilogue == 0, split_k, sms);
-  if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
-    best = {g_force_block_n ? g_force_block_n : 128, 1, slice_split > 1 ? slice_split : ((accumulate && split_k >= 1) ? split_k : 1), 0.0};
-  }
-  const int best_bn = best.bn, cg = best.cg;
-  int sk = best.sk;
+  const int best_bn = plan.bn, cg = plan.cg;
+  int sk = slice_split > 1 ? slice_split : plan.sk;
   const int num_m = (int)nfb_cdiv(M, BLOCK_M * cg);
   const int num_n = (int)nfb_cdiv(N, best_bn);
-  int kbps = (int)nfb_cdiv(k_blocks, sk);
-  if (slice_split <= 1) sk = (int)nfb_cdiv(k_blocks, kbps);   // (slice mode: the caller already passes the rounded factor, every split is non-empty)
+  const int kbps = (int)nfb_cdiv(k_blocks, sk);
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -938,17 +977,7 @@ static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const voi
   p.num_m = num_m; p.num_n = num_n; p.split_k = sk; p.k_blocks_per_split = kbps; p.k_blocks_total = k_blocks;
   p.slice_rows = slice_split > 1 ? slice_rows : 0;
   if (slice_split > 1 && (sk != slice_split || (long long)(sk - 1) * kbps >= k_blocks)) return NFB_FAIL("gemm_bf16: internal split-K factor %d does not fit %d k-blocks", slice_split, k_blocks);
-  {
-    // Tile order for L2 reuse.  The tiles of one wave run concurrently and walk K roughly in lockstep, so a panel they
-    // share is fetched from HBM once; a panel they do not share is fetched again for every tile that needs it unless the
-    // whole operand stays in L2.  m fastest: a wave shares B panels, A is read num_n times if it does not fit; n fastest:
-    // the other way round.  Only the LM-head weight gradient (A = dlogits^T, 412 MB, num_n = 3) cares: 1.56 -> 0.73 GB.
-    const double l2_keep = 48e6;   // what an operand may occupy and still survive in the 126 MB L2 next to the other traffic
-    const double a_bytes = 2.0 * (double)M * K, b_bytes = 2.0 * (double)N * K;
-    const double m_fast_cost = (a_bytes > l2_keep ? num_n * a_bytes : a_bytes) + b_bytes;
-    const double n_fast_cost = a_bytes + (b_bytes > l2_keep ? num_m * b_bytes : b_bytes);
-    p.n_fast = g_force_raster ? (g_force_raster == 2) : (n_fast_cost < m_fast_cost);
-  }
+  p.n_fast = plan.n_fast;
   p.C = C; p.c_bf16 = (c_dtype == NFB_BF16); p.ldc = ldc;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.aux = aux; p.ldaux = ldaux;
   p.epilogue = epilogue; p.accumulate = accumulate; p.clip = clip;

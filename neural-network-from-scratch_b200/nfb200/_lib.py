@@ -106,6 +106,7 @@ _SIGNATURES = {
     "nfb_gemm_bf16_force_cta_group": [i32],
     "nfb_gemm_bf16_force_raster": [i32],
     "nfb_gemm_bf16_set_auto_split": [i32],
+    "nfb_gemm_bf16_plan": [i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)],
     "nfb_set_pdl": [i32],
     "nfb_set_aux_stream": [vp],
     "nfb_gemm_bf16_set_tma_store": [i32],

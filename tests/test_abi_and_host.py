@@ -41,6 +41,40 @@ def test_ctypes_table_matches_header():
         assert n == len(args), f"{name}: header has {n} parameters, ctypes table has {len(args)}"
 
 
+def _plan(trans_b, M, N, K, accumulate=0, epilogue=0, split_k=0, sms=148):
+    from nfb200 import _lib
+    out = (ctypes.c_int * 5)()
+    _lib.call("nfb_gemm_bf16_plan", int(trans_b), M, N, K, accumulate, epilogue, split_k, sms, out)
+    return dict(zip(("bn", "cg", "sk", "n_fast", "internal_split"), out))
+
+
+def test_gemm_launch_plans_for_the_gpt2_small_step():
+    """The host-side launch decisions of csrc/gemm_tc.cu (tile width, SM pairing, split-K, tile order, internal split-K)
+    for the GEMM shapes of the bench configuration (T = 4096 tokens, d = 768, V = 50257) on 148 SMs.  Pure host logic:
+    guards the measured choices (profiles/r01_gemm_shapes.txt) against accidental changes."""
+    T, d, V = 4096, 768, 50257
+    # forward x.W^T (B stored (N,K): transB=1): SM pairs on 256-row tiles; N = 768 takes 192-wide tiles (64 pairs of 74)
+    assert _plan(1, T, 2304, d) == dict(bn=256, cg=2, sk=1, n_fast=0, internal_split=0)
+    assert _plan(1, T, d, d)["bn"] == 192 and _plan(1, T, d, 1536)["bn"] == 192
+    # layer input gradients dY.W (MN-major B: 192-wide pair tiles are not available) stay one launch
+    for N, K in ((1536, d), (d, 3072), (d, 2304), (d, d)):
+        pl = _plan(0, T, N, K)
+        assert pl["cg"] == 2 and pl["bn"] == 256 and pl["internal_split"] == 0, (N, K, pl)
+    # LM head: logits and their input gradient; the latter fills 48 of 74 SM pairs -> cut 3 ways along K = 50257
+    assert _plan(1, T, V, d)["internal_split"] == 0 and _plan(1, T, V, d)["n_fast"] == 0
+    assert _plan(0, T, d, V) == dict(bn=256, cg=2, sk=3, n_fast=0, internal_split=3)
+    assert _plan(0, T, d, V, epilogue=1)["internal_split"] == 0          # a fused activation cannot be split
+    # weight gradients accumulate (split-K by reduce-add); the LM-head one reads dlogits^T (412 MB > L2) once: n fastest
+    lm = _plan(0, V, d, T, accumulate=1)
+    assert lm["n_fast"] == 1 and lm["cg"] == 2 and lm["internal_split"] == 0
+    for M, N in ((d, 1536), (3072, d), (d, d), (2304, d)):
+        pl = _plan(0, M, N, T, accumulate=1)
+        assert pl["sk"] > 1 and pl["n_fast"] == 0 and pl["internal_split"] == 0, (M, N, pl)
+    assert _plan(0, d, d, T, accumulate=1, split_k=5)["sk"] == 5        # an explicit factor is honoured
+    # a single-row-block problem cannot pair SMs
+    assert _plan(1, 128, 512, 256)["cg"] == 1
+
+
 def test_no_cpu_fallback_without_gpu():
     import nfb200
     from nfb200 import _lib

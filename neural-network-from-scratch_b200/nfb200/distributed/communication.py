@@ -340,6 +340,52 @@ def broadcast(tensor, src: int = 0):
     return get_backend().broadcast(tensor, src)
 
 
+def _to_host(tensor):
+    data = tensor.data if isinstance(tensor, Tensor) else tensor
+    return data.get() if isinstance(data, B200Array) else np.ascontiguousarray(data)
+
+
+def _store(tensor, host: np.ndarray):
+    """Write a received host array into `tensor` (device tensors get one host->device copy) and return it."""
+    if isinstance(tensor, Tensor):
+        tensor.data = B200Array.from_numpy(host) if isinstance(tensor.data, B200Array) else host
+        return tensor
+    if isinstance(tensor, B200Array):
+        tensor._assign(B200Array.from_numpy(host))
+        return tensor
+    tensor[...] = host
+    return tensor
+
+
+def send(tensor, dst: int, tag: int = 0):
+    """Point-to-point send (communication.py:317-321, 585-587; the reference fakes it with a broadcast).  Here the payload
+    really travels over the rendezvous sockets: a star with rank 0 in the middle, so one end of every pair must be rank 0
+    (control-plane traffic such as metrics or shards of a checkpoint; gradients go through the NCCL collectives)."""
+    g = get_backend()
+    if dst == g.rank:
+        raise ValueError("send: destination is this rank")
+    if not 0 <= dst < g.world_size:
+        raise ValueError(f"send: rank {dst} is out of range for world size {g.world_size}")
+    if g.rank != 0 and dst != 0:
+        raise NotImplementedError("send/recv between two non-zero ranks is not routed; use broadcast / all_gather")
+    _send_msg(g.tcp.sock if g.rank != 0 else g.tcp.peers[dst], (int(tag), _to_host(tensor)))
+
+
+def recv(tensor, src: int, tag: int = 0):
+    """Point-to-point receive into `tensor` (communication.py:323-326, 590-592); returns it."""
+    g = get_backend()
+    if src == g.rank:
+        raise ValueError("recv: source is this rank")
+    if not 0 <= src < g.world_size:
+        raise ValueError(f"recv: rank {src} is out of range for world size {g.world_size}")
+    if g.rank != 0 and src != 0:
+        raise NotImplementedError("send/recv between two non-zero ranks is not routed; use broadcast / all_gather")
+    got_tag, host = _recv_msg(g.tcp.sock if g.rank != 0 else g.tcp.peers[src])
+    if got_tag != int(tag):
+        raise RuntimeError(f"recv: expected tag {tag} from rank {src}, got {got_tag}")
+    return _store(tensor, host)
+
+
 def all_reduce_max_host(value: float) -> float:
     """max over ranks of a host scalar (bench timing: the job's time is the slowest rank's)."""
     g = get_backend()

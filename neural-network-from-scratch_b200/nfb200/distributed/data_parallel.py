@@ -10,6 +10,7 @@ transfer overlaps the rest of backward; finish_gradient_sync() fences the comput
 from __future__ import annotations
 
 import os
+import weakref
 
 from contextlib import contextmanager
 from typing import List, Optional
@@ -51,6 +52,7 @@ class DistributedDataParallel(Module):
         self.world_size = self.group.world_size if self.group else 1
         self.rank = self.group.rank if self.group else 0
         self._require_sync = True
+        _LIVE_DDP.add(self)
         params = list(module.parameters())
         self._dev_params = [p for p in params if isinstance(p.data, B200Array)]
         self._host_params = [p for p in params if not isinstance(p.data, B200Array)]
@@ -270,3 +272,67 @@ class DistributedSampler:
 
     def set_epoch(self, epoch: int):
         self.epoch = epoch
+
+
+# ---------------------------------------------------------------------- module-level helpers (data_parallel.py:391-476)
+def gather(tensor, dst: int = 0, async_op: bool = False):
+    """All ranks contribute `tensor`; rank `dst` gets the list ordered by rank, the others None (data_parallel.py:391-412:
+    an all_gather whose result only `dst` keeps).  Without a process group: `[tensor]`."""
+    if not comm.is_initialized():
+        return [tensor]
+    parts = comm.all_gather(tensor)
+    return parts if comm.get_rank() == dst else None
+
+
+def scatter(tensor_list, src: int = 0):
+    """Rank r receives `tensor_list[r]` of rank `src` (data_parallel.py:415-446 -- whose non-source branch returns the
+    broadcast of a dummy; this does what its docstring says).  Only `src` needs the list; it must hold one tensor per
+    rank (`ValueError` otherwise, as upstream).  Host path over the rendezvous sockets; device tensors are staged through
+    the host (control-plane use: the batch itself is sharded by `DistributedSampler`, gradients go through NCCL)."""
+    if not comm.is_initialized():
+        return tensor_list[0] if tensor_list else Tensor(np.zeros((0,), np.float32))
+    g = comm.get_backend()
+    mine = None
+    if g.rank == src:
+        if tensor_list is None or len(tensor_list) != g.world_size:
+            raise ValueError("tensor_list must contain tensors for all processes")
+        mine = [comm._to_host(t) for t in tensor_list]
+    parts = g.tcp.allgather(mine)[src]
+    if parts is None:
+        raise RuntimeError(f"scatter: rank {src} did not provide a tensor list")
+    if g.rank == src:
+        return tensor_list[src]
+    on_device = g.backend == "nccl"
+    return Tensor(parts[g.rank], device="cuda" if on_device else "cpu")
+
+
+_LIVE_DDP = weakref.WeakSet()
+
+
+@contextmanager
+def no_sync():
+    """Suspend gradient synchronisation of every live DistributedDataParallel wrapper (data_parallel.py:449-457 is a
+    placeholder that only yields): backward passes inside the block accumulate local gradients, the first backward after
+    it all-reduces the sum."""
+    wrappers = list(_LIVE_DDP)
+    prev = [w._require_sync for w in wrappers]
+    for w in wrappers:
+        w._require_sync = False
+    try:
+        yield
+    finally:
+        for w, pv in zip(wrappers, prev):
+            w._require_sync = pv
+
+
+def is_distributed_training_available() -> bool:
+    """data_parallel.py:460-462."""
+    return comm.is_initialized() and comm.get_world_size() > 1
+
+
+def get_distributed_info():
+    """data_parallel.py:465-476 (the backend entry names the transport instead of the upstream constant "distributed")."""
+    if not comm.is_initialized():
+        return {"available": False, "world_size": 1, "rank": 0, "backend": None}
+    g = comm.get_backend()
+    return {"available": True, "world_size": g.world_size, "rank": g.rank, "backend": g.backend}

@@ -32,6 +32,46 @@ def collectives(out):
     json.dump(res, open(os.path.join(out, f"coll_{rank}.json"), "w"))
 
 
+def helpers(out):
+    """gather / scatter / send / recv / no_sync / info helpers of distributed/data_parallel.py:391-476."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    res = {"info": dist.get_distributed_info(), "avail": dist.is_distributed_training_available()}
+    x = np.arange(4, dtype=np.float32) + 100 * rank
+    g = dist.gather(Tensor(x), dst=1)
+    res["gather"] = None if g is None else [t.numpy().tolist() for t in g]
+    pieces = [Tensor(np.full((2, 2), 7.0 + r, np.float32)) for r in range(world)] if rank == 1 else None
+    res["scatter"] = dist.scatter(pieces, src=1).numpy().tolist()
+    if rank == 1:
+        try:
+            dist.scatter([Tensor(np.zeros(1, np.float32))] * (world + 1), src=1)
+            res["scatter_err"] = False
+        except ValueError:
+            res["scatter_err"] = True
+    buf = Tensor(np.zeros(3, np.float32))
+    if rank == 0:
+        dist.send(Tensor(np.array([1.0, 2.0, 3.0], np.float32)), dst=1, tag=5)
+        res["recv"] = dist.recv(buf, src=1, tag=6).numpy().tolist()
+    else:
+        got = dist.recv(buf, src=0, tag=5).numpy()
+        dist.send(Tensor(got * 2), dst=0, tag=6)
+        res["recv"] = got.tolist()
+    # no_sync: two local backward passes accumulate, the first synchronised one averages the accumulated sums
+    from nfb200 import nn
+    np.random.seed(0)
+    lin = nn.Linear(3, 2)
+    ddp = dist.DistributedDataParallel(lin)
+    xin = Tensor(np.full((1, 3), 1.0 + rank, np.float32))
+    lin.zero_grad()
+    with dist.no_sync():
+        ddp(xin).sum().backward()
+        res["local"] = np.asarray(lin.weight.grad).tolist()
+    ddp(xin).sum().backward()
+    ddp.sync_gradients()
+    res["synced"] = np.asarray(lin.weight.grad).tolist()
+    dist.barrier()
+    json.dump(res, open(os.path.join(out, f"help_{rank}.json"), "w"))
+
+
 def ddp_train(out, device):
     """2 steps of data-parallel training of a tiny GPT-2; every rank sees its own half of the global batch."""
     from nfb200.models import GPT2
@@ -78,6 +118,8 @@ if __name__ == "__main__":
     dist.init_process_group(backend)
     if mode == "collectives":
         collectives(out)
+    elif mode == "helpers":
+        helpers(out)
     elif mode == "ddp_cpu":
         ddp_train(out, "cpu")
     elif mode == "ddp_gpu":

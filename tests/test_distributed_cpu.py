@@ -58,6 +58,37 @@ def test_collectives_world2(tmp_path):
     assert r0["sampler"] == perm[0::2] and r1["sampler"] == perm[1::2]
 
 
+def test_gather_scatter_send_recv_no_sync_world2(tmp_path):
+    """The module-level helpers of distributed/data_parallel.py:391-476 and communication.py:585-592 between two processes."""
+    _spawn("helpers", tmp_path)
+    r0 = json.load(open(tmp_path / "help_0.json"))
+    r1 = json.load(open(tmp_path / "help_1.json"))
+    for r, h in enumerate((r0, r1)):
+        assert h["info"] == {"available": True, "world_size": 2, "rank": r, "backend": "gloo"} and h["avail"] is True
+        assert np.array_equal(h["scatter"], np.full((2, 2), 7.0 + r))          # rank r receives piece r of rank 1's list
+    x0 = np.arange(4, dtype=np.float32)
+    assert r0["gather"] is None and np.array_equal(r1["gather"], [x0, x0 + 100])   # only dst = 1 keeps the list
+    assert r1["scatter_err"] is True                                             # wrong list length -> ValueError (upstream)
+    assert r1["recv"] == [1.0, 2.0, 3.0] and r0["recv"] == [2.0, 4.0, 6.0]        # 0 -> 1, doubled, 1 -> 0
+    # no_sync: inside the block each rank holds its own gradient of sum(x W): every row of dW equals x_r (or its transpose)
+    g0, g1 = np.asarray(r0["local"]), np.asarray(r1["local"])
+    assert np.all(g0 == 1.0) and np.all(g1 == 2.0)
+    # the next synchronised backward accumulates once more locally (2 x_r) and averages over ranks: (2*1 + 2*2) / 2 = 3
+    assert np.all(np.asarray(r0["synced"]) == 3.0) and np.all(np.asarray(r1["synced"]) == 3.0)
+
+
+def test_helpers_without_process_group():
+    from nfb200 import distributed as dist
+    from nfb200.core import Tensor
+    assert not dist.is_initialized()
+    t = Tensor(np.ones(3, np.float32))
+    assert dist.gather(t) == [t] and dist.scatter([t]) is t
+    assert dist.get_distributed_info() == {"available": False, "world_size": 1, "rank": 0, "backend": None}
+    assert dist.is_distributed_training_available() is False
+    with dist.no_sync():
+        pass
+
+
 def test_sampler_padding_and_epoch():
     from nfb200.distributed import DistributedSampler
     s0 = DistributedSampler(10, num_replicas=4, rank=0, shuffle=False)

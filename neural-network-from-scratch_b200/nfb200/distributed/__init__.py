@@ -4,4 +4,4 @@ from .communication import (ProcessGroup, ReduceOp, all_gather, all_reduce, all_
                             is_initialized, recv, reduce_scatter, send)
 from .data_parallel import (DataParallel, DistributedDataParallel, DistributedSampler, gather, get_distributed_info,
                             is_distributed_training_available, no_sync, scatter)
-from .launcher import launch
+from .launcher import DistributedLauncher, LaunchConfig, find_free_port, get_local_ip, launch, launch_distributed_training

@@ -89,6 +89,44 @@ def test_helpers_without_process_group():
         pass
 
 
+def test_launcher_config_validation():
+    """distributed/launcher.py:267-286: the same ValueErrors."""
+    from nfb200.distributed import DistributedLauncher, LaunchConfig, find_free_port, get_local_ip
+    for kw in (dict(nproc_per_node=0), dict(nnodes=0), dict(nnodes=2, node_rank=2), dict(master_addr="not-an-ip"), dict(master_port=80)):
+        with pytest.raises(ValueError):
+            DistributedLauncher(LaunchConfig(**kw))
+    DistributedLauncher(LaunchConfig(nproc_per_node=8, nnodes=2, node_rank=1, master_addr="10.0.0.1", master_port=29500))
+    assert 1024 <= find_free_port() <= 65535 and socket.inet_aton(get_local_ip())
+
+
+def test_launcher_env_contract_logs_and_fail_fast(tmp_path):
+    """Ranks get RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (launcher.py:145-162), per-rank log files (:164-183); one failing
+    rank ends the job at once with that rank's exit code."""
+    import time
+    from nfb200.distributed import launch_distributed_training
+    script = tmp_path / "train.py"
+    script.write_text(
+        "import json, os, sys, time\n"
+        "keys = ['RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'NCCL_ASYNC_ERROR_HANDLING', 'OMP_NUM_THREADS']\n"
+        "json.dump({k: os.environ.get(k) for k in keys} | {'argv': sys.argv[1:]}, open(os.path.join(sys.argv[1], 'env_' + os.environ['RANK'] + '.json'), 'w'))\n"
+        "print('hello from', os.environ['RANK'])\n"
+        "if sys.argv[2] == 'fail':\n"
+        "    if os.environ['RANK'] == '3': sys.exit(7)\n"
+        "    time.sleep(120)\n")
+    logs = tmp_path / "logs"
+    rc = launch_distributed_training(str(script), 2, 2, 1, "127.0.0.1", 29611, "auto", str(logs), str(tmp_path), "ok")
+    assert rc == 0
+    for local, rank in ((0, 2), (1, 3)):                      # node 1 of 2, two ranks per node
+        e = json.load(open(tmp_path / f"env_{rank}.json"))
+        assert e == {"RANK": str(rank), "WORLD_SIZE": "4", "LOCAL_RANK": str(local), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29611",
+                     "NCCL_ASYNC_ERROR_HANDLING": "1", "OMP_NUM_THREADS": "1", "argv": [str(tmp_path), "ok"]}
+        assert (logs / f"rank_{rank}_stdout.log").read_text().strip() == f"hello from {rank}"
+        assert (logs / f"rank_{rank}_stderr.log").exists()
+    t0 = time.time()
+    rc = launch_distributed_training(str(script), 2, 2, 1, "127.0.0.1", 29611, "auto", None, str(tmp_path), "fail")
+    assert rc == 7 and time.time() - t0 < 30
+
+
 def test_sampler_padding_and_epoch():
     from nfb200.distributed import DistributedSampler
     s0 = DistributedSampler(10, num_replicas=4, rank=0, shuffle=False)

@@ -208,3 +208,35 @@ def test_sgd_lr_schedule_acts_on_graph_replays(be):
     finally:
         K.set_precision("fp32")
         set_default_device("cpu")
+
+
+def test_clip_grad_norm_wrapper_on_device(be):
+    """optim/clip.py on cuda tensors: the norm, the directly scaled gradients, and the form deferred into the fused AdamW
+    kernel (device coefficient) against the host path of the same function."""
+    from nfb200.core import Parameter
+    from nfb200.optim import AdamW, clip_grad_norm
+    rng = np.random.default_rng(21)
+    shapes = [(40, 33), (517,), (64, 64)]
+    vals = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    grads = [rng.standard_normal(s).astype(np.float32) * 3 for s in shapes]
+
+    def run(device, deferred):
+        ps = {f"p{i}": Parameter(v.copy(), device=device) for i, v in enumerate(vals)}
+        opt = AdamW(ps, lr=1e-2, weight_decay=0.0, moment_dtype="float32")
+        for p, g in zip(ps.values(), grads):
+            p.grad = g.copy()
+        norm = clip_grad_norm(ps, 1.0, optimizer=opt if deferred else None)
+        norm = float(np.asarray(norm.get() if hasattr(norm, "get") else norm).reshape(-1)[0])
+        g_after = [np.asarray(p.grad.get() if hasattr(p.grad, "get") else p.grad) for p in ps.values()]
+        opt.step()
+        return norm, g_after, [p.numpy() for p in ps.values()]
+
+    n_host, g_host, p_host = run("cpu", False)
+    for deferred in (False, True):
+        n_dev, g_dev, p_dev = run("cuda", deferred)
+        np.testing.assert_allclose(n_dev, n_host, rtol=1e-6)
+        if not deferred:
+            for a, b in zip(g_dev, g_host):
+                np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)
+        for a, b in zip(p_dev, p_host):
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)

@@ -36,3 +36,33 @@ def test_gpt2_training_example_on_the_host_path(tmp_path):
     load_checkpoint(str(tmp_path / "ck" / "gpt2_epoch_3"), model)
     with np.load(tmp_path / "ck" / "gpt2_epoch_3.npz") as z:
         assert np.array_equal(model.state_dict()["transformer.wte.weight"], z["model/transformer.wte.weight"])
+
+
+def test_gpt2_training_example_two_ranks_under_the_launcher(tmp_path):
+    """The same script under `nfb200.distributed.launcher` with two host ranks (gloo): DistributedSampler shards,
+    DistributedDataParallel averages the gradients, rank 0 alone writes the metrics and the checkpoints."""
+    import socket
+    from nfb200.distributed import launch_distributed_training
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    args = ["--device", "cpu", "--vocab-size", "64", "--n-embd", "32", "--n-layer", "2", "--n-head", "2", "--n-ctx", "16", "--batch-size", "4",
+            "--learning-rate", "0.003", "--num-epochs", "2", "--train-size", "96", "--val-size", "16", "--checkpoint-dir", str(tmp_path / "ck"),
+            "--out", str(tmp_path / "metrics.json")]
+    env_before = os.environ.get("NFB200_PORT_OFFSET")
+    os.environ["NFB200_PORT_OFFSET"] = "0"
+    try:
+        rc = launch_distributed_training(os.path.join(ROOT, "examples", "train_gpt2.py"), 2, 1, 0, "127.0.0.1", port, "auto", str(tmp_path / "logs"), *args)
+    finally:
+        if env_before is None:
+            os.environ.pop("NFB200_PORT_OFFSET", None)
+        else:
+            os.environ["NFB200_PORT_OFFSET"] = env_before
+    assert rc == 0, (tmp_path / "logs" / "rank_0_stderr.log").read_text()[-2000:] + (tmp_path / "logs" / "rank_1_stderr.log").read_text()[-2000:]
+    res = json.load(open(tmp_path / "metrics.json"))
+    assert len(res["train_losses"]) == 2 and np.isfinite(res["train_losses"]).all() and res["train_losses"][1] < res["train_losses"][0]
+    rec = json.load(open(tmp_path / "ck" / "gpt2_epoch_2.json"))
+    assert rec["step"] == 2 * (48 // 4)                       # each rank sees half of the 96 sequences per epoch
+    assert "Epoch 2/2" in (tmp_path / "logs" / "rank_0_stdout.log").read_text()
+    assert "Epoch" not in (tmp_path / "logs" / "rank_1_stdout.log").read_text()

@@ -554,12 +554,44 @@ def gen_lion(g):
         g[f"{name}_traj"], g[f"{name}_m"] = np.stack(traj), np.asarray(opt.state["w"]["momentum_buffer"])
 
 
+def gen_translation(g):
+    """BASELINE configs[0]: the encoder-decoder Transformer of examples/translation/model_v2.py (the reference's own
+    CPU-runnable case), seeded, at the config's width (d_model 128, 4 heads, 3 + 3 layers, d_ff 256) with a small vocabulary:
+    forward logits for a padded synthetic batch (ids uniform in [4, V), trailing pad 0 of random length), with and
+    without the look-ahead / padding masks the training script passes."""
+    import importlib.util
+    from neural_arch.core import Tensor
+    spec = importlib.util.spec_from_file_location("ref_translation_model_v2", "/root/reference/examples/translation/model_v2.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(900)
+    V, B, S = 120, 4, 12
+    np.random.seed(0)
+    model = mod.TranslationTransformer(src_vocab_size=V, tgt_vocab_size=V + 7, d_model=128, n_heads=4, n_layers=3, d_ff=256, max_seq_len=32)
+    src = rng.integers(4, V, (B, S))
+    tgt = rng.integers(4, V + 7, (B, S))
+    for r in range(B):
+        pad = int(rng.integers(0, 6))
+        if pad:
+            src[r, S - pad:] = 0
+            tgt[r, S - pad:] = 0
+    g["src"], g["tgt"] = src, tgt
+    g["logits"] = model(Tensor(src), Tensor(tgt)).data
+    src_mask = model.create_padding_mask(src)
+    tgt_mask = model.create_look_ahead_mask(S)
+    g["src_mask"], g["tgt_mask"] = (src_mask if src_mask is not None else np.zeros((B, S), np.float32)), tgt_mask
+    g["logits_masked"] = model(Tensor(src), Tensor(tgt), src_mask=src_mask, tgt_mask=tgt_mask).data
+    g["src_emb_sample"] = model.src_embedding.weight.data[:3]
+    g["out_w_sample"] = model.output_projection.weight.data[:2]
+    g["n_params"] = np.array(sum(int(np.prod(p.data.shape)) for p in model.parameters()))
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])
     for name, fn in (("functional", gen_functional), ("layers", gen_layers), ("optim", gen_optim), ("gpt2", gen_gpt2_pieces), ("bert_vit", gen_bert_vit),
-                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip), ("prenorm", gen_prenorm), ("lion", gen_lion)):
+                     ("sampler", gen_sampler), ("train_glue", gen_train_glue), ("modern", gen_modern), ("roberta", gen_roberta), ("clip", gen_clip), ("prenorm", gen_prenorm), ("lion", gen_lion), ("translation", gen_translation)):
         if only and name not in only:
             continue
         g = {}

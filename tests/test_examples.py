@@ -1,6 +1,6 @@
-"""examples/train_gpt2.py (the workload of the reference's examples/training/gpt2_training.py on this package's API) at a
-size the host path finishes in seconds: the loss falls, every epoch leaves a reference-layout checkpoint record plus
-weights, and the weights load back."""
+"""examples/train_{gpt2,bert_mlm,vit}.py (the workloads of the reference's examples/training/*_training.py on this
+package's API) at sizes the host path finishes in seconds: the loss falls, every epoch leaves a reference-layout checkpoint
+record plus weights, and the weights load back; the GPT-2 script also runs as two ranks under the launcher."""
 import json
 import os
 import sys
@@ -10,12 +10,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_gpt2_training_example_on_the_host_path(tmp_path):
+def _example(name):
+    import importlib
     sys.path.insert(0, os.path.join(ROOT, "examples"))
     try:
-        import train_gpt2
+        return importlib.import_module(name)
     finally:
         sys.path.pop(0)
+
+
+def test_gpt2_training_example_on_the_host_path(tmp_path):
+    train_gpt2 = _example("train_gpt2")
     from nfb200.core import set_default_device
     try:
         res = train_gpt2.main(["--device", "cpu", "--vocab-size", "64", "--n-embd", "32", "--n-layer", "2", "--n-head", "2", "--n-ctx", "16",
@@ -66,3 +71,24 @@ def test_gpt2_training_example_two_ranks_under_the_launcher(tmp_path):
     assert rec["step"] == 2 * (48 // 4)                       # each rank sees half of the 96 sequences per epoch
     assert "Epoch 2/2" in (tmp_path / "logs" / "rank_0_stdout.log").read_text()
     assert "Epoch" not in (tmp_path / "logs" / "rank_1_stdout.log").read_text()
+
+
+def test_bert_mlm_and_vit_training_examples_on_the_host_path(tmp_path):
+    from nfb200.core import set_default_device
+    try:
+        bert = _example("train_bert_mlm").main(
+            ["--device", "cpu", "--vocab-size", "50", "--hidden-size", "32", "--num-hidden-layers", "2", "--num-attention-heads", "2",
+             "--intermediate-size", "64", "--max-seq-length", "16", "--batch-size", "8", "--learning-rate", "0.003", "--num-epochs", "3",
+             "--train-size", "96", "--val-size", "16", "--checkpoint-dir", str(tmp_path / "bert")])
+        vit = _example("train_vit").main(
+            ["--device", "cpu", "--image-size", "16", "--patch-size", "4", "--num-classes", "4", "--d-model", "32", "--depth", "2", "--num-heads", "2",
+             "--batch-size", "8", "--learning-rate", "0.003", "--num-epochs", "3", "--train-size", "96", "--val-size", "16",
+             "--checkpoint-dir", str(tmp_path / "vit")])
+    finally:
+        set_default_device("cpu")
+    for res in (bert, vit):
+        assert np.isfinite(res["train_losses"]).all() and res["train_losses"][-1] < res["train_losses"][0]
+    rec = json.load(open(tmp_path / "bert" / "bert_epoch_3.json"))
+    assert rec["config"]["hidden_size"] == 32 and rec["step"] == 36
+    rec = json.load(open(tmp_path / "vit" / "vit_epoch_3.json"))
+    assert rec["config"]["patch_size"] == 4 and (tmp_path / "vit" / "vit_epoch_3.npz").exists()

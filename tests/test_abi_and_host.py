@@ -249,3 +249,45 @@ def test_gradients_by_finite_differences_on_host():
         check(lambda a: F.mean(F.reshape(F.transpose(a, (1, 0, 2)), (4, 6)), axis=1), (2, 4, 3))
     finally:
         set_grad_clip(10.0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/neural_arch/backends"), reason="needs the reference checkout (build container only)")
+def test_drop_in_registration_into_the_real_reference_registry():
+    """INTEGRATION.md step 1 against the UNMODIFIED reference package: `nfb200.install_into_reference()` registers a class that
+    IS a `neural_arch.backends.Backend` (the reference's own ABC) with every abstract member implemented, under the names
+    "b200" and "cuda"; without a GPU the reference's registry answers as it does for any unavailable backend
+    (`RuntimeError`, backends/backend.py:348-349) and never lists it as available -- no silent fallback.  Runs in a child
+    process so the reference package does not leak into this one."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path[:0] = [%r, %r]
+import neural_arch.backends.backend as rb          # the reference's registry, through the namespace shim of oracle/compat
+import nfb200
+assert nfb200.install_into_reference() is True
+cls = rb._BACKENDS["b200"]
+assert rb._BACKENDS["cuda"] is cls and issubclass(cls, rb.Backend)
+res = {"abstract_left": sorted(getattr(cls, "__abstractmethods__", ())), "n_abstract": len(rb.Backend.__abstractmethods__)}
+be = cls()                                           # instantiation fails if any abstract member were missing
+res["name"], res["available"] = be.name, bool(be.is_available)
+try:
+    rb.get_backend("b200")
+    res["get_backend"] = "returned"
+except RuntimeError as e:
+    res["get_backend"] = "RuntimeError"
+try:
+    rb.get_backend("no-such-backend")
+except ValueError:
+    res["unknown"] = "ValueError"
+res["listed"] = "b200" in rb.available_backends()
+print(json.dumps(res))
+''' % (os.path.join(ROOT, "oracle", "compat"), os.path.join(ROOT, "neural-network-from-scratch_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-3000:]
+    import json
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["abstract_left"] == [] and res["n_abstract"] >= 50
+    assert res["name"] == "b200" and res["unknown"] == "ValueError"
+    if not res["available"]:                                             # this container: no GPU
+        assert res["get_backend"] == "RuntimeError" and res["listed"] is False

@@ -352,6 +352,13 @@ class Tensor:
                 g = reduce_gradient(g, self.shape)
         return g
 
+    def _backward(self) -> None:
+        """Upstream, a layer hangs a `_backward` closure on its result and callers run it by hand after `backward()` to push
+        the gradient one level down (tests/test_layers.py:123-124, utils `propagate_gradients`).  Here `backward()` has already
+        walked the whole graph, so there is nothing left to do; the attribute exists so that such call sites keep working
+        without applying any gradient twice."""
+        return None
+
     def backward(self, gradient=None) -> None:
         if not self.requires_grad:
             return

@@ -20,6 +20,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
+from .. import exceptions as _exc
 from .. import functional as F
 from ..array import B200Array, bfloat16
 from ..core import Module, Parameter, Tensor
@@ -28,7 +29,7 @@ from ..nn import Dropout, LayerNorm, Linear, RMSNorm
 from ..nn.positional import RotaryPositionalEmbedding
 
 
-class ModelError(ValueError):
+class ModelError(_exc.ModelError, ValueError):
     """exceptions.py ModelError of the reference."""
 
 

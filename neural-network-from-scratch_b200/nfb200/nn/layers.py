@@ -6,11 +6,12 @@ from typing import Optional
 
 import numpy as np
 
+from .. import exceptions as _exc
 from .. import functional as F
 from ..core import Module, Parameter, Tensor
 
 
-class LayerError(ValueError):
+class LayerError(_exc.LayerError, ValueError):
     """Shape / argument errors raised by layers (exceptions.py LayerError in the reference)."""
 
 

@@ -12,14 +12,15 @@ from typing import Dict, Optional
 
 import numpy as np
 
+from .. import exceptions as _exc
 from .._lib import F32 as C_F32, F64 as C_F64, call
 from ..array import B200Array
 from ..core import Optimizer
 from .arena import ParamArena
 
 
-class OptimizerError(ValueError):
-    pass
+class OptimizerError(_exc.OptimizerError, ValueError):
+    """The reference's OptimizerError (exceptions.py:267-291); also a ValueError, as it has always been here."""
 
 
 class _AdamBase(Optimizer):
@@ -48,8 +49,8 @@ class _AdamBase(Optimizer):
             raise OptimizerError(f"Invalid epsilon: {eps}")
         if not 0.0 <= weight_decay:
             raise OptimizerError(f"Invalid weight decay: {weight_decay}")
-        if amsgrad:
-            raise NotImplementedError("amsgrad is not implemented on the b200 backend (not used by the named configs)")
+        if amsgrad and any(isinstance(p.data, B200Array) for p in param_dict.values()):
+            raise NotImplementedError("amsgrad is not implemented on the b200 backend (not used by the named configs); host tensors only")
         self._lr_dev = None      # device copy of lr (capturable mode): schedulers act on replays of a captured step
         self._replay_lag = 0     # replays of a captured step not yet reflected in the per-parameter "step" entries
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
@@ -78,6 +79,8 @@ class _AdamBase(Optimizer):
             else:
                 ea, es = np.zeros(p.shape, dtype=np.float64), np.zeros(p.shape, dtype=np.float64)
             self.state[name] = {"step": 0, "exp_avg": ea, "exp_avg_sq": es}
+            if amsgrad:   # host tensors only (checked above); float32 like the parameter, as upstream (optim/adam.py:119-120)
+                self.state[name]["max_exp_avg_sq"] = np.zeros_like(np.asarray(p.data))
             self.m[name], self.v[name] = ea, es
 
     # ------------------------------------------------------------------ learning rate (host value + device mirror)
@@ -307,7 +310,11 @@ class _AdamBase(Optimizer):
         st["exp_avg_sq"] = self.beta2 * st["exp_avg_sq"] + (1 - self.beta2) * (g.astype(np.float64) ** 2)
         self.m[name], self.v[name] = st["exp_avg"], st["exp_avg_sq"]
         bc1, bc2 = 1 - self.beta1 ** t, 1 - self.beta2 ** t
-        denom = np.sqrt(st["exp_avg_sq"] / bc2 + self.eps)
+        if self.amsgrad:   # maximum of the bias-corrected second moments so far, epsilon OUTSIDE the root (optim/adam.py:222-226)
+            np.maximum(st["max_exp_avg_sq"], st["exp_avg_sq"] / bc2, out=st["max_exp_avg_sq"], casting="unsafe")
+            denom = np.sqrt(st["max_exp_avg_sq"]) + self.eps
+        else:
+            denom = np.sqrt(st["exp_avg_sq"] / bc2 + self.eps)
         if self._variant == 0:
             eff = self.lr * min(5.0, 0.1 / self.lr) if (0 < self.lr <= 0.02) else self.lr
         else:
@@ -320,6 +327,33 @@ class _AdamBase(Optimizer):
         if not np.all(np.isfinite(new)):
             new = np.nan_to_num(new, nan=0.0, posinf=1.0, neginf=-1.0)
         p.data = np.asarray(new, dtype=pd.dtype)
+
+    # ------------------------------------------------------------------ small host-side API of optim/adam.py:263-372
+    def get_lr(self) -> float:
+        return self.lr
+
+    def set_lr(self, lr: float) -> None:
+        if not 0.0 <= lr:
+            raise OptimizerError(f"Invalid learning rate: {lr}", learning_rate=lr)
+        self.lr = lr
+
+    def __repr__(self) -> str:
+        return (f"{type(self).__name__}(lr={self.lr}, beta1={self.beta1}, beta2={self.beta2}, eps={self.eps}, "
+                f"weight_decay={self.weight_decay}, amsgrad={self.amsgrad})")
+
+    def get_statistics(self) -> Dict:
+        """lr, parameter count, steps taken and the avg / max / min L2 norms of the gradients and parameters (one device->host
+        copy per tensor for cuda parameters: a monitoring call, not part of the step)."""
+        def host(x):
+            return x.get() if isinstance(x, B200Array) else np.asarray(x)
+        stats = {"lr": self.lr, "num_parameters": len(self.parameters),
+                 "total_steps": max((st["step"] for st in self.state.values()), default=0) + self._replay_lag}
+        gn = [float(np.linalg.norm(host(p.grad))) for p in self.parameters.values() if p.grad is not None]
+        pn = [float(np.linalg.norm(host(p.data))) for p in self.parameters.values()]
+        for key, vals in (("grad", gn), ("param", pn)):
+            if vals:
+                stats.update({f"avg_{key}_norm": float(np.mean(vals)), f"max_{key}_norm": float(np.max(vals)), f"min_{key}_norm": float(np.min(vals))})
+        return stats
 
     def zero_grad(self) -> None:
         if self.arena is not None:

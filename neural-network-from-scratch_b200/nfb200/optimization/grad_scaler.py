@@ -25,6 +25,7 @@ from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
+from .. import exceptions as _exc
 from .._lib import call
 from ..array import B200Array
 from ..core import Tensor
@@ -34,7 +35,7 @@ logger = logging.getLogger(__name__)
 _CHUNK = 1 << 14   # elements per block of the unscale kernels (64 KB of fp32)
 
 
-class NumericalError(ArithmeticError):
+class NumericalError(_exc.NumericalError, ArithmeticError):
     pass
 
 

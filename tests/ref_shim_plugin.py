@@ -1,9 +1,7 @@
 """pytest plugin (`-p ref_shim_plugin`) used by tests/test_reference_suite.py: makes `neural_arch.backends` (and its
 `backend`, `numpy_backend` and `utils` submodules) resolve to THIS package's mirror of the reference's backend registry
 (nfb200.plugin + nfb200.numpy_backend), so that the reference's own backend test files can be run, unmodified and from
-where they lie, against it.  `neural_arch.exceptions` is the reference's own file loaded by path (it imports standalone,
-SURVEY F2).  Nothing else of `neural_arch` is provided: a test that needs more fails at import and is reported as such."""
-import importlib.util
+where they lie, against it.  `neural_arch.exceptions` is this package's mirror of the exception tree (nfb200/exceptions.py).  Nothing else of `neural_arch` is provided: a test that needs more fails at import and is reported as such."""
 import os
 import sys
 import types
@@ -38,10 +36,7 @@ backends.numpy_backend = _module("neural_arch.backends.numpy_backend", numpy_bac
 backends.utils = _module("neural_arch.backends.utils", plugin, UTILS)
 pkg.backends = backends
 
-_exc = "/root/reference/src/neural_arch/exceptions.py"
-if os.path.exists(_exc):
-    spec = importlib.util.spec_from_file_location("neural_arch.exceptions", _exc)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules["neural_arch.exceptions"] = mod
-    spec.loader.exec_module(mod)
-    pkg.exceptions = mod
+import nfb200.exceptions  # noqa: E402
+
+sys.modules["neural_arch.exceptions"] = nfb200.exceptions
+pkg.exceptions = nfb200.exceptions

@@ -40,7 +40,10 @@ def _outcomes(plugin, fname):
 
 
 # op-level files: `neural_arch` as a whole (core / functional / nn / optim) resolves to this package (tests/ref_full_shim_plugin.py)
-OP_FILES = ["test_adam_optimizer.py", "test_adam_comprehensive.py", "test_nn_embedding_95_coverage.py"]
+OP_FILES = ["test_adam_optimizer.py", "test_adam_comprehensive.py", "test_nn_embedding_95_coverage.py", "test_core_base_comprehensive.py",
+            "test_core_dtype_comprehensive.py", "test_core_tensor_coverage_boost.py", "test_real_tensor_core.py", "test_tensor_operations.py",
+            "test_functional_operations.py", "test_real_arithmetic.py", "test_lr_schedulers.py", "test_optimizers_95_coverage.py",
+            "test_real_optimizers.py", "test_transformer.py", "test_translation_model.py", "test_comprehensive_coverage.py"]
 # files that cannot even be collected on the reference in this snapshot (they import names from the top-level package, whose
 # `__init__` needs the missing `core` / `config`): run on the mirror alone, every test must pass
 MIRROR_ONLY = {"test_tensor.py": 19, "test_optimizer.py": 15}
@@ -48,8 +51,11 @@ MIRROR_ONLY = {"test_tensor.py": 19, "test_optimizer.py": 15}
 
 @pytest.mark.parametrize("fname", FILES + OP_FILES)
 def test_mirror_passes_what_the_reference_passes(fname):
-    real, log_real = _outcomes("ref_real_plugin", fname)
-    mirror, log_mirror = _outcomes("ref_full_shim_plugin" if fname in OP_FILES else "ref_shim_plugin", fname)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:                       # the two child processes run side by side
+        fut_real = pool.submit(_outcomes, "ref_real_plugin", fname)
+        fut_mirror = pool.submit(_outcomes, "ref_full_shim_plugin" if fname in OP_FILES else "ref_shim_plugin", fname)
+        (real, log_real), (mirror, log_mirror) = fut_real.result(), fut_mirror.result()
     passed_real = sorted(t for t, o in real.items() if o == "PASSED")
     assert passed_real, f"no test of {fname} passes on the reference itself here:\n{log_real}"
     # (pytest's -rA lists skips by file:line, not by test id: a skipped test is simply absent from `mirror`)

@@ -1,8 +1,8 @@
 """The reference's exception vocabulary (exceptions.py:7-424): same class names and hierarchy, the same keyword
 arguments feeding `context`, `[ERROR_CODE] message` formatting, `to_dict()`, and the `handle_exception` decorator that
 turns stray `ValueError` / `TypeError` / `MemoryError` into `ShapeError` / `DTypeError` / `NumericalError` / `ResourceError`
-(error conventions).  Built from one table instead of eleven hand-written classes; the suggestion texts of the
-reference are advice for its own users and are not reproduced.
+(error conventions).  Built from one table instead of eleven hand-written classes; every leaf class carries a short list
+of suggestions (own wording; upstream's tests look for the API names in them: `reshape()`, `tensor.to(dtype)`, ...).
 
 The package's own error classes (`optim.OptimizerError`, `nn.LayerError`, `models.ModelError`, the scaler's
 `NumericalError`) derive from these AND from the builtin they always derived from, so `except ValueError` call sites and the
@@ -42,6 +42,23 @@ class NeuralArchError(Exception):
                 "suggestions": self.suggestions, "original_exception": str(self.original_exception) if self.original_exception else None}
 
 
+_ADVICE = {
+    "ShapeError": ("Check tensor dimensions against what the operation expects", "reshape() or transpose the operand into the expected layout",
+                   "Remember the broadcasting rule: trailing axes must be equal or 1"),
+    "DTypeError": ("Convert explicitly with tensor.to(dtype) / astype() before the call", "Mixed operands follow NumPy type promotion; state the intended dtype"),
+    "DeviceError": ("Bring the operands together with tensor.to(device)", "get_default_device() / set_default_device() decide where new tensors are created",
+                    "A cuda tensor needs the b200 backend: there is no silent CPU fallback"),
+    "GradientError": ("Create the tensor with requires_grad=True", "Call backward() on a scalar, or pass the upstream gradient explicitly"),
+    "NumericalError": ("Look for NaN / inf in the inputs", "Lower the learning rate or clip the gradients"),
+    "LayerError": ("Compare the layer's constructor arguments with the input shape",),
+    "ParameterError": ("Check the parameter's shape against the layer that owns it",),
+    "OptimizerError": ("Check the learning rate and the other hyper-parameters", "Make sure backward() ran and zero_grad() is called once per step"),
+    "ConfigurationError": ("Validate the value against the type the option expects",),
+    "ResourceError": ("Reduce the batch size or free cached device memory",),
+    "DataError": ("Check the format and dtype of the input data",),
+}
+
+
 def _family(name: str, parent: type, code: Optional[str] = None, keys: tuple = ()):
     """A subclass whose keyword arguments (`keys`) land in `context` when given -- the shape of every leaf class upstream."""
     if not keys:
@@ -53,7 +70,8 @@ def _family(name: str, parent: type, code: Optional[str] = None, keys: tuple = (
         unknown = [k for k in kwargs if k not in keys]
         if unknown:
             raise TypeError(f"{name}() got unexpected keyword arguments {unknown}")
-        NeuralArchError.__init__(self, message, error_code=code, context={k: v for k, v in given.items() if v is not None})
+        NeuralArchError.__init__(self, message, error_code=code, context={k: v for k, v in given.items() if v is not None},
+                                 suggestions=list(_ADVICE.get(name, ())))
 
     return type(name, (parent,), {"__init__": __init__, "__doc__": f"{name}: context keys {keys} (exceptions.py)", "__module__": __name__})
 

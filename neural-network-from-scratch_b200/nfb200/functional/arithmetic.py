@@ -48,7 +48,7 @@ def mul(a, b) -> Tensor:
 def div(a, b) -> Tensor:
     if is_scalar(b):
         if b == 0:
-            raise ValueError("Division by zero")
+            raise ValueError("Division by zero detected")
         return make_result(a.data / b, [a], lambda g: (g / b,), "div")
     if is_scalar(a):
         bd = b.data
@@ -59,7 +59,7 @@ def div(a, b) -> Tensor:
     check_same_device(a, b, "div")
     ad, bd = a.data, b.data
     if isinstance(bd, np.ndarray) and np.any(bd == 0):
-        raise ValueError("Division by zero")  # functional/arithmetic.py:319 (host tensors only: no device sync)
+        raise ValueError("Division by zero detected")  # functional/arithmetic.py:319 (host tensors only: no device sync)
     return make_result(ad / bd, [a, b],
                        lambda g: (reduce_gradient(g / bd, ad.shape), reduce_gradient(-g * ad / (bd * bd), bd.shape)), "div")
 
@@ -86,9 +86,9 @@ def matmul(a, b) -> Tensor:
     b = as_tensor(b, a)
     check_same_device(a, b, "matmul")
     if a.ndim < 2 or b.ndim < 2:
-        raise ValueError("matmul requires tensors with at least 2 dimensions")
+        raise ValueError(f"matmul requires 2D+ tensors, got shapes {a.shape} and {b.shape}")
     if a.shape[-1] != b.shape[-2]:
-        raise ValueError(f"matmul: inner dimensions do not match: {a.shape} @ {b.shape}")
+        raise ValueError(f"Incompatible matrix dimensions: {a.shape} @ {b.shape}")
     ad, bd = a.data, b.data
 
     def backward(g):

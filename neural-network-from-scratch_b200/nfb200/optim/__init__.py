@@ -5,4 +5,4 @@ from . import lr_scheduler
 from .lr_scheduler import (ChainedScheduler, CosineAnnealingLR, ExponentialLR, LinearLR, LRScheduler, PolynomialLR, ReduceLROnPlateau,
                            StepLR, WarmupLR, get_cosine_schedule_with_warmup, get_linear_schedule_with_warmup)
 from .lion import Lion
-from .sgd import SGD
+from .sgd import SGD, SGDMomentum

@@ -29,7 +29,7 @@ class SGD(Optimizer):
     def __init__(self, parameters, lr: float = 0.01, momentum: float = 0.0, weight_decay: float = 0.0, dampening: float = 0.0,
                  nesterov: bool = False, maximize: bool = False):
         if hasattr(parameters, "items"):
-            param_dict = dict(parameters.items())
+            param_dict = parameters if isinstance(parameters, dict) else dict(parameters.items())   # the caller's dict itself, as upstream
         else:
             param_dict = {f"param_{i}": p for i, p in enumerate(parameters)}
         super().__init__(param_dict, lr=lr)
@@ -91,3 +91,6 @@ class SGD(Optimizer):
         for p in self.parameters.values():
             if self.arena is None or id(p) not in self.arena.offsets:
                 p.zero_grad()
+
+
+SGDMomentum = SGD   # alias kept by the reference (optim/sgd.py:123)

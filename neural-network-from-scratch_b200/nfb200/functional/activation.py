@@ -21,6 +21,9 @@ def _dev(x: Tensor) -> bool:
 
 
 def _host_sigmoid(x):
+    x = np.asarray(x)
+    if x.dtype.kind != "f":          # integer / bool input: NumPy's own promotion (float64), not a truncating empty_like
+        x = x.astype(np.float64)
     out = np.empty_like(x)
     pos = x >= 0
     out[pos] = 1.0 / (1.0 + np.exp(-x[pos]))
@@ -38,7 +41,7 @@ _HOST = {
                  lambda g, x: (g * (0.5 * (1.0 + _erf(x / np.sqrt(2.0))) + x * np.exp(-0.5 * x * x) / np.sqrt(2.0 * np.pi))).astype(x.dtype), False),
     "gelu_tanh": (lambda x: (0.5 * x * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * x ** 3)))).astype(x.dtype),
                   None, False),
-    "silu": (lambda x: x * _host_sigmoid(x), lambda g, x: g * (_host_sigmoid(x) * (1.0 + x * (1.0 - _host_sigmoid(x)))), False),
+    "silu": (lambda x: x * _host_sigmoid(x), lambda g, x: g * (_host_sigmoid(x) * (1.0 + x * (1.0 - _host_sigmoid(x)))), False),   # int x: float64 result
 }
 
 

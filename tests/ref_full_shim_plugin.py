@@ -27,6 +27,42 @@ import nfb200.optim.adam  # noqa: E402
 import nfb200.optim.sgd  # noqa: E402
 
 pkg = sys.modules["neural_arch"]
+
+# every module of this package under the same dotted path below `neural_arch` (one module object, two names): an import such as
+# `neural_arch.nn.positional` must not load a second copy of the file under the other name
+import importlib  # noqa: E402
+import pkgutil  # noqa: E402
+
+import nfb200  # noqa: E402
+
+for info in pkgutil.walk_packages(nfb200.__path__, "nfb200."):
+    if info.name.split(".")[-1].startswith("_") and not info.name.endswith("__init__"):
+        continue
+    try:
+        mod = importlib.import_module(info.name)
+    except Exception:
+        continue
+    alias = "neural_arch." + info.name[len("nfb200."):]
+    if alias not in sys.modules or alias.startswith("neural_arch.backends") is False:
+        sys.modules.setdefault(alias, mod)
+
+# file names of the reference that differ from this package's layout
+import nfb200.distributed  # noqa: E402
+import nfb200.models  # noqa: E402
+import nfb200.models.bert  # noqa: E402
+import nfb200.models.gpt2  # noqa: E402
+import nfb200.models.vit  # noqa: E402
+import nfb200.nn.transformer  # noqa: E402
+
+sys.modules.setdefault("neural_arch.nn.attention", nfb200.nn.transformer)
+for sub, mod in (("language", None), ("vision", None)):
+    m = types.ModuleType("neural_arch.models." + sub)
+    m.__path__ = []
+    sys.modules.setdefault("neural_arch.models." + sub, m)
+sys.modules.setdefault("neural_arch.models.language.gpt2", nfb200.models.gpt2)
+sys.modules.setdefault("neural_arch.models.language.bert", nfb200.models.bert)
+sys.modules.setdefault("neural_arch.models.vision.vision_transformer", nfb200.models.vit)
+pkg.models, pkg.distributed = nfb200.models, nfb200.distributed
 ALIASES = {"core": nfb200.core, "core.base": nfb200.core.base, "core.tensor": nfb200.core.tensor, "core.device": nfb200.core.device,
            "core.dtype": nfb200.core.dtype, "functional": nfb200.functional, "functional.arithmetic": nfb200.functional.arithmetic,
            "functional.activation": nfb200.functional.activation, "functional.loss": nfb200.functional.loss,

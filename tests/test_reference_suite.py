@@ -44,7 +44,9 @@ OP_FILES = ["test_adam_optimizer.py", "test_adam_comprehensive.py", "test_nn_emb
             "test_core_dtype_comprehensive.py", "test_core_tensor_coverage_boost.py", "test_real_tensor_core.py", "test_tensor_operations.py",
             "test_functional_operations.py", "test_real_arithmetic.py", "test_lr_schedulers.py", "test_optimizers_95_coverage.py",
             "test_real_optimizers.py", "test_transformer.py", "test_translation_model.py", "test_comprehensive_coverage.py",
-            "test_sgd_comprehensive.py", "test_exceptions_comprehensive.py", "test_arithmetic_comprehensive.py"]
+            "test_sgd_comprehensive.py", "test_exceptions_comprehensive.py", "test_arithmetic_comprehensive.py",
+            "test_nn_attention_comprehensive.py", "test_nn_attention_95_coverage.py", "test_nn_positional_95_coverage.py",
+            "test_rope_implementation.py", "test_modern_components.py", "test_differential_attention.py"]
 # files that cannot even be collected on the reference in this snapshot (they import names from the top-level package, whose
 # `__init__` needs the missing `core` / `config`): run on the mirror alone, every test must pass
 MIRROR_ONLY = {"test_tensor.py": 19, "test_optimizer.py": 15}
@@ -61,6 +63,9 @@ def test_mirror_passes_what_the_reference_passes(fname):
     assert passed_real, f"no test of {fname} passes on the reference itself here:\n{log_real}"
     # (pytest's -rA lists skips by file:line, not by test id: a skipped test is simply absent from `mirror`)
     lost = [t for t in passed_real if mirror.get(t) != "PASSED" and not (t in NEEDS_TWO_BACKENDS and t not in mirror)]
+    if lost:   # some of these files draw unseeded random inputs: a loss must reproduce to count
+        again, log_mirror = _outcomes("ref_full_shim_plugin" if fname in OP_FILES else "ref_shim_plugin", fname)
+        lost = [t for t in lost if again.get(t) != "PASSED"]
     if fname == "test_backends.py":
         assert "Only one backend available" in log_mirror
     assert not lost, f"{fname}: pass on the reference, not on the mirror: {lost}\n{log_mirror}"

@@ -66,7 +66,7 @@ pkg.models, pkg.distributed = nfb200.models, nfb200.distributed
 ALIASES = {"core": nfb200.core, "core.base": nfb200.core.base, "core.tensor": nfb200.core.tensor, "core.device": nfb200.core.device,
            "core.dtype": nfb200.core.dtype, "functional": nfb200.functional, "functional.arithmetic": nfb200.functional.arithmetic,
            "functional.activation": nfb200.functional.activation, "functional.loss": nfb200.functional.loss,
-           "functional.utils": nfb200.functional.utils, "nn": nfb200.nn, "nn.linear": nfb200.nn.linear, "optim": nfb200.optim,
+           "functional.utils": nfb200.functional.utils, "nn": nfb200.nn, "optim": nfb200.optim,
            "optim.adam": nfb200.optim.adam, "optim.sgd": nfb200.optim.sgd}
 for name, mod in ALIASES.items():
     sys.modules["neural_arch." + name] = mod
@@ -82,3 +82,8 @@ for src in (nfb200.core, nfb200.functional, nfb200.nn, nfb200.optim):     # `fro
             setattr(pkg, k, v)
 for k in ("core", "functional", "nn", "optim"):
     setattr(pkg, k, ALIASES[k])
+
+_lin = types.ModuleType("neural_arch.nn.linear")        # nn/linear.py of the reference holds the (in, out) layer under the name Linear
+_lin.__dict__.update({k: v for k, v in vars(nfb200.nn.linear).items() if not k.startswith("__")})
+_lin.Linear = nfb200.nn.linear.StandardLinear
+sys.modules["neural_arch.nn.linear"] = _lin

@@ -123,45 +123,107 @@ class Dropout(Module):
 
 
 class ModuleList(Module):
+    """A list of sub-modules that the parent sees (nn/container.py:8-171): registered under "0", "1", ... so parameters(),
+    state_dict() and .to() reach them; the whole list protocol (index / slice / assign / delete / + / += / append / extend /
+    insert) with the reference's type and range errors.  Entries are re-registered after every structural change."""
+
     def __init__(self, modules=None):
         super().__init__()
-        self._list = []
-        for m in modules or []:
-            self.append(m)
+        object.__setattr__(self, "_modules_list", [])
+        if modules is not None:
+            self.extend(modules)
 
-    def append(self, module: Module):
-        setattr(self, str(len(self._list)), module)
-        self._list.append(module)
-        return self
+    # ---- bookkeeping
+    @staticmethod
+    def _check(module):
+        if not isinstance(module, Module):
+            raise TypeError(f"ModuleList can only contain Module instances, got {type(module)}")
+        return module
+
+    def _index(self, idx) -> int:
+        if isinstance(idx, bool) or not isinstance(idx, int):
+            raise TypeError(f"ModuleList indices must be integers, not {type(idx).__name__}")
+        n = len(self._modules_list)
+        if not -n <= idx < n:
+            raise IndexError("ModuleList index out of range")
+        return idx + n if idx < 0 else idx
+
+    def _reregister(self):
+        mods = self.__dict__["_modules"]
+        for key in [k for k in mods if k.isdigit()]:
+            mods.pop(key)
+            self.__dict__.pop(key, None)
+        for i, m in enumerate(self._modules_list):
+            setattr(self, str(i), m)
+
+    # ---- list protocol
+    def __len__(self) -> int:
+        return len(self._modules_list)
 
     def __iter__(self):
-        return iter(self._list)
+        return iter(self._modules_list)
 
-    def __len__(self):
-        return len(self._list)
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return type(self)(self._modules_list[idx]) if type(self) is ModuleList else ModuleList(self._modules_list[idx])
+        return self._modules_list[self._index(idx)]
 
-    def __getitem__(self, i):
-        return self._list[i]
+    def __setitem__(self, idx, module) -> None:
+        self._check(module)
+        i = self._index(idx)
+        self._modules_list[i] = module
+        setattr(self, str(i), module)
 
+    def __delitem__(self, idx) -> None:
+        if isinstance(idx, slice):
+            del self._modules_list[idx]
+        else:
+            del self._modules_list[self._index(idx)]
+        self._reregister()
 
-class Sequential(Module):
-    def __init__(self, *modules):
-        super().__init__()
-        self._list = []
-        for i, m in enumerate(modules):
-            setattr(self, str(i), m)
-            self._list.append(m)
+    def __iadd__(self, modules):
+        return self.extend(modules)
+
+    def __add__(self, other):
+        out = ModuleList(self._modules_list)
+        out.extend(other)
+        return out
+
+    def append(self, module):
+        self._check(module)
+        setattr(self, str(len(self._modules_list)), module)
+        self._modules_list.append(module)
+        return self
+
+    def extend(self, modules):
+        if isinstance(modules, Module) and not isinstance(modules, ModuleList):
+            raise TypeError(f"ModuleList.extend should be called with an iterable, but got {type(modules).__name__}")
+        try:
+            items = list(modules)
+        except TypeError:
+            raise TypeError(f"ModuleList.extend should be called with an iterable, but got {type(modules).__name__}") from None
+        for m in items:
+            self.append(m)
+        return self
+
+    def insert(self, index: int, module) -> None:
+        self._check(module)
+        if isinstance(index, bool) or not isinstance(index, int):
+            raise TypeError(f"ModuleList indices must be integers, not {type(index).__name__}")
+        self._modules_list.insert(index, module)
+        self._reregister()
 
     def forward(self, x):
-        for m in self._list:
+        """Chains the entries (nn/container.py:163-171); a ModuleList is normally iterated by its owner instead."""
+        for m in self._modules_list:
             x = m(x)
         return x
 
-    def __iter__(self):
-        return iter(self._list)
 
-    def __len__(self):
-        return len(self._list)
+class Sequential(ModuleList):
+    """Modules applied one after the other (nn/container.py:174-197); a ModuleList, as upstream."""
 
-    def __getitem__(self, i):
-        return self._list[i]
+    def __init__(self, *modules):
+        super().__init__()
+        for m in modules:
+            self.append(m)

@@ -103,9 +103,11 @@ class Sigmoid(Module):
 
 
 class Softmax(Module):
-    def __init__(self, axis: int = -1):
+    """nn/activation.py:14-22 of the reference spells the axis `dim`; `axis` is kept as a synonym."""
+
+    def __init__(self, dim: int = -1, axis: int = None):
         super().__init__()
-        self.axis = axis
+        self.dim = self.axis = dim if axis is None else axis
 
     def forward(self, x):
         return F.softmax(x, self.axis)

@@ -48,7 +48,11 @@ OP_FILES = ["test_adam_optimizer.py", "test_adam_comprehensive.py", "test_nn_emb
             "test_nn_attention_comprehensive.py", "test_nn_attention_95_coverage.py", "test_nn_positional_95_coverage.py",
             "test_rope_implementation.py", "test_modern_components.py", "test_differential_attention.py",
             "test_linear_layer_comprehensive.py", "test_nn_linear_95_coverage.py", "test_linear_missing_coverage.py",
-            "test_nn_container_95_coverage.py", "test_nn_layers.py"]
+            "test_nn_container_95_coverage.py", "test_nn_layers.py", "test_functional_utils_final.py",
+            "test_functional_utils_real_comprehensive.py", "test_functional_utils_complete.py", "test_functional_utils_comprehensive.py"]
+# deliberate divergences (PARITY.md): a test that passes on the reference only because of behaviour this package refuses
+DIVERGES = {"TestFunctionalUtilsComplete::test_validate_tensor_operation_device_warning":
+            "creates a Device.cuda tensor without a GPU and relies on the silent NumPy fallback; here that raises (PARITY.md #5)"}
 # files that cannot even be collected on the reference in this snapshot (they import names from the top-level package, whose
 # `__init__` needs the missing `core` / `config`): run on the mirror alone, every test must pass
 MIRROR_ONLY = {"test_tensor.py": 19, "test_optimizer.py": 15}
@@ -64,7 +68,7 @@ def test_mirror_passes_what_the_reference_passes(fname):
     passed_real = sorted(t for t, o in real.items() if o == "PASSED")
     assert passed_real, f"no test of {fname} passes on the reference itself here:\n{log_real}"
     # (pytest's -rA lists skips by file:line, not by test id: a skipped test is simply absent from `mirror`)
-    lost = [t for t in passed_real if mirror.get(t) != "PASSED" and not (t in NEEDS_TWO_BACKENDS and t not in mirror)]
+    lost = [t for t in passed_real if mirror.get(t) != "PASSED" and not (t in NEEDS_TWO_BACKENDS and t not in mirror) and t not in DIVERGES]
     if lost:   # some of these files draw unseeded random inputs: a loss must reproduce to count
         again, log_mirror = _outcomes("ref_full_shim_plugin" if fname in OP_FILES else "ref_shim_plugin", fname)
         lost = [t for t in lost if again.get(t) != "PASSED"]

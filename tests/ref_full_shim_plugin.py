@@ -62,6 +62,16 @@ for sub, mod in (("language", None), ("vision", None)):
 sys.modules.setdefault("neural_arch.models.language.gpt2", nfb200.models.gpt2)
 sys.modules.setdefault("neural_arch.models.language.bert", nfb200.models.bert)
 sys.modules.setdefault("neural_arch.models.vision.vision_transformer", nfb200.models.vit)
+import nfb200.models.clip  # noqa: E402
+import nfb200.models.modern_transformer  # noqa: E402
+import nfb200.models.roberta  # noqa: E402
+
+sys.modules.setdefault("neural_arch.models.language.modern_transformer", nfb200.models.modern_transformer)
+sys.modules.setdefault("neural_arch.models.language.roberta", nfb200.models.roberta)
+_mm = types.ModuleType("neural_arch.models.multimodal")
+_mm.__path__ = []
+sys.modules.setdefault("neural_arch.models.multimodal", _mm)
+sys.modules.setdefault("neural_arch.models.multimodal.clip", nfb200.models.clip)
 pkg.models, pkg.distributed = nfb200.models, nfb200.distributed
 ALIASES = {"core": nfb200.core, "core.base": nfb200.core.base, "core.tensor": nfb200.core.tensor, "core.device": nfb200.core.device,
            "core.dtype": nfb200.core.dtype, "functional": nfb200.functional, "functional.arithmetic": nfb200.functional.arithmetic,

@@ -52,7 +52,9 @@ def cross_entropy_loss(predictions: Tensor, targets, reduction: str = "mean") ->
             return (d * np.reshape(g, (B, 1)),)
         return (d * (g.item() if np.size(g) == 1 else g),)
 
-    return make_result(np.asarray(loss, dtype=z.dtype), [predictions], backward, "cross_entropy_loss")
+    # (host path: a targets Tensor is listed among the graph inputs, as upstream; it never receives a gradient)
+    inputs = [predictions, targets] if isinstance(targets, Tensor) else [predictions]
+    return make_result(np.asarray(loss, dtype=z.dtype), inputs, backward, "cross_entropy_loss")
 
 
 def mse_loss(predictions: Tensor, targets, reduction: str = "mean") -> Tensor:
@@ -71,4 +73,10 @@ def mse_loss(predictions: Tensor, targets, reduction: str = "mean") -> Tensor:
         out, coef = sq, 2.0
     else:
         raise ValueError(f"Unknown reduction: {reduction}")
-    return make_result(out if not isinstance(out, np.generic) else np.asarray(out), [predictions], lambda g: (d * coef * g,), "mse_loss")
+    inputs = [predictions, targets] if isinstance(targets, Tensor) else [predictions]   # a targets Tensor is a graph input too
+
+    def backward(g):
+        gp = d * coef * g
+        return (gp, -gp) if len(inputs) == 2 and targets.requires_grad else (gp,)
+
+    return make_result(out if not isinstance(out, np.generic) else np.asarray(out), inputs, backward, "mse_loss")

@@ -130,8 +130,16 @@ int nfb_gemm_bf16_force_cta_group(int cg);           /* test hook: 1 = single-CT
 int nfb_gemm_bf16_force_raster(int order);           /* test hook: tile order 1 = m fastest, 2 = n fastest, 0 = automatic (L2-reuse estimate) */
 int nfb_gemm_bf16_set_auto_split(int mode);          /* internal split-K of under-filled non-accumulating launches: 0 = off, 1 = automatic, 2 = whenever eligible (test hook) */
 /* What nfb_gemm_bf16 would do with a launch of this shape on `sms` SMs (aligned operands, no bias / residual / aux):
-   out[5] = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices}.  Host logic only, no device needed. */
+   out[6] = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices, stream-K}.  Host logic only, no device needed. */
 int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epilogue, int split_k, int sms, int* out);
+/* Grouped launch: n <= 4 independent contractions C_g (+)= opA_g . opB_g with the same operand layouts / output type in ONE
+   persistent stream-K kernel (no epilogue operands) -- the four weight-gradient GEMMs dW = dY^T X of a Transformer layer
+   (nn/optimized.py:286-317 computes them one np.matmul at a time).  Every output element gets exactly one store / reduce-add. */
+int nfb_gemm_bf16_grouped(int n, int transA, int transB, const int* Ms, const int* Ns, const int* Ks, const void* const* As, const int64_t* ldas,
+                          const void* const* Bs, const int64_t* ldbs, void* const* Cs, const int64_t* ldcs, int c_dtype, int accumulate);
+int nfb_gemm_bf16_set_stream_k(int mode);            /* stream-K schedule (balanced (tile, k-block) ranges per SM pair + in-kernel fix-up): 0 = never, 1 = automatic (cost model), 2 = whenever possible (test hook) */
+int nfb_gemm_bf16_set_sm_limit(int sms);             /* SMs the persistent GEMM grids may occupy (0 = all): data-parallel steps leave room for NCCL's channel CTAs */
+int nfb_gemm_bf16_set_span(void* dev_two_u64);      /* measurement: the NEXT launch writes min(%globaltimer after griddepcontrol.wait) and ~max(%globaltimer at exit) into two u64 words armed to all-ones */
 int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */
 int nfb_gemm_bf16_set_tma_store(int on);             /* test hook: 0 = register epilogue everywhere (default 1: TMA store when C rows are 16-byte addressable) */
 int nfb_set_aux_stream(void* stream);   /* side stream for optimizer-only work (norm-parameter reductions; the host also issues wgrad GEMMs / bias sums there); NULL = none */

@@ -44,27 +44,55 @@
 #define UMMA_K 16
 #define GEMM_THREADS 320
 
-struct GemmParams {
+#define GEMM_MAX_GROUP 4
+
+// One contraction of a (possibly grouped) launch.  A grouped launch runs up to GEMM_MAX_GROUP independent problems with the
+// same operand layouts / output type in ONE persistent kernel (the four weight-gradient GEMMs of a Transformer layer).
+struct GemmProblem {
   int M, N, K;
-  int a_mn, b_mn;       // operand major-ness (1 = MN-major)
-  int num_m, num_n, split_k, k_blocks_per_split, k_blocks_total;
-  int slice_rows;       // > 0: k-split ks stores (no add) its partial product at row offset ks * slice_rows of C (deterministic split-K)
-  int n_fast;           // tile order inside a k-split: 0 = m fastest (concurrent tiles share a B panel), 1 = n fastest (share an A panel)
+  int num_m, num_n, k_blocks;   // num_m counts (128 * CG)-row tiles
+  int tile_base;                // index of this problem's first tile in the launch-wide tile order
+  long long unit_base;          // stream-K: index of this problem's first (tile, k-block) unit in the launch-wide order
   void* C;
-  int c_bf16;
   long long ldc;
+};
+
+struct GemmParams {
+  int nprob;
+  int mode;             // 0 = static persistent schedule (tile t -> cluster t % clusters, optional split-K over ks); 1 = stream-K
+  GemmProblem pr[GEMM_MAX_GROUP];
+  int a_mn, b_mn;       // operand major-ness (1 = MN-major)
+  int split_k, k_blocks_per_split;   // static mode (single problem)
+  int slice_rows;       // > 0: k-split ks stores (no add) its partial product at row offset ks * slice_rows of C (deterministic split-K)
+  int n_fast;           // tile order: 0 = m fastest (concurrent tiles share a B panel), 1 = n fastest (share an A panel)
+  // stream-K (hybrid): the LAST tiles of the launch-wide order -- the ones that do not fill a whole wave -- are pooled: their
+  // (tile, k-block) units [sk_unit_base, total_units) are cut into equal contiguous ranges, one per cluster; a tile cut by a
+  // range boundary is finished by the cluster that holds its LAST k-block (the owner), which adds the fp32 partial tiles the
+  // earlier clusters left in `ws` (one tile-sized slot per cluster) in cluster order -- deterministic, no atomics on the
+  // data.  flags[c] counts the epilogue warps that have delivered a partial for cluster c's owned tile.  The first dp_tiles
+  // tiles are whole-tile work (tile t -> cluster t % clusters) done AFTER the pooled part, so the fix-up traffic of the
+  // pooled part overlaps their main loops and the launch ends on a plain epilogue.
+  long long total_units, sk_unit_base;
+  int units_per_cluster;
+  int dp_tiles;
+  float4* ws;
+  int* flags;
+  int c_bf16;
   const float* bias;
   const float* residual;
   long long ldr;
   void* aux;            // optional bf16 pre-activation output (same shape as C)
   long long ldaux;
   int epilogue;         // 0 none, 1 gelu_tanh, 2 relu
-  int accumulate;       // C += (fp32 only, red.global.add)
+  int accumulate;       // C += (fp32 only: TMA reduce-add / red.global.add of the finished tile)
   float clip;           // > 0: clamp the result to [-clip, clip]
   int vec_ok;           // C / residual / aux pitches and bases allow 128-bit (fp32) / 64-bit (bf16) accesses
   int tma_store;        // epilogue through shared memory + TMA store / reduce-add (C 16-byte aligned rows, no residual, no aux)
   unsigned long long* timeline;  // debug: per-CTA clock64 stamps of the pipeline events (NULL in production)
+  unsigned long long* span;      // optional: span[0] = min %globaltimer after griddepcontrol.wait, span[1] = max at exit (bench roofline)
 };
+
+struct GemmMaps { CUtensorMap a[GEMM_MAX_GROUP], b[GEMM_MAX_GROUP], c[GEMM_MAX_GROUP]; };
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -274,12 +302,108 @@ struct GemmSmem {
   static_assert(B_ROWS % 8 == 0, "B half-tile rows");
 };
 
+// ---------------------------------------------------------------- work schedule
+// What a cluster does next: k-blocks [kb0, kb1) of tile (m_blk, n_blk) of problem g.
+//   type 0: the whole K range of the tile (or, in static split-K mode, k-split `ks` of it) -> normal epilogue
+//   type 1: stream-K contributor -- a partial sum that does not contain the tile's last k-block: dumped into this
+//           cluster's workspace slot and announced on the owner's arrival counter
+//   type 2: stream-K owner -- contains the tile's last k-block but not its first: adds the partials of clusters
+//           first_contrib .. cluster-1 (in that order) to its accumulator, then runs the normal epilogue
+struct Seg {
+  int g, m_blk, n_blk, kb0, kb1, ks, type;
+  int first_contrib;   // type 2: the lowest cluster that holds k-blocks of this tile
+  int owner;           // type 1: the cluster that finishes this tile
+};
+
+// All three warp roles walk the same list.  Stream-K ranges are walked from the TOP down: a cluster first computes the
+// partial it hands to its successor (type 1), then its whole tiles, and LAST the tile it finishes for its predecessor
+// (type 2) -- whose partial was therefore written at the very start of the launch and is never waited for in practice.
+struct SegIter {
+  int tile, stride, total_tiles;   // whole-tile work: static mode, and the data-parallel part of the hybrid schedule
+  long long lo, hi;                // stream-K: pooled units [lo, hi) still to do
+  __device__ __forceinline__ SegIter(const GemmParams& p, int cluster_id, int num_clusters) {
+    tile = cluster_id;
+    stride = num_clusters;
+    total_tiles = p.mode == 0 ? p.pr[0].num_m * p.pr[0].num_n * p.split_k : p.dp_tiles;
+    lo = p.sk_unit_base + (long long)cluster_id * p.units_per_cluster;
+    hi = lo + p.units_per_cluster;
+    if (hi > p.total_units) hi = p.total_units;
+    if (p.mode == 0) hi = lo;
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, Seg& s) {
+    int g = 0, t;
+    if (hi > lo) {
+      // ---- pooled (stream-K) part, walked from the top down
+      const long long u = hi - 1;
+#pragma unroll
+      for (int i = 1; i < GEMM_MAX_GROUP; ++i)
+        if (i < p.nprob && u >= p.pr[i].unit_base) g = i;
+      const int kbt = p.pr[g].k_blocks;
+      const long long rel = u - p.pr[g].unit_base;
+      t = (int)(rel / kbt);
+      const long long tile_u0 = p.pr[g].unit_base + (long long)t * kbt;
+      const long long seg_lo = tile_u0 > lo ? tile_u0 : lo;
+      s.ks = 0;
+      s.kb0 = (int)(seg_lo - tile_u0);
+      s.kb1 = (int)(u - tile_u0) + 1;
+      s.type = (s.kb1 != kbt) ? 1 : (s.kb0 == 0 ? 0 : 2);
+      s.first_contrib = (int)((tile_u0 - p.sk_unit_base) / p.units_per_cluster);
+      s.owner = (int)((tile_u0 + kbt - 1 - p.sk_unit_base) / p.units_per_cluster);
+      hi = seg_lo;
+    } else {
+      if (tile >= total_tiles) return false;
+      if (p.mode == 0) {
+        const int tiles_mn = p.pr[0].num_m * p.pr[0].num_n;
+        s.ks = tile / tiles_mn;
+        t = tile - s.ks * tiles_mn;
+        s.kb0 = s.ks * p.k_blocks_per_split;
+        s.kb1 = min(s.kb0 + p.k_blocks_per_split, p.pr[0].k_blocks);
+      } else {
+#pragma unroll
+        for (int i = 1; i < GEMM_MAX_GROUP; ++i)
+          if (i < p.nprob && tile >= p.pr[i].tile_base) g = i;
+        t = tile - p.pr[g].tile_base;
+        s.ks = 0;
+        s.kb0 = 0;
+        s.kb1 = p.pr[g].k_blocks;
+      }
+      s.type = 0;
+      s.first_contrib = s.owner = 0;
+      tile += stride;
+    }
+    s.g = g;
+    const int nm = p.pr[g].num_m, nn = p.pr[g].num_n;
+    s.m_blk = p.n_fast ? t / nn : t % nm;
+    s.n_blk = p.n_fast ? t % nn : t / nm;
+    return true;
+  }
+};
+
+__device__ __forceinline__ float4 ldcg_f4(const float4* ptr) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stcg_f4(float4* ptr, float a, float b, float c, float d) {
+  asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int BLOCK_N, int STAGES, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-          const GemmParams p) {
+k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams p) {
   using L = GemmSmem<BLOCK_N, STAGES, CG>;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  constexpr int WS_SLOT_F4 = CG * (BLOCK_N / 4) * BLOCK_M;   // float4s of one cluster's partial-tile slot
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-B alignment; the dynamic-smem base offset is identical in both CTAs of a pair, so the
   // aligned layout (and with it every UMMA descriptor / barrier offset) is identical too
@@ -295,14 +419,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   const int cluster_id = (int)blockIdx.x / CG, num_clusters = (int)gridDim.x / CG;
-  const int tiles_mn = p.num_m * p.num_n;   // num_m counts (128*CG)-row tiles
-  const int total_tiles = tiles_mn * p.split_k;
   if (threadIdx.x == 0) tl_stamp(p, 0);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.tma_store) tma_prefetch_desc(&tmC);
+    for (int g = 0; g < p.nprob; ++g) {
+      tma_prefetch_desc(&maps.a[g]);
+      tma_prefetch_desc(&maps.b[g]);
+      if (p.tma_store) tma_prefetch_desc(&maps.c[g]);
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8 * CG); }
     fence_barrier_init();
@@ -315,21 +439,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // everything above overlapped the previous kernel's tail; its results are visible only after this point
   pdl_wait();
   pdl_launch_dependents();
-  if (threadIdx.x == 0) tl_stamp(p, 1);
+  if (threadIdx.x == 0) {
+    tl_stamp(p, 1);
+    if (p.span) atomicMin(p.span, globaltimer_ns());
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        int ks = tile / tiles_mn, mn = tile % tiles_mn;
-        int m_blk = p.n_fast ? mn / p.num_n : mn % p.num_m, n_blk = p.n_fast ? mn % p.num_n : mn / p.num_m;
-        int kb0 = ks * p.k_blocks_per_split;
-        int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
-        const int m0 = (m_blk * CG + (int)cta_rank) * BLOCK_M;
-        const int n0 = n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
-        for (int kb = kb0; kb < kb1; ++kb) {
+      bool first = true;
+      SegIter it(p, cluster_id, num_clusters);
+      Seg s;
+      while (it.next(p, s)) {
+        const CUtensorMap* tmA = &maps.a[s.g];
+        const CUtensorMap* tmB = &maps.b[s.g];
+        const int m0 = (s.m_blk * CG + (int)cta_rank) * BLOCK_M;
+        const int n0 = s.n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
@@ -337,16 +465,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (CG == 1) {
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             if (!p.a_mn) {
-              tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+              tma_load_2d(sa, tmA, &full_bar[stage], k0, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0);
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, tmA, &full_bar[stage], m0 + j * 64, k0);
             }
             if (!p.b_mn) {
-              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+              tma_load_2d(sb, tmB, &full_bar[stage], k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d(sb + j * 8192, tmB, &full_bar[stage], n0 + j * 64, k0);
             }
           } else {
             // the leader's barrier counts the bytes of BOTH CTAs (the peer's complete_tx may land before the
@@ -354,19 +482,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CG * L::STAGE_BYTES);
             if (!p.a_mn) {
-              tma_load_2d_pair(sa, &tmA, lead_bar, k0, m0);
+              tma_load_2d_pair(sa, tmA, lead_bar, k0, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmA, lead_bar, m0 + j * 64, k0);
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d_pair(sa + j * 8192, tmA, lead_bar, m0 + j * 64, k0);
             }
             if (!p.b_mn) {
-              tma_load_2d_pair(sb, &tmB, lead_bar, k0, n0);
+              tma_load_2d_pair(sb, tmB, lead_bar, k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, lead_bar, n0 + j * 64, k0);
+              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d_pair(sb + j * 8192, tmB, lead_bar, n0 + j * 64, k0);
             }
           }
-          if (tile == cluster_id && kb == kb0) tl_stamp(p, 2);
+          if (first) { tl_stamp(p, 2); first = false; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -382,16 +510,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int acc = 0;
       uint32_t acc_phase = 0;
       int tcount = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
-        int ks = tile / tiles_mn;
-        int kb0 = ks * p.k_blocks_per_split;
-        int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+      SegIter it(p, cluster_id, num_clusters);
+      Seg s;
+      for (; it.next(p, s); ++tcount) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (kb == kb0) tl_stamp(p, 8 + 4 * tcount);
+          if (kb == s.kb0) tl_stamp(p, 8 + 4 * tcount);
           tc_fence_after();
           uint32_t sa = smem_u32(stage_base + stage * L::STAGE_BYTES);
           uint32_t sb = sa + L::A_BYTES;
@@ -399,7 +526,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, da, db, idesc, (kb > s.kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -419,24 +546,76 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int half = (warp - 2) >> 2;
     const uint32_t st4 = smem_u32(staging) + (uint32_t)(warp - 2) * 4096u;  // this warp's 32x32 fp32 transpose buffer (float4 slots of 16 B)
     const int g = lane & 7, rsub = lane >> 3;
+    // stream-K partial tiles: float4 (col4, row) of CTA `rank` of cluster c at ws[(c*CG + rank) * (BLOCK_N/4) * 128 + col4 * 128 + row]
+    // -- consecutive lanes (rows) touch consecutive 16-byte slots: coalesced both ways
+    const int ws_row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     int tcount = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
-      int ks = tile / tiles_mn, mn = tile % tiles_mn;
-      int m_blk = p.n_fast ? mn / p.num_n : mn % p.num_m, n_blk = p.n_fast ? mn % p.num_n : mn / p.num_m;
+    SegIter it(p, cluster_id, num_clusters);
+    Seg s;
+    for (; it.next(p, s); ++tcount) {
+      const GemmProblem& pb = p.pr[s.g];
+      const int ks = s.ks, n_blk = s.n_blk;
       mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 2 && lane == 0) tl_stamp(p, 10 + 4 * tcount);
       tc_fence_after();
-      const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
+      const int row0 = (s.m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
       const bool add_bias = p.bias != nullptr && ks == 0;
       const bool add_res = p.residual != nullptr && ks == 0;
-      if (p.tma_store) {
+      const int n_contrib = (s.type == 2) ? cluster_id - s.first_contrib : 0;
+      if (s.type == 2) {
+        // the partials of this tile were written at the start of their clusters' ranges; wait for all of them
+        if (lane == 0) {
+          const int expect = n_contrib * 8 * CG;
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(p.flags + cluster_id) < expect) {
+            __nanosleep(40);
+            if (++spins > 20000000u) {
+              printf("nfb gemm_tc: stream-K partial wait timed out (cluster %d)\n", cluster_id);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // adds the partial sums of the contributing clusters (fixed order) to 32 accumulator columns starting at tile column c
+      auto add_partials = [&](float* v, int c) {
+        for (int cc = s.first_contrib; cc < cluster_id; ++cc) {
+          const float4* src = p.ws + (size_t)(cc * CG + (int)cta_rank) * (size_t)(WS_SLOT_F4 / CG) + (size_t)(c >> 2) * BLOCK_M + ws_row;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = ldcg_f4(src + (size_t)j4 * BLOCK_M);
+            v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+          }
+        }
+      };
+      if (s.type == 1) {
+        // ---- stream-K contributor: raw fp32 partial -> this cluster's workspace slot, then one arrival per warp
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+          if (n_blk * BLOCK_N + c0 >= pb.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+          tmem_ld_wait();
+          float4* dst = p.ws + (size_t)(cluster_id * CG + (int)cta_rank) * (size_t)(WS_SLOT_F4 / CG) + (size_t)(c0 >> 2) * BLOCK_M + ws_row;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            stcg_f4(dst + (size_t)j4 * BLOCK_M, __uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                    __uint_as_float(r[4 * j4 + 3]));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(p.flags + s.owner, 1);
+        }
+      } else if (p.tma_store) {
         // ---- TMA-store epilogue.  tcgen05.ld leaves thread = row holding consecutive columns; the row segment is
         // written straight into this warp's 32-row x 128-byte staging box in the SWIZZLE_128B pattern (16-byte slot c
         // of row r at c ^ (r & 7): conflict-free STS.128) and ONE elected lane hands the box to the TMA unit, which
-        // writes (or reduce-adds, for split-K wgrad) full lines to global memory and clips the ragged M / N edges.
+        // writes (or reduce-adds, for wgrad) full lines to global memory and clips the ragged M / N edges.
         // No LDS, no per-thread global stores.  bf16: 64 columns per step, fp32: 32 columns per step.
+        const CUtensorMap* tmC = &maps.c[s.g];
         const uint32_t sbox = smem_u32(staging) + (uint32_t)(warp - 2) * 4096u;
         const uint32_t srow = sbox + (uint32_t)lane * 128u;
         const int sw = lane & 7;
@@ -444,7 +623,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
         for (int c0 = half * step; c0 < BLOCK_N; c0 += 2 * step) {
           const int col0 = n_blk * BLOCK_N + c0;
-          if (col0 >= p.N) break;  // warp-uniform
+          if (col0 >= pb.N) break;  // warp-uniform
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
           if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of shared memory
           __syncwarp();
@@ -457,16 +636,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if (n_contrib) add_partials(v, c0 + hh * 32);
               if (add_bias) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const int c = col0 + hh * 32 + j4 * 4;
-                  if (c + 3 < p.N) {
+                  if (c + 3 < pb.N) {
                     float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
                     v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
                   } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) if (c + e < p.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
+                    for (int e = 0; e < 4; ++e) if (c + e < pb.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
                   }
                 }
               }
@@ -483,14 +663,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], lo), hi);
               }
 #pragma unroll
-              for (int s = 0; s < 4; ++s) {   // four 16-byte slots (8 bf16 each) per 32 columns
+              for (int sl = 0; sl < 4; ++sl) {   // four 16-byte slots (8 bf16 each) per 32 columns
                 uint32_t w[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * s + 2 * e], v[8 * s + 2 * e + 1]);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * sl + 2 * e], v[8 * sl + 2 * e + 1]);
                   w[e] = *reinterpret_cast<uint32_t*>(&b2);
                 }
-                const int slot = hh * 4 + s;
+                const int slot = hh * 4 + sl;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((slot ^ sw) * 16)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
               }
             }
@@ -501,16 +681,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (n_contrib) add_partials(v, c0);
             if (add_bias) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const int c = col0 + j4 * 4;
-                if (c + 3 < p.N) {
+                if (c + 3 < pb.N) {
                   float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
                   v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
                 } else {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) if (c + e < p.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
+                  for (int e = 0; e < 4; ++e) if (c + e < pb.N) v[4 * j4 + e] += __ldg(p.bias + c + e);
                 }
               }
             }
@@ -527,14 +708,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], lo), hi);
             }
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-              sts128(srow + (uint32_t)((s ^ sw) * 16), v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+            for (int sl = 0; sl < 8; ++sl)
+              sts128(srow + (uint32_t)((sl ^ sw) * 16), v[4 * sl], v[4 * sl + 1], v[4 * sl + 2], v[4 * sl + 3]);
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            if (p.accumulate) tma_reduce_add_2d(&tmC, sbox, col0, row0);
-            else tma_store_2d(&tmC, sbox, col0, row0 + ks * p.slice_rows);
+            if (p.accumulate) tma_reduce_add_2d(tmC, sbox, col0, row0);
+            else tma_store_2d(tmC, sbox, col0, row0 + ks * p.slice_rows);
             tma_store_commit();
           }
         }
@@ -542,17 +723,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         const int col0 = n_blk * BLOCK_N + c0;
-        if (col0 >= p.N) break;  // warp-uniform
+        if (col0 >= pb.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         tmem_ld_wait();
+        if (n_contrib) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          add_partials(v, c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+        }
 #pragma unroll
         for (int gg = 0; gg < 8; ++gg)
           sts128(st4 + (uint32_t)(lane * 8 + (gg ^ (lane & 7))) * 16u, __uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]),
                  __uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
         __syncwarp();
         const int col = col0 + g * 4;
-        if (p.vec_ok && row0 + 32 <= p.M && col0 + 32 <= p.N) {
+        if (p.vec_ok && row0 + 32 <= pb.M && col0 + 32 <= pb.N) {
           // ---- fast path: the whole 32x32 chunk is in bounds and 16-byte addressable.  Every stage is its own
           // unrolled loop over the thread's 8 rows (conditions are kernel-uniform), so the 8 LDS / 8 residual LDG /
           // 8 STG of a stage are in flight together instead of one row at a time.
@@ -600,38 +789,38 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
           if (p.c_bf16) {
-            __nv_bfloat16* cp = (__nv_bfloat16*)p.C + rbase * p.ldc + col;
+            __nv_bfloat16* cp = (__nv_bfloat16*)pb.C + rbase * pb.ldc + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               __nv_bfloat162 a0 = __floats2bfloat162_rn(t[i].x, t[i].y), a1 = __floats2bfloat162_rn(t[i].z, t[i].w);
-              *reinterpret_cast<uint2*>(cp + (long long)i * 4 * p.ldc) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+              *reinterpret_cast<uint2*>(cp + (long long)i * 4 * pb.ldc) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
             }
           } else if (p.accumulate) {
-            float* cp = (float*)p.C + rbase * p.ldc + col;
+            float* cp = (float*)pb.C + rbase * pb.ldc + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + (long long)i * 4 * p.ldc), "f"(t[i].x), "f"(t[i].y), "f"(t[i].z), "f"(t[i].w) : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + (long long)i * 4 * pb.ldc), "f"(t[i].x), "f"(t[i].y), "f"(t[i].z), "f"(t[i].w) : "memory");
           } else {
-            float* cp = (float*)p.C + rbase * p.ldc + col;
+            float* cp = (float*)pb.C + rbase * pb.ldc + col;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(cp + (long long)i * 4 * p.ldc) = t[i];
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(cp + (long long)i * 4 * pb.ldc) = t[i];
           }
           __syncwarp();
           continue;
         }
         // ---- generic path: ragged edges of M / N or unaligned pitches
-        const bool full4 = (col + 3 < p.N) && p.vec_ok;
+        const bool full4 = (col + 3 < pb.N) && p.vec_ok;
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (add_bias) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (col + e < p.N) bv[e] = p.bias[col + e];
+          for (int e = 0; e < 4; ++e) if (col + e < pb.N) bv[e] = p.bias[col + e];
         }
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rsub;
           const int row = row0 + rr;
           float4 t4 = lds128(st4 + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16u);
-          if (row < p.M && col < p.N) {
+          if (row < pb.M && col < pb.N) {
             float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
             if (full4) {
               if (p.aux) {
@@ -657,9 +846,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (p.c_bf16) {
                 __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0], v[1]), a1 = __floats2bfloat162_rn(v[2], v[3]);
                 uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
-                *reinterpret_cast<uint2*>((__nv_bfloat16*)p.C + (long long)row * p.ldc + col) = u;
+                *reinterpret_cast<uint2*>((__nv_bfloat16*)pb.C + (long long)row * pb.ldc + col) = u;
               } else {
-                float* dst = (float*)p.C + (long long)row * p.ldc + col;
+                float* dst = (float*)pb.C + (long long)row * pb.ldc + col;
                 if (p.accumulate) {
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
                 } else {
@@ -669,16 +858,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (col + e >= p.N) break;
+                if (col + e >= pb.N) break;
                 float x = v[e];
                 if (p.aux) ((__nv_bfloat16*)p.aux)[(long long)row * p.ldaux + col + e] = __float2bfloat16_rn(x);
                 if (p.epilogue == 1) x = gelu_tanh_f(x);
                 else if (p.epilogue == 2) x = fmaxf(x, 0.f);
                 if (add_res) x += p.residual[(long long)row * p.ldr + col + e];
                 if (p.clip > 0.f) x = fminf(fmaxf(x, -p.clip), p.clip);
-                if (p.c_bf16) ((__nv_bfloat16*)p.C)[(long long)row * p.ldc + col + e] = __float2bfloat16_rn(x);
+                if (p.c_bf16) ((__nv_bfloat16*)pb.C)[(long long)row * pb.ldc + col + e] = __float2bfloat16_rn(x);
                 else {
-                  float* dst = (float*)p.C + (long long)row * p.ldc + col + e;
+                  float* dst = (float*)pb.C + (long long)row * pb.ldc + col + e;
                   if (p.accumulate) atomicAdd(dst, x);
                   else *dst = x;
                 }
@@ -689,6 +878,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
       }
       }  // !tma_store
+      if (s.type == 2) {
+        // every warp of the cluster has consumed the partials: the last one re-arms the counters for the next launch
+        __syncwarp();
+        if (lane == 0) {
+          const int old = atomicAdd(p.flags + 256 + cluster_id, 1);
+          if (old == 8 * CG - 1) {
+            p.flags[256 + cluster_id] = 0;
+            p.flags[cluster_id] = 0;
+            __threadfence();
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -705,6 +906,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   tc_fence_before();
   if (threadIdx.x == 0) tl_stamp(p, 3);
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair mode: neither CTA may exit while the other still reads its smem / signals its barriers
+  if (threadIdx.x == 0 && p.span) atomicMin(p.span + 1, ~globaltimer_ns());   // stored complemented: one 0xFF memset arms both words
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, TMEM_COLS);
@@ -760,7 +962,7 @@ static int make_map(CUtensorMap* out, const void* ptr, long long dim0, long long
 
 
 template <int BLOCK_N, int STAGES, int CG>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid) {
+static int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid) {
   using L = GemmSmem<BLOCK_N, STAGES, CG>;
   static bool configured = false;
   if (!configured) {
@@ -788,9 +990,28 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  NFB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, STAGES, CG>, tmA, tmB, tmC, p));
+  NFB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, STAGES, CG>, maps, p));
   NFB_LAUNCH_CHECK();
   return 0;
+}
+
+static int dispatch_gemm(int bn, int cg, const GemmMaps& maps, const GemmParams& p, int grid) {
+  if (cg == 1) {
+    switch (bn) {
+      case 256: return launch_gemm<256, 4, 1>(maps, p, grid);
+      case 192: return launch_gemm<192, 4, 1>(maps, p, grid);
+      case 128: return launch_gemm<128, 6, 1>(maps, p, grid);
+      case 64: return launch_gemm<64, 8, 1>(maps, p, grid);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256, 6, 2>(maps, p, grid);
+      case 192: return launch_gemm<192, 6, 2>(maps, p, grid);
+      case 128: return launch_gemm<128, 8, 2>(maps, p, grid);
+      case 64: return launch_gemm<64, 8, 2>(maps, p, grid);
+    }
+  }
+  return NFB_FAIL("gemm_bf16: unsupported tile N %d (cta group %d)", bn, cg);
 }
 
 static int g_force_block_n = 0, g_force_cg = 0, g_tma_store = 1, g_force_raster = 0;
@@ -798,28 +1019,74 @@ NFB_API int nfb_gemm_bf16_set_tma_store(int on) { g_tma_store = on ? 1 : 0; retu
 static unsigned long long* g_timeline = nullptr;
 // debug: device buffer of 8 x 64 u64 that the next launches fill with clock64 stamps (NULL = off)
 NFB_API int nfb_gemm_bf16_set_timeline(void* dev_buf) { g_timeline = (unsigned long long*)dev_buf; return 0; }
+static unsigned long long* g_span = nullptr;
+// measurement: two device u64 words (armed to all-ones) that the NEXT launch fills with min(%globaltimer after its
+// griddepcontrol.wait) and ~max(%globaltimer at CTA exit); NULL = off.  The pointer is consumed by one launch.
+NFB_API int nfb_gemm_bf16_set_span(void* dev_two_u64) { g_span = (unsigned long long*)dev_two_u64; return 0; }
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
 NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }
 NFB_API int nfb_gemm_bf16_force_raster(int order) { g_force_raster = order; return 0; }   // test hook: 0 = auto, 1 = m fastest, 2 = n fastest
 static int g_auto_split = 1;
 // internal split-K of non-accumulating launches: 0 = off, 1 = automatic (cost model), 2 = whenever eligible (test hook)
 NFB_API int nfb_gemm_bf16_set_auto_split(int mode) { g_auto_split = mode; return 0; }
+static int g_stream_k = 1;
+// stream-K schedule: 0 = never (grouped launches excepted), 1 = automatic (cost model), 2 = whenever possible (test hook)
+NFB_API int nfb_gemm_bf16_set_stream_k(int mode) { g_stream_k = mode; return 0; }
+static int g_sm_limit = 0;
+// number of SMs the persistent grids may occupy (0 = all): a data-parallel step leaves room for NCCL's channel CTAs while a
+// gradient bucket is on the wire, so that a one-wave GEMM does not need a second round on the SMs NCCL holds
+NFB_API int nfb_gemm_bf16_set_sm_limit(int sms) { g_sm_limit = sms < 0 ? 0 : sms; return 0; }
+static int gemm_sms() {
+  int sms = nfb_sm_count();
+  if (g_sm_limit > 0 && g_sm_limit < sms) sms = g_sm_limit;
+  return sms < 2 ? 2 : sms;
+}
 
 // Tile choice: a small cost model in SM clocks.  Per CTA and 64-deep k-block the MMA needs 2*BLOCK_N clk (tcgen05
 // floor, 128 x BLOCK_N x 16 per BLOCK_N/2 clk) and the smem fill needs (16 KB + BLOCK_N/CG * 128 B) / 64 B/clk
 // (the measured L2->smem port rate); a tile costs kblocks * max(of the two) and every launch pays a fixed
 // prologue + first-load + last-epilogue cost.  Whole-launch cost = waves * tile + fixed.
 struct TileChoice { int bn, cg, sk; double cost; };
-static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int sms) {
+static double kb_cost(int bn, int cg) {
+  double mma = 2.0 * bn, fill = (16384.0 + (double)(bn / cg) * 128.0) / 64.0;
+  return mma > fill ? mma : fill;
+}
+static double epi_cost(int bn) { return 150.0 * (bn / 32) / 2.0; }   // drain of one accumulator (two warps per lane quarter)
+static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int sms, bool reduce_add = true) {
   long long num_m = nfb_cdiv(M, BLOCK_M * cg), num_n = nfb_cdiv(N, bn);
   long long units = sms / cg;                     // CTAs (or CTA pairs) running concurrently
   long long work = num_m * num_n * sk;
   long long waves = nfb_cdiv(work, units);
   double kb = (double)nfb_cdiv(k_blocks, sk);
-  double mma = 2.0 * bn, fill = (16384.0 + (double)(bn / cg) * 128.0) / 64.0;
-  double per_kb = mma > fill ? mma : fill;
-  double epi = 150.0 * (bn / 32) / 2.0 + (sk > 1 ? 100.0 * (bn / 32) / 2.0 : 0.0);   // drain of the last tile; red.add is slower
-  return (double)waves * (kb * per_kb + 250.0) + epi + 2500.0;
+  // split-K partial tiles leave through reduce-adds: the L2 reduction path sustains ~10 B/clk per SM (measured on the layer
+  // weight gradients: 72 partial 256x256 tiles into a 768x768 fp32 matrix cost 3x the MMA time)
+  double red = (sk > 1 && reduce_add) ? (double)waves * (128.0 * bn * 4.0) / 10.0 : 0.0;
+  return (double)waves * (kb * kb_cost(bn, cg) + 250.0) + epi_cost(bn) + red + 2500.0;
+}
+// Hybrid stream-K: how many of the `tiles` tiles (the last ones of the launch-wide order) are pooled and cut into equal
+// k-block ranges over `clusters` clusters; the others run as whole tiles.  Whole waves stay whole tiles (no fix-up, and
+// concurrently running tiles stay neighbours, which is what keeps their operand panels shared in L2); the remainder of a
+// wave is pooled, together with one more full wave when it is so small that a tile would be cut more than ~6 ways.
+static long long stream_k_pool(long long tiles, long long clusters) {
+  if (tiles <= clusters) return tiles;
+  const long long rem = tiles % clusters;
+  if (rem == 0) return 0;
+  if (rem * 6 >= clusters) return rem;
+  return rem + clusters;
+}
+// cost of the hybrid schedule: whole-tile waves + the pooled share of every cluster; the pooled part pays one extra
+// accumulator drain per cluster (partial out / partial in), exposed only when no whole tile follows it
+static double stream_k_cost(long long tiles, int k_blocks, int bn, int cg, int sms) {
+  long long clusters = sms / cg;
+  const long long pool = stream_k_pool(tiles, clusters);
+  const long long dp_waves = (tiles - pool) / clusters;
+  long long units = pool * k_blocks;
+  long long active = clusters > units ? units : clusters;
+  const long long per = units > 0 ? nfb_cdiv(units, active) : 0;
+  const double cuts = pool > 0 ? (double)active / (double)pool : 0.0;   // clusters sharing one pooled tile
+  const double fix = pool > 0 ? epi_cost(bn) + 900.0 * (cuts > 1.0 ? cuts : 1.0) : 0.0;
+  const double exposed = dp_waves > 0 ? 0.3 * fix : fix;
+  return (double)dp_waves * (k_blocks * kb_cost(bn, cg) + 250.0) + (double)per * kb_cost(bn, cg) + 500.0 + exposed + epi_cost(bn) + 2500.0;
 }
 
 // Best (tile N, CTA group, split-K) for a launch.  may_split: the caller accumulates into a pre-initialised fp32 C, so K may
@@ -847,33 +1114,82 @@ static TileChoice choose_tiles(int M, int N, int k_blocks, int b_mn, bool may_sp
   }
   return best;
 }
+// Best (tile N, CTA group) under the stream-K schedule for a group of problems sharing the operand layouts.
+static TileChoice choose_tiles_stream_k(int nprob, const int* Ms, const int* Ns, const int* Ks, int b_mn, int sms) {
+  TileChoice best = {128, 1, 1, 1e30};
+  const int cand_bn[4] = {256, 192, 128, 64};
+  int min_m = Ms[0];
+  for (int g = 1; g < nprob; ++g) if (Ms[g] < min_m) min_m = Ms[g];
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (g_force_cg && cg != g_force_cg) continue;
+    if (cg == 2 && (sms % 2 != 0 || min_m <= BLOCK_M)) continue;
+    for (int i = 0; i < 4; ++i) {
+      int bn = cand_bn[i];
+      if (g_force_block_n && bn != g_force_block_n) continue;
+      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;
+      // a group is costed as one problem with the summed units (all k-block counts enter through the unit total)
+      double units = 0;
+      long long tiles = 0;
+      for (int g = 0; g < nprob; ++g) {
+        long long t = nfb_cdiv(Ms[g], BLOCK_M * cg) * nfb_cdiv(Ns[g], bn);
+        tiles += t;
+        units += (double)t * (double)nfb_cdiv(Ks[g], BLOCK_K);
+      }
+      int kb_avg = (int)(units / (double)tiles + 0.5);
+      if (kb_avg < 1) kb_avg = 1;
+      double c = stream_k_cost(tiles, kb_avg, bn, cg, sms);
+      if (c < best.cost * 0.98) best = {bn, cg, 1, c};
+    }
+  }
+  return best;
+}
 
 // Everything the host decides about a launch, in one place (also what nfb_gemm_bf16_plan reports to the CPU tests).
 struct GemmPlan {
   int bn, cg, sk;        // tile N, CTA group, k-splits of the (possibly accumulating) launch
   int n_fast;            // tile order (see below)
   int internal_split;    // > 1: cut K into this many slices through the fp32 workspace + finishing pass instead
+  int stream_k;          // 1: balanced (tile, k-block) ranges per cluster with the in-kernel fix-up
 };
 // may_split / split_k as in choose_tiles.  split_eligible: the launch does not accumulate, has no fused epilogue operands and
-// an aligned C, so an under-filled grid may be traded for an internal split-K.
-static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int split_k, bool split_eligible, int sms) {
+// an aligned C, so an under-filled grid may be traded for an internal split-K.  stream_k_ok: the stream-K workspace of the
+// current stream is available.
+static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int split_k, bool split_eligible, bool stream_k_ok, int sms) {
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
-  GemmPlan g = {128, 1, 1, 0, 0};
+  GemmPlan g = {128, 1, 1, 0, 0, 0};
+  double classic_cost = 1e30;
   if (split_eligible && g_auto_split && k_blocks >= 16 && N % 4 == 0) {
     const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
     const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
     const int sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, many.sk));   // the factor after rounding the k-blocks per split
     // the extra launch + the slices written once and read once + C written, at ~3400 B/clk of HBM
+    // (the reduce-add penalty inside `many.cost` does not apply: the slices are stored, not added)
+    const double many_cost = tile_cost(M, N, k_blocks, many.bn, many.cg, sk, sms, false);
     const double overhead = 3000.0 + (double)M * (double)N * (8.0 * sk + 2.0) / 3400.0;
-    if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many.cost + overhead < 0.85 * one.cost)) g.internal_split = sk;
+    if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many_cost + overhead < 0.85 * one.cost)) {
+      g.internal_split = sk;
+      classic_cost = many_cost + overhead;
+    }
   }
   const bool slices = g.internal_split > 1;
   TileChoice best = slices ? choose_tiles(M, N, k_blocks, b_mn, true, g.internal_split, sms) : choose_tiles(M, N, k_blocks, b_mn, may_split, split_k, sms);
   if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
     best = {g_force_block_n ? g_force_block_n : 128, 1, slices ? g.internal_split : ((may_split && split_k >= 1) ? split_k : 1), 0.0};
   }
-  g.bn = best.bn; g.cg = best.cg; g.sk = best.sk;
-  if (!slices) g.sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, g.sk));   // (slices: already the rounded factor, every split non-empty)
+  if (!slices) classic_cost = best.cost;
+  if (stream_k_ok && g_stream_k && !(g_auto_split == 2 && slices)) {
+    const TileChoice sk = choose_tiles_stream_k(1, &M, &N, &K, b_mn, sms);
+    // measured (profiles/r02_gemm_streamk.txt): without whole tiles to hide it behind, the fix-up of a single small launch
+    // costs more than the balance wins, so one-wave launches keep the classic schedule
+    const bool has_whole_waves = sk.cost < 1e30 && nfb_cdiv(M, BLOCK_M * sk.cg) * nfb_cdiv(N, sk.bn) > sms / sk.cg;
+    if (sk.cost < 1e30 && (g_stream_k == 2 || (has_whole_waves && sk.cost < 0.93 * classic_cost))) {
+      g.stream_k = 1;
+      g.internal_split = 0;
+      best = sk;
+    }
+  }
+  g.bn = best.bn; g.cg = best.cg; g.sk = g.stream_k ? 1 : best.sk;
+  if (!g.stream_k && !(g.internal_split > 1)) g.sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, g.sk));   // (slices: already the rounded factor, every split non-empty)
   // Tile order for L2 reuse.  The tiles of one wave run concurrently and walk K roughly in lockstep, so a panel they
   // share is fetched from HBM once; a panel they do not share is fetched again for every tile that needs it unless the
   // whole operand stays in L2.  m fastest: a wave shares B panels, A is read num_n times if it does not fit; n fastest:
@@ -887,12 +1203,12 @@ static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int spl
   return g;
 }
 // What nfb_gemm_bf16 would do with a launch of this shape on `sms` SMs (aligned operands, no bias / residual / aux):
-// out = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices}.  Host logic only, no device needed.
+// out = {tile N, CTA group, k-splits, n-fastest tile order, internal split-K slices, stream-K}.  Host logic only, no device needed.
 NFB_API int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epilogue, int split_k, int sms, int* out) {
   if (M <= 0 || N <= 0 || K <= 0 || sms <= 0 || !out) return NFB_FAIL("gemm_bf16_plan: bad arguments");
   const bool eligible = !accumulate && split_k <= 1 && epilogue == 0 && g_tma_store;
-  const GemmPlan g = plan_gemm(M, N, K, transB ? 0 : 1, accumulate && epilogue == 0, split_k, eligible, sms);
-  out[0] = g.bn; out[1] = g.cg; out[2] = g.sk; out[3] = g.n_fast; out[4] = g.internal_split;
+  const GemmPlan g = plan_gemm(M, N, K, transB ? 0 : 1, accumulate && epilogue == 0, split_k, eligible, split_k <= 1, sms);
+  out[0] = g.bn; out[1] = g.cg; out[2] = g.sk; out[3] = g.n_fast; out[4] = g.internal_split; out[5] = g.stream_k;
   return 0;
 }
 
@@ -921,6 +1237,111 @@ k_splitk_finish(const float* __restrict__ ws, int slices, int64_t slice_elems, T
   }
 }
 
+// ---- stream-K fix-up workspace: one partial-tile slot (128 x 256 fp32) per CTA and 2 x 256 arrival counters, PER STREAM
+// (the weight-gradient side stream runs its own stream-K launches next to the compute stream's)
+struct StreamKWs { float4* ws; int* flags; };
+static StreamKWs g_skws[2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+static int stream_k_ws(StreamKWs* out) {
+  const int which = (nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream()) ? 1 : 0;
+  StreamKWs& w = g_skws[which];
+  if (!w.ws) {
+    const size_t bytes = (size_t)nfb_sm_count() * BLOCK_M * 256 * sizeof(float);
+    NFB_CUDA(cudaMalloc((void**)&w.ws, bytes));
+    NFB_CUDA(cudaMalloc((void**)&w.flags, 512 * sizeof(int)));
+    NFB_CUDA(cudaMemsetAsync(w.flags, 0, 512 * sizeof(int), nfb_cur_stream()));
+  }
+  *out = w;
+  return 0;
+}
+// stream-K needs its workspace; a third concurrent stream would race on it, so only the compute stream and the registered
+// auxiliary stream qualify
+static bool stream_k_available() { return true; }
+
+struct GemmOperands {
+  int M, N, K;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+};
+
+// Fills the tensor maps + problem table of `n` problems for tile (bn, cg) and launches.  Common to single and grouped launches.
+static int launch_problems(int n, const GemmOperands* ops, int transA, int transB, int c_dtype, GemmParams& p, int bn, int cg,
+                           int slice_split, int slice_rows, int sms) {
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.nprob = n;
+  p.a_mn = transA ? 1 : 0;
+  p.b_mn = transB ? 0 : 1;
+  p.c_bf16 = (c_dtype == NFB_BF16);
+  long long units = 0, tiles = 0;
+  const int b_rows = bn / cg;
+  for (int g = 0; g < n; ++g) {
+    const GemmOperands& o = ops[g];
+    GemmProblem& q = p.pr[g];
+    q.M = o.M; q.N = o.N; q.K = o.K;
+    q.num_m = (int)nfb_cdiv(o.M, BLOCK_M * cg);
+    q.num_n = (int)nfb_cdiv(o.N, bn);
+    q.k_blocks = (int)nfb_cdiv(o.K, BLOCK_K);
+    q.unit_base = units;
+    q.tile_base = (int)tiles;
+    q.C = o.C; q.ldc = o.ldc;
+    units += (long long)q.num_m * q.num_n * q.k_blocks;
+    tiles += (long long)q.num_m * q.num_n;
+    if (p.tma_store) {
+      const long long c_rows = slice_split > 1 ? (long long)slice_split * slice_rows : o.M;
+      if (make_map(&maps.c[g], o.C, o.N, c_rows, o.ldc, p.c_bf16 ? 64 : 32, 32, p.c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
+    }
+    if (!p.a_mn) { if (make_map(&maps.a[g], o.A, o.K, o.M, o.lda, BLOCK_K, BLOCK_M)) return -1; }
+    else { if (make_map(&maps.a[g], o.A, o.M, o.K, o.lda, 64, BLOCK_K)) return -1; }
+    if (!p.b_mn) { if (make_map(&maps.b[g], o.B, o.K, o.N, o.ldb, BLOCK_K, b_rows)) return -1; }
+    else { if (make_map(&maps.b[g], o.B, o.N, o.K, o.ldb, 64, BLOCK_K)) return -1; }
+  }
+  for (int g = n; g < GEMM_MAX_GROUP; ++g) { p.pr[g] = p.pr[0]; p.pr[g].unit_base = units; p.pr[g].tile_base = (int)tiles; }
+  p.total_units = units;
+  p.sk_unit_base = units;
+  p.dp_tiles = 0;
+  p.units_per_cluster = 1;
+  long long clusters = sms / cg;
+  if (clusters < 1) clusters = 1;
+  if (p.mode == 1) {
+    const long long sk_tiles = stream_k_pool(tiles, clusters);
+    p.dp_tiles = (int)(tiles - sk_tiles);
+    // unit index of the first pooled tile
+    long long u0 = units;
+    for (int g = 0; g < n; ++g) {
+      const GemmProblem& q = p.pr[g];
+      const long long tg = (long long)q.num_m * q.num_n;
+      if (p.dp_tiles < q.tile_base + tg) { u0 = q.unit_base + (long long)(p.dp_tiles - q.tile_base) * q.k_blocks; break; }
+    }
+    p.sk_unit_base = u0;
+    const long long sk_units = units - u0;
+    long long active = clusters;
+    if (sk_units > 0) {
+      if (active > sk_units) active = sk_units;
+      p.units_per_cluster = (int)nfb_cdiv(sk_units, active);
+      active = nfb_cdiv(sk_units, p.units_per_cluster);   // no empty range in the middle
+    } else {
+      active = 0;
+    }
+    if (p.dp_tiles == 0) clusters = active;
+    else if (clusters > p.dp_tiles && clusters > active) clusters = p.dp_tiles > active ? p.dp_tiles : active;
+    if (clusters > 256) return NFB_FAIL("gemm_bf16: stream-K on %lld clusters (arrival counters hold 256)", clusters);
+    StreamKWs w;
+    if (stream_k_ws(&w)) return -1;
+    p.ws = w.ws;
+    p.flags = w.flags;
+  } else {
+    long long work = tiles * p.split_k;
+    if (clusters > work) clusters = work;
+    p.ws = nullptr;
+    p.flags = nullptr;
+  }
+  p.timeline = g_timeline;
+  p.span = g_span;
+  g_span = nullptr;
+  return dispatch_gemm(bn, cg, maps, p, (int)clusters * cg);
+}
+
 // C (+)= epi(opA . opB + bias) + residual.  A, B bf16; C fp32 (c_dtype = NFB_F32) or bf16.
 // split_k: 0 = choose automatically (only used when accumulate != 0), >= 1 = explicit.
 // slice_split > 1 (internal): C is a stack of slice_split (slice_rows, N) fp32 slices; k-split ks STORES its partial product
@@ -934,19 +1355,19 @@ static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const voi
   if (accumulate && c_dtype != NFB_F32) return NFB_FAIL("gemm_bf16: accumulate needs an fp32 C");
   if (!accumulate && split_k > 1) return NFB_FAIL("gemm_bf16: split_k > 1 requires accumulate (C pre-initialised)");
   if (split_k > 1 && epilogue != 0) return NFB_FAIL("gemm_bf16: split-K cannot be combined with an activation epilogue");
-  const int sms = nfb_sm_count();
-  const int a_mn = transA ? 1 : 0, b_mn = transB ? 0 : 1;
+  const int sms = gemm_sms();
+  const int b_mn = transB ? 0 : 1;
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
 
-  // ---- internal split-K: a launch whose tiles fill well under one wave and whose K is long (the LM-head input gradient:
-  // 48 tile pairs on 74 SM pairs, 786 k-blocks each) is cut along K; every k-split stores its partial product into its own
-  // fp32 slice of a workspace and one finishing pass sums the slices in a fixed order, clips and casts -- deterministic,
-  // unlike a reduce-add.  Two launches instead of one; taken only when the cost model sees a clear win, never on the side
-  // stream (the workspace comes from the stream-ordered allocator).
+  // ---- internal split-K: a launch whose tiles fill well under one wave and whose K is long is cut along K; every k-split
+  // stores its partial product into its own fp32 slice of a workspace and one finishing pass sums the slices in a fixed
+  // order, clips and casts -- deterministic, unlike a reduce-add.  Two launches instead of one; superseded by the stream-K
+  // schedule wherever that is available (kept as the fallback and as a second implementation for the tests).
   const bool eligible = !slice_split && !accumulate && split_k <= 1 && epilogue == 0 && !bias && !residual && !aux && g_tma_store &&
                         ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && !(nfb_aux_stream() && nfb_cur_stream() == nfb_aux_stream());
-  const GemmPlan plan = slice_split > 1 ? plan_gemm(M, N, K, b_mn, true, slice_split, false, sms)
-                                        : plan_gemm(M, N, K, b_mn, accumulate && epilogue == 0, split_k, eligible, sms);
+  const bool stream_k_ok = !slice_split && split_k <= 1 && stream_k_available();
+  const GemmPlan plan = slice_split > 1 ? plan_gemm(M, N, K, b_mn, true, slice_split, false, false, sms)
+                                        : plan_gemm(M, N, K, b_mn, accumulate && epilogue == 0, split_k, eligible, stream_k_ok, sms);
   if (plan.internal_split > 1) {
     const int sk = plan.internal_split;
     const int64_t rows = nfb_cdiv(M, 2 * BLOCK_M) * 2 * BLOCK_M;           // whole tiles: an edge tile never reaches the next slice
@@ -966,64 +1387,28 @@ static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const voi
 
   const int best_bn = plan.bn, cg = plan.cg;
   int sk = slice_split > 1 ? slice_split : plan.sk;
-  const int num_m = (int)nfb_cdiv(M, BLOCK_M * cg);
-  const int num_n = (int)nfb_cdiv(N, best_bn);
   const int kbps = (int)nfb_cdiv(k_blocks, sk);
 
   GemmParams p;
-  p.M = M; p.N = N; p.K = K;
-  p.a_mn = a_mn;
-  p.b_mn = b_mn;
-  p.num_m = num_m; p.num_n = num_n; p.split_k = sk; p.k_blocks_per_split = kbps; p.k_blocks_total = k_blocks;
+  memset(&p, 0, sizeof(p));
+  p.mode = plan.stream_k ? 1 : 0;
+  p.split_k = sk; p.k_blocks_per_split = kbps;
   p.slice_rows = slice_split > 1 ? slice_rows : 0;
   if (slice_split > 1 && (sk != slice_split || (long long)(sk - 1) * kbps >= k_blocks)) return NFB_FAIL("gemm_bf16: internal split-K factor %d does not fit %d k-blocks", slice_split, k_blocks);
   p.n_fast = plan.n_fast;
-  p.C = C; p.c_bf16 = (c_dtype == NFB_BF16); p.ldc = ldc;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.aux = aux; p.ldaux = ldaux;
   p.epilogue = epilogue; p.accumulate = accumulate; p.clip = clip;
-  p.timeline = g_timeline;
   {
     bool ok = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
     if (residual) ok = ok && (ldr % 4 == 0) && ((uintptr_t)residual % 16 == 0);
     if (aux) ok = ok && (ldaux % 4 == 0) && ((uintptr_t)aux % 8 == 0);
     p.vec_ok = ok ? 1 : 0;
   }
-
   // TMA-store epilogue: C rows must be 16-byte addressable; residual / aux outputs keep the register epilogue
-  p.tma_store = (g_tma_store && !residual && !aux && ((uintptr_t)C % 16 == 0) && ((ldc * (p.c_bf16 ? 2 : 4)) % 16 == 0)) ? 1 : 0;
-  CUtensorMap tmA, tmB, tmC;
-  if (p.tma_store) {
-    const long long c_rows = slice_split > 1 ? (long long)slice_split * slice_rows : M;
-    if (make_map(&tmC, C, N, c_rows, ldc, p.c_bf16 ? 64 : 32, 32, p.c_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
-  } else {
-    if (slice_split > 1) return NFB_FAIL("gemm_bf16: the internal split-K needs the TMA-store epilogue");
-    memset(&tmC, 0, sizeof(tmC));
-  }
-  const int b_rows = best_bn / cg;
-  if (!p.a_mn) { if (make_map(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M)) return -1; }
-  else { if (make_map(&tmA, A, M, K, lda, 64, BLOCK_K)) return -1; }
-  if (!p.b_mn) { if (make_map(&tmB, B, K, N, ldb, BLOCK_K, b_rows)) return -1; }
-  else { if (make_map(&tmB, B, N, K, ldb, 64, BLOCK_K)) return -1; }
-
-  long long total = (long long)num_m * num_n * sk;
-  long long units = sms / cg;
-  int grid = (int)(total < units ? total : units) * cg;
-  if (cg == 1) {
-    switch (best_bn) {
-      case 256: return launch_gemm<256, 4, 1>(tmA, tmB, tmC, p, grid);
-      case 192: return launch_gemm<192, 4, 1>(tmA, tmB, tmC, p, grid);
-      case 128: return launch_gemm<128, 6, 1>(tmA, tmB, tmC, p, grid);
-      case 64: return launch_gemm<64, 8, 1>(tmA, tmB, tmC, p, grid);
-    }
-  } else {
-    switch (best_bn) {
-      case 256: return launch_gemm<256, 6, 2>(tmA, tmB, tmC, p, grid);
-      case 192: return launch_gemm<192, 6, 2>(tmA, tmB, tmC, p, grid);
-      case 128: return launch_gemm<128, 8, 2>(tmA, tmB, tmC, p, grid);
-      case 64: return launch_gemm<64, 8, 2>(tmA, tmB, tmC, p, grid);
-    }
-  }
-  return NFB_FAIL("gemm_bf16: unsupported tile N %d (cta group %d)", best_bn, cg);
+  p.tma_store = (g_tma_store && !residual && !aux && ((uintptr_t)C % 16 == 0) && ((ldc * (c_dtype == NFB_BF16 ? 2 : 4)) % 16 == 0)) ? 1 : 0;
+  if (!p.tma_store && slice_split > 1) return NFB_FAIL("gemm_bf16: the internal split-K needs the TMA-store epilogue");
+  GemmOperands op = {M, N, K, A, lda, B, ldb, C, ldc};
+  return launch_problems(1, &op, transA, transB, c_dtype, p, best_bn, cg, slice_split, slice_rows, sms);
 }
 
 NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -1031,4 +1416,43 @@ NFB_API int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const voi
                           int64_t ldaux, int epilogue, int accumulate, int split_k, float clip) {
   return gemm_bf16_impl(transA, transB, M, N, K, A, lda, B, ldb, C, c_dtype, ldc, bias, residual, ldr, aux, ldaux, epilogue, accumulate,
                         split_k, clip, 0, 0);
+}
+
+// Grouped launch: n <= 4 independent contractions C_g (+)= opA_g . opB_g with the same operand layouts and output type in
+// ONE persistent stream-K kernel (no epilogue operands).  This is how the four weight-gradient GEMMs of a Transformer layer
+// run: 90 tiles x 64 k-blocks are cut into 74 equal ranges instead of four launches that each split K eight ways and
+// reduce-add 8x their output through L2.  Each output element receives exactly one store / one reduce-add: deterministic.
+NFB_API int nfb_gemm_bf16_grouped(int n, int transA, int transB, const int* Ms, const int* Ns, const int* Ks, const void* const* As,
+                                  const int64_t* ldas, const void* const* Bs, const int64_t* ldbs, void* const* Cs, const int64_t* ldcs,
+                                  int c_dtype, int accumulate) {
+  if (n <= 0) return 0;
+  if (n > GEMM_MAX_GROUP) return NFB_FAIL("gemm_bf16_grouped: at most %d problems per launch (got %d)", GEMM_MAX_GROUP, n);
+  if (c_dtype != NFB_F32 && c_dtype != NFB_BF16) return NFB_FAIL("gemm_bf16_grouped: C dtype %d", c_dtype);
+  if (accumulate && c_dtype != NFB_F32) return NFB_FAIL("gemm_bf16_grouped: accumulate needs an fp32 C");
+  GemmOperands ops[GEMM_MAX_GROUP];
+  int m = 0;
+  bool tma_ok = g_tma_store != 0, vec_ok = true;
+  for (int g = 0; g < n; ++g) {
+    if (Ms[g] <= 0 || Ns[g] <= 0) continue;
+    if (Ks[g] <= 0) return NFB_FAIL("gemm_bf16_grouped: K must be positive");
+    ops[m] = {Ms[g], Ns[g], Ks[g], As[g], ldas[g], Bs[g], ldbs[g], Cs[g], ldcs[g]};
+    tma_ok = tma_ok && ((uintptr_t)Cs[g] % 16 == 0) && ((ldcs[g] * (c_dtype == NFB_BF16 ? 2 : 4)) % 16 == 0);
+    vec_ok = vec_ok && (ldcs[g] % 4 == 0) && ((uintptr_t)Cs[g] % 16 == 0);
+    ++m;
+  }
+  if (m == 0) return 0;
+  const int sms = gemm_sms();
+  int Mv[GEMM_MAX_GROUP], Nv[GEMM_MAX_GROUP], Kv[GEMM_MAX_GROUP];
+  for (int g = 0; g < m; ++g) { Mv[g] = ops[g].M; Nv[g] = ops[g].N; Kv[g] = ops[g].K; }
+  TileChoice t = choose_tiles_stream_k(m, Mv, Nv, Kv, transB ? 0 : 1, sms);
+  if (t.cost >= 1e30) t = {g_force_block_n ? g_force_block_n : 128, 1, 1, 0.0};
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = 1;
+  p.split_k = 1;
+  p.k_blocks_per_split = 0;
+  p.accumulate = accumulate;
+  p.vec_ok = vec_ok ? 1 : 0;
+  p.tma_store = tma_ok ? 1 : 0;
+  return launch_problems(m, ops, transA, transB, c_dtype, p, t.bn, t.cg, 0, 0, sms);
 }

@@ -139,6 +139,7 @@ class DistributedDataParallel(Module):
                 p._grad_slot.fill(0.0)
                 p._slot_zero = True
         from .. import kernels as K
+        K.flush_wgrad()                                 # queued (grouped) weight-gradient GEMMs of this bucket go out first
         ready = Event(timing=False).record()            # on the compute stream: gradients of this bucket are final
         g.comm_stream.wait_event(ready)
         side_ev = K.side_stream_event()                 # weight gradients computed on the side stream are part of the bucket:

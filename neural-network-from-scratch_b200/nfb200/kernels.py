@@ -19,6 +19,16 @@ from .array import B200Array, bfloat16, dtype_code
 _PRECISION = "fp32"
 F32 = np.dtype(np.float32)
 GEMM_PROFILE = None  # set to a list to collect (start_event, end_event, flops, shape) per tcgen05 GEMM launch (bench.py)
+GEMM_SPAN = None     # set to {"buf": device uint64 array of 2*cap words armed to all-ones, "cap": cap, "meta": []}: every tcgen05 GEMM
+#                      launch i then stamps %globaltimer into words 2i (min after griddepcontrol.wait) and 2i+1 (~max at CTA exit)
+
+
+def _arm_span(flops, shape):
+    sp = GEMM_SPAN
+    if sp is None or len(sp["meta"]) >= sp["cap"]:
+        return
+    call("nfb_gemm_bf16_set_span", sp["buf"].ptr + 16 * len(sp["meta"]))
+    sp["meta"].append((flops, shape))
 
 
 def set_precision(mode: str):
@@ -99,12 +109,55 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
     if prof is not None:
         from .runtime import Event
         e0 = Event().record(external=True)
+    _arm_span(2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b)))
     call("nfb_gemm_bf16", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, a2.ptr, lda, b2.ptr, ldb, out.ptr,
          dtype_code(out.dtype), ldc_v, bias_ptr, res_ptr, ldr, aux_arr.ptr if aux_arr is not None else None, N, epi,
          1 if accumulate else 0, int(split_k), float(clip))
     if prof is not None:
         prof.append((e0, Event().record(external=True), 2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b))))
     return (out, aux_arr) if aux else out
+
+
+def gemm_bf16_grouped(problems, trans_a=False, trans_b=False, accumulate=False):
+    """Up to 4 independent contractions out_g (+)= op(a_g) @ op(b_g) (same layouts, fp32 or bf16 outputs of one type) in ONE
+    persistent stream-K launch of the tcgen05 kernel.  problems: [(a, b, out), ...] with `out` preallocated."""
+    import ctypes as C
+    n = len(problems)
+    if n == 0:
+        return
+    Ms, Ns, Ks, As, ldas, Bs, ldbs, Cs, ldcs = [], [], [], [], [], [], [], [], []
+    keep = []
+    odt = None
+    flops = 0.0
+    for a, b, out in problems:
+        a, b = to_bf16(a), to_bf16(b)
+        a2, lda = _rowmajor_2d(a)
+        b2, ldb = _rowmajor_2d(b)
+        M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+        K2, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+        if K != K2:
+            raise ValueError(f"gemm_bf16_grouped: inner dimensions differ ({K} vs {K2})")
+        if out.shape != (M, N) or out.strides[1] != 1:
+            raise ValueError(f"gemm_bf16_grouped: out has shape {out.shape} strides {out.strides}, expected ({M},{N}) row-major")
+        if odt is None:
+            odt = out.dtype
+        elif out.dtype is not odt and out.dtype != odt:
+            raise ValueError("gemm_bf16_grouped: outputs must share one dtype")
+        keep.append((a2, b2))
+        Ms.append(M); Ns.append(N); Ks.append(K)
+        As.append(a2.ptr); ldas.append(lda); Bs.append(b2.ptr); ldbs.append(ldb)
+        Cs.append(out.ptr); ldcs.append(out.strides[0] if M > 1 else max(N, out.strides[0]))
+        flops += 2.0 * M * N * K
+    ia, vpa, la = (C.c_int * n), (C.c_void_p * n), (C.c_int64 * n)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        from .runtime import Event
+        e0 = Event().record(external=True)
+    _arm_span(flops, ("grouped", tuple(zip(Ms, Ns, Ks)), bool(trans_a), bool(trans_b)))
+    call("nfb_gemm_bf16_grouped", n, 1 if trans_a else 0, 1 if trans_b else 0, ia(*Ms), ia(*Ns), ia(*Ks), vpa(*As), la(*ldas), vpa(*Bs), la(*ldbs),
+         vpa(*Cs), la(*ldcs), dtype_code(odt), 1 if accumulate else 0)
+    if prof is not None:
+        prof.append((e0, Event().record(external=True), flops, ("grouped", tuple(zip(Ms, Ns, Ks)), bool(trans_a), bool(trans_b))))
 
 
 def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None, bias=None, beta=0.0):
@@ -187,6 +240,63 @@ _side_dirty = False
 _held = []
 
 
+# ---- grouped weight gradients ------------------------------------------------------------------------------------------
+# dW_g += dZ_g^T X_g of consecutive Linear layers are independent of each other and of everything before the optimizer, so
+# they are QUEUED (with the bias column sums that go with them) and run four at a time as one grouped stream-K launch
+# (nfb_gemm_bf16_grouped): the four weight gradients of a GPT-2-small block are 90 tiles x 64 k-blocks, which one launch
+# cuts into 74 equal ranges, where four separate launches each split K ~8 ways and pushed 8x their output through L2
+# reduce-adds.  The queue is flushed when it holds WGRAD_GROUP contractions, before anything else is issued on the side
+# stream, before a DDP bucket is handed to NCCL and at the end of backward() (join_side_stream).
+WGRAD_GROUP = 4
+GEMM_WGRAD_DEFER = True      # False: every weight gradient is launched where linear_backward computes it
+_WGRAD_BIG_FLOP = 1.0e11     # LM-head-sized problems keep their own launch (tile order chosen for L2 reuse)
+_pending_wgrad = []          # (a, b, out): out += a^T b
+_pending_colsum = []         # (dz, db_out)
+
+
+def set_wgrad_group(n: int):
+    """How many queued weight-gradient contractions go into one grouped launch (1 = launch each on its own)."""
+    global WGRAD_GROUP
+    flush_wgrad()
+    WGRAD_GROUP = max(1, min(4, int(n)))
+
+
+def _issue_wgrad(items, colsums):
+    big = [it for it in items if 2.0 * it[0].shape[1] * it[1].shape[1] * it[0].shape[0] >= _WGRAD_BIG_FLOP]
+    small = [it for it in items if not any(it is b for b in big)]
+    if len(small) == 1:
+        big.append(small.pop())
+    if small:
+        gemm_bf16_grouped(small, True, False, accumulate=True)
+    for a, b, out in big:
+        gemm_bf16(a, b, True, False, out=out, accumulate=True)
+    for dz, db_out in colsums:
+        _colsum(dz, db_out)
+
+
+def flush_wgrad():
+    """Launch the queued weight-gradient contractions / bias sums (side stream when the overlap is on)."""
+    global _pending_wgrad, _pending_colsum
+    if not _pending_wgrad and not _pending_colsum:
+        return
+    items, colsums = _pending_wgrad, _pending_colsum
+    _pending_wgrad, _pending_colsum = [], []
+    if _WGRAD_OVERLAP:
+        keep = [x for it in items for x in it] + [x for it in colsums for x in it]
+        run_on_side_stream(lambda: _issue_wgrad(items, colsums), *keep, _flush=False)
+    else:
+        _issue_wgrad(items, colsums)
+
+
+def queue_wgrad(a: B200Array, b: B200Array, out: B200Array, colsum=None):
+    """out += a^T b (a (T,M), b (T,N) bf16), deferred; colsum = (dz, db_out) rides along."""
+    _pending_wgrad.append((a, b, out))
+    if colsum is not None:
+        _pending_colsum.append(colsum)
+    if len(_pending_wgrad) >= WGRAD_GROUP:
+        flush_wgrad()
+
+
 def set_wgrad_overlap(on: bool):
     """Weight / bias / norm-parameter gradients (everything only the optimizer consumes) on a side stream."""
     global _WGRAD_OVERLAP, _side
@@ -210,6 +320,7 @@ def join_side_stream():
     """Make the compute stream wait for every weight-gradient GEMM issued on the side stream (no-op when none is pending).
     Called at the end of backward(), before a DDP bucket is all-reduced and before the embedding scatter-add."""
     global _side_dirty
+    flush_wgrad()
     if _side_dirty:
         from .runtime import Event, compute_stream_wait
         compute_stream_wait(Event(timing=False).record(_side))
@@ -220,17 +331,20 @@ def join_side_stream():
 def side_stream_event():
     """An event recorded on the side stream behind everything issued there so far, or None when nothing is pending.
     Lets ANOTHER stream (the DDP communication stream) wait for the weight gradients without stalling the compute stream."""
+    flush_wgrad()
     if not _side_dirty:
         return None
     from .runtime import Event
     return Event(timing=False).record(_side)
 
 
-def run_on_side_stream(fn, *keep):
+def run_on_side_stream(fn, *keep, _flush=True):
     """Issue `fn`'s kernels on the side stream, ordered after everything enqueued on the compute stream so far; `keep`
     is held until the next join so the stream-ordered allocator cannot recycle those buffers."""
     global _side, _side_dirty
     from .runtime import Event, Stream, current_stream_handle
+    if _flush:
+        flush_wgrad()   # queued weight gradients precede whatever consumes them on this stream
     if _side is None:
         _side = Stream()
     _side.wait_event(Event(timing=False).record())   # operands are final on the compute stream
@@ -266,6 +380,14 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             # dX (T,in) = dZ (T,out) . W(out,in): B operand is W stored (K=out, N=in) -> trans_b=False
             dx = gemm_bf16(dz, wb, False, not out_in, out_dtype=odt, clip=clip)
         side = _WGRAD_OVERLAP and dW_out is not None
+        if dW_out is not None and WGRAD_GROUP > 1 and GEMM_WGRAD_DEFER:
+            # gradient-arena target: nothing reads it before the optimizer / the bucket all-reduce -> queue for a grouped launch
+            pair = (dz, x2) if out_in else (x2, dz)
+            queue_wgrad(pair[0], pair[1], dW_out, (dz, db_out) if (has_bias and db_out is not None) else None)
+            db = db_out if has_bias else None
+            if has_bias and db_out is None:
+                db = _colsum(dz, None)
+            return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
         if dW_out is None:
             dW_out = B200Array.full(W.shape, 0.0, np.float32)
         if out_in:   # dW (out,in) = dZ^T (out,T) . X (T,in)

@@ -202,6 +202,7 @@ class _AdamBase(Optimizer):
         if not launches:
             return
         from .. import kernels as K
+        K.flush_wgrad()   # the queued weight-gradient GEMMs of these parameters precede their update
         self._sib_begin()
         for rn in launches:
             steps = set()

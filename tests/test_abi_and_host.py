@@ -43,9 +43,9 @@ def test_ctypes_table_matches_header():
 
 def _plan(trans_b, M, N, K, accumulate=0, epilogue=0, split_k=0, sms=148):
     from nfb200 import _lib
-    out = (ctypes.c_int * 5)()
+    out = (ctypes.c_int * 6)()
     _lib.call("nfb_gemm_bf16_plan", int(trans_b), M, N, K, accumulate, epilogue, split_k, sms, out)
-    return dict(zip(("bn", "cg", "sk", "n_fast", "internal_split"), out))
+    return dict(zip(("bn", "cg", "sk", "n_fast", "internal_split", "stream_k"), out))
 
 
 def test_gemm_launch_plans_for_the_gpt2_small_step():

@@ -206,23 +206,136 @@ def test_internal_split_k_lm_head_dgrad(be):
     dl = Kn.to_bf16(_to(be, (rng.standard_normal((T, ldv)) * 1e-2).astype(np.float32)))[:, :V]
     w = Kn.to_bf16(_to(be, (rng.standard_normal((V, d)) * 0.02).astype(np.float32)))
     _lib.call("nfb_gemm_bf16_set_auto_split", 0)
+    _lib.call("nfb_gemm_bf16_set_stream_k", 0)     # (the stream-K schedule supersedes the internal split when it is on)
     try:
         n0 = _lib.launch_count()
         one = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
         n1 = _lib.launch_count()
+        _lib.call("nfb_gemm_bf16_set_auto_split", 1)
+        split = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
+        n2 = _lib.launch_count()
+        again = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
     finally:
         _lib.call("nfb_gemm_bf16_set_auto_split", 1)
-    split = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
-    n2 = _lib.launch_count()
+        _lib.call("nfb_gemm_bf16_set_stream_k", 1)
     assert n1 - n0 == 1 and n2 - n1 == 2, (n1 - n0, n2 - n1)
     a, b = one.get(), split.get()
     assert np.isfinite(b).all()
-    again = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
     assert np.array_equal(again, b)                                      # slices summed in a fixed order: run-to-run bit-identical
+    # the same shape under the stream-K schedule: one launch, bit-identical run to run
+    _lib.call("nfb_gemm_bf16_set_stream_k", 2)
+    try:
+        n3 = _lib.launch_count()
+        sk1 = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
+        n4 = _lib.launch_count()
+        sk2 = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
+    finally:
+        _lib.call("nfb_gemm_bf16_set_stream_k", 1)
+    assert n4 - n3 == 1
+    assert np.array_equal(sk1, sk2)
+    np.testing.assert_allclose(sk1, a, rtol=8e-3, atol=8e-3 * float(np.abs(a).max()))
     np.testing.assert_allclose(b, a, rtol=8e-3, atol=8e-3 * float(np.abs(a).max()))   # one bf16 ulp of the larger values
     # against fp64 on a slice of rows
     ref = dl[:64].get().astype(np.float64) @ w.get().astype(np.float64)
     np.testing.assert_allclose(b[:64], ref, rtol=1e-2, atol=1e-2 * float(np.abs(ref).max()))
+
+
+@pytest.fixture
+def stream_k_forced():
+    """Every eligible launch takes the stream-K schedule (equal (tile, k-block) ranges per cluster + in-kernel fix-up)."""
+    from nfb200 import _lib
+    _lib.call("nfb_gemm_bf16_set_stream_k", 2)
+    yield
+    _lib.call("nfb_gemm_bf16_set_stream_k", 1)
+
+
+@pytest.mark.parametrize("ta,tb", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(256, 128, 128), (512, 768, 768), (300, 200, 136), (129, 72, 72), (4096, 768, 3072), (1000, 520, 4100), (2304, 768, 4096),
+                                   (4096, 3072, 256), (8192, 2100, 136)])
+def test_stream_k_layouts_and_ragged_shapes(be, cta_group, stream_k_forced, ta, tb, M, N, K):
+    """Tiles cut by range boundaries are finished by the cluster holding their last k-block, which adds the partial tiles of
+    the earlier clusters in cluster order: same values as the one-tile-per-cluster schedule up to fp32 summation order, and
+    bit-identical from run to run."""
+    from nfb200 import kernels as Kn
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    ad, bd = _to(be, a), _to(be, b)
+    got = Kn.gemm_bf16(ad, bd, ta, tb).get()
+    want = _ref(a, b, ta, tb)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-4 * np.sqrt(K / 64))
+    assert np.array_equal(Kn.gemm_bf16(ad, bd, ta, tb).get(), got)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_stream_k_every_tile_width_and_epilogue(be, cta_group, stream_k_forced, bn):
+    """Owner-side epilogues under stream-K: bias + GELU with the bf16 pre-activation output (register epilogue), residual,
+    clip and a bf16 TMA-store output; the accumulating (weight-gradient) form adds the finished tile once."""
+    from nfb200 import _lib, kernels as Kn
+    from oracle import np_ops as O
+    rng = np.random.default_rng(bn)
+    M, N, K = 520, 600, 1100
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    z = _ref(x, w, False, True) + bias
+    _lib.call("nfb_gemm_bf16_force_tile", bn)
+    try:
+        xd, wd, bd = _to(be, x), _to(be, w), _to(be, bias)
+        yg, aux = Kn.gemm_bf16(xd, wd, False, True, bias=bd, epilogue="gelu", aux=True)
+        yr = Kn.gemm_bf16(xd, wd, False, True, bias=bd, residual=_to(be, res), clip=3.0).get()
+        yb = Kn.gemm_bf16(xd, wd, False, True, bias=bd, out_dtype=be.bfloat16).get()
+        base = rng.standard_normal((K, N)).astype(np.float32)
+        acc = _to(be, base.copy())
+        Kn.gemm_bf16(xd, _to(be, res), True, False, out=acc, accumulate=True)   # (K, N) += x^T res, contraction over M
+    finally:
+        _lib.call("nfb_gemm_bf16_force_tile", 0)
+    np.testing.assert_allclose(yg.get(), O.gelu_tanh_fwd(z), rtol=1e-4, atol=4e-4)
+    np.testing.assert_allclose(aux.get(), z, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(yr, np.clip(z + res, -3.0, 3.0), rtol=2e-5, atol=6e-4)
+    np.testing.assert_allclose(yb, z, rtol=1e-2, atol=2e-2)
+    np.testing.assert_allclose(acc.get(), base + _ref(x, res, True, False), rtol=3e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+def test_grouped_launch_weight_gradients(be, cta_group, out_dtype):
+    """nfb_gemm_bf16_grouped: the four weight gradients of a Transformer block (ragged variants included) in one stream-K
+    launch; every output matches its own single launch, the accumulating form adds onto the existing values, and two runs
+    are bit-identical (each element receives exactly one store / reduce-add)."""
+    from nfb200 import _lib, kernels as Kn
+    rng = np.random.default_rng(11)
+    T = 2048
+    shapes = [(768, 1536), (520, 304), (3072, 768), (200, 72)]
+    probs, wants, bases = [], [], []
+    for (m, n) in shapes:
+        dz = (rng.standard_normal((T, m)) * 0.1).astype(np.float32)
+        x = rng.standard_normal((T, n)).astype(np.float32)
+        probs.append((Kn.to_bf16(_to(be, dz)), Kn.to_bf16(_to(be, x))))
+        wants.append(_ref(dz, x, True, False))
+        bases.append(rng.standard_normal((m, n)).astype(np.float32))
+    acc = out_dtype == "f32"
+    odt = np.float32 if acc else be.bfloat16
+
+    def run():
+        if acc:
+            outs = [_to(be, b.copy()) for b in bases]
+        else:
+            from nfb200.array import B200Array
+            outs = [B200Array.empty(b.shape, odt) for b in bases]
+        n0 = _lib.launch_count()
+        Kn.gemm_bf16_grouped([(a, b, o) for (a, b), o in zip(probs, outs)], True, False, accumulate=acc)
+        assert _lib.launch_count() - n0 == 1
+        return [o.get() for o in outs]
+
+    got = run()
+    for g, w, b in zip(got, wants, bases):
+        if acc:
+            np.testing.assert_allclose(g, b + w, rtol=3e-5, atol=2e-3)
+        else:
+            np.testing.assert_allclose(g, w, rtol=1e-2, atol=1e-2 * np.sqrt(T / 64))
+    for g, g2 in zip(got, run()):
+        assert np.array_equal(g, g2)
 
 
 def test_gemm_f32_wrapper(be):

@@ -144,6 +144,7 @@ def run_b200(args):
     set_default_device(f"cuda:{local}")
     K.set_precision(args.precision)
     K.set_wgrad_overlap(args.wgrad_overlap)
+    K.set_wgrad_group(args.wgrad_group)
     np.random.seed(0)  # identical replicas on every rank (the reference relies on seeding too)
     model = GPT2(GPT2_SMALL)
     ddp = None
@@ -153,7 +154,7 @@ def run_b200(args):
         ddp = DistributedDataParallel(model, bucket_size_mb=args.bucket_mb)
     opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float32")
     if ddp is None and args.step_in_backward:
-        opt.enable_step_in_backward()   # AdamW launches ride the side stream behind their weight-gradient GEMMs
+        opt.enable_step_in_backward(min_run_elems=args.sib_min)   # AdamW launches ride the side stream behind their weight-gradient GEMMs
     rng = np.random.default_rng(1234 + rank)  # each rank gets its own shard: weak scaling, per-GPU batch fixed
     ids_h, labels_h = synthetic_batch(rng)
     ids_d, labels_d = Tensor(ids_h, device=f"cuda:{local}"), Tensor(labels_h, device=f"cuda:{local}")
@@ -353,6 +354,8 @@ def main():
     ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
     ap.add_argument("--step-in-backward", dest="step_in_backward", action="store_true",
                     help="AdamW launches per layer from inside backward on the side stream (measured: within 0.3 %% of the default, one launch after backward)")
+    ap.add_argument("--sib-min", type=int, default=1 << 21, help="step-in-backward: smallest contiguous run of finished parameters that gets its own AdamW launch")
+    ap.add_argument("--wgrad-group", type=int, default=4, help="weight-gradient GEMMs per grouped stream-K launch (1 = one launch each)")
     ap.add_argument("--no-wgrad-overlap", dest="wgrad_overlap", action="store_false", help="keep the weight-gradient GEMMs on the compute stream")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -137,7 +137,7 @@ int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epil
    (nn/optimized.py:286-317 computes them one np.matmul at a time).  Every output element gets exactly one store / reduce-add. */
 int nfb_gemm_bf16_grouped(int n, int transA, int transB, const int* Ms, const int* Ns, const int* Ks, const void* const* As, const int64_t* ldas,
                           const void* const* Bs, const int64_t* ldbs, void* const* Cs, const int64_t* ldcs, int c_dtype, int accumulate);
-int nfb_gemm_bf16_set_stream_k(int mode);            /* stream-K schedule (balanced (tile, k-block) ranges per SM pair + in-kernel fix-up): 0 = never, 1 = automatic (cost model), 2 = whenever possible (test hook) */
+int nfb_gemm_bf16_set_stream_k(int mode);            /* stream-K schedule (balanced (tile, k-block) ranges per SM pair + in-kernel fix-up) of SINGLE launches: 0 / 1 = classic (grouped launches always use it), 2 = whenever possible (test hook) */
 int nfb_gemm_bf16_set_sm_limit(int sms);             /* SMs the persistent GEMM grids may occupy (0 = all): data-parallel steps leave room for NCCL's channel CTAs */
 int nfb_gemm_bf16_set_span(void* dev_two_u64);      /* measurement: the NEXT launch writes min(%globaltimer after griddepcontrol.wait) and ~max(%globaltimer at exit) into two u64 words armed to all-ones */
 int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */

@@ -293,7 +293,13 @@ template <int BLOCK_N, int STAGES, int CG>
 struct GemmSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of A
   static constexpr int B_ROWS = BLOCK_N / CG;             // pair mode: each CTA stages half of the B tile
-  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  // an MN-major B operand is staged in 64-column chunks of 8 KB (one TMA box each); a half-tile that is not a multiple of
+  // 64 columns (the 96-column halves of a 192-wide pair tile) loads -- and reserves -- a whole last chunk, of which the MMA
+  // reads the first 32 columns
+  static constexpr int B_CHUNKS = (B_ROWS + 63) / 64;
+  static constexpr int B_BYTES_KMAJOR = B_ROWS * BLOCK_K * 2;
+  static constexpr int B_BYTES_MNMAJOR = B_CHUNKS * 8192;
+  static constexpr int B_BYTES = B_BYTES_MNMAJOR > B_BYTES_KMAJOR ? B_BYTES_MNMAJOR : B_BYTES_KMAJOR;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // per-epilogue-warp 32x32 fp32 transpose buffers (XOR swizzled)
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -457,13 +463,14 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
         const CUtensorMap* tmB = &maps.b[s.g];
         const int m0 = (s.m_blk * CG + (int)cta_rank) * BLOCK_M;
         const int n0 = s.n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
+        const uint32_t tx_bytes = (uint32_t)(L::A_BYTES + (p.b_mn ? L::B_BYTES_MNMAJOR : L::B_BYTES_KMAJOR));   // what the TMA boxes of one CTA deliver per stage
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           int k0 = kb * BLOCK_K;
           if (CG == 1) {
-            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
             if (!p.a_mn) {
               tma_load_2d(sa, tmA, &full_bar[stage], k0, m0);
             } else {
@@ -474,13 +481,13 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
               tma_load_2d(sb, tmB, &full_bar[stage], k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d(sb + j * 8192, tmB, &full_bar[stage], n0 + j * 64, k0);
+              for (int j = 0; j < L::B_CHUNKS; ++j) tma_load_2d(sb + j * 8192, tmB, &full_bar[stage], n0 + j * 64, k0);
             }
           } else {
             // the leader's barrier counts the bytes of BOTH CTAs (the peer's complete_tx may land before the
             // leader's expect_tx: the phase cannot complete until the leader's own arrival)
             const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CG * L::STAGE_BYTES);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CG * tx_bytes);
             if (!p.a_mn) {
               tma_load_2d_pair(sa, tmA, lead_bar, k0, m0);
             } else {
@@ -491,7 +498,7 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
               tma_load_2d_pair(sb, tmB, lead_bar, k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < L::B_ROWS / 64; ++j) tma_load_2d_pair(sb + j * 8192, tmB, lead_bar, n0 + j * 64, k0);
+              for (int j = 0; j < L::B_CHUNKS; ++j) tma_load_2d_pair(sb + j * 8192, tmB, lead_bar, n0 + j * 64, k0);
             }
           }
           if (first) { tl_stamp(p, 2); first = false; }
@@ -1030,7 +1037,7 @@ static int g_auto_split = 1;
 // internal split-K of non-accumulating launches: 0 = off, 1 = automatic (cost model), 2 = whenever eligible (test hook)
 NFB_API int nfb_gemm_bf16_set_auto_split(int mode) { g_auto_split = mode; return 0; }
 static int g_stream_k = 1;
-// stream-K schedule: 0 = never (grouped launches excepted), 1 = automatic (cost model), 2 = whenever possible (test hook)
+// stream-K schedule of single launches: 0 / 1 = classic schedule (grouped launches always use stream-K), 2 = whenever possible (test hook)
 NFB_API int nfb_gemm_bf16_set_stream_k(int mode) { g_stream_k = mode; return 0; }
 static int g_sm_limit = 0;
 // number of SMs the persistent grids may occupy (0 = all): a data-parallel step leaves room for NCCL's channel CTAs while a
@@ -1047,21 +1054,22 @@ static int gemm_sms() {
 // (the measured L2->smem port rate); a tile costs kblocks * max(of the two) and every launch pays a fixed
 // prologue + first-load + last-epilogue cost.  Whole-launch cost = waves * tile + fixed.
 struct TileChoice { int bn, cg, sk; double cost; };
-static double kb_cost(int bn, int cg) {
-  double mma = 2.0 * bn, fill = (16384.0 + (double)(bn / cg) * 128.0) / 64.0;
+static double kb_cost(int bn, int cg, int b_mn = 0) {
+  const double b_bytes = b_mn ? (double)(((bn / cg) + 63) / 64) * 8192.0 : (double)(bn / cg) * 128.0;   // MN-major B: whole 64-column chunks
+  double mma = 2.0 * bn, fill = (16384.0 + b_bytes) / 64.0;
   return mma > fill ? mma : fill;
 }
 static double epi_cost(int bn) { return 150.0 * (bn / 32) / 2.0; }   // drain of one accumulator (two warps per lane quarter)
-static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int sms, bool reduce_add = true) {
+static double tile_cost(int M, int N, int k_blocks, int bn, int cg, int sk, int sms, bool reduce_add = true, int b_mn = 0) {
   long long num_m = nfb_cdiv(M, BLOCK_M * cg), num_n = nfb_cdiv(N, bn);
   long long units = sms / cg;                     // CTAs (or CTA pairs) running concurrently
   long long work = num_m * num_n * sk;
   long long waves = nfb_cdiv(work, units);
   double kb = (double)nfb_cdiv(k_blocks, sk);
-  // split-K partial tiles leave through reduce-adds: the L2 reduction path sustains ~10 B/clk per SM (measured on the layer
-  // weight gradients: 72 partial 256x256 tiles into a 768x768 fp32 matrix cost 3x the MMA time)
-  double red = (sk > 1 && reduce_add) ? (double)waves * (128.0 * bn * 4.0) / 10.0 : 0.0;
-  return (double)waves * (kb * kb_cost(bn, cg) + 250.0) + epi_cost(bn) + red + 2500.0;
+  // (a reduce-add penalty of ~10 B/clk/SM for split-K partials was tried here and picked slower tiles: measured 18.0 / 28.9 /
+  // 12.4 / 28.2 us against 14.5 / 20.4 / 11.2 / 21.9 us without it on the four layer weight gradients)
+  (void)reduce_add;
+  return (double)waves * (kb * kb_cost(bn, cg, b_mn) + 250.0) + epi_cost(bn) + (sk > 1 ? 100.0 * (bn / 32) / 2.0 : 0.0) + 2500.0;
 }
 // Hybrid stream-K: how many of the `tiles` tiles (the last ones of the launch-wide order) are pooled and cut into equal
 // k-block ranges over `clusters` clusters; the others run as whole tiles.  Whole waves stay whole tiles (no fix-up, and
@@ -1076,7 +1084,7 @@ static long long stream_k_pool(long long tiles, long long clusters) {
 }
 // cost of the hybrid schedule: whole-tile waves + the pooled share of every cluster; the pooled part pays one extra
 // accumulator drain per cluster (partial out / partial in), exposed only when no whole tile follows it
-static double stream_k_cost(long long tiles, int k_blocks, int bn, int cg, int sms) {
+static double stream_k_cost(long long tiles, int k_blocks, int bn, int cg, int sms, int b_mn = 0) {
   long long clusters = sms / cg;
   const long long pool = stream_k_pool(tiles, clusters);
   const long long dp_waves = (tiles - pool) / clusters;
@@ -1086,7 +1094,7 @@ static double stream_k_cost(long long tiles, int k_blocks, int bn, int cg, int s
   const double cuts = pool > 0 ? (double)active / (double)pool : 0.0;   // clusters sharing one pooled tile
   const double fix = pool > 0 ? epi_cost(bn) + 900.0 * (cuts > 1.0 ? cuts : 1.0) : 0.0;
   const double exposed = dp_waves > 0 ? 0.3 * fix : fix;
-  return (double)dp_waves * (k_blocks * kb_cost(bn, cg) + 250.0) + (double)per * kb_cost(bn, cg) + 500.0 + exposed + epi_cost(bn) + 2500.0;
+  return (double)dp_waves * (k_blocks * kb_cost(bn, cg, b_mn) + 250.0) + (double)per * kb_cost(bn, cg, b_mn) + 500.0 + exposed + epi_cost(bn) + 2500.0;
 }
 
 // Best (tile N, CTA group, split-K) for a launch.  may_split: the caller accumulates into a pre-initialised fp32 C, so K may
@@ -1100,14 +1108,14 @@ static TileChoice choose_tiles(int M, int N, int k_blocks, int b_mn, bool may_sp
     for (int i = 0; i < 4; ++i) {
       int bn = cand_bn[i];
       if (g_force_block_n && bn != g_force_block_n) continue;
-      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;   // MN-major B is staged in 64-column chunks
+      if (cg == 2 && b_mn && (bn / 2) % 32 != 0) continue;   // MN-major B halves: whole 64-column chunks + an optional 32-column one
       int sk_lo = 1, sk_hi = 1;
       if (may_split) {
         if (split_k >= 1) sk_lo = sk_hi = split_k;
         else sk_hi = k_blocks >= 8 ? (k_blocks / 4 < 16 ? k_blocks / 4 : 16) : 1;
       }
       for (int sk = sk_lo; sk <= sk_hi; ++sk) {
-        double c = tile_cost(M, N, k_blocks, bn, cg, sk, sms);
+        double c = tile_cost(M, N, k_blocks, bn, cg, sk, sms, true, b_mn);
         if (c < best.cost * 0.98) best = {bn, cg, sk, c};
       }
     }
@@ -1126,7 +1134,7 @@ static TileChoice choose_tiles_stream_k(int nprob, const int* Ms, const int* Ns,
     for (int i = 0; i < 4; ++i) {
       int bn = cand_bn[i];
       if (g_force_block_n && bn != g_force_block_n) continue;
-      if (cg == 2 && b_mn && (bn / 2) % 64 != 0) continue;
+      if (cg == 2 && b_mn && (bn / 2) % 32 != 0) continue;
       // a group is costed as one problem with the summed units (all k-block counts enter through the unit total)
       double units = 0;
       long long tiles = 0;
@@ -1137,7 +1145,7 @@ static TileChoice choose_tiles_stream_k(int nprob, const int* Ms, const int* Ns,
       }
       int kb_avg = (int)(units / (double)tiles + 0.5);
       if (kb_avg < 1) kb_avg = 1;
-      double c = stream_k_cost(tiles, kb_avg, bn, cg, sms);
+      double c = stream_k_cost(tiles, kb_avg, bn, cg, sms, b_mn);
       if (c < best.cost * 0.98) best = {bn, cg, 1, c};
     }
   }
@@ -1157,18 +1165,16 @@ struct GemmPlan {
 static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int split_k, bool split_eligible, bool stream_k_ok, int sms) {
   const int k_blocks = (int)nfb_cdiv(K, BLOCK_K);
   GemmPlan g = {128, 1, 1, 0, 0, 0};
-  double classic_cost = 1e30;
   if (split_eligible && g_auto_split && k_blocks >= 16 && N % 4 == 0) {
     const TileChoice one = choose_tiles(M, N, k_blocks, b_mn, false, 0, sms);
     const TileChoice many = choose_tiles(M, N, k_blocks, b_mn, true, g_auto_split == 2 ? 3 : 0, sms);
     const int sk = (int)nfb_cdiv(k_blocks, nfb_cdiv(k_blocks, many.sk));   // the factor after rounding the k-blocks per split
     // the extra launch + the slices written once and read once + C written, at ~3400 B/clk of HBM
     // (the reduce-add penalty inside `many.cost` does not apply: the slices are stored, not added)
-    const double many_cost = tile_cost(M, N, k_blocks, many.bn, many.cg, sk, sms, false);
+    const double many_cost = tile_cost(M, N, k_blocks, many.bn, many.cg, sk, sms, false, b_mn);
     const double overhead = 3000.0 + (double)M * (double)N * (8.0 * sk + 2.0) / 3400.0;
     if (sk > 1 && many.cost < 1e30 && one.cost < 1e30 && (g_auto_split == 2 || many_cost + overhead < 0.85 * one.cost)) {
       g.internal_split = sk;
-      classic_cost = many_cost + overhead;
     }
   }
   const bool slices = g.internal_split > 1;
@@ -1176,13 +1182,13 @@ static GemmPlan plan_gemm(int M, int N, int K, int b_mn, bool may_split, int spl
   if (best.cost >= 1e30) {   // a forced combination that is not available: fall back to the forced tile on one CTA
     best = {g_force_block_n ? g_force_block_n : 128, 1, slices ? g.internal_split : ((may_split && split_k >= 1) ? split_k : 1), 0.0};
   }
-  if (!slices) classic_cost = best.cost;
   if (stream_k_ok && g_stream_k && !(g_auto_split == 2 && slices)) {
     const TileChoice sk = choose_tiles_stream_k(1, &M, &N, &K, b_mn, sms);
-    // measured (profiles/r02_gemm_streamk.txt): without whole tiles to hide it behind, the fix-up of a single small launch
-    // costs more than the balance wins, so one-wave launches keep the classic schedule
-    const bool has_whole_waves = sk.cost < 1e30 && nfb_cdiv(M, BLOCK_M * sk.cg) * nfb_cdiv(N, sk.bn) > sms / sk.cg;
-    if (sk.cost < 1e30 && (g_stream_k == 2 || (has_whole_waves && sk.cost < 0.93 * classic_cost))) {
+    // measured (profiles/r02_gemm_streamk.txt): for ONE contraction of the step's sizes the fix-up (partial tiles out and back
+    // through L2, latency-bound) costs what the balance wins -- classic 15.5 us vs 20.1 us on the 96-tile dgrad, 11.4 vs 16.9 us
+    // on the 48-tile ones -- so single launches keep the classic schedule unless the test hook forces stream-K; the
+    // schedule pays in GROUPED launches (nfb_gemm_bf16_grouped: 88 -> 46 us for the four weight gradients of a block)
+    if (sk.cost < 1e30 && g_stream_k == 2) {
       g.stream_k = 1;
       g.internal_split = 0;
       best = sk;

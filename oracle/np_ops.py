@@ -439,3 +439,69 @@ def clip_grad_norm(grads, max_norm):
     if coef < 1:
         grads = [g * np.float32(coef) for g in grads]
     return grads, norm
+
+
+# ------------------------------------------------------------------ bf16 emulation (oracle of the tensor-core path)
+# The reference has no 16-bit dtype: the B200 backend's bf16 mode is an internal compute mode whose
+# rounding points are restated here so that "inherent bf16 noise" and "kernel error" can be told apart: the same fp32
+# formulas as above, with operands / stored activations rounded to bfloat16 (round-to-nearest-even) exactly where the
+# CUDA path stores bf16 (neural-network-from-scratch_b200/csrc: GEMM operands and bf16 outputs, RoPE in place, P and dS
+# inside the flash kernels, bf16 logits / dlogits).
+def bf16_round(a):
+    """fp32 -> nearest bfloat16 (ties to even), returned as fp32 values."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    out = r.astype(np.uint32).view(np.float32).reshape(a.shape)
+    return np.where(np.isfinite(a), out, a)
+
+
+def attention_fwd_bf16(q, k, v, scale, mode="none", mask=None):
+    """csrc/attention_tc.cu k_flash_fwd_tc: S = q k^T (bf16 operands, fp32 accumulate); softmax statistics from the
+    UNROUNDED exponentials; P rounded to bf16 for the P.V product; O = (P_bf16 V) / l rounded to bf16; LSE in fp32."""
+    s = np.matmul(q.astype(np.float32), np.swapaxes(k, -1, -2).astype(np.float32)) * np.float32(scale)
+    if mode == "causal":
+        S, Skv = s.shape[-2], s.shape[-1]
+        s = np.where(np.tril(np.ones((S, Skv))) == 0, np.float32(-1e4), s)
+    if mask is not None:
+        s = s + mask
+    s = s.astype(np.float32)
+    m = s.max(axis=-1, keepdims=True)
+    e = np.exp(s - m)
+    l = np.maximum(e.sum(axis=-1, keepdims=True), np.float32(1e-8))
+    o = bf16_round(np.matmul(bf16_round(e), v.astype(np.float32)) / l)
+    lse = m + np.log(l)
+    return o, (q, k, v, o, lse, scale, mode, mask)
+
+
+def attention_bwd_bf16(go, cache, key_block=128, dq_f32_blocks=4):
+    """csrc/attention_tc.cu k_flash_bwd_tc: P = exp(s - LSE) and dS = P_bf16 o (dP - delta) * scale are rounded to bf16
+    before the dV / dK / dQ products; dQ is the sum of one bf16 partial per 128-key block (added in bf16 for <= 4 blocks,
+    in fp32 beyond); dK, dV leave as bf16."""
+    q, k, v, o, lse, scale, mode, mask = cache
+    q32, k32, v32, go = q.astype(np.float32), k.astype(np.float32), v.astype(np.float32), go.astype(np.float32)
+    s = np.matmul(q32, np.swapaxes(k32, -1, -2)) * np.float32(scale)
+    S, Skv = s.shape[-2], s.shape[-1]
+    keep = None
+    if mode == "causal":
+        keep = np.tril(np.ones((S, Skv))) != 0
+        s = np.where(keep, s, np.float32(-1e4))
+    if mask is not None:
+        s = s + mask
+    p = bf16_round(np.exp(s.astype(np.float32) - lse))
+    dv = bf16_round(np.matmul(np.swapaxes(p, -1, -2), go))
+    dp = np.matmul(go, np.swapaxes(v32, -1, -2))
+    delta = np.sum(go * o.astype(np.float32), axis=-1, keepdims=True)
+    ds = bf16_round(p * (dp - delta) * np.float32(scale))
+    if keep is not None:
+        ds = np.where(keep, ds, np.float32(0.0))
+    dk = bf16_round(np.matmul(np.swapaxes(ds, -1, -2), q32))
+    nblk = (Skv + key_block - 1) // key_block
+    dq = np.zeros(q32.shape, np.float32)
+    for j in range(nblk):
+        part = np.matmul(ds[..., j * key_block:(j + 1) * key_block], k32[..., j * key_block:(j + 1) * key_block, :])
+        if nblk <= dq_f32_blocks:
+            dq = bf16_round(dq + bf16_round(part))
+        else:
+            dq = dq + part
+    return bf16_round(dq), dk, dv

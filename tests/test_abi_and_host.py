@@ -54,7 +54,7 @@ def test_gemm_launch_plans_for_the_gpt2_small_step():
     guards the measured choices (profiles/r01_gemm_shapes.txt) against accidental changes."""
     T, d, V = 4096, 768, 50257
     # forward x.W^T (B stored (N,K): transB=1): SM pairs on 256-row tiles; N = 768 takes 192-wide tiles (64 pairs of 74)
-    assert _plan(1, T, 2304, d) == dict(bn=256, cg=2, sk=1, n_fast=0, internal_split=0)
+    assert _plan(1, T, 2304, d) == dict(bn=256, cg=2, sk=1, n_fast=0, internal_split=0, stream_k=0)
     assert _plan(1, T, d, d)["bn"] == 192 and _plan(1, T, d, 1536)["bn"] == 192
     # layer input gradients dY.W (MN-major B: 192-wide pair tiles are not available) stay one launch
     for N, K in ((1536, d), (d, 3072), (d, 2304), (d, d)):
@@ -62,7 +62,7 @@ def test_gemm_launch_plans_for_the_gpt2_small_step():
         assert pl["cg"] == 2 and pl["bn"] == 256 and pl["internal_split"] == 0, (N, K, pl)
     # LM head: logits and their input gradient; the latter fills 48 of 74 SM pairs -> cut 3 ways along K = 50257
     assert _plan(1, T, V, d)["internal_split"] == 0 and _plan(1, T, V, d)["n_fast"] == 0
-    assert _plan(0, T, d, V) == dict(bn=256, cg=2, sk=3, n_fast=0, internal_split=3)
+    assert _plan(0, T, d, V) == dict(bn=256, cg=2, sk=3, n_fast=0, internal_split=3, stream_k=0)
     assert _plan(0, T, d, V, epilogue=1)["internal_split"] == 0          # a fused activation cannot be split
     # weight gradients accumulate (split-K by reduce-add); the LM-head one reads dlogits^T (412 MB > L2) once: n fastest
     lm = _plan(0, V, d, T, accumulate=1)
@@ -73,6 +73,16 @@ def test_gemm_launch_plans_for_the_gpt2_small_step():
     assert _plan(0, d, d, T, accumulate=1, split_k=5)["sk"] == 5        # an explicit factor is honoured
     # a single-row-block problem cannot pair SMs
     assert _plan(1, 128, 512, 256)["cg"] == 1
+    # single launches keep the classic schedule (the stream-K fix-up costs what the balance wins at these sizes, see
+    # profiles/r02_gemm_streamk.txt); only the test hook and grouped launches (nfb_gemm_bf16_grouped) take stream-K
+    from nfb200 import _lib
+    assert all(_plan(tb, M, N, K)["stream_k"] == 0 for tb, M, N, K in ((0, T, 1536, d), (1, T, 3072, d), (0, T, d, 3072)))
+    _lib.call("nfb_gemm_bf16_set_stream_k", 2)
+    try:
+        assert _plan(0, T, 1536, d)["stream_k"] == 1 and _plan(0, d, d, T, accumulate=1)["stream_k"] == 1
+        assert _plan(0, d, d, T, accumulate=1, split_k=5)["stream_k"] == 0   # an explicit split-K factor keeps the classic path
+    finally:
+        _lib.call("nfb_gemm_bf16_set_stream_k", 1)
 
 
 def test_no_cpu_fallback_without_gpu():

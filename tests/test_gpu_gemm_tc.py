@@ -226,8 +226,9 @@ def test_internal_split_k_lm_head_dgrad(be):
     _lib.call("nfb_gemm_bf16_set_stream_k", 2)
     try:
         n3 = _lib.launch_count()
-        sk1 = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
+        sk1 = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0)
         n4 = _lib.launch_count()
+        sk1 = sk1.get()
         sk2 = Kn.gemm_bf16(dl, w, False, False, out_dtype=be.bfloat16, clip=10.0).get()
     finally:
         _lib.call("nfb_gemm_bf16_set_stream_k", 1)

@@ -35,19 +35,58 @@ def _oracle(n_steps, lr, wd):
     return losses, first_grads
 
 
+def _first_step_grads(cls, cfg, ids, labels, **kw):
+    np.random.seed(0)
+    orc = cls(cfg, **kw)
+    loss = float(orc.forward(ids, labels)["loss"])
+    return loss, {k: np.asarray(v, np.float64) for k, v in orc.backward().items()}
+
+
+def _errs(got, want):
+    """(max |got - want| / max |want|, ||got - want|| / ||want||) of one gradient tensor."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    d = got - want
+    return float(np.abs(d).max() / (np.abs(want).max() + 1e-300)), float(np.linalg.norm(d.ravel()) / (np.linalg.norm(want.ravel()) + 1e-300))
+
+
+# north_star tolerances (BASELINE.json): fp32 path 1e-5 relative, bf16 tensor-core path 1e-2 relative / abs
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
 @pytest.fixture(scope="module")
 def oracle_run():
     return _oracle(10, 5e-4, 0.1)
 
 
+@pytest.fixture(scope="module")
+def yardsticks():
+    """First-step gradients of the 2-layer config from the fp64 evaluation of the oracle (what both fp32 implementations
+    approximate) and from the bf16-emulating oracle (np_model.GPT2OracleBF16: the same rounding points as the CUDA path)."""
+    from oracle.np_model import GPT2Oracle, GPT2OracleBF16
+    ids, labels = _batches(1)[0]
+    _, g64 = _first_step_grads(GPT2Oracle, CFG, ids, labels, dtype=np.float64)
+    l16, g16 = _first_step_grads(GPT2OracleBF16, CFG, ids, labels)
+    return g64, l16, g16
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+wgrad_overlap", "bf16+wgrad_overlap+step_in_backward", "fp32+step_in_backward"])
-def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
-    """bf16+wgrad_overlap: the weight-gradient GEMMs run on a side stream (kernels.set_wgrad_overlap), as bench.py does."""
+def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, yardsticks, precision):
+    """bf16+wgrad_overlap: the weight-gradient GEMMs run on a side stream (kernels.set_wgrad_overlap), as bench.py does.
+
+    Gates (north_star): the fp32 path's first-step gradients are within 1e-5 (relative to the tensor's largest entry, and
+    in relative L2) of the NumPy oracle's; the bf16 tensor-core path's are within 1e-2 of the bf16-EMULATING oracle -- the
+    reference's formulas with operands rounded to bfloat16 at the points where the kernels store bfloat16 -- so what is
+    left is kernel error, not the rounding the mode is defined by.  The distance of the bf16 path from the fp32 oracle
+    (the rounding noise inherent to bf16 operands: 2-3 % at this model's he_uniform init, the emulating oracle shows the
+    same figure on the CPU) is printed and bounded loosely.  Loss trajectories: fp32 2e-5, bf16 1e-2 against the fp32
+    oracle."""
     from nfb200 import kernels as K
     from nfb200.core import Tensor, set_default_device
     from nfb200.models import GPT2
     from nfb200.optim import AdamW
     want_losses, want_grads = oracle_run
+    g64, l16, g16 = yardsticks
     set_default_device("cuda")
     overlap = "+wgrad_overlap" in precision
     sib = "+step_in_backward" in precision   # AdamW launches from inside backward (optimizer.enable_step_in_backward)
@@ -61,31 +100,75 @@ def test_ten_step_loss_trajectory_and_gradients(be, oracle_run, precision):
         if sib:
             opt.enable_step_in_backward(min_run_elems=1 << 14)
         losses = []
+        report = []
         for i, (ids, labels) in enumerate(_batches(10)):
             opt.zero_grad()
             loss = model(Tensor(ids, device="cuda"), labels=Tensor(labels, device="cuda"))["loss"]
             loss.backward()
             if i == 0:
                 for name, p in model.named_parameters():
-                    got, want = p.grad.get(), want_grads[name]
-                    scale = float(np.abs(want).max()) + 1e-12
-                    err = float(np.abs(got - want).max()) / scale
-                    l2 = float(np.linalg.norm((got - want).ravel()) / (np.linalg.norm(want.ravel()) + 1e-30))
+                    got = p.grad.get()
+                    e32, l32 = _errs(got, want_grads[name])
                     if precision == "fp32":
-                        assert err <= 2e-4 and l2 <= 1e-4, f"grad {name}: rel-to-max {err}, rel-L2 {l2}"
+                        e64, l64 = _errs(got, g64[name])
+                        o64 = _errs(want_grads[name], g64[name])
+                        report.append(f"{name}: vs oracle {e32:.2e}/{l32:.2e}  vs fp64 {e64:.2e}/{l64:.2e}  (oracle vs fp64 {o64[0]:.2e}/{o64[1]:.2e})")
+                        assert e32 <= FP32_TOL and l32 <= FP32_TOL, f"fp32 grad {name}: rel-to-max {e32:.3e}, rel-L2 {l32:.3e} (> {FP32_TOL})"
                     else:
-                        # bf16 end to end: every kernel holds 1e-2 in isolation (tests/test_gpu_{gemm_tc,attention,fused_ops}.py),
-                        # but the reference's he_uniform init gives attention scores of magnitude ~2-6, where a 2^-9 relative
-                        # operand rounding is a ~1 % error in the softmax probabilities, and the noise compounds through the
-                        # layers: measured fp32-vs-bf16 on identical code is 1.7 % on the logits and 2-3.5 % on the gradients
-                        # of this 2-layer model (PARITY.md #7).  The bound here is therefore 5e-2; the 10-step LOSS trajectory
-                        # below holds the stated 1e-2 (it agrees to ~1e-6).
-                        assert l2 <= 5e-2 and err <= 8e-2, f"grad {name}: rel-to-max {err}, rel-L2 {l2}"
+                        ee, le = _errs(got, g16[name])
+                        report.append(f"{name}: vs bf16-emulating oracle {ee:.2e}/{le:.2e}  vs fp32 oracle (inherent bf16 noise) {e32:.2e}/{l32:.2e}")
+                        assert ee <= BF16_TOL and le <= BF16_TOL, f"bf16 grad {name}: rel-to-max {ee:.3e}, rel-L2 {le:.3e} vs the bf16-emulating oracle (> {BF16_TOL})"
+                        assert l32 <= 5e-2 and e32 <= 8e-2, f"bf16 grad {name} vs the fp32 oracle: rel-to-max {e32}, rel-L2 {l32}"
+                if precision == "bf16":
+                    assert abs(float(loss.item()) - l16) <= 1e-3 * abs(l16)
             opt.step()
             losses.append(float(loss.item()))
-        tol = 2e-5 if precision == "fp32" else 1e-2
+        print("\n".join(report))
+        tol = 2e-5 if precision == "fp32" else BF16_TOL
         for a, b in zip(losses, want_losses):
             assert abs(a - b) <= tol * abs(b), f"{precision} loss trajectory {losses} vs oracle {want_losses}"
+    finally:
+        K.set_wgrad_overlap(False)
+        K.set_precision("fp32")
+        set_default_device("cpu")
+
+
+def test_full_size_gpt2_small_vs_bf16_emulating_oracle(be):
+    """The FULL GPT-2 small stack (12 layers, d 768, 12 heads, V 50257; one 512-token sequence so the NumPy oracles finish
+    in seconds): first-step gradients of the bf16 tensor-core path within 1e-2 of the bf16-emulating oracle for every
+    parameter tensor, loss within 1e-3; the distance from the fp32 oracle is printed (rounding noise of the mode)."""
+    from nfb200 import kernels as K
+    from nfb200.core import Tensor, set_default_device
+    from nfb200.models import gpt2_small
+    from oracle.np_model import GPT2Oracle, GPT2OracleBF16
+    cfg = {"vocab_size": 50257, "n_positions": 1024, "n_embd": 768, "n_layer": 12, "n_head": 12}
+    rng = np.random.default_rng(77)
+    ids = rng.integers(0, 50257, (1, 512)).astype(np.int64)
+    labels = np.concatenate([ids[:, 1:], np.zeros((1, 1), dtype=np.int64)], axis=1)
+    l32, g32 = _first_step_grads(GPT2Oracle, cfg, ids, labels)
+    l16, g16 = _first_step_grads(GPT2OracleBF16, cfg, ids, labels)
+    set_default_device("cuda")
+    K.set_precision("bf16")
+    K.set_wgrad_overlap(True)
+    try:
+        np.random.seed(0)
+        model = gpt2_small()
+        loss = model(Tensor(ids, device="cuda"), labels=Tensor(labels, device="cuda"))["loss"]
+        loss.backward()
+        got_loss = float(loss.item())
+        worst = (0.0, 0.0, "")
+        worst32 = 0.0
+        for name, p in model.named_parameters():
+            got = p.grad.get()
+            ee, le = _errs(got, g16[name])
+            e32, l32n = _errs(got, g32[name])
+            worst32 = max(worst32, l32n)
+            if le > worst[1]:
+                worst = (ee, le, name)
+            assert ee <= BF16_TOL and le <= BF16_TOL, f"full-size bf16 grad {name}: rel-to-max {ee:.3e}, rel-L2 {le:.3e} vs the bf16-emulating oracle"
+        print(f"full-size GPT-2 small: worst gradient vs bf16-emulating oracle {worst}; worst rel-L2 vs the fp32 oracle {worst32:.3e}; "
+              f"loss {got_loss} (emulated {l16}, fp32 {l32})")
+        assert abs(got_loss - l16) <= 1e-3 * abs(l16) and abs(got_loss - l32) <= BF16_TOL * abs(l32)
     finally:
         K.set_wgrad_overlap(False)
         K.set_precision("fp32")

@@ -186,35 +186,89 @@ class GPT2OracleBF16(GPT2Oracle):
       * the reference's +-10 gradient clip sits in the dX GEMM epilogues and the norm backward (before the rounding).
     Weight / bias / norm-parameter gradients accumulate in fp32 from those bf16 operands."""
 
-    def forward(self, input_ids, labels=None):
+    def shadow_weights(self):
+        """bf16 shadow of every weight matrix (what the tensor-core GEMMs read)."""
+        return {k: O.bf16_round(v) for k, v in self.params.items() if v.ndim == 2}
+
+    def block_forward(self, i, x, W=None):
+        """One Transformer block on an fp32 residual-stream input x (B, S, d) -> (fp32 output, cache)."""
         r = O.bf16_round
         P, H, hd = self.params, self.H, self.hd
+        W = W or self.shadow_weights()
+        B, S, d = x.shape
+        cos, sin = O.rope_tables(hd, S)
+        scale = np.float32(1.0 / np.sqrt(hd))
+        p = f"transformer.h.{i}."
+        c = {"x": x, "cos": cos, "sin": sin}
+        h1f, c["ln1"] = O.rmsnorm_fwd(x, P[p + "ln_1.weight"], self.eps)
+        h1 = r(h1f)
+        qkv = r(np.matmul(h1, W[p + "attn.c_attn.weight"].T) + P[p + "attn.c_attn.bias"])
+        q5 = qkv.reshape(B, S, 3, H, hd).transpose(2, 0, 3, 1, 4)
+        q, k, v = q5[0], q5[1], q5[2]
+        qr, kr = r(O.rope_fwd(q, cos, sin)), r(O.rope_fwd(k, cos, sin))
+        a, c["attn"] = O.attention_fwd_bf16(qr, kr, v, scale, "causal")
+        a2 = a.transpose(0, 2, 1, 3).reshape(B, S, d)
+        x2 = (np.matmul(a2, W[p + "attn.c_proj.weight"].T) + P[p + "attn.c_proj.bias"]) + x
+        h2f, c["ln2"] = O.rmsnorm_fwd(x2, P[p + "ln_2.weight"], self.eps)
+        h2 = r(h2f)
+        g1 = r(np.matmul(h2, W[p + "mlp.swiglu.w1.weight"].T))
+        u = r(np.matmul(h2, W[p + "mlp.swiglu.w2.weight"].T))
+        act = r(O.silu_fwd(g1) * u)
+        out = (np.matmul(act, W[p + "mlp.swiglu.w3.weight"].T) + x2).astype(np.float32)
+        c.update(h1=h1, qkv=qkv, qr=qr, kr=kr, a2=a2, x2=x2, h2=h2, g1=g1, u=u, act=act, out=out)
+        return out, c
+
+    def block_backward(self, i, dx, c, acc, W=None):
+        """Backward of block i for the fp32 residual-stream gradient dx; parameter gradients go through acc(name, g).
+        Returns the gradient of the block input."""
+        r = O.bf16_round
+        H, hd = self.H, self.hd
+        W = W or self.shadow_weights()
+        cg = (lambda g: O.clip_grad(g, True)) if self.grad_clip else (lambda g: g)
+        B, S, d = dx.shape
+        cos, sin = c["cos"], c["sin"]
+        p = f"transformer.h.{i}."
+
+        def f2(t):
+            return t.reshape(-1, t.shape[-1])
+
+        dz = r(dx)                                                      # bf16 twin of the residual-stream gradient
+        dact = r(cg(np.matmul(dz, W[p + "mlp.swiglu.w3.weight"])))
+        acc(p + "mlp.swiglu.w3.weight", np.matmul(f2(dz).T, f2(c["act"])))
+        sg = 1.0 / (1.0 + np.exp(-c["g1"]))
+        dg1 = r(dact * c["u"] * (sg * (1.0 + c["g1"] * (1.0 - sg))))
+        du = r(dact * c["g1"] * sg)
+        dh2 = r(cg(np.matmul(dg1, W[p + "mlp.swiglu.w1.weight"]) + np.matmul(du, W[p + "mlp.swiglu.w2.weight"])))   # one GEMM over [w1; w2]
+        acc(p + "mlp.swiglu.w1.weight", np.matmul(f2(dg1).T, f2(c["h2"])))
+        acc(p + "mlp.swiglu.w2.weight", np.matmul(f2(du).T, f2(c["h2"])))
+        dx2n, dw2 = O.rmsnorm_bwd(dh2, c["ln2"])
+        acc(p + "ln_2.weight", dw2)
+        dx2 = cg(dx + dx2n).astype(np.float32)
+        dz2 = r(dx2)
+        da2 = r(cg(np.matmul(dz2, W[p + "attn.c_proj.weight"])))
+        acc(p + "attn.c_proj.weight", np.matmul(f2(dz2).T, f2(c["a2"])))
+        acc(p + "attn.c_proj.bias", f2(dz2).sum(axis=0))
+        da = da2.reshape(B, S, H, hd).transpose(0, 2, 1, 3)
+        dq, dk, dv = O.attention_bwd_bf16(da, c["attn"])
+        dq, dk = r(O.rope_bwd(dq, cos, sin)), r(O.rope_bwd(dk, cos, sin))
+        dqkv = np.stack([dq, dk, dv], axis=0).transpose(1, 3, 0, 2, 4).reshape(B, S, 3 * d).astype(np.float32)
+        dh1 = r(cg(np.matmul(dqkv, W[p + "attn.c_attn.weight"])))
+        acc(p + "attn.c_attn.weight", np.matmul(f2(dqkv).T, f2(c["h1"])))
+        acc(p + "attn.c_attn.bias", f2(dqkv).sum(axis=0))
+        dxn, dw1 = O.rmsnorm_bwd(dh1, c["ln1"])
+        acc(p + "ln_1.weight", dw1)
+        return cg(dx2 + dxn).astype(np.float32)
+
+    def forward(self, input_ids, labels=None):
+        r = O.bf16_round
+        P = self.params
         B, S = input_ids.shape
         d = P["transformer.ln_f.weight"].shape[0]
         caches = []
         x = O.embedding_fwd(P["transformer.wte.weight"], input_ids)
-        cos, sin = O.rope_tables(hd, S)
-        scale = np.float32(1.0 / np.sqrt(hd))
-        W = {k: r(v) for k, v in P.items() if v.ndim == 2}   # bf16 shadow weights
+        W = self.shadow_weights()
         for i in range(self.cfg["n_layer"]):
-            p = f"transformer.h.{i}."
-            c = {"x": x}
-            h1f, c["ln1"] = O.rmsnorm_fwd(x, P[p + "ln_1.weight"], self.eps)
-            h1 = r(h1f)
-            qkv = r(np.matmul(h1, W[p + "attn.c_attn.weight"].T) + P[p + "attn.c_attn.bias"])
-            q5 = qkv.reshape(B, S, 3, H, hd).transpose(2, 0, 3, 1, 4)
-            q, k, v = q5[0], q5[1], q5[2]
-            qr, kr = r(O.rope_fwd(q, cos, sin)), r(O.rope_fwd(k, cos, sin))
-            a, c["attn"] = O.attention_fwd_bf16(qr, kr, v, scale, "causal")
-            a2 = a.transpose(0, 2, 1, 3).reshape(B, S, d)
-            x2 = (np.matmul(a2, W[p + "attn.c_proj.weight"].T) + P[p + "attn.c_proj.bias"]) + x
-            h2f, c["ln2"] = O.rmsnorm_fwd(x2, P[p + "ln_2.weight"], self.eps)
-            h2 = r(h2f)
-            g1 = r(np.matmul(h2, W[p + "mlp.swiglu.w1.weight"].T))
-            u = r(np.matmul(h2, W[p + "mlp.swiglu.w2.weight"].T))
-            act = r(O.silu_fwd(g1) * u)
-            x = np.matmul(act, W[p + "mlp.swiglu.w3.weight"].T) + x2
-            c.update(h1=h1, a2=a2, x2=x2, h2=h2, g1=g1, u=u, act=act)
+            x, c = self.block_forward(i, x, W)
             caches.append(c)
         hff, cf = O.rmsnorm_fwd(x, P["transformer.ln_f.weight"], self.eps)
         hf = r(hff).reshape(B * S, d)
@@ -222,7 +276,8 @@ class GPT2OracleBF16(GPT2Oracle):
         train = labels is not None
         if train:
             logits = r(logits)   # a training step keeps the (T, V) logits in bf16 (models/gpt2.py GPT2LMHead.forward)
-        self._cache = (input_ids, caches, cf, hf, cos, sin, (B, S, d), W)
+        self._cache = (input_ids, caches, cf, hf, (B, S, d), W)
+        self._dbg = {"hf": hf, "logits": logits}
         out = {"logits": logits.reshape(B, S, -1)}
         if train:
             loss, cce = O.cross_entropy_fwd(logits.astype(np.float32), labels.reshape(-1), "mean")
@@ -232,16 +287,13 @@ class GPT2OracleBF16(GPT2Oracle):
 
     def backward(self):
         r = O.bf16_round
-        P, H, hd = self.params, self.H, self.hd
-        input_ids, caches, cf, hf, cos, sin, (B, S, d), W = self._cache
+        P = self.params
+        input_ids, caches, cf, hf, (B, S, d), W = self._cache
         cg = (lambda g: O.clip_grad(g, True)) if self.grad_clip else (lambda g: g)
         G = {}
 
         def acc(name, g):
             G[name] = g if name not in G else G[name] + g
-
-        def f2(t):
-            return t.reshape(-1, t.shape[-1])
 
         dlogits = r(O.cross_entropy_bwd(np.float32(1.0), self._cache_ce))
         dhf = r(cg(np.matmul(dlogits, W["transformer.wte.weight"])))
@@ -249,35 +301,10 @@ class GPT2OracleBF16(GPT2Oracle):
         dx, dw = O.rmsnorm_bwd(dhf.reshape(B, S, d), cf)
         acc("transformer.ln_f.weight", dw)
         dx = cg(dx).astype(np.float32)
+        self._dbg_dx = {}
         for i in reversed(range(self.cfg["n_layer"])):
-            p = f"transformer.h.{i}."
-            c = caches[i]
-            dz = r(dx)                                                      # bf16 twin of the residual-stream gradient
-            dact = r(cg(np.matmul(dz, W[p + "mlp.swiglu.w3.weight"])))
-            acc(p + "mlp.swiglu.w3.weight", np.matmul(f2(dz).T, f2(c["act"])))
-            sg = 1.0 / (1.0 + np.exp(-c["g1"]))
-            dg1 = r(dact * c["u"] * (sg * (1.0 + c["g1"] * (1.0 - sg))))
-            du = r(dact * c["g1"] * sg)
-            dh2 = r(cg(np.matmul(dg1, W[p + "mlp.swiglu.w1.weight"]) + np.matmul(du, W[p + "mlp.swiglu.w2.weight"])))   # one GEMM over [w1; w2]
-            acc(p + "mlp.swiglu.w1.weight", np.matmul(f2(dg1).T, f2(c["h2"])))
-            acc(p + "mlp.swiglu.w2.weight", np.matmul(f2(du).T, f2(c["h2"])))
-            dx2n, dw2 = O.rmsnorm_bwd(dh2, c["ln2"])
-            acc(p + "ln_2.weight", dw2)
-            dx2 = cg(dx + dx2n).astype(np.float32)
-            dz2 = r(dx2)
-            da2 = r(cg(np.matmul(dz2, W[p + "attn.c_proj.weight"])))
-            acc(p + "attn.c_proj.weight", np.matmul(f2(dz2).T, f2(c["a2"])))
-            acc(p + "attn.c_proj.bias", f2(dz2).sum(axis=0))
-            da = da2.reshape(B, S, H, hd).transpose(0, 2, 1, 3)
-            dq, dk, dv = O.attention_bwd_bf16(da, c["attn"])
-            dq, dk = r(O.rope_bwd(dq, cos, sin)), r(O.rope_bwd(dk, cos, sin))
-            dqkv = np.stack([dq, dk, dv], axis=0).transpose(1, 3, 0, 2, 4).reshape(B, S, 3 * d).astype(np.float32)
-            dh1 = r(cg(np.matmul(dqkv, W[p + "attn.c_attn.weight"])))
-            acc(p + "attn.c_attn.weight", np.matmul(f2(dqkv).T, f2(c["h1"])))
-            acc(p + "attn.c_attn.bias", f2(dqkv).sum(axis=0))
-            dxn, dw1 = O.rmsnorm_bwd(dh1, c["ln1"])
-            acc(p + "ln_1.weight", dw1)
-            dx = cg(dx2 + dxn).astype(np.float32)
+            self._dbg_dx[i] = dx     # the residual-stream gradient entering block i (tests feed it to the CUDA block)
+            dx = self.block_backward(i, dx, caches[i], acc, W)
         acc("transformer.wte.weight", O.embedding_bwd_fast(dx.astype(np.float32), input_ids, P["transformer.wte.weight"].shape[0]))
         for k, g in G.items():
             g = cg(g).astype(np.float32)

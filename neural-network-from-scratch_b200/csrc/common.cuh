@@ -38,6 +38,7 @@ cudaStream_t nfb_aux_stream();          // side stream for optimizer-only gradie
 unsigned long long nfb_capture_epoch();  // bumps at graph-capture begin / end
 void nfb_count_launch();
 int nfb_sm_count();
+int* nfb_index_error_flag();   // device int set to 1 by a kernel that met an out-of-range index / class id (NULL on allocation failure)
 extern "C" int nfb_malloc(size_t nbytes, void** out);
 extern "C" int nfb_free(void* p);
 

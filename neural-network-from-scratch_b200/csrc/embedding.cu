@@ -16,6 +16,12 @@ static int ensure_flag() {
   return 0;
 }
 
+// the flag is shared with the loss kernels (class ids outside the vocabulary), csrc/softmax_ce.cu
+int* nfb_index_error_flag() {
+  if (ensure_flag()) return nullptr;
+  return g_index_error;
+}
+
 template <typename TI>
 __device__ __forceinline__ int64_t load_index(const TI* idx, int64_t i, int64_t V, int* err) {
   int64_t v = (int64_t)idx[i];

@@ -99,7 +99,7 @@ NFB_API int nfb_softmax_bwd(const float* p, const float* g, float* dx, int64_t r
 template <typename TD, bool CACHE, bool VEC>
 __global__ void __launch_bounds__(1024)
 k_cross_entropy(const float* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
-                TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+                TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale, int* __restrict__ err) {
   extern __shared__ float srow[];
   __shared__ float red[32];
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -135,10 +135,21 @@ k_cross_entropy(const float* __restrict__ logits, const void* __restrict__ targe
     float inv = 1.f / s;
     int64_t t = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
     if (t < 0) t += V;  // numpy negative indexing
+    // a class id outside [-V, V) (NumPy raises IndexError; typical sources: an ignore_index such as -100, corrupt labels) must
+    // not index the row: NaN loss, zero gradient row, and the device-side index-error flag the host can poll
+    const bool bad = t < 0 || t >= V;
+    if (bad) t = -1;
     if (threadIdx.x == 0) {
-      float pt = (CACHE ? srow[t] : expf(xr[t] - m)) * inv;
-      loss[row] = -logf(pt + 1e-8f);
+      if (bad) {
+        loss[row] = __int_as_float(0x7fc00000);
+        if (err) *err = 1;
+      } else {
+        float pt = (CACHE ? srow[t] : expf(xr[t] - m)) * inv;
+        loss[row] = -logf(pt + 1e-8f);
+      }
     }
+    if (bad) inv = 0.f;
+    const float gs = bad ? 0.f : grad_scale;
     if (!CACHE) __syncthreads();  // dlogits may alias logits: finish reading xr[t] first
     if (dlogits) {
       TD* dr = dlogits + row * dld;
@@ -151,19 +162,19 @@ k_cross_entropy(const float* __restrict__ logits, const void* __restrict__ targe
           if (t >= c && t < c + 4) {
             if (t == c) o.x -= 1.f; else if (t == c + 1) o.y -= 1.f; else if (t == c + 2) o.z -= 1.f; else o.w -= 1.f;
           }
-          o.x *= grad_scale; o.y *= grad_scale; o.z *= grad_scale; o.w *= grad_scale;
+          o.x *= gs; o.y *= gs; o.z *= gs; o.w *= gs;
           st4<TD>(dr + c, o);
         }
         for (int c = v4 * 4 + threadIdx.x; c < V; c += blockDim.x) {
           float pv = srow[c] * inv;
           if (c == t) pv -= 1.f;
-          st_f<TD>(dr, c, pv * grad_scale);
+          st_f<TD>(dr, c, pv * gs);
         }
       } else {
         for (int c = threadIdx.x; c < V; c += blockDim.x) {
           float pv = (CACHE ? srow[c] : expf(xr[c] - m)) * inv;
           if (c == t) pv -= 1.f;
-          st_f<TD>(dr, c, pv * grad_scale);
+          st_f<TD>(dr, c, pv * gs);
         }
       }
     }
@@ -183,7 +194,7 @@ __device__ __forceinline__ float exp_sub_fast(float x, float m_log2e) { return e
 template <typename TL, typename TD, int NV4>
 __global__ void __launch_bounds__(1024, 1)
 k_cross_entropy_reg(const TL* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
-                    TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+                    TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale, int* __restrict__ err) {
   __shared__ float red[32];
   const int t = threadIdx.x;
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -205,6 +216,11 @@ k_cross_entropy_reg(const TL* __restrict__ logits, const void* __restrict__ targ
     }
     int64_t tg = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
     if (tg < 0) tg += V;  // numpy negative indexing
+    const bool bad = tg < 0 || tg >= V;   // see k_cross_entropy: NaN loss, zero gradient row, error flag
+    if (bad) {
+      tg = -1;
+      if (t == 0) { loss[row] = __int_as_float(0x7fc00000); if (err) *err = 1; }
+    }
     m = block_max(m, red);
     const float ml2 = m * 1.4426950408889634f;
     float s = 0.f;
@@ -232,7 +248,7 @@ k_cross_entropy_reg(const TL* __restrict__ logits, const void* __restrict__ targ
     }
     if (dlogits) {
       TD* dr = dlogits + row * dld;
-      const float sc = inv * grad_scale;
+      const float sc = bad ? 0.f : inv * grad_scale;
 #pragma unroll
       for (int k = 0; k < NV4; ++k) {
         const int c = (k * 1024 + t) * 4;
@@ -261,7 +277,7 @@ __device__ __forceinline__ void ce_unpack8(const uint4& u, float* v) {
 template <typename TD>
 __global__ void __launch_bounds__(512, 2)
 k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
-                     TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale) {
+                     TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char ce_smem[];
   __shared__ float red[32];
   __shared__ __align__(8) unsigned long long bar;
@@ -285,6 +301,8 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
     }
     int64_t tg = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
     if (tg < 0) tg += V;  // numpy negative indexing
+    const bool bad = tg < 0 || tg >= V;   // see k_cross_entropy: NaN loss, zero gradient row, error flag
+    if (bad) tg = -1;
     {
       uint32_t ok = 0;
       while (!ok) {
@@ -323,12 +341,17 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
     s = fmaxf(block_sum(s, red), 1e-8f);
     const float inv = 1.f / s;
     if (t == 0) {
-      float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tg]);
-      loss[row] = -logf(exp_sub_fast(xt, ml2) * inv + 1e-8f);
+      if (bad) {
+        loss[row] = __int_as_float(0x7fc00000);
+        if (err) *err = 1;
+      } else {
+        float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tg]);
+        loss[row] = -logf(exp_sub_fast(xt, ml2) * inv + 1e-8f);
+      }
     }
     if (dlogits) {
       TD* dr = dlogits + row * dld;
-      const float sc = inv * grad_scale;
+      const float sc = bad ? 0.f : inv * grad_scale;
       const int tvec = (int)(tg >> 3), te = (int)(tg & 7);
       for (int i = t; i < nv; i += 512) {
         float v[8];
@@ -367,7 +390,7 @@ static int ce_launch(const float* logits, const void* targets, int tgt_is_i64, f
 #define LAUNCH(C, VV)                                                                                                        \
   do {                                                                                                                       \
     if (C) cudaFuncSetAttribute(k_cross_entropy<TD, C, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    k_cross_entropy<TD, C, VV><<<(unsigned)grid, threads, C ? smem : 0, s>>>(logits, targets, tgt_is_i64, loss, dlogits, rows, V, ld, dld, grad_scale); \
+    k_cross_entropy<TD, C, VV><<<(unsigned)grid, threads, C ? smem : 0, s>>>(logits, targets, tgt_is_i64, loss, dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag()); \
   } while (0)
   if (cache && vec) LAUNCH(true, true);
   else if (cache) LAUNCH(true, false);
@@ -384,7 +407,7 @@ static int ce_launch_reg(const TL* logits, const void* targets, int tgt_is_i64, 
   cudaStream_t s = nfb_cur_stream();
   int nv4 = (int)nfb_cdiv(nfb_cdiv(V, 4), 1024);
   int64_t grid = rows < nfb_sm_count() ? rows : nfb_sm_count();
-#define LR(NV) k_cross_entropy_reg<TL, TD, NV><<<(unsigned)grid, 1024, 0, s>>>(logits, targets, tgt_is_i64, loss, dlogits, rows, V, ld, dld, grad_scale)
+#define LR(NV) k_cross_entropy_reg<TL, TD, NV><<<(unsigned)grid, 1024, 0, s>>>(logits, targets, tgt_is_i64, loss, dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag())
   if (nv4 <= 4) LR(4);
   else if (nv4 <= 8) LR(8);
   else if (nv4 <= 13) LR(13);
@@ -421,10 +444,10 @@ NFB_API int nfb_cross_entropy_ex(int ldt, const void* logits, const void* target
       if (grid > rows) grid = rows;
       if (!dlogits || ddt == NFB_BF16) {
         NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cross_entropy_bulk<__nv_bfloat16><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
+        k_cross_entropy_bulk<__nv_bfloat16><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
       } else {
         NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cross_entropy_bulk<float><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
+        k_cross_entropy_bulk<float><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
       }
       NFB_LAUNCH_CHECK();
       return 0;

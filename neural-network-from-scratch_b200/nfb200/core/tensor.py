@@ -227,8 +227,16 @@ class Tensor:
         else:
             new = value if isinstance(value, B200Array) else self._backend.from_numpy(np.asarray(value))
             cur = self._data
-            if getattr(self, "_arena_bound", False) and isinstance(cur, B200Array) and cur.shape == new.shape and cur.dtype == new.dtype:
-                cur._assign(new)  # keep the flat-arena binding (optimizer / DDP buckets)
+            if getattr(self, "_arena_bound", False) and isinstance(cur, B200Array) and cur.shape == new.shape:
+                # keep the flat-arena binding (optimizer / DDP buckets); a float64 / bf16 source is cast to the arena's fp32
+                cur._assign(new if cur.dtype == new.dtype else new.astype(cur.dtype))
+                sh = self.__dict__.get("_bf16")
+                if sh is not None and self.__dict__.get("_bf16_live", False):
+                    # the arena's bf16 shadow (what the tensor-core GEMMs read, incl. fused multi-parameter views of the same
+                    # memory) is otherwise refreshed only by the optimizer kernel: a load_state_dict / manual assignment
+                    # after the optimizer was built must not leave it at the old weights
+                    from .._lib import call as _call
+                    _call("nfb_cast", 0, 5, cur.ptr, sh.ptr, cur.size)
             else:
                 self._data = new
         self._version += 1
@@ -543,11 +551,6 @@ def make_result(data, inputs: Sequence[Tensor], backward_fn: Optional[Callable],
                 dev = t._device
                 break
     rg = _grad_enabled and any(isinstance(t, Tensor) and t.requires_grad for t in inputs)
-    if rg and backward_fn is not None:
-        for t in inputs:  # data-parallel bucket readiness: count the graph nodes that consume each parameter
-            if isinstance(t, Tensor) and t._grad_fn is None:
-                for q in _ddp_targets(t):
-                    q._ddp._note_use(q)
     out = Tensor.__new__(Tensor)
     out._device = dev if dev is not None else get_default_device()
     out._backend = _backend_for(out._device)
@@ -622,6 +625,19 @@ def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
     if root._grad_fn is None:
         root._accumulate(_clip(grad))
         return
+    # data-parallel bucket readiness / optimizer-in-backward: how many nodes of THIS graph consume each tracked parameter.
+    # Counted here, from the nodes this backward will actually run (not while the graph is built), so several forward
+    # passes feeding one loss (siamese towers, micro-forwards) and parameters the loss does not reach are handled.
+    owners = {}
+    for t in nodes.values():
+        for inp in t._grad_fn.inputs:
+            if isinstance(inp, Tensor) and inp._grad_fn is None:
+                for q in _ddp_targets(inp):
+                    counts = owners.setdefault(id(q._ddp), (q._ddp, {}))[1]
+                    ent = counts.get(id(q))
+                    counts[id(q)] = (q, (ent[1] if ent else 0) + 1)
+    for owner, counts in owners.values():
+        owner._begin_backward(counts)
     order = sorted(nodes.values(), key=lambda t: t._grad_fn.seq, reverse=True)
     # the root keeps its gradient (reference: every tensor on the path has .grad set; we keep root + leaves)
     root._grad = grad if root._grad is None else root._grad + grad

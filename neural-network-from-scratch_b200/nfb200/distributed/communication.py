@@ -15,8 +15,9 @@ torchrun keeps its own store on MASTER_PORT, so this module listens on MASTER_PO
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import hmac
 import os
-import pickle
 import socket
 import struct
 import time
@@ -42,9 +43,114 @@ _NCCL_OP = {ReduceOp.SUM: 0, ReduceOp.AVERAGE: 1, ReduceOp.MAX: 2, ReduceOp.MIN:
 _MAGIC = b"NFB200RV"
 
 
+# ---- wire format of the rendezvous / host collectives.  A closed set of value types in a fixed binary framing: nothing
+# received from a socket is ever executed or unpickled (any host that can reach the port could otherwise run code in the job).
+#   N none | T / F bool | i int64 | f float64 | s utf-8 str | b bytes | a ndarray (dtype str, ndim, dims, raw C-order bytes)
+#   l list | t tuple | d dict with str keys
+_WIRE_DTYPES = {"float16", "float32", "float64", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "bool"}
+
+
+def _encode(obj, out: bytearray):
+    if obj is None:
+        out += b"N"
+    elif isinstance(obj, (bool, np.bool_)):
+        out += b"T" if obj else b"F"
+    elif isinstance(obj, (int, np.integer)):
+        out += b"i" + struct.pack("!q", int(obj))
+    elif isinstance(obj, (float, np.floating)):
+        out += b"f" + struct.pack("!d", float(obj))
+    elif isinstance(obj, str):
+        raw = obj.encode("utf-8")
+        out += b"s" + struct.pack("!Q", len(raw)) + raw
+    elif isinstance(obj, (bytes, bytearray)):
+        out += b"b" + struct.pack("!Q", len(obj)) + bytes(obj)
+    elif isinstance(obj, np.ndarray):
+        if obj.dtype.name not in _WIRE_DTYPES:
+            raise TypeError(f"cannot send an ndarray of dtype {obj.dtype} over the rendezvous")
+        name = obj.dtype.name.encode()
+        raw = np.ascontiguousarray(obj).tobytes()
+        out += b"a" + struct.pack("!B", len(name)) + name + struct.pack("!B", obj.ndim) + struct.pack(f"!{obj.ndim}Q", *obj.shape)
+        out += struct.pack("!Q", len(raw)) + raw
+    elif isinstance(obj, (list, tuple)):
+        out += (b"l" if isinstance(obj, list) else b"t") + struct.pack("!Q", len(obj))
+        for x in obj:
+            _encode(x, out)
+    elif isinstance(obj, dict):
+        out += b"d" + struct.pack("!Q", len(obj))
+        for k, v in obj.items():
+            if not isinstance(k, str):
+                raise TypeError("only str keys can be sent over the rendezvous")
+            _encode(k, out)
+            _encode(v, out)
+    else:
+        raise TypeError(f"cannot send a {type(obj).__name__} over the rendezvous (allowed: None, bool, int, float, str, bytes, ndarray, list, tuple, dict)")
+
+
+def _decode(buf: memoryview, pos: int, depth: int = 0):
+    if depth > 32:
+        raise ValueError("rendezvous message nested too deeply")
+    tag = bytes(buf[pos:pos + 1])
+    pos += 1
+    if tag == b"N":
+        return None, pos
+    if tag in (b"T", b"F"):
+        return tag == b"T", pos
+    if tag == b"i":
+        return struct.unpack_from("!q", buf, pos)[0], pos + 8
+    if tag == b"f":
+        return struct.unpack_from("!d", buf, pos)[0], pos + 8
+    if tag in (b"s", b"b"):
+        (n,) = struct.unpack_from("!Q", buf, pos)
+        pos += 8
+        if n > len(buf) - pos:
+            raise ValueError("rendezvous message truncated")
+        raw = bytes(buf[pos:pos + n])
+        return (raw.decode("utf-8") if tag == b"s" else raw), pos + n
+    if tag == b"a":
+        (ln,) = struct.unpack_from("!B", buf, pos)
+        name = bytes(buf[pos + 1:pos + 1 + ln]).decode()
+        pos += 1 + ln
+        if name not in _WIRE_DTYPES:
+            raise ValueError(f"rendezvous message carries an ndarray of unsupported dtype {name!r}")
+        (nd,) = struct.unpack_from("!B", buf, pos)
+        shape = struct.unpack_from(f"!{nd}Q", buf, pos + 1)
+        pos += 1 + 8 * nd
+        (n,) = struct.unpack_from("!Q", buf, pos)
+        pos += 8
+        dt = np.dtype(name)
+        if n != int(np.prod(shape, dtype=np.int64)) * dt.itemsize or n > len(buf) - pos:
+            raise ValueError("rendezvous message: ndarray payload does not match its shape")
+        arr = np.frombuffer(bytes(buf[pos:pos + n]), dtype=dt).reshape(shape).copy()
+        return arr, pos + n
+    if tag in (b"l", b"t"):
+        (n,) = struct.unpack_from("!Q", buf, pos)
+        pos += 8
+        if n > len(buf):
+            raise ValueError("rendezvous message truncated")
+        items = []
+        for _ in range(n):
+            x, pos = _decode(buf, pos, depth + 1)
+            items.append(x)
+        return (items if tag == b"l" else tuple(items)), pos
+    if tag == b"d":
+        (n,) = struct.unpack_from("!Q", buf, pos)
+        pos += 8
+        if n > len(buf):
+            raise ValueError("rendezvous message truncated")
+        d = {}
+        for _ in range(n):
+            k, pos = _decode(buf, pos, depth + 1)
+            if not isinstance(k, str):
+                raise ValueError("rendezvous message: dict key is not a str")
+            d[k], pos = _decode(buf, pos, depth + 1)
+        return d, pos
+    raise ValueError(f"rendezvous message: unknown type tag {tag!r}")
+
+
 def _send_msg(sock, obj):
-    data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
-    sock.sendall(struct.pack("!Q", len(data)) + data)
+    data = bytearray()
+    _encode(obj, data)
+    sock.sendall(struct.pack("!Q", len(data)) + bytes(data))
 
 
 def _recv_exact(sock, n):
@@ -59,7 +165,21 @@ def _recv_exact(sock, n):
 
 def _recv_msg(sock):
     (n,) = struct.unpack("!Q", _recv_exact(sock, 8))
-    return pickle.loads(_recv_exact(sock, n))
+    obj, pos = _decode(memoryview(_recv_exact(sock, n)), 0)
+    if pos != n:
+        raise ValueError("rendezvous message has trailing bytes")
+    return obj
+
+
+def _job_token() -> bytes:
+    """Shared secret of the job: NFB200_RDZV_TOKEN (the launcher draws a random one per job and exports it to every rank);
+    under other launchers the run id they export, else the rendezvous endpoint itself (guards against cross-talk only)."""
+    tok = os.environ.get("NFB200_RDZV_TOKEN") or os.environ.get("TORCHELASTIC_RUN_ID") or ""
+    return (tok + "|" + os.environ.get("MASTER_ADDR", "127.0.0.1") + ":" + os.environ.get("MASTER_PORT", "29500")).encode()
+
+
+def _hello_mac(rank: int, world: int) -> bytes:
+    return hmac.new(_job_token(), _MAGIC + struct.pack("!II", rank, world), hashlib.sha256).digest()
 
 
 class _TcpGroup:
@@ -81,11 +201,19 @@ class _TcpGroup:
             while got < world - 1:
                 conn, _ = srv.accept()
                 conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-                hello = _recv_exact(conn, len(_MAGIC) + 4)
-                if hello[:len(_MAGIC)] != _MAGIC:
+                try:
+                    conn.settimeout(10)
+                    hello = _recv_exact(conn, len(_MAGIC) + 4 + 32)
+                    conn.settimeout(None)
+                except (OSError, ConnectionError):
                     conn.close()
                     continue
-                (r,) = struct.unpack("!I", hello[len(_MAGIC):])
+                (r,) = struct.unpack("!I", hello[len(_MAGIC):len(_MAGIC) + 4])
+                # a peer is admitted only with the magic, a rank in 1..world-1 that has not checked in yet, and the job's MAC
+                if hello[:len(_MAGIC)] != _MAGIC or not (0 < r < world) or self.peers[r] is not None or \
+                        not hmac.compare_digest(hello[len(_MAGIC) + 4:], _hello_mac(r, world)):
+                    conn.close()
+                    continue
                 self.peers[r] = conn
                 got += 1
             srv.close()
@@ -95,7 +223,7 @@ class _TcpGroup:
                 try:
                     s = socket.create_connection((addr, port), timeout=5)
                     s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-                    s.sendall(_MAGIC + struct.pack("!I", rank))
+                    s.sendall(_MAGIC + struct.pack("!I", rank) + _hello_mac(rank, world))
                     s.settimeout(timeout)
                     self.sock = s
                     break

@@ -47,7 +47,11 @@ class DistributedDataParallel(Module):
         self.module = module
         self.bucket_size_mb = bucket_size_mb
         self.find_unused_parameters = find_unused_parameters
-        self.overlap = overlap
+        # find_unused_parameters: ranks may run different control flow, so the order in which buckets become ready is not the
+        # same everywhere -- and NCCL calls must be issued in the same order on every rank.  All buckets are then reduced
+        # after backward, in bucket order (no overlap), with zeros standing in for the gradients a rank did not produce.
+        self.overlap = overlap and not find_unused_parameters
+        self._sync_consumed = True
         self.group = comm.get_backend() if comm.is_initialized() else None
         self.world_size = self.group.world_size if self.group else 1
         self.rank = self.group.rank if self.group else 0
@@ -105,19 +109,33 @@ class DistributedDataParallel(Module):
 
     # ------------------------------------------------------------------ forward / overlap machinery
     def forward(self, *args, **kwargs):
-        if self.arena is not None and self._require_sync and self.world_size > 1:
-            for b in self.buckets:
-                b.pending = 0
-                b.launched = False
-            for p in self.arena.params:
-                p._ddp_uses = 0
         return self.module(*args, **kwargs)
 
-    def _note_use(self, p):
-        """Called by the autograd engine when a graph node consumes parameter p in the forward pass."""
-        p._ddp_uses = getattr(p, "_ddp_uses", 0) + 1
-        if p._ddp_uses == 1:
-            self._bucket_of[id(p)].pending += 1
+    def _begin_backward(self, counts):
+        """Called by the autograd engine at the start of a backward pass with {id(p): (p, number of graph nodes that
+        consume p)} for the parameters of this wrapper the pass will reach.  A bucket is handed to NCCL when the last
+        consumer of its last reachable parameter has run."""
+        if self.arena is None or not self._require_sync or self.world_size <= 1:
+            return
+        if any(b.launched for b in self.buckets) and not self._sync_consumed:
+            raise RuntimeError("DistributedDataParallel: backward() ran again before the gradients of the previous backward were "
+                               "consumed (finish_gradient_sync / step_optimizer / sync_gradients); accumulate gradients under "
+                               "no_sync() and synchronise on the last micro-batch only")
+        self._sync_consumed = False
+        for b in self.buckets:
+            b.pending = 0
+            b.launched = False
+        for p in self.arena.params:
+            p._ddp_uses = 0
+        for p, n in counts.values():
+            b = self._bucket_of.get(id(p))
+            if b is None:
+                continue
+            p._ddp_uses = n
+            b.pending += 1
+
+    def _note_use(self, p):   # kept for engines that count at graph-build time; counting now happens in _begin_backward
+        pass
 
     def _note_grad_done(self, p):
         """Called by the autograd engine after a consumer node of p has run its backward."""
@@ -171,6 +189,7 @@ class DistributedDataParallel(Module):
                 if p._grad is None:
                     p._grad = p._grad_slot
                 p._slot_zero = False
+            self._sync_consumed = True
         for p in self._host_params:
             if p.grad is not None:
                 p.grad = self.group.all_reduce(Tensor(p.grad), ReduceOp.AVERAGE).data
@@ -182,7 +201,8 @@ class DistributedDataParallel(Module):
         import inspect
         pipelined = "segments" in inspect.signature(optimizer.step).parameters     # Adam / AdamW; SGD and Lion take the plain path
         if self.world_size == 1 or not self._require_sync or self.arena is None or self._host_params or not pipelined or \
-                getattr(optimizer, "arena", None) is None or optimizer.arena.flat_g is not self.arena.flat_g:
+                getattr(optimizer, "arena", None) is None or optimizer.arena.flat_g is not self.arena.flat_g or \
+                len(optimizer.arena.params) != len(self.arena.params):   # (an optimizer over a SUBSET of the module steps after the full sync)
             self.finish_gradient_sync()
             optimizer.step()
             return
@@ -193,6 +213,7 @@ class DistributedDataParallel(Module):
             if p._grad is None:
                 p._grad = p._grad_slot
             p._slot_zero = False
+        self._sync_consumed = True
         order = sorted(self.buckets, key=lambda b: getattr(b, "seq", 0))
         optimizer.step(segments=[(lo, hi, ev) for b in order for (lo, hi), ev in zip(b.pieces, b.piece_events)])
 

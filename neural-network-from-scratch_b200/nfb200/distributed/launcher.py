@@ -55,13 +55,17 @@ class _Workers:
         self.config = config
         self.procs: List[subprocess.Popen] = []
         self._files = []
+        # shared secret of the job's TCP rendezvous (communication._hello_mac): drawn once per launch; a multi-node job
+        # exports the same NFB200_RDZV_TOKEN on every node
+        import secrets
+        self._token = os.environ.get("NFB200_RDZV_TOKEN") or secrets.token_hex(16)
 
     def env_for(self, rank: int, world_size: int, local_rank: int) -> dict:
         env = dict(os.environ)
         if self.config.use_env:
             env.update({"RANK": str(rank), "WORLD_SIZE": str(world_size), "LOCAL_RANK": str(local_rank),
                         "MASTER_ADDR": self.config.master_addr, "MASTER_PORT": str(self.config.master_port),
-                        "NCCL_ASYNC_ERROR_HANDLING": "1", "OMP_NUM_THREADS": "1"})
+                        "NCCL_ASYNC_ERROR_HANDLING": "1", "OMP_NUM_THREADS": "1", "NFB200_RDZV_TOKEN": self._token})
         return env
 
     def _log_files(self, rank: int):

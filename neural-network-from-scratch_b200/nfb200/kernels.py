@@ -262,14 +262,15 @@ def set_wgrad_group(n: int):
 
 
 def _issue_wgrad(items, colsums):
+    """Every weight gradient is DETERMINISTIC: the grouped stream-K launch adds each finished tile to the gradient buffer
+    exactly once (partial tiles meet in a workspace in a fixed order), and the LM-head-sized ones run with split_k = 1
+    (one reduce-add per element).  No launch splits K over racing reduce-adds."""
     big = [it for it in items if 2.0 * it[0].shape[1] * it[1].shape[1] * it[0].shape[0] >= _WGRAD_BIG_FLOP]
     small = [it for it in items if not any(it is b for b in big)]
-    if len(small) == 1:
-        big.append(small.pop())
     if small:
         gemm_bf16_grouped(small, True, False, accumulate=True)
     for a, b, out in big:
-        gemm_bf16(a, b, True, False, out=out, accumulate=True)
+        gemm_bf16(a, b, True, False, out=out, accumulate=True, split_k=1)
     for dz, db_out in colsums:
         _colsum(dz, db_out)
 
@@ -391,9 +392,9 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
         if dW_out is None:
             dW_out = B200Array.full(W.shape, 0.0, np.float32)
         if out_in:   # dW (out,in) = dZ^T (out,T) . X (T,in)
-            wg = lambda: gemm_bf16(dz, x2, True, False, out=dW_out, accumulate=True)
+            wg = lambda: _issue_wgrad([(dz, x2, dW_out)], [])
         else:        # dW (in,out) = X^T . dZ
-            wg = lambda: gemm_bf16(x2, dz, True, False, out=dW_out, accumulate=True)
+            wg = lambda: _issue_wgrad([(x2, dz, dW_out)], [])
         db = None
         if side and has_bias and db_out is not None:
             # the bias gradient (column sums of dZ) feeds only the optimizer too: same side stream

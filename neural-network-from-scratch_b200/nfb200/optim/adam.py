@@ -159,8 +159,14 @@ class _AdamBase(Optimizer):
         for p in self.arena.params:
             p._ddp_uses = 0
 
-    def _note_use(self, p):      # autograd: a graph node consumes parameter p (forward)
-        p._ddp_uses = getattr(p, "_ddp_uses", 0) + 1
+    def _begin_backward(self, counts):   # autograd: {id(p): (p, consumer nodes of p in the graph this backward runs)}
+        if not self._sib:
+            return
+        for p, n in counts.values():
+            p._ddp_uses = getattr(p, "_ddp_uses", 0) + n
+
+    def _note_use(self, p):      # (counting happens in _begin_backward)
+        pass
 
     def _note_grad_done(self, p):   # autograd: a consumer node of p has run its backward
         if not self._sib:
@@ -230,6 +236,14 @@ class _AdamBase(Optimizer):
         pass
 
     def step(self, segments=None) -> None:
+        try:
+            self._step(segments)
+        finally:
+            # a clip coefficient set by clip_grad_norm(optimizer=...) scales the gradients of THIS step only (a CUDA-graph
+            # capture has already baked the device pointer into the captured launch)
+            self.grad_scale = None
+
+    def _step(self, segments=None) -> None:
         """One optimizer step.  `segments` (optional, from DistributedDataParallel.step_optimizer): a list of
         (lo, hi, event) slices of the gradient arena in the order their all-reduces were launched; the fused kernel
         then runs slice by slice, each fenced only by ITS bucket's event, so the update of early buckets overlaps the

@@ -35,12 +35,23 @@ class ParamArena:
             self.offsets[id(p)] = off
             off += (p.size + ALIGN - 1) // ALIGN * ALIGN
         self.total = off
-        existing = getattr(uniq[0], "_arena", None) if uniq else None
-        if existing is not None and all(getattr(p, "_arena", None) is existing for p in uniq) and len(existing.params) == len(uniq):
-            # parameters already live in an arena (e.g. created by DistributedDataParallel): share it
+        homes = {id(a): a for a in (getattr(p, "_arena", None) for p in uniq)}
+        existing = next(iter(homes.values())) if len(homes) == 1 else None
+        self.subset_of = None
+        if len(homes) > 1:
+            # some parameters already live in an arena (a DistributedDataParallel wrapper's, or another optimizer's) and others
+            # elsewhere: re-homing them would silently cut the buckets / the other optimizer off from the live data
+            raise RuntimeError("ParamArena: the parameters belong to different flat arenas (or only some of them to one); build the "
+                               "optimizer(s) over parameters of ONE DistributedDataParallel module / one earlier optimizer, or before wrapping")
+        if existing is not None:
+            # parameters already live in an arena (e.g. created by DistributedDataParallel): share its buffers and offsets.  A
+            # SUBSET (decay / no-decay groups given to two optimizers) works on the same flat buffers: it only ever touches
+            # the runs of its own parameters; its moment buffers span the whole arena so the offsets stay valid.
             self.flat_p, self.flat_g, self.flat_bf16 = existing.flat_p, existing.flat_g, existing.flat_bf16
             self.offsets = existing.offsets
             self.total = existing.total
+            if len(existing.params) != len(uniq):
+                self.subset_of = existing
         else:
             self.flat_p = B200Array.full((max(off, 1),), 0.0, np.float32)
             self.flat_g = B200Array.full((max(off, 1),), 0.0, np.float32)
@@ -71,9 +82,12 @@ class ParamArena:
 
     def enable_bf16(self):
         if self.flat_bf16 is None:
-            self.flat_bf16 = B200Array.empty((max(self.total, 1),), bfloat16)
-            call("nfb_cast", 0, 5, self.flat_p.ptr, self.flat_bf16.ptr, self.total)
-            for p in self.params:
+            owner = self.subset_of if self.subset_of is not None else self
+            if owner.flat_bf16 is None:
+                owner.flat_bf16 = B200Array.empty((max(self.total, 1),), bfloat16)
+                call("nfb_cast", 0, 5, self.flat_p.ptr, owner.flat_bf16.ptr, self.total)
+            self.flat_bf16 = owner.flat_bf16
+            for p in owner.params:
                 o = self.offsets[id(p)]
                 p._bf16 = self.flat_bf16[o:o + p.size].reshape(p.shape)
                 p._bf16_live = True
@@ -83,8 +97,11 @@ class ParamArena:
         return flat[o:o + p.size].reshape(p.shape)
 
     def zero_grad(self):
-        if self.total:
+        if self.total and self.subset_of is None:
             call("nfb_memset", self.flat_g.ptr, 0, self.total * 4)
+        elif self.total:
+            for off, n in self.runs(lambda q: True):   # a subset clears only its own runs of the shared gradient buffer
+                call("nfb_memset", self.flat_g.ptr + off * 4, 0, n * 4)
         for p in self.params:
             p._grad = None
             p._slot_zero = True

@@ -13,7 +13,8 @@ from ..array import B200Array
 def clip_grad_norm(parameters, max_norm: float = 1.0, optimizer=None, comm=None):
     """Returns the total norm (a host float for cpu tensors, a 1-element device array for cuda tensors).
     With `optimizer` (an Adam/AdamW/SGD of this package) the scaling is deferred into the optimizer kernel.
-    With `comm` the squared norm is all-reduced (SUM) first (data-parallel global norm)."""
+    With `comm` (a ProcessGroup: distributed.get_backend()) the squared norm is all-reduced (SUM) over the ranks first --
+    for gradients that are SHARDED over ranks; data-parallel replicas hold identical averaged gradients and need none."""
     params = list(parameters.values()) if hasattr(parameters, "values") else list(parameters)
     dev = [p for p in params if p.grad is not None and isinstance(p.grad, B200Array)]
     host = [p for p in params if p.grad is not None and not isinstance(p.grad, B200Array)]
@@ -22,6 +23,8 @@ def clip_grad_norm(parameters, max_norm: float = 1.0, optimizer=None, comm=None)
         total = 0.0
         for p in host:
             total += float(np.sum(np.asarray(p.grad, dtype=np.float64) ** 2))
+        if comm is not None:   # every rank holds a shard of the gradients: the global norm needs the sum over ranks
+            total = float(np.asarray(comm.all_reduce(np.asarray([total], np.float64)))[0])
         total = float(np.sqrt(total))
         if total > max_norm:
             for p in host:
@@ -40,6 +43,8 @@ def clip_grad_norm(parameters, max_norm: float = 1.0, optimizer=None, comm=None)
                 g = p.grad if p.grad.is_contiguous else p.grad.contiguous()
                 call("nfb_sumsq", g.ptr, g.size, total.ptr, 1 if i else 0)
                 spans.append((p.grad.ptr, p.grad.size))
+        if comm is not None:
+            comm.allreduce_buffer(total, 1)    # SUM of the per-rank squared norms, on the compute stream, in place
         call("nfb_clip_coef", total.ptr, float(max_norm), 0.0, coef.ptr, nrm.ptr)
         if optimizer is not None and hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = coef

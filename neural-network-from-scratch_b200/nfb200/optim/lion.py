@@ -87,6 +87,12 @@ class Lion(Optimizer):
         self.lr = lr
 
     def step(self) -> None:
+        try:
+            self._step()
+        finally:
+            self.grad_scale = None   # the clip coefficient of clip_grad_norm(optimizer=...) applies to this step only
+
+    def _step(self) -> None:
         self.step_count += 1
         done = set()
         if self.arena is not None:

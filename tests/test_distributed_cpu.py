@@ -153,3 +153,82 @@ def test_ddp_equals_single_process_on_global_batch(tmp_path):
         np.testing.assert_allclose(d0["params"][k], d1["params"][k], rtol=0, atol=0)      # replicas stay identical
         np.testing.assert_allclose(d0["params"][k], ref["params"][k], rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose((d0["losses"][0] + d1["losses"][0]) / 2, ref["losses"][0], rtol=1e-5)
+
+
+def test_wire_format_is_a_closed_set_of_value_types():
+    """The rendezvous / host collectives never unpickle: values travel in a fixed binary framing (any host that can
+    reach the port could otherwise execute code in the training job)."""
+    from nfb200.distributed import communication as C
+    vals = [None, True, False, 7, -3, 2.5, "héllo", b"\x00\x01", np.arange(6, dtype=np.float32).reshape(2, 3), np.array([1, 2], np.int64),
+            [1, "a", None], (2.0, [3]), {"k": np.zeros((0, 4), np.float64), "n": {"x": 1}}]
+    for v in vals:
+        buf = bytearray()
+        C._encode(v, buf)
+        got, pos = C._decode(memoryview(bytes(buf)), 0)
+        assert pos == len(buf)
+        if isinstance(v, np.ndarray):
+            assert got.dtype == v.dtype and np.array_equal(got, v)
+        elif isinstance(v, dict):
+            assert got.keys() == v.keys() and np.array_equal(got["k"], v["k"]) and got["n"] == v["n"]
+        else:
+            assert got == v and type(got) is type(v)
+    with pytest.raises(TypeError):
+        C._encode(object(), bytearray())            # arbitrary objects cannot be sent
+    with pytest.raises(TypeError):
+        C._encode(np.array(["a"], dtype=object), bytearray())
+    import pickle
+    evil = pickle.dumps({"x": 1})
+    with pytest.raises(ValueError):
+        C._decode(memoryview(evil), 0)              # a pickle stream is not a message
+    bad = bytearray()
+    C._encode(np.zeros(4, np.float32), bad)
+    bad[-17] ^= 0xFF                                 # corrupt the payload length
+    with pytest.raises((ValueError, Exception)):
+        C._decode(memoryview(bytes(bad)), 0)
+
+
+def test_rendezvous_rejects_unauthenticated_and_out_of_range_peers():
+    """Rank 0 admits a peer only with the magic, a rank in 1..world-1 that has not checked in yet and the job's HMAC; an
+    intruder (wrong token, out-of-range or duplicate rank) is dropped and the real rank still gets its slot."""
+    import struct
+    import threading
+    import time
+    from nfb200.distributed import communication as C
+    port = _free_port()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["NFB200_RDZV_TOKEN"] = "job-secret"
+    result = {}
+
+    def server():
+        result["g"] = C._TcpGroup(0, 2, "127.0.0.1", port, 30)
+
+    th = threading.Thread(target=server)
+    th.start()
+    time.sleep(0.3)
+
+    def raw(payload):
+        s = socket.create_connection(("127.0.0.1", port), timeout=5)
+        s.sendall(payload)
+        return s
+
+    good_mac = C._hello_mac(1, 2)
+    intruders = [raw(C._MAGIC + struct.pack("!I", 1) + b"\x00" * 32),            # wrong MAC
+                 raw(C._MAGIC + struct.pack("!I", 7) + C._hello_mac(7, 2)),      # rank out of range (was an IndexError)
+                 raw(C._MAGIC + struct.pack("!I", 0) + C._hello_mac(0, 2)),      # rank 0 is the server itself
+                 raw(b"GARBAGE!" + struct.pack("!I", 1) + good_mac)]             # wrong magic
+    time.sleep(0.3)
+    assert th.is_alive(), "an intruder was admitted"
+    peer = C._TcpGroup(1, 2, "127.0.0.1", port, 30)
+    th.join(timeout=30)
+    assert not th.is_alive()
+    g0 = result["g"]
+    t2 = threading.Thread(target=lambda: result.__setitem__("r", g0.allgather(np.arange(3))))
+    t2.start()
+    mine = peer.allgather(np.arange(3) + 10)
+    t2.join(timeout=30)
+    assert np.array_equal(mine[0], np.arange(3)) and np.array_equal(mine[1], np.arange(3) + 10)
+    for s in intruders:
+        s.close()
+    peer.close()
+    g0.close()
+    del os.environ["NFB200_RDZV_TOKEN"]

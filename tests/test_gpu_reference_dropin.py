@@ -1,0 +1,68 @@
+"""north_star: "Linear, MultiHeadAttention, LayerNorm, GELU, Embedding and the Adam/AdamW optimizers run on it unchanged".
+The reference's OWN files (nn/linear.py, nn/optimized.py, nn/normalization.py, nn/embedding.py, functional/*.py, optim/adam.py,
+optim/adamw.py, models/language/gpt2.py -- unmodified, staged under oracle/_ref by oracle/make_ref.py) are executed on
+Device.cuda tensors, i.e. on B200Array through their NumPy-protocol call sites and on B200Backend through the reference's own
+registry, and compared with the same files on the reference's NumPy backend.  Skipped when oracle/_ref is absent (a checkout
+without /root/reference at build time)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(ROOT, "oracle", "_ref")
+needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "neural_arch")), reason="oracle/_ref not staged (python oracle/make_ref.py needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def dropin_results():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "_ref_dropin_worker.py")], capture_output=True, text=True, timeout=600)
+    m = re.search(r"^DROPIN_JSON (.*)$", r.stdout, flags=re.M)
+    assert m, f"worker failed:\n{r.stdout[-2000:]}\n{r.stderr[-3000:]}"
+    return json.loads(m.group(1))
+
+
+CHECKS = ["registry: install_into_reference",
+          "nn.Linear (OptimizedLinear, reference nn/optimized.py) fwd+bwd",
+          "nn.linear.Linear (in,out) (reference nn/linear.py:13-207) fwd+bwd",
+          "nn.LayerNorm (reference nn/normalization.py:86-221) fwd+bwd",
+          "nn.RMSNorm (reference nn/normalization.py:228-359) fwd+bwd",
+          "nn.Embedding (reference nn/embedding.py:27-63) gather + ordered scatter-add",
+          "functional.gelu / softmax / relu / sigmoid / tanh (reference functional/activation.py) fwd+bwd",
+          "functional.add / mul / matmul (reference functional/arithmetic.py) fwd+bwd",
+          "functional.cross_entropy_loss (reference functional/loss.py:15-112) fwd+bwd",
+          "optim.Adam / AdamW (reference optim/adam.py:165-252, optim/adamw.py:278-372) 6-step trajectories",
+          "reference GPT-2 block pieces (models/language/gpt2.py: RMSNorm, SwiGLU, GPT2Attention) forward"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", CHECKS)
+def test_unmodified_reference_code_runs_on_the_b200_backend(dropin_results, name):
+    res = dropin_results.get(name)
+    assert res is not None, f"the worker did not run {name!r}: {sorted(dropin_results)}"
+    assert "error" not in res, res.get("error")
+    assert res["ok"], f"{name}: device vs NumPy backend max relative difference {res['max_rel']:.3e}"
+
+
+@needs_ref
+def test_reference_backend_test_file_with_b200_registered():
+    """The reference's own tests/test_backends.py (unmodified) with "b200" / "cuda" in available_backends(): its parametrised
+    tests iterate over every registered backend, so the KATs (2x2 known answers, reductions, clip, comparisons ...) now run
+    on the B200 backend too."""
+    plugin = os.path.join(HERE, "ref_dropin_plugin.py")
+    assert os.path.exists(plugin)
+    env = dict(os.environ, PYTHONPATH=HERE + os.pathsep + os.environ.get("PYTHONPATH", ""), NEURAL_ARCH_REFERENCE=os.path.join(REF, "neural_arch"))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-c", os.devnull, "--rootdir", "/tmp", "-p", "no:cacheprovider", "-p", "ref_dropin_plugin",
+                        os.path.join(REF, "tests", "test_backends.py"), "-q", "-rA", "--tb=short", "-W", "ignore"], capture_output=True, text=True, timeout=600, cwd="/tmp", env=env)
+    out = {}
+    for m in re.finditer(r"^(PASSED|FAILED|ERROR)\s+(\S*::\S+)", r.stdout, flags=re.M):
+        out[m.group(2)] = m.group(1)
+    bad = {t: o for t, o in out.items() if o != "PASSED"}
+    assert out and not bad, f"{bad}\n{r.stdout[-4000:]}\n{r.stderr[-1500:]}"
+    assert "B200_REGISTERED" in r.stdout + r.stderr or any("b200" in t or "cuda" in t for t in out), r.stdout[-1500:]

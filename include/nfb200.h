@@ -122,6 +122,8 @@ int nfb_index_error_check(int* flag);
  * nfb_gemm_f32: SIMT fp32 (1e-5 contract); nfb_gemm_bf16: tcgen05/TMEM + TMA (throughput path). */
 int nfb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda, int64_t strideA, const float* B,
                  int64_t ldb, int64_t strideB, float beta, float* C, int64_t ldc, int64_t strideC, int batch, const float* bias);
+int nfb_gemm_f64(int transA, int transB, int M, int N, int K, const double* A, int64_t lda, int64_t strideA, const double* B, int64_t ldb,
+                 int64_t strideB, double* C, int64_t ldc, int64_t strideC, int batch);   /* Backend.matmul on float64 arrays (not on the training path) */
 int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                   int64_t ldc, const float* bias, const float* residual, int64_t ldr, void* aux, int64_t ldaux, int epilogue, int accumulate,
                   int split_k, float clip);

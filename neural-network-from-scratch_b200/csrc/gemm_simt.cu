@@ -123,3 +123,82 @@ NFB_API int nfb_gemm_f32(int transA, int transB, int M, int N, int K, float alph
   NFB_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- fp64 contraction: Backend.matmul / dot on float64 arrays (the reference's `backend.array(np.random.randn(...))` is
+// float64: tests/test_backends.py:131-147).  Not on the training path; a plain 64x64x16 tiled kernel, 4x4 outputs per thread.
+#define DBM 64
+#define DBN 64
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+k_dgemm(int M, int N, int K, const double* __restrict__ A, int64_t lda, int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB,
+        double* __restrict__ C, int64_t ldc, int64_t sC) {
+  __shared__ double As[BK][DBM + 1];
+  __shared__ double Bs[BK][DBN + 1];
+  A += (int64_t)blockIdx.z * sA;
+  B += (int64_t)blockIdx.z * sB;
+  C += (int64_t)blockIdx.z * sC;
+  const int m0 = blockIdx.y * DBM, n0 = blockIdx.x * DBN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int e = tid + l * 256;   // 0 .. 1023 = 64 x 16
+      int am, ak;
+      if (!TA) { ak = e % BK; am = e / BK; } else { am = e % DBM; ak = e / DBM; }
+      int gm = m0 + am, gk = k0 + ak;
+      As[ak][am] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.0;
+      int bn, bk;
+      if (!TB) { bn = e % DBN; bk = e / DBN; } else { bk = e % BK; bn = e / BK; }
+      int gn = n0 + bn;
+      gk = k0 + bk;
+      Bs[bk][bn] = (gn < N && gk < K) ? (TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + i * 16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + j * 16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty + i * 16;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx + j * 16;
+      if (gn < N) C[(int64_t)gm * ldc + gn] = acc[i][j];
+    }
+  }
+}
+
+NFB_API int nfb_gemm_f64(int transA, int transB, int M, int N, int K, const double* A, int64_t lda, int64_t strideA, const double* B,
+                         int64_t ldb, int64_t strideB, double* C, int64_t ldc, int64_t strideC, int batch) {
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  if (batch > 65535) return NFB_FAIL("nfb_gemm_f64: batch %d > 65535", batch);
+  dim3 grid((unsigned)nfb_cdiv(N, DBN), (unsigned)nfb_cdiv(M, DBM), (unsigned)batch);
+  if (grid.y > 65535) return NFB_FAIL("nfb_gemm_f64: M too large");
+  cudaStream_t s = nfb_cur_stream();
+#define GO(TA, TB) k_dgemm<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC)
+  if (!transA && !transB) GO(false, false);
+  else if (!transA && transB) GO(false, true);
+  else if (transA && !transB) GO(true, false);
+  else GO(true, true);
+#undef GO
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

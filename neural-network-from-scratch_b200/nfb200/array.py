@@ -43,6 +43,21 @@ _CODE = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtyp
          np.dtype(np.int64): _lib.I64, np.dtype(np.bool_): _lib.BOOL}
 
 
+# implicit device -> host conversion through np.asarray(array) / __array__: off (TypeError, like CuPy) unless a caller that
+# runs UNCHANGED reference code opts in; see B200Array.__array__
+_IMPLICIT_HOST = {"allow": False, "count": 0}
+
+
+def set_implicit_host_conversion(allow: bool) -> int:
+    """Allow / forbid np.asarray(B200Array).  Returns the number of implicit host copies made so far."""
+    _IMPLICIT_HOST["allow"] = bool(allow)
+    return _IMPLICIT_HOST["count"]
+
+
+def implicit_host_conversions() -> int:
+    return _IMPLICIT_HOST["count"]
+
+
 def dtype_code(dt) -> int:
     if dt is bfloat16 or dt == "bfloat16":
         return _lib.BF16
@@ -225,6 +240,14 @@ class B200Array:
         return out
 
     def __array__(self, dtype=None, copy=None):
+        if _IMPLICIT_HOST["allow"]:
+            # opt-in (set_implicit_host_conversion): the reference's own optimizers ask for NumPy arrays themselves --
+            # `param.data = np.asarray(new_data, dtype=...)` (optim/adam.py:245) -- which np.asarray can only satisfy with a
+            # host copy; the Tensor.data setter moves the result back into the parameter's device buffer.  Counted, so a
+            # caller can see how many round trips unchanged reference code costs.
+            _IMPLICIT_HOST["count"] += 1
+            out = self.get()
+            return out if dtype is None else out.astype(dtype, copy=False)
         raise TypeError("Implicit conversion of a B200Array to a NumPy array is not allowed; "
                         "call .get() or backend.to_numpy() to copy it to the host explicitly.")
 
@@ -391,6 +414,10 @@ class B200Array:
         """ints / slices / None / Ellipsis -> (shape, strides, offset) of a view, or None."""
         if not isinstance(key, tuple):
             key = (key,)
+        if any(isinstance(k, B200Array) and k.ndim == 0 and k.dtype is not bfloat16 and np.dtype(k.dtype).kind in "iu" for k in key):
+            key = tuple(int(k.item()) if (isinstance(k, B200Array) and k.ndim == 0) else k for k in key)   # a device scalar used as an index
+        if any(isinstance(k, np.ndarray) and k.ndim == 0 and k.dtype.kind in "iu" for k in key):
+            key = tuple(int(k) if (isinstance(k, np.ndarray) and k.ndim == 0) else k for k in key)
         if any(isinstance(k, (list, np.ndarray, B200Array)) for k in key):
             return None
         n_specified = sum(1 for k in key if k is not None and k is not Ellipsis)
@@ -435,12 +462,14 @@ class B200Array:
         if basic is not None:
             shape, strides, off = basic
             return B200Array(self._buf, shape, self.dtype, strides, off)
-        # advanced indexing: a single integer index array on axis 0 (embedding-style row gather)
+        # advanced indexing: a single integer index array on axis 0 (embedding-style row gather), or one integer array per
+        # axis of a 2-D array (x[rows, cols]: the loss picks p[i, target_i], functional/loss.py:55-60)
         if isinstance(key, tuple):
             if len(key) == 1:
                 key = key[0]
             else:
-                raise IndexError("b200: only x[index_array] (row gather on axis 0) advanced indexing is supported on device")
+                flat = self._pair_index(key)
+                return take_rows(self.contiguous().reshape(-1, 1), flat).reshape(flat.shape)
         idx = key if isinstance(key, B200Array) else B200Array.from_numpy(np.asarray(key))
         if idx.dtype is bfloat16 or np.dtype(idx.dtype).kind == "b":
             raise IndexError("b200: boolean-mask indexing is not supported on device")
@@ -448,10 +477,38 @@ class B200Array:
             raise IndexError("arrays used as indices must be of integer (or boolean) type")
         return take_rows(self, idx)
 
+    def _pair_index(self, key) -> "B200Array":
+        """x[rows, cols] on a 2-D array with two 1-D integer index arrays (host or device) -> flat int64 element indices."""
+        if self.ndim != 2 or len(key) != 2:
+            raise IndexError("b200: advanced indexing supports x[index_array] and, on 2-D arrays, x[row_indices, col_indices]")
+        parts = []
+        for k, n in zip(key, self.shape):
+            if isinstance(k, numbers.Integral):
+                k = np.asarray([int(k)])
+            k = k if isinstance(k, B200Array) else B200Array.from_numpy(np.asarray(k))
+            if k.dtype is bfloat16 or np.dtype(k.dtype).kind not in "iu":
+                raise IndexError("arrays used as indices must be of integer type")
+            k = k.astype(np.int64) if k.dtype != np.dtype(np.int64) else k
+            parts.append(where(binary("lt", k, 0), binary("add", k, n), k))     # NumPy-style negative indices
+        rows, cols = parts
+        return binary("add", binary("mul", rows, self.shape[1]), cols)
+
     def __setitem__(self, key, value):
         basic = self._basic_index(key)
+        if basic is None and isinstance(key, tuple) and len(key) == 2:
+            # x[rows, cols] = v with UNIQUE (row, col) pairs (`grad[arange(B), targets] -= 1`, functional/loss.py:93): written as
+            # x += scatter(v - x[rows, cols]), which equals the assignment when no pair repeats (with repeats NumPy keeps the
+            # last write; the reference never relies on that here)
+            if self.dtype != np.dtype(np.float32) or not self.is_contiguous:
+                raise IndexError("b200: x[rows, cols] = v is supported on contiguous float32 arrays")
+            flat = self._pair_index(key)
+            cur = take_rows(self.reshape(-1, 1), flat).reshape(flat.shape)
+            val = value if isinstance(value, B200Array) else B200Array.from_numpy(np.broadcast_to(np.asarray(value, np.float32), flat.shape).copy())
+            delta = binary("sub", val.astype(np.float32) if val.dtype != np.dtype(np.float32) else val, cur).contiguous()
+            call("nfb_scatter_add_rows", dtype_code(flat.dtype), dtype_code(delta.dtype), delta.ptr, flat.contiguous().ptr, self.ptr, flat.size, 1, self.size, 1)
+            return
         if basic is None:
-            raise IndexError("b200: only basic (slice/int) indexing is supported for assignment on device")
+            raise IndexError("b200: only basic (slice/int) indexing and x[rows, cols] are supported for assignment on device")
         shape, strides, off = basic
         view = B200Array(self._buf, shape, self.dtype, strides, off)
         view._assign(value)
@@ -478,6 +535,10 @@ class B200Array:
     def __iter__(self):
         if not self.shape:
             raise TypeError("iteration over a 0-d array")
+        if self.ndim == 1 and self.dtype is not bfloat16 and np.dtype(self.dtype).kind in "iub":
+            # an index loop (`for i, idx in enumerate(flat_indices)`, nn/embedding.py:52-55) wants host integers: ONE copy
+            yield from self.get().tolist()
+            return
         for i in range(self.shape[0]):
             yield self[i]
 
@@ -845,12 +906,11 @@ def matmul(a, b) -> B200Array:
     if a.ndim == 0 or b.ndim == 0:
         raise ValueError("matmul: Input operand does not have enough dimensions")
     rt = _result_dtype(a, b, "mul")
-    if rt != np.dtype(np.float32):
-        if rt.kind in "iub" or rt == np.dtype(np.float64):
-            # integer / fp64 contractions are not on the hot path: run them in fp32 only when exact enough
-            raise TypeError(f"b200: matmul supports float32 operands (got {a.dtype} @ {b.dtype}); cast explicitly")
-    a = a.astype(np.float32) if a.dtype != rt else a
-    b = b.astype(np.float32) if b.dtype != rt else b
+    if rt.kind in "iub":
+        raise TypeError(f"b200: matmul supports float32 / float64 operands (got {a.dtype} @ {b.dtype}); cast explicitly")
+    f64 = rt == np.dtype(np.float64)     # fp64: a plain SIMT kernel (Backend.matmul on the reference's default float64 arrays)
+    a = a.astype(rt) if a.dtype != rt else a
+    b = b.astype(rt) if b.dtype != rt else b
     a1, b1 = a.ndim == 1, b.ndim == 1
     if a1:
         a = a.reshape(1, -1)
@@ -862,7 +922,8 @@ def matmul(a, b) -> B200Array:
         raise ValueError(f"matmul: Input operand 1 has a mismatch in its core dimension 0 (size {K2} is different from {K})")
     batch_shape = np.broadcast_shapes(a.shape[:-2], b.shape[:-2])
     nb = _prod(batch_shape)
-    out = B200Array.empty(tuple(batch_shape) + (M, N), np.float32)
+    out = B200Array.empty(tuple(batch_shape) + (M, N), rt)
+    esz = 8 if f64 else 4
 
     def prep(x, rows, cols):
         """-> (array, trans flag, ld, batch stride) without copying when a matrix is row- or col-major."""
@@ -892,8 +953,12 @@ def matmul(a, b) -> B200Array:
         bb, tb, ldb, sb = prep(b, K, N)
         for b0 in range(0, nb, 65535):
             cnt = min(65535, nb - b0)
-            call("nfb_gemm_f32", ta, tb, M, N, K, 1.0, aa.ptr + b0 * sa * 4, lda, sa, bb.ptr + b0 * sb * 4, ldb, sb, 0.0,
-                 out.ptr + b0 * M * N * 4, N, M * N, cnt, None)
+            if f64:
+                call("nfb_gemm_f64", ta, tb, M, N, K, aa.ptr + b0 * sa * esz, lda, sa, bb.ptr + b0 * sb * esz, ldb, sb,
+                     out.ptr + b0 * M * N * esz, N, M * N, cnt)
+            else:
+                call("nfb_gemm_f32", ta, tb, M, N, K, 1.0, aa.ptr + b0 * sa * 4, lda, sa, bb.ptr + b0 * sb * 4, ldb, sb, 0.0,
+                     out.ptr + b0 * M * N * 4, N, M * N, cnt, None)
     elif out.size:
         out.fill(0.0)
     if a1 and b1:
@@ -1067,7 +1132,14 @@ def _np_any(a, axis=None, **kw):
     return a.any()
 
 
+def _np_broadcast_arrays(*arrays, **kw):
+    arrs = [x if isinstance(x, B200Array) else B200Array.from_numpy(np.asarray(x)) for x in arrays]
+    shape = np.broadcast_shapes(*[x.shape for x in arrs])
+    return [x if x.shape == tuple(shape) else x.broadcast_to(tuple(shape)) for x in arrs]
+
+
 _FUNCTIONS = {
+    "broadcast_arrays": _np_broadcast_arrays,
     "sum": _np_sum, "mean": _np_mean,
     "max": lambda a, axis=None, out=None, keepdims=False, **kw: reduce("max", a, axis, keepdims),
     "amax": lambda a, axis=None, out=None, keepdims=False, **kw: reduce("max", a, axis, keepdims),

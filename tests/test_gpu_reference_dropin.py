@@ -41,6 +41,7 @@ CHECKS = ["registry: install_into_reference",
           "reference GPT-2 block pieces (models/language/gpt2.py: RMSNorm, SwiGLU, GPT2Attention) forward"]
 
 
+
 @needs_ref
 @pytest.mark.parametrize("name", CHECKS)
 def test_unmodified_reference_code_runs_on_the_b200_backend(dropin_results, name):
@@ -55,14 +56,23 @@ def test_reference_backend_test_file_with_b200_registered():
     """The reference's own tests/test_backends.py (unmodified) with "b200" / "cuda" in available_backends(): its parametrised
     tests iterate over every registered backend, so the KATs (2x2 known answers, reductions, clip, comparisons ...) now run
     on the B200 backend too."""
-    plugin = os.path.join(HERE, "ref_dropin_plugin.py")
-    assert os.path.exists(plugin)
     env = dict(os.environ, PYTHONPATH=HERE + os.pathsep + os.environ.get("PYTHONPATH", ""), NEURAL_ARCH_REFERENCE=os.path.join(REF, "neural_arch"))
-    r = subprocess.run([sys.executable, "-m", "pytest", "-c", os.devnull, "--rootdir", "/tmp", "-p", "no:cacheprovider", "-p", "ref_dropin_plugin",
-                        os.path.join(REF, "tests", "test_backends.py"), "-q", "-rA", "--tb=short", "-W", "ignore"], capture_output=True, text=True, timeout=600, cwd="/tmp", env=env)
-    out = {}
-    for m in re.finditer(r"^(PASSED|FAILED|ERROR)\s+(\S*::\S+)", r.stdout, flags=re.M):
-        out[m.group(2)] = m.group(1)
-    bad = {t: o for t, o in out.items() if o != "PASSED"}
-    assert out and not bad, f"{bad}\n{r.stdout[-4000:]}\n{r.stderr[-1500:]}"
-    assert "B200_REGISTERED" in r.stdout + r.stderr or any("b200" in t or "cuda" in t for t in out), r.stdout[-1500:]
+
+    def run(plugin):
+        r = subprocess.run([sys.executable, "-m", "pytest", "-c", os.devnull, "--rootdir", "/tmp", "-p", "no:cacheprovider", "-p", plugin,
+                            os.path.join(REF, "tests", "test_backends.py"), "-q", "-rA", "--tb=short", "-W", "ignore"], capture_output=True, text=True, timeout=600, cwd="/tmp", env=env)
+        out = {}
+        for m in re.finditer(r"^(PASSED|FAILED|ERROR)\s+\S*(::\S+)", r.stdout, flags=re.M):
+            out[m.group(2)] = m.group(1)
+        return out, r.stdout[-4000:] + r.stderr[-1500:]
+
+    base, log0 = run("ref_real_plugin")          # the reference's own backends only (numpy + its Numba "jit" backend)
+    with_b200, log1 = run("ref_dropin_plugin")   # + "b200" / "cuda" registered into the reference's registry
+    assert "B200_REGISTERED" in log1, log1
+    passed0 = {t for t, o in base.items() if o == "PASSED"}
+    assert len(passed0) >= 10, log0
+    lost = sorted(t for t in passed0 if with_b200.get(t) != "PASSED")
+    # (two tests of that file fail on the reference itself here -- its Numba backend is "not faster than CPU" and maps 'mps' to
+    # 'cpu' -- with or without this backend; everything that passes without it must pass with it)
+    assert not lost, f"pass on the reference's own backends, fail once b200 is registered: {lost}\n{log1}"
+    assert [o for t, o in with_b200.items() if t.endswith("::test_matrix_operations")] == ["PASSED"], log1   # float64 (batched) matmul on the device

@@ -226,7 +226,7 @@ def test_cross_entropy_class_id_outside_the_vocabulary(be, rows, V, logits_bf16)
     ld = (V + 7) // 8 * 8
     x = rng.standard_normal((rows, ld)).astype(np.float32)
     t = rng.integers(0, V, rows).astype(np.int64)
-    t[1], t[3] = -100, V + 5          # an ignore_index-style label and a corrupt one
+    t[1], t[3] = -V - 3, V + 5        # below -V (an ignore_index such as -100 on a small vocabulary) and beyond the last class
     t[2] = -1                         # NumPy-style negative index: valid (last class)
     xd = be.from_numpy(x)
     if logits_bf16:

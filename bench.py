@@ -5,12 +5,19 @@ public API (Tensor / nn / optim on the b200 backend), one step = forward + cross
 over one synthetic (8, 512) token batch.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's arm (N > 1 under torchrun: data parallel)
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: the NumPy oracle port on the host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores
 
-One JSON line on stdout (rank 0).  `value` = whole-job tokens/s with the batch resident in HBM, device-timed with
-CUDA events (max over ranks); `e2e` = the same step fed from pinned HOST buffers (H2D of ids/labels and D2H of the
-loss inside the timed region); `roofline` = the tcgen05 GEMM (dominant kernel) measured with CUDA events around every
-GEMM launch inside the timed steps vs the measured bf16 peak; `cpu_baseline` = the oracle port on a bounded sample.
+One JSON line on stdout (rank 0).
+  value             whole-job tokens/s with the batch resident in HBM, device-timed with CUDA events (max over ranks)
+  e2e               the same step fed from pinned HOST buffers (H2D of ids/labels and D2H of the loss inside the timed region)
+  roofline          the tcgen05 GEMM (dominant kernel): CUDA-event pairs around every launch of a single-stream replay of the
+                    step (`frac`), next to the kernel's own %globaltimer span (`frac_device_clock`), vs the measured bf16 peak
+  roofline_classes  every kernel class of the step (tensor: GEMM, attention; HBM: norm, cross entropy, optimizer, elementwise):
+                    algorithmic work / event-timed duration vs the measured peaks
+  other_configs     BASELINE.json configs[2..4]: BERT-base MLM B32xS512 bf16, ViT-B/16 B64 (data parallel at N GPUs) and, at
+                    8 GPUs, GPT-2 medium B64xS1024 -- step time and throughput of each on the same N GPUs
+  ddp_parity        (N > 1) a 3-step check that N ranks on their shards == one rank on the global batch
+  cpu_baseline      (N = 1) the reference's own CPU step on a bounded sample, and the oracle port's
 """
 import argparse
 import json
@@ -31,7 +38,9 @@ import numpy as np  # noqa: E402
 GPT2_SMALL = {"vocab_size": 50257, "n_positions": 1024, "n_embd": 768, "n_layer": 12, "n_head": 12}
 BATCH, SEQ = 8, 512
 TRAIN_FLOP_PER_TOKEN = 712.88e6  # SURVEY App. C (GEMM + logits + attention, x3 for training)
-GEMM_DRAM_BYTES_PER_LAUNCH = 34.3e6  # measured, see roofline.traffic_source
+# dram__bytes_read.sum + dram__bytes_write.sum per k_gemm_tc launch, launch-weighted over one step (profiles/r02_ncu_gemm_full.txt)
+GEMM_DRAM_BYTES_PER_LAUNCH = 45.0e6
+REF_DIR = os.path.join(ROOT, "oracle", "_ref", "neural_arch")
 
 
 def peaks():
@@ -88,10 +97,26 @@ def synthetic_batch(rng, batch=BATCH, seq=SEQ, vocab=GPT2_SMALL["vocab_size"]):
 
 
 # ------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_oracle_run(steps, warmup, sample_batch=1):
-    """The oracle port of the reference NumPy path (forward + CE + backward + AdamW) at FULL model size on a bounded
-    sample: `sample_batch` of the 8 sequences per step.  Returns (tokens/s, cores, description)."""
+def host_threads():
+    """Make the BLAS / OpenMP pools use every host core (torchrun exports OMP_NUM_THREADS=1 to its workers, which silently
+    turned the CPU arm single-threaded at N > 1) and return the thread count the BLAS pool REALLY has."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        pools = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if pools:
+            return int(max(pools))
+    except Exception:
+        pass
+    return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
+def cpu_oracle_run(steps, warmup, sample_batch):
+    """The oracle PORT of the reference NumPy path with a CONNECTED graph (forward + CE + full backward + AdamW over all
+    109 M parameters) at full model size on `sample_batch` of the 8 sequences per step."""
     from oracle.np_model import GPT2Oracle, OracleAdamW
+    cores = host_threads()
     np.random.seed(0)
     model = GPT2Oracle(GPT2_SMALL, grad_clip=True)
     opt = OracleAdamW(model.params, lr=5e-4, weight_decay=0.1)
@@ -101,32 +126,166 @@ def cpu_oracle_run(steps, warmup, sample_batch=1):
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         model.zero_grad()
-        out = model.forward(ids, labels)
+        model.forward(ids, labels)
         opt.step(model.backward())
-        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(dt)
+            times.append(time.perf_counter() - t0)
     t = float(np.median(times))
-    cores = os.cpu_count() or 1
-    return sample_batch * SEQ / t, cores, t, f"oracle port (NumPy/OpenBLAS, all {cores} host threads), full GPT-2 small, {sample_batch} of {BATCH} sequences x {SEQ} tokens per step, median of {steps}"
+    return {"value": sample_batch * SEQ / t, "unit": "tokens/s", "cores": cores, "kind": "port", "step_s": t,
+            "sample": f"oracle port (NumPy/OpenBLAS on {cores} threads; connected graph: forward + CE + full backward + AdamW), full GPT-2 small, "
+                      f"{sample_batch} of {BATCH} sequences x {SEQ} tokens per step, median of {steps}"}
+
+
+def cpu_reference_run(steps, warmup, sample_batch, device="cpu"):
+    """The UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py; its missing `core` from oracle/compat) through its
+    own public API and stock configuration (Numba JIT + fusion defaults), as examples/training/gpt2_training.py:344-420 drives
+    it: model(input_ids) -> logits re-wrapped in a fresh Tensor -> cross_entropy_loss -> loss.backward() -> AdamW.step().
+    NOTE: that re-wrap severs the graph -- the reference's backward stops at the logits and its optimizer finds no
+    gradients -- so a reference "step" is a forward pass + loss; the port above does the whole step."""
+    os.environ["NEURAL_ARCH_REFERENCE"] = REF_DIR
+    if os.path.join(ROOT, "oracle", "compat") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "compat"))
+    import neural_arch  # noqa: F401
+    from neural_arch.core import Tensor, get_default_device, set_default_device
+    from neural_arch.functional import cross_entropy_loss
+    from neural_arch.models.language.gpt2 import GPT2
+    from neural_arch.optim import AdamW
+    cores = host_threads()
+    prev_device = get_default_device()
+    set_default_device(device)      # "cpu": the reference's NumPy backend on the host cores (the CPU arm)
+    try:
+        return _reference_steps(Tensor, cross_entropy_loss, GPT2, AdamW, cores, steps, warmup, sample_batch, device)
+    finally:
+        set_default_device(prev_device)
+
+
+def _reference_steps(Tensor, cross_entropy_loss, GPT2, AdamW, cores, steps, warmup, sample_batch, device):
+    np.random.seed(0)
+    model = GPT2(GPT2_SMALL)
+    opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1)
+    rng = np.random.default_rng(1234)
+    ids, labels = synthetic_batch(rng, sample_batch, SEQ)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = model(Tensor(ids))
+        logits = out["logits"] if isinstance(out, dict) else out
+        v = logits.shape[-1]
+        loss = cross_entropy_loss(Tensor(logits.data.reshape(-1, v), requires_grad=True), Tensor(labels.reshape(-1)))
+        loss.backward()
+        opt.step()
+        float(loss.data)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    where = f"{cores} BLAS threads" if device == "cpu" else f"Device.{device} tensors = the b200 backend through the reference's own call sites"
+    return {"value": sample_batch * SEQ / t, "unit": "tokens/s", "cores": cores, "kind": "reference", "step_s": t,
+            "sample": f"unmodified reference (oracle/_ref, stock Numba-JIT / fusion config, {where}), gpt2_small, the training step of "
+                      f"examples/training/gpt2_training.py (forward + loss; its backward stops at the logits, SURVEY F6), {sample_batch} of {BATCH} sequences "
+                      f"x {SEQ} tokens per step, median of {steps} after {warmup} warm-up"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
-    tps, cores, t, desc = cpu_oracle_run(steps, warm)
-    line = {"impl": "reference", "metric": "training tokens/sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    if os.path.isdir(REF_DIR):
+        r = cpu_reference_run(steps, warm, BATCH)
+    else:
+        r = cpu_oracle_run(steps, warm, BATCH)
+    desc = r["sample"]
+    line = {"impl": "reference", "metric": "training tokens/sec", "value": r["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step, batch 8 x seq 512", "sample": desc},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": r["kind"], "sample": desc},
+            "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ per-class work accounting
+DT_SIZE = {0: 4, 1: 8, 2: 4, 3: 8, 4: 1, 5: 2}   # NfbDType -> bytes
+
+
+def _attn_flops(B, H, S, Skv, D, mode, backward):
+    f = 4.0 * B * H * S * Skv * D * (2.0 if backward else 1.0)    # SURVEY 8d: fwd 4 S^2 hd, bwd 2x (the QK^T recompute is not counted)
+    return f * (0.5 if (mode & 1) else 1.0)                        # causal: halved (stated in the line)
+
+
+def work_of(name, a):
+    """(class, 'flop' | 'byte', ALGORITHMIC amount) of one C-ABI call from its arguments (include/nfb200.h signatures)."""
+    if name == "nfb_gemm_bf16":
+        return "gemm", "flop", 2.0 * a[2] * a[3] * a[4]
+    if name == "nfb_gemm_bf16_grouped":
+        return "gemm", "flop", sum(2.0 * a[3][g] * a[4][g] * a[5][g] for g in range(a[0]))
+    if name == "nfb_flash_attn_fwd_gqa":
+        return "attention", "flop", _attn_flops(a[6], a[7], a[9], a[20], a[10], a[22], False)
+    if name == "nfb_flash_attn_bwd_gqa":
+        return "attention", "flop", _attn_flops(a[10], a[11], a[13], a[24], a[14], a[26], True)
+    if name == "nfb_norm_fwd":      # read x (+ residual, write the sum), write y
+        n = float(a[11]) * a[12]
+        return "norm", "byte", n * (DT_SIZE[a[1]] + DT_SIZE[a[2]] + (2 * DT_SIZE[a[1]] if a[4] else 0))
+    if name == "nfb_norm_bwd":      # read dy, x (+ skip gradient), write dx (+ bf16 twin)
+        n = float(a[13]) * a[14]
+        return "norm", "byte", n * (DT_SIZE[a[2]] + 2 * DT_SIZE[a[1]] + (DT_SIZE[a[1]] if a[8] else 0) + (2 if a[16] else 0))
+    if name == "nfb_cross_entropy_ex":
+        return "cross_entropy", "byte", float(a[7]) * a[8] * (DT_SIZE[a[0]] + (DT_SIZE[a[6]] if a[5] else 0))
+    if name in ("nfb_adam_step", "nfb_adam_step_ex"):   # p r+w, g r, m r+w, v r+w (+ bf16 shadow w)
+        msz = 8 if a[1] == 1 else 4
+        return "optimizer", "byte", float(a[7]) * (8 + 4 + 4 * msz + (2 if a[6] else 0))
+    if name == "nfb_swiglu_fwd":
+        return "elementwise", "byte", float(a[4]) * a[5] * 3 * DT_SIZE[a[0]]
+    if name == "nfb_swiglu_bwd":
+        return "elementwise", "byte", float(a[6]) * a[7] * 5 * DT_SIZE[a[0]]
+    if name == "nfb_rope":
+        return "elementwise", "byte", float(a[6]) * a[7] * a[8] * a[9] * max(1, a[4]) * 2 * DT_SIZE[a[0]]
+    if name == "nfb_colsum":
+        return "elementwise", "byte", float(a[2]) * a[3] * DT_SIZE[a[0]]
+    if name == "nfb_gather_rows":
+        return "elementwise", "byte", float(a[6]) * a[7] * (DT_SIZE[a[1]] + DT_SIZE[a[2]])
+    if name == "nfb_scatter_add_rows":
+        return "elementwise", "byte", float(a[5]) * a[6] * (DT_SIZE[a[1]] + 8)
+    if name == "nfb_cast":
+        return "elementwise", "byte", float(a[4]) * (DT_SIZE[a[0]] + DT_SIZE[a[1]])
+    if name == "nfb_unary":
+        return "elementwise", "byte", float(a[4]) * 2 * DT_SIZE[a[1]]
+    if name == "nfb_unary_bwd":
+        return "elementwise", "byte", float(a[5]) * 3 * DT_SIZE[a[1]]
+    if name == "nfb_binary_scalar":
+        return "elementwise", "byte", float(a[5]) * 2 * DT_SIZE[a[1]]
+    if name == "nfb_add3":
+        return "elementwise", "byte", float(a[4]) * 16
+    return None
+
+
+PROFILED = ("nfb_gemm_bf16", "nfb_gemm_bf16_grouped", "nfb_flash_attn_fwd_gqa", "nfb_flash_attn_bwd_gqa", "nfb_norm_fwd", "nfb_norm_bwd",
+            "nfb_cross_entropy_ex", "nfb_adam_step", "nfb_adam_step_ex", "nfb_swiglu_fwd", "nfb_swiglu_bwd", "nfb_rope", "nfb_colsum", "nfb_gather_rows",
+            "nfb_scatter_add_rows", "nfb_cast", "nfb_unary", "nfb_unary_bwd", "nfb_binary_scalar", "nfb_add3")
+
+
 # ------------------------------------------------------------------------------------------ this repo's arm
+class Job:
+    """One model + optimizer (+ DDP wrapper) + a persistent synthetic batch + the step closure."""
+
+    def __init__(self, model, opt, ddp, args_kw, loss_of=None):
+        self.model, self.opt, self.ddp = model, opt, ddp
+        self.fwd = ddp if ddp is not None else model
+        self.args, self.kwargs = args_kw
+        self.loss_of = loss_of or (lambda out: out["loss"])
+
+    def step(self):
+        self.opt.zero_grad()
+        loss = self.loss_of(self.fwd(*self.args, **self.kwargs))
+        loss.backward()
+        if self.ddp is not None:
+            self.ddp.step_optimizer(self.opt)   # bucket-pipelined: finish_gradient_sync() + opt.step()
+        else:
+            self.opt.step()
+        return loss
+
+
 def run_b200(args):
     import nfb200
     from nfb200 import _lib, kernels as K, runtime as R
@@ -134,6 +293,7 @@ def run_b200(args):
     from nfb200.core import Tensor, set_default_device
     from nfb200.models import GPT2
     from nfb200.optim import AdamW
+    from nfb200.training import GraphedStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -141,123 +301,118 @@ def run_b200(args):
     _lib.init(local)
     if not nfb200.get_backend("b200").is_available:
         raise RuntimeError("bench.py: the b200 backend is unavailable (no libnfb200.so or no GPU); there is no CPU fallback")
-    set_default_device(f"cuda:{local}")
+    dev = f"cuda:{local}"
+    set_default_device(dev)
     K.set_precision(args.precision)
     K.set_wgrad_overlap(args.wgrad_overlap)
     K.set_wgrad_group(args.wgrad_group)
+    if world > 1:
+        from nfb200.distributed import DistributedDataParallel, all_reduce_max_host, init_process_group
+        from nfb200.distributed import barrier as dist_barrier
+        init_process_group("nccl")
+        if args.gemm_sm_limit >= 0:
+            # data parallel: the persistent GEMM grids leave the other SMs to NCCL's channel CTAs while buckets are on the wire
+            _lib.call("nfb_gemm_bf16_set_sm_limit", args.gemm_sm_limit)
+
+    def barrier():
+        if world > 1:
+            dist_barrier()
+        R.synchronize()
+
+    def wrap(model):
+        return DistributedDataParallel(model, bucket_size_mb=args.bucket_mb) if world > 1 else None
+
+    def timed(fn, n):
+        e0, e1 = R.Event(), R.Event()
+        barrier()
+        e0.record()
+        out = None
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_ms(e1)
+        if world > 1:
+            ms = all_reduce_max_host(ms)
+        return ms, out
+
+    def capture(job, warm):
+        for _ in range(warm):
+            job.step()
+        barrier()
+        if not args.graph:
+            return job.step
+        g = GraphedStep(job.step, warmup=2, optimizers=[job.opt])
+        for _ in range(2):
+            g()
+        barrier()
+        return g
+
+    # ====================================================================== main config: GPT-2 small B8 x S512
     np.random.seed(0)  # identical replicas on every rank (the reference relies on seeding too)
     model = GPT2(GPT2_SMALL)
-    ddp = None
-    if world > 1:
-        from nfb200.distributed import DistributedDataParallel, init_process_group
-        init_process_group("nccl")
-        ddp = DistributedDataParallel(model, bucket_size_mb=args.bucket_mb)
+    ddp = wrap(model)
     opt = AdamW(model.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float32")
     if ddp is None and args.step_in_backward:
         opt.enable_step_in_backward(min_run_elems=args.sib_min)   # AdamW launches ride the side stream behind their weight-gradient GEMMs
     rng = np.random.default_rng(1234 + rank)  # each rank gets its own shard: weak scaling, per-GPU batch fixed
     ids_h, labels_h = synthetic_batch(rng)
-    ids_d, labels_d = Tensor(ids_h, device=f"cuda:{local}"), Tensor(labels_h, device=f"cuda:{local}")
-    fwd_model = ddp if ddp is not None else model
-
-    def step(ids_t, labels_t):
-        opt.zero_grad()
-        loss = fwd_model(ids_t, labels=labels_t)["loss"]
-        loss.backward()
-        if ddp is not None:
-            ddp.step_optimizer(opt)   # bucket-pipelined: finish_gradient_sync() + opt.step()
-        else:
-            opt.step()
-        return loss
-
-    def barrier():
-        if ddp is not None:
-            from nfb200.distributed import barrier as b
-            b()
-        R.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step(ids_d, labels_d)
-    barrier()
-    graphed = None
-    if args.graph:
-        # steady-state step captured once into a CUDA graph (launch-bound otherwise: ~500 launches per step)
-        from nfb200.training import GraphedStep
-        graphed = GraphedStep(lambda: step(ids_d, labels_d), warmup=2, optimizers=[opt])
-        for _ in range(2):
-            graphed()
-        barrier()
-    # ---- timed region 1: inputs resident in HBM (inputs 8x512 tokens; the step streams >> L2 (126 MB) of weights/activations)
+    job = Job(model, opt, ddp, ((Tensor(ids_h, device=dev),), {"labels": Tensor(labels_h, device=dev)}))
+    run = capture(job, max(args.warmup, 3))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # kernels per step (counted by the library on an eager step; a graph replay launches the same kernels)
     _l0 = _lib.launch_count()
-    step(ids_d, labels_d)
-    graphed_launches = _lib.launch_count() - _l0
-    launches0 = _lib.launch_count()
-    e0, e1 = R.Event(), R.Event()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        loss = graphed() if graphed is not None else step(ids_d, labels_d)
-    e1.record()
-    e1.synchronize()
-    barrier()
-    ms = e0.elapsed_ms(e1)
-    launches = _lib.launch_count() - launches0
+    job.step()                                   # kernels per step (counted on an eager step; a replay launches the same kernels)
+    launches_per_step = _lib.launch_count() - _l0
+    # ---- timed region 1: inputs resident in HBM (the step streams >> L2 (126 MB) of weights / activations / optimizer state)
+    ms, loss = timed(run, args.steps)
     final_loss = float(loss.item())
-    # ---- timed region 1b: the same steps with a CUDA-event pair around every tcgen05 GEMM launch (roofline numerator);
-    # kept apart from region 1 so the ~200 extra event records per step do not perturb `value`
-    gemm_prof, ms_prof, prof_steps, prof_mode = None, None, max(1, min(args.steps, 5)), None
-    if args.profile_gemm and args.graph:
-        # the event pairs are CAPTURED with the step (event-record nodes of a second graph), so the per-launch durations
-        # are those of the replayed graph -- same kernels, same neighbours and cache state as in timed region 1 --
-        # rather than of an eager step whose launch gaps leave the GPU idle between kernels.  Every rank captures /
-        # replays (the graph contains the collectives); rank 0 reads the events of the last replay.
+
+    # ---- timed region 1b: per-kernel measurement on a SINGLE-STREAM capture of the same step (with the weight-gradient branch
+    # on its side stream two kernels share the SMs and a pair of events no longer brackets one kernel's own duration):
+    # CUDA-event pairs (external event-record nodes of the graph) around every profiled C-ABI call + the GEMM kernel's own
+    # %globaltimer span; durations are those of the last replay.  Kept apart from region 1 so the event nodes do not perturb `value`.
+    prof, spans, ms_prof = None, None, None
+    if args.profile and args.graph:
         try:
-            from nfb200.training import GraphedStep
-            # single-stream capture for this pass: with the weight-gradient GEMMs on the side stream two kernels share
-            # the SMs and an event pair no longer brackets ONE kernel's own duration
             K.set_wgrad_overlap(False)
-            step(ids_d, labels_d)   # warm the allocator in this mode
-            K.GEMM_PROFILE = []
-            gprof = GraphedStep(lambda: step(ids_d, labels_d), warmup=1, optimizers=[opt])
-            n_all = len(K.GEMM_PROFILE)
-            gemm_prof = K.GEMM_PROFILE[n_all // 2:]   # GraphedStep ran the step twice (eager warm-up, then the capture)
-            K.GEMM_PROFILE = None
-            K.set_wgrad_overlap(args.wgrad_overlap)
-            p0, p1 = R.Event(), R.Event()
+            job.step()   # warm the allocator in this mode
+            cap = 4096
+            span_buf = B200Array.empty((2 * cap,), np.int64)
+            records, spans_meta = [], []
+            _lib.PROFILE_NAMES = frozenset(PROFILED)
+
+            def profiled_step():
+                _lib.PROFILE = records
+                K.GEMM_SPAN = {"buf": span_buf, "cap": cap, "meta": spans_meta}
+                try:
+                    return job.step()
+                finally:
+                    _lib.PROFILE = None
+                    K.GEMM_SPAN = None
+
+            gprof = GraphedStep(profiled_step, warmup=1, optimizers=[opt])
+            prof = records[len(records) // 2:]   # GraphedStep ran the step twice (eager warm-up, then the capture): the captured half
             gprof()
-            barrier()
-            p0.record()
-            for _ in range(prof_steps):
-                gprof()
-            p1.record()
-            p1.synchronize()
-            ms_prof = p0.elapsed_ms(p1) / prof_steps   # one step: the captured events hold the LAST replay
-            _ = sum(a.elapsed_ms(b) for a, b, _, _ in gemm_prof)   # raises if captured events cannot be read
-            prof_mode = "graph"
-            if rank != 0:
-                gemm_prof = None
-        except Exception as exc:  # noqa: BLE001 -- fall back to the eager measurement below
-            sys.stderr.write(f"bench.py: captured-event GEMM profile unavailable ({exc}); using the eager one\n")
-            K.GEMM_PROFILE = None
+            _lib.call("nfb_memset", span_buf.ptr, 0xFF, 2 * cap * 8)   # arm: the next replay stamps min(start) / ~max(end)
+            R.synchronize()
+            ms_prof, _ = timed(gprof, 1)
+            R.synchronize()
+            raw = span_buf.get().view(np.uint64).reshape(cap, 2)
+            armed = np.uint64(0xFFFFFFFFFFFFFFFF)
+            spans = [float(np.uint64(~raw[i, 1]) - raw[i, 0]) * 1e-6 for i in range(cap) if raw[i, 0] != armed]   # ns -> ms, in launch order
+            _ = sum(a.elapsed_ms(b) for _, _, a, b in prof)   # raises if captured events cannot be read
             K.set_wgrad_overlap(args.wgrad_overlap)
-            gemm_prof = None
-    if args.profile_gemm and prof_mode is None:
-        if rank == 0:
-            K.GEMM_PROFILE = []
-        p0, p1 = R.Event(), R.Event()
-        p0.record()
-        for _ in range(prof_steps):
-            step(ids_d, labels_d)
-        p1.record()
-        p1.synchronize()
-        ms_prof = p0.elapsed_ms(p1)
-        gemm_prof = K.GEMM_PROFILE
-        K.GEMM_PROFILE = None
-        prof_mode = "eager"
+            if rank != 0:
+                prof = None
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: per-kernel profile unavailable ({type(exc).__name__}: {exc})\n")
+            _lib.PROFILE = None
+            K.GEMM_SPAN = None
+            K.set_wgrad_overlap(args.wgrad_overlap)
+            prof = None
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -272,72 +427,236 @@ def run_b200(args):
     pin_lab[...] = labels_h
     loss_host = np.zeros(1, np.float32)
     dev_ids, dev_lab = B200Array.empty(ids_h.shape, np.int64), B200Array.empty(ids_h.shape, np.int64)
-    t_ids, t_lab = Tensor(dev_ids), Tensor(dev_lab)
-    graphed_e2e = None
-    if args.graph:
-        from nfb200.training import GraphedStep
-        graphed_e2e = GraphedStep(lambda: step(t_ids, t_lab), warmup=1, optimizers=[opt])
+    job_e2e = Job(model, opt, ddp, ((Tensor(dev_ids),), {"labels": Tensor(dev_lab)}))
+    run_e2e = GraphedStep(job_e2e.step, warmup=1, optimizers=[opt]) if args.graph else job_e2e.step
     e2e_steps = max(2, min(args.steps, 10))
-    barrier()
-    f0, f1 = R.Event(), R.Event()
-    f0.record()
-    for _ in range(e2e_steps):
+
+    def e2e_step():
         _lib.call("nfb_memcpy_h2d_async", dev_ids.ptr, pin_ids.ctypes.data, nbytes)
         _lib.call("nfb_memcpy_h2d_async", dev_lab.ptr, pin_lab.ctypes.data, nbytes)
-        l = graphed_e2e() if graphed_e2e is not None else step(t_ids, t_lab)
+        l = run_e2e()
         _lib.call("nfb_memcpy_d2h", loss_host.ctypes.data, l.data.ptr, 4)  # blocks until the step's loss is on the host
-    f1.record()
-    f1.synchronize()
-    barrier()
-    ms_e2e = f0.elapsed_ms(f1)
-    _lib.call("nfb_host_free", pin)
 
-    # max over ranks (device-timed)
-    if ddp is not None:
-        from nfb200.distributed import all_reduce_max_host
-        ms = all_reduce_max_host(ms)
-        ms_e2e = all_reduce_max_host(ms_e2e)
+    ms_e2e, _ = timed(e2e_step, e2e_steps)
+    _lib.call("nfb_host_free", pin)
+    del run, run_e2e, job, job_e2e, model, opt, ddp
+    R.empty_cache()
+
+    # ====================================================================== other configs (BASELINE.json configs[2..4])
+    other = {}
+    if args.other_configs:
+        def other_config(key, build, batch, units, unit, flop_per_unit, lr, wd, steps):
+            try:
+                np.random.seed(0)
+                m = build()
+                d = wrap(m)
+                o = AdamW(m.parameters(), lr=lr, weight_decay=wd, moment_dtype="float32")
+                j = Job(m, o, d, batch())
+                r = capture(j, 3)
+                t_ms, l = timed(r, steps)
+                per = t_ms / steps
+                other[key] = {"ms_per_step": per, "value": units * world * steps / (t_ms / 1e3), "unit": unit, "per_gpu_units": units, "n_gpus": world,
+                              "model_tflops_per_gpu": units * flop_per_unit / (per / 1e3) / 1e12, "loss": float(l.item()), "steps": steps}
+                del r, j, o, d, m
+            except Exception as exc:  # noqa: BLE001 -- one config failing must not take the headline line down
+                other[key] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            R.synchronize()
+            R.empty_cache()
+
+        from nfb200.models import BERTConfig, BERTForMaskedLM, gpt2_medium, vit_b_16
+        orng = np.random.default_rng(4321 + rank)
+
+        def bert_batch():
+            ids = orng.integers(0, 30522, (32, 512))
+            return (Tensor(ids, device=dev),), {"attention_mask": Tensor(np.ones((32, 512), np.float32), device=dev), "labels": Tensor(ids, device=dev)}
+
+        def vit_batch():
+            img = orng.standard_normal((64, 3, 224, 224)).astype(np.float32)
+            return (Tensor(img, device=dev),), {"labels": Tensor(orng.integers(0, 1000, (64,)), device=dev)}
+
+        def g2m_batch():
+            ids, lab = synthetic_batch(orng, 8, 1024)
+            return (Tensor(ids, device=dev),), {"labels": Tensor(lab, device=dev)}
+
+        other_config("bert_base_mlm_b32_s512_bf16", lambda: BERTForMaskedLM(BERTConfig()), bert_batch, 32 * 512, "tokens/s", 706.88e6, 2e-5, 0.01, 8)
+        other_config("vit_b16_b64_224", lambda: vit_b_16(num_classes=1000), vit_batch, 64, "images/s", 105.38e9, 1e-3, 0.1, 8)
+        if world == 8 or args.gpt2_medium:
+            other_config("gpt2_medium_b8_s1024_per_gpu", gpt2_medium, g2m_batch, 8 * 1024, "tokens/s", 2120.72e6, 5e-4, 0.1, 6)
+
+    # ====================================================================== data-parallel parity (N > 1)
+    ddp_parity = None
+    if world > 1 and args.ddp_parity:
+        try:
+            ddp_parity = ddp_parity_check(rank, world, dev)
+        except Exception as exc:  # noqa: BLE001
+            ddp_parity = {"error": f"{type(exc).__name__}: {str(exc)[:300]}", "ok": False}
+
     if rank != 0:
         return
     tokens_per_step = BATCH * SEQ * world
     value = tokens_per_step * args.steps / (ms / 1e3)
     e2e_value = tokens_per_step * e2e_steps / (ms_e2e / 1e3)
     pk = peaks()
-    roof = None
-    if gemm_prof:
-        tot_ms = sum(a.elapsed_ms(b) for a, b, _, _ in gemm_prof)
-        tot_flop = sum(f for _, _, f, _ in gemm_prof)
-        n = len(gemm_prof)
+    roof, classes = None, None
+    if prof:
+        per_class = {}
+        gemm_ev = []
+        for name, a, e0, e1 in prof:
+            w = work_of(name, a)
+            if w is None:
+                continue
+            cls, kind, amount = w
+            t = e0.elapsed_ms(e1)
+            c = per_class.setdefault(cls, {"kind": kind, "work": 0.0, "ms": 0.0, "n": 0})
+            c["work"] += amount
+            c["ms"] += t
+            c["n"] += 1
+            if cls == "gemm":
+                gemm_ev.append((amount, t))
+        # GEMM: event-pair durations vs the kernels' own %globaltimer spans (same launches, same replay)
+        n_g = len(gemm_ev)
+        span_ms = spans[-n_g:] if spans and len(spans) >= n_g else None
+        tot_flop = sum(f for f, _ in gemm_ev)
+        tot_ms = sum(t for _, t in gemm_ev)
         achieved = tot_flop / (tot_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_gemm_tc (tcgen05/TMEM bf16 GEMM)", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": GEMM_DRAM_BYTES_PER_LAUNCH,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per k_gemm_tc launch, ncu --set full capture of this command "
-                                  "(profiles/r01_ncu_gemm_full.txt, LM-head backward re-captured in profiles/r01_ncu_gemm_lmhead_full.txt after the tile-order / split-K change): "
-                                  "LM-head GEMMs 0.44 / 0.66 / 0.74 GB (0.44 / 0.49 / 1.56 before), layer GEMMs 8-41 MB; launch-weighted mean over the 147 launches of a step",
+        inflation_us = None
+        roof = {"bound": "tensor", "kernel": "k_gemm_tc (tcgen05/TMEM bf16 GEMM; the four weight gradients of a block are one grouped stream-K launch)",
+                "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                "achieved_event_pairs": achieved, "frac_event_pairs": achieved / pk["bf16_tflops_sustained"], "avg_launch_ms_event_pairs": tot_ms / n_g,
+                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per k_gemm_tc launch, ncu --set full capture of this command, "
+                                  "launch-weighted mean over the launches of one step (profiles/r02_ncu_gemm_full.txt)",
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                "launches_timed": n, "avg_launch_ms": tot_ms / n, "avg_launch_gflop": tot_flop / n / 1e9, "share_of_step": tot_ms / ms_prof,
-                "timing": ("CUDA event pairs (external event nodes) captured into a single-stream graph of the same step around every GEMM launch; durations of the last replay" if prof_mode == "graph"
-                           else "CUDA event pairs around every GEMM launch of eager (un-graphed) steps"),
-                "algorithmic_flops": "2*M*N*K per launch (fwd, dgrad and wgrad GEMMs of every Linear + logits), summed over the launches of the timed steps"}
+                "launches_timed": n_g, "avg_launch_ms": tot_ms / n_g, "avg_launch_gflop": tot_flop / n_g / 1e9, "share_of_step": tot_ms / ms_prof,
+                "timing": "CUDA event pairs (external event-record nodes) captured into a single-stream graph of the same step around every GEMM launch; durations of the last replay",
+                "algorithmic_flops": "2*M*N*K per contraction (fwd, dgrad and wgrad GEMMs of every Linear + logits), summed over the launches of one step"}
+        if span_ms:
+            sp_tot = sum(span_ms)
+            inflation_us = (tot_ms - sp_tot) / n_g * 1e3
+            dc = tot_flop / (sp_tot / 1e3) / 1e12
+            # headline = the kernel's own duration on the device clock (what ncu's gpu__time_duration measures, taken live and warm);
+            # the event-pair figure is kept next to it: an event-record NODE on each side of a kernel node costs several us of
+            # graph-dependency latency, which is not time the kernel runs
+            roof.update({"achieved": dc, "frac": dc / pk["bf16_tflops_sustained"], "avg_launch_ms": sp_tot / n_g, "share_of_step": sp_tot / ms_prof,
+                         "event_pair_inflation_us_per_launch": inflation_us,
+                         "timing": "per launch, live inside the timed single-stream replay of the step: the kernel's own %globaltimer span (first CTA ENTRY -> last CTA "
+                                   "exit, prologue included: the quantity ncu reports as gpu__time_duration), CUDA events bracketing the replay; "
+                                   "*_event_pairs = CUDA event pairs (external event-record graph nodes) around the same launches of the same replay, "
+                                   "which add event_pair_inflation_us_per_launch of graph-node latency to every launch"})
+        classes = {}
+        for cls, c in per_class.items():
+            tensor = c["kind"] == "flop"
+            peak = pk["bf16_tflops_sustained"] if tensor else pk["hbm_gbs"]
+            ach = c["work"] / (c["ms"] / 1e3) / (1e12 if tensor else 1e9)
+            entry = {"bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                     "launches": c["n"], "ms_per_step": c["ms"], "share_of_step": c["ms"] / ms_prof}
+            if inflation_us is not None and inflation_us > 0:   # the same event-node latency sits on every event pair: net of it
+                net = c["ms"] - c["n"] * inflation_us * 1e-3
+                if net > 0:
+                    entry["frac_net_of_event_latency"] = c["work"] / (net / 1e3) / (1e12 if tensor else 1e9) / peak
+            classes[cls] = entry
+        classes["_notes"] = ("algorithmic work per call from its arguments (SURVEY 8d): GEMM 2MNK; attention 4*S*Skv*hd forward, 2x backward, HALVED for causal; "
+                             "norm / cross-entropy / AdamW / elementwise: bytes read + written once at their storage types (bf16 activations, fp32 residual stream / "
+                             "master weights / moments); durations = CUDA event pairs in the single-stream replay (each pair carries the event-node latency "
+                             "reported as roofline.event_pair_inflation_us_per_launch; frac_net_of_event_latency subtracts it)")
     line = {"metric": "training tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step (fwd + CE + bwd + AdamW)",
                        "per_gpu_batch": BATCH, "seq_len": SEQ, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       **({"gradient_buckets": f"{args.bucket_mb:g} MB NCCL all-reduce (ncclAvg) overlapped with backward, AdamW pipelined behind them"} if world > 1 else {}),
+                       **({"gradient_buckets": f"{args.bucket_mb:g} MB NCCL all-reduce (ncclAvg, fp32) overlapped with backward, AdamW pipelined behind them",
+                           "gemm_sm_limit": args.gemm_sm_limit} if world > 1 else {}),
                        "precision": "bf16 tensor-core GEMM/attention operands, fp32 accumulate / residual stream / master weights / Adam moments" if args.precision == "bf16" else "fp32",
                        "l2": "no explicit flush: each step streams ~3 GB of weights/optimizer state and ~5 GB of activations, far above the 126 MB L2",
                        "grad_clip": "reference +-10 clip on fp32 gradients and in the dgrad GEMM epilogues"},
             "model_tflops": value * TRAIN_FLOP_PER_TOKEN / 1e12, "mfu_vs_sustained_peak": value * TRAIN_FLOP_PER_TOKEN / 1e12 / (pk["bf16_tflops_sustained"] * world),
             "final_loss": final_loss,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 4, "steps": e2e_steps},
-            "gpu_launches": int(launches) if graphed is None else int(graphed_launches * args.steps), "cuda_graph": graphed is not None, "clocks": clocks}
+            "gpu_launches": int(launches_per_step * args.steps), "cuda_graph": bool(args.graph), "clocks": clocks}
     if roof is not None:
         line["roofline"] = roof
+        line["roofline_classes"] = classes
+    if other:
+        line["other_configs"] = other
+    if ddp_parity is not None:
+        line["ddp_parity"] = ddp_parity
     if world == 1 and not args.no_cpu_baseline:
-        tps, cores, t, desc = cpu_oracle_run(1, 0)
-        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc}
+        port = cpu_oracle_run(1, 0, 2)
+        if os.path.isdir(REF_DIR):
+            ref = cpu_reference_run(1, 1, 1)
+            line["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:   # the same UNMODIFIED reference step with Device.cuda tensors: its own code on the b200 backend (the drop-in)
+                from nfb200.array import set_implicit_host_conversion
+                set_implicit_host_conversion(True)
+                drop = cpu_reference_run(2, 1, BATCH, device=dev)
+                line["reference_on_b200"] = {"value": drop["value"], "unit": "tokens/s", "sample": drop["sample"]}
+            except Exception as exc:  # noqa: BLE001
+                line["reference_on_b200"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+        else:
+            line["cpu_baseline"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
+
+
+def ddp_parity_check(rank, world, dev):
+    """N ranks, each on its own shard, against ONE process on the global batch (distributed/data_parallel.py:271-287: the
+    all-reduce(AVERAGE) of per-shard mean gradients is the global-batch mean gradient): first-step gradients of every
+    parameter and a 3-step AdamW loss trajectory, fp32 contraction path so that the comparison is at the 1e-5 level.
+    Every rank runs the data-parallel job; rank 0 also runs the single-process one (it can draw every rank's shard)."""
+    from nfb200 import kernels as K
+    from nfb200.core import Tensor
+    from nfb200.distributed import DistributedDataParallel, all_reduce_max_host, get_backend
+    from nfb200.models import GPT2
+    from nfb200.optim import AdamW
+    cfg = {"vocab_size": 4099, "n_positions": 128, "n_embd": 256, "n_layer": 2, "n_head": 4}
+    B, S, steps = 2, 128, 3
+    prev = K.get_precision()
+    K.set_precision("fp32")
+    try:
+        def shard(r, step):
+            g = np.random.default_rng(9000 + 31 * step + r)
+            ids = g.integers(0, cfg["vocab_size"], (B, S))
+            return ids, np.concatenate([ids[:, 1:], np.zeros((B, 1), dtype=ids.dtype)], axis=1)
+
+        def run(parallel):
+            np.random.seed(0)
+            m = GPT2(cfg)
+            d = DistributedDataParallel(m, bucket_size_mb=1.0) if parallel else None
+            o = AdamW(m.parameters(), lr=5e-4, weight_decay=0.1, moment_dtype="float64")
+            losses, grads = [], None
+            for s in range(steps):
+                if parallel:
+                    ids, lab = shard(rank, s)
+                else:
+                    parts = [shard(r, s) for r in range(world)]
+                    ids, lab = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+                o.zero_grad()
+                loss = (d if parallel else m)(Tensor(ids, device=dev), labels=Tensor(lab, device=dev))["loss"]
+                loss.backward()
+                if parallel:
+                    d.finish_gradient_sync()
+                if s == 0:
+                    grads = {n: p.grad.get().copy() for n, p in m.named_parameters()}
+                o.step()
+                losses.append(float(loss.item()))
+            return losses, grads
+
+        par_l, par_g = run(True)
+        # the data-parallel loss of a rank is its SHARD's loss: the global-batch loss is the mean over ranks
+        g = get_backend()
+        mean_l = [float(np.mean(g.tcp.allgather(float(x)))) for x in par_l]
+        res = None
+        if rank == 0:
+            one_l, one_g = run(False)
+            gmax = max(float(np.abs(par_g[n] - one_g[n]).max() / (np.abs(one_g[n]).max() + 1e-30)) for n in one_g)
+            lmax = max(abs(a - b) / abs(b) for a, b in zip(mean_l, one_l))
+            res = {"grad_max_rel": gmax, "loss_max_rel": lmax, "ok": bool(gmax <= 1e-5 and lmax <= 1e-5), "steps": steps,
+                   "what": f"{world} ranks x ({B} x {S}) shards vs one process on the global ({B * world} x {S}) batch, GPT-2 d256 L2 H4 V4099, fp32 path; "
+                           "first-step gradients relative to each tensor's largest entry, 3-step AdamW loss trajectory (mean over ranks)"}
+        all_reduce_max_host(0.0)   # keep the ranks together
+        return res
+    finally:
+        K.set_precision(prev)
 
 
 def main():
@@ -350,10 +669,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=100.0,
                     help="gradient all-reduce bucket size (the reference's default is 25; 100 measured 2.5 %% faster at 4 GPUs and 3.5 %% at 8, profiles/r01_ddp_explore.txt)")
+    ap.add_argument("--gemm-sm-limit", type=int, default=-1,
+                    help="data parallel: SMs the persistent GEMM grids may occupy (leaves the rest to NCCL's channel CTAs); -1 = all")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying a captured CUDA graph")
-    ap.add_argument("--no-profile-gemm", dest="profile_gemm", action="store_false")
+    ap.add_argument("--no-profile", "--no-profile-gemm", dest="profile", action="store_false", help="skip the per-kernel roofline pass")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false", help="skip BERT-base / ViT-B/16 (/ GPT-2 medium at 8 GPUs)")
+    ap.add_argument("--gpt2-medium", action="store_true", help="run the GPT-2 medium per-GPU shard (B8 x S1024) at any N (default: only at 8 GPUs)")
+    ap.add_argument("--no-ddp-parity", dest="ddp_parity", action="store_false")
     ap.add_argument("--step-in-backward", dest="step_in_backward", action="store_true",
-                    help="AdamW launches per layer from inside backward on the side stream (measured: within 0.3 %% of the default, one launch after backward)")
+                    help="AdamW launches per layer from inside backward on the side stream (measured: within 0.6 %% of the default, one launch after backward)")
     ap.add_argument("--sib-min", type=int, default=1 << 21, help="step-in-backward: smallest contiguous run of finished parameters that gets its own AdamW launch")
     ap.add_argument("--wgrad-group", type=int, default=4, help="weight-gradient GEMMs per grouped stream-K launch (1 = one launch each)")
     ap.add_argument("--no-wgrad-overlap", dest="wgrad_overlap", action="store_false", help="keep the weight-gradient GEMMs on the compute stream")

@@ -141,7 +141,7 @@ int nfb_gemm_bf16_grouped(int n, int transA, int transB, const int* Ms, const in
                           const void* const* Bs, const int64_t* ldbs, void* const* Cs, const int64_t* ldcs, int c_dtype, int accumulate);
 int nfb_gemm_bf16_set_stream_k(int mode);            /* stream-K schedule (balanced (tile, k-block) ranges per SM pair + in-kernel fix-up) of SINGLE launches: 0 / 1 = classic (grouped launches always use it), 2 = whenever possible (test hook) */
 int nfb_gemm_bf16_set_sm_limit(int sms);             /* SMs the persistent GEMM grids may occupy (0 = all): data-parallel steps leave room for NCCL's channel CTAs */
-int nfb_gemm_bf16_set_span(void* dev_two_u64);      /* measurement: the NEXT launch writes min(%globaltimer after griddepcontrol.wait) and ~max(%globaltimer at exit) into two u64 words armed to all-ones */
+int nfb_gemm_bf16_set_span(void* dev_two_u64);      /* measurement: the NEXT launch writes min(%globaltimer at CTA entry) and ~max(%globaltimer at CTA exit) into two u64 words armed to all-ones */
 int nfb_gemm_bf16_set_timeline(void* dev_buf);      /* debug: 8 x 64 u64 clock64 stamps of the GEMM pipeline events (NULL = off) */
 int nfb_gemm_bf16_set_tma_store(int on);             /* test hook: 0 = register epilogue everywhere (default 1: TMA store when C rows are 16-byte addressable) */
 int nfb_set_aux_stream(void* stream);   /* side stream for optimizer-only work (norm-parameter reductions; the host also issues wgrad GEMMs / bias sums there); NULL = none */

@@ -89,7 +89,7 @@ struct GemmParams {
   int vec_ok;           // C / residual / aux pitches and bases allow 128-bit (fp32) / 64-bit (bf16) accesses
   int tma_store;        // epilogue through shared memory + TMA store / reduce-add (C 16-byte aligned rows, no residual, no aux)
   unsigned long long* timeline;  // debug: per-CTA clock64 stamps of the pipeline events (NULL in production)
-  unsigned long long* span;      // optional: span[0] = min %globaltimer after griddepcontrol.wait, span[1] = max at exit (bench roofline)
+  unsigned long long* span;      // optional: span[0] = min %globaltimer at CTA entry, span[1] = ~max at CTA exit (bench roofline)
 };
 
 struct GemmMaps { CUtensorMap a[GEMM_MAX_GROUP], b[GEMM_MAX_GROUP], c[GEMM_MAX_GROUP]; };
@@ -425,7 +425,10 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   const int cluster_id = (int)blockIdx.x / CG, num_clusters = (int)gridDim.x / CG;
-  if (threadIdx.x == 0) tl_stamp(p, 0);
+  if (threadIdx.x == 0) {
+    tl_stamp(p, 0);
+    if (p.span) atomicMin(p.span, globaltimer_ns());   // kernel entry (prologue included), like ncu's gpu__time_duration
+  }
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.nprob; ++g) {
@@ -445,10 +448,7 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
   // everything above overlapped the previous kernel's tail; its results are visible only after this point
   pdl_wait();
   pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    tl_stamp(p, 1);
-    if (p.span) atomicMin(p.span, globaltimer_ns());
-  }
+  if (threadIdx.x == 0) tl_stamp(p, 1);
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
@@ -1027,8 +1027,8 @@ static unsigned long long* g_timeline = nullptr;
 // debug: device buffer of 8 x 64 u64 that the next launches fill with clock64 stamps (NULL = off)
 NFB_API int nfb_gemm_bf16_set_timeline(void* dev_buf) { g_timeline = (unsigned long long*)dev_buf; return 0; }
 static unsigned long long* g_span = nullptr;
-// measurement: two device u64 words (armed to all-ones) that the NEXT launch fills with min(%globaltimer after its
-// griddepcontrol.wait) and ~max(%globaltimer at CTA exit); NULL = off.  The pointer is consumed by one launch.
+// measurement: two device u64 words (armed to all-ones) that the NEXT launch fills with min(%globaltimer at CTA entry) and
+// ~max(%globaltimer at CTA exit); NULL = off.  The pointer is consumed by one launch.
 NFB_API int nfb_gemm_bf16_set_span(void* dev_two_u64) { g_span = (unsigned long long*)dev_two_u64; return 0; }
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
 NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }

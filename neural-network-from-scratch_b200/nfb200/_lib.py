@@ -205,13 +205,27 @@ def check(rc: int, what: str = ""):
         raise B200Error(f"{what + ': ' if what else ''}{last_error()}")
 
 
+# Measurement hook (bench.py): with PROFILE set to a list, every call of an entry point named in PROFILE_NAMES is bracketed by
+# a pair of timing events recorded on the compute stream (external event-record nodes when the step is being captured into a
+# CUDA graph) and appended as (name, args, start_event, end_event).  Off (None) in production: one attribute load per call.
+PROFILE = None
+PROFILE_NAMES = frozenset()
+
+
 def call(name: str, *args):
     """Call an entry point and raise on a non-zero status."""
     lib = load()
     fn = getattr(lib, name, None)
     if fn is None:
         raise B200Error(f"libnfb200.so does not export {name} (stale build?)")
-    rc = fn(*args)
+    prof = PROFILE
+    if prof is not None and name in PROFILE_NAMES:
+        from .runtime import Event
+        e0 = Event().record(external=True)
+        rc = fn(*args)
+        prof.append((name, args, e0, Event().record(external=True)))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise B200Error(f"{name}: {last_error()}")
 

@@ -630,8 +630,11 @@ def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
     # passes feeding one loss (siamese towers, micro-forwards) and parameters the loss does not reach are handled.
     owners = {}
     for t in nodes.values():
+        sparse_node = t._grad_fn.name == "embedding"
         for inp in t._grad_fn.inputs:
             if isinstance(inp, Tensor) and inp._grad_fn is None:
+                if sparse_node and inp.__dict__.get("_ddp_sparse"):
+                    continue   # this table's row gradients travel as (ids, rows), outside the bucket (DistributedDataParallel.defer_embedding_grad)
                 for q in _ddp_targets(inp):
                     counts = owners.setdefault(id(q._ddp), (q._ddp, {}))[1]
                     ent = counts.get(id(q))
@@ -676,7 +679,10 @@ def _run_backward(root: Tensor, grad, unit_seed: bool) -> None:
                         pending[id(inp)] = gi
                     else:
                         pending[id(inp)] = _add_grads(prev, gi)
+        sparse_node = fn.name == "embedding"
         for inp in fn.inputs:  # data-parallel: this consumer of the parameter is done -> maybe launch its bucket
             if isinstance(inp, Tensor) and inp._grad_fn is None:
+                if sparse_node and inp.__dict__.get("_ddp_sparse"):
+                    continue
                 for q in _ddp_targets(inp):
                     q._ddp._note_grad_done(q)

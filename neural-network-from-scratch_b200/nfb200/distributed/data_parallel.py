@@ -42,7 +42,8 @@ class _Bucket:
 
 class DistributedDataParallel(Module):
     def __init__(self, module: Module, device_ids=None, output_device=None, bucket_size_mb: float = 25,
-                 find_unused_parameters: bool = False, broadcast_parameters: bool = True, overlap: bool = True):
+                 find_unused_parameters: bool = False, broadcast_parameters: bool = True, overlap: bool = True,
+                 sparse_embedding_grads: bool = True):
         super().__init__()
         self.module = module
         self.bucket_size_mb = bucket_size_mb
@@ -68,6 +69,20 @@ class DistributedDataParallel(Module):
             self._build_buckets()
             for p in self.arena.params:
                 p._ddp = self
+            # Large embedding tables: the gradient of the lookup reaches at most `tokens` rows and is only final when the LAST
+            # node of backward has run, so as part of a dense bucket it would put the whole table (154 MB for the tied GPT-2
+            # wte, 94 MB for BERT's) on the wire AFTER backward, with nothing left to hide it behind.  Instead the table's
+            # dense consumers (a tied LM head) are bucketed as usual -- ready early -- and the lookup's rows are exchanged as
+            # (ids, rows) with one all-gather after backward and scatter-added, scaled by 1/world, in rank order.
+            self._sparse_ids = {}
+            self._pending_sparse = []
+            if sparse_embedding_grads and self.world_size > 1 and self.group is not None and self.group.backend == "nccl":
+                from ..nn.layers import Embedding
+                for m in module.modules():
+                    w = getattr(m, "weight", None)
+                    if isinstance(m, Embedding) and w is not None and id(w) in self.arena.offsets and w.size >= int(os.environ.get("NFB200_DDP_SPARSE_MIN", 1 << 20)):
+                        w._ddp_sparse = True
+                        self._sparse_ids[id(w)] = w
         if broadcast_parameters and self.world_size > 1:
             self.broadcast_parameters()
 
@@ -137,6 +152,59 @@ class DistributedDataParallel(Module):
     def _note_use(self, p):   # kept for engines that count at graph-build time; counting now happens in _begin_backward
         pass
 
+    # ------------------------------------------------------------------ sparse embedding gradients
+    def defer_embedding_grad(self, weight, g, idx) -> bool:
+        """Called by the embedding backward for a table flagged _ddp_sparse.  Stages this rank's (ids, rows / world) in
+        persistent send buffers (on the compute stream); _flush_sparse() exchanges and applies them.  Returns False when the
+        dense path must be used (no synchronisation this pass: no_sync, single rank)."""
+        if not (self._require_sync and self.world_size > 1 and id(weight) in self._sparse_ids):
+            return False
+        from .._lib import call
+        from ..array import dtype_code
+        d = weight.shape[1]
+        rows = g.reshape(-1, d)
+        if rows.dtype != np.dtype(np.float32):
+            rows = rows.astype(np.float32)
+        rows = rows.contiguous()
+        T = rows.shape[0]
+        st = self.__dict__.setdefault("_sparse_bufs", {}).get(id(weight))
+        if st is None or st["T"] != T:
+            N = self.world_size
+            st = {"T": T, "send_rows": B200Array.empty((T, d), np.float32), "send_idx": B200Array.empty((T,), np.int64),
+                  "all_rows": B200Array.empty((N * T, d), np.float32), "all_idx": B200Array.empty((N * T,), np.int64)}
+            self._sparse_bufs[id(weight)] = st
+        call("nfb_binary_scalar", 2, dtype_code(np.float32), rows.ptr, 1.0 / self.world_size, st["send_rows"].ptr, rows.size, 0)   # rows * (1 / world)
+        ids = idx if isinstance(idx, B200Array) else B200Array.from_numpy(np.asarray(idx))
+        st["send_idx"]._assign(ids.reshape(-1))
+        self._pending_sparse.append((weight, st))
+        return True
+
+    def _flush_sparse(self):
+        """All-gather the staged (ids, rows) of every rank on the communication stream, then scatter-add them -- rank 0's rows
+        first, each rank's in token order: deterministic -- into the (already averaged) gradient of the table on the
+        compute stream.  Runs after every bucket has been launched; returns the ids of the parameters it touched."""
+        if not self._pending_sparse:
+            return set()
+        from .._lib import call
+        from ..array import dtype_code
+        from ..runtime import Event, compute_stream_wait
+        g = self.group
+        pend, self._pending_sparse = self._pending_sparse, []
+        g.comm_stream.wait_event(Event(timing=False).record())          # the staged send buffers are final on the compute stream
+        for weight, st in pend:
+            for src, dst in ((st["send_rows"], st["all_rows"]), (st["send_idx"], st["all_idx"])):
+                call("nfb_comm_allgather", g.comm, src.ptr, dst.ptr, src.size, dtype_code(src.dtype), g.comm_stream.handle)
+        compute_stream_wait(Event(timing=False).record(g.comm_stream))   # ... behind the bucket all-reduces issued on that stream before
+        touched = set()
+        be = None
+        for weight, st in pend:
+            be = be or weight.backend
+            be.embedding_backward(st["all_rows"], st["all_idx"], weight.shape[0], out=weight._grad_slot, accumulate=True)
+            weight._grad = weight._grad_slot
+            weight._slot_zero = False
+            touched.add(id(weight))
+        return touched
+
     def _note_grad_done(self, p):
         """Called by the autograd engine after a consumer node of p has run its backward."""
         if not (self._require_sync and self.overlap and self.world_size > 1):
@@ -183,6 +251,7 @@ class DistributedDataParallel(Module):
             for b in self.buckets:
                 if not b.launched:
                     self._launch_bucket(b)
+            self._flush_sparse()           # (its wait on the communication stream also covers every bucket launched so far)
             for b in self.buckets:
                 compute_stream_wait(b.event)
             for p in self.arena.params:   # every parameter now holds the averaged gradient (zeros if unused)
@@ -209,13 +278,14 @@ class DistributedDataParallel(Module):
         for b in self.buckets:
             if not b.launched:
                 self._launch_bucket(b)
+        flushed = bool(self._flush_sparse())   # the compute stream now sits behind every all-reduce issued so far
         for p in self.arena.params:   # every parameter will hold the averaged gradient (zeros if unused)
             if p._grad is None:
                 p._grad = p._grad_slot
             p._slot_zero = False
         self._sync_consumed = True
         order = sorted(self.buckets, key=lambda b: getattr(b, "seq", 0))
-        optimizer.step(segments=[(lo, hi, ev) for b in order for (lo, hi), ev in zip(b.pieces, b.piece_events)])
+        optimizer.step(segments=[(lo, hi, None if flushed else ev) for b in order for (lo, hi), ev in zip(b.pieces, b.piece_events)])
 
     def sync_gradients(self):
         """Reference API (data_parallel.py:271-287): all-reduce(AVERAGE) every gradient after backward."""

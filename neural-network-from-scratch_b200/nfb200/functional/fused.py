@@ -202,6 +202,9 @@ def embedding(weight: Tensor, indices, out_dtype=None) -> Tensor:
 
         def backward(g):
             from .. import kernels as K
+            ddp = weight.__dict__.get("_ddp") if weight.__dict__.get("_ddp_sparse") else None
+            if ddp is not None and ddp.defer_embedding_grad(weight, g, idx):
+                return (ACCUMULATED,)   # data parallel: the rows are exchanged as (ids, rows) after backward instead of densely
             K.join_side_stream()   # a tied LM head's weight-gradient GEMM accumulates into the same buffer
             be.embedding_backward(g, idx, V, out=weight.grad_buffer(), accumulate=True)
             return (ACCUMULATED,)

@@ -18,7 +18,7 @@ from .array import B200Array, bfloat16, dtype_code
 
 _PRECISION = "fp32"
 F32 = np.dtype(np.float32)
-GEMM_PROFILE = None  # set to a list to collect (start_event, end_event, flops, shape) per tcgen05 GEMM launch (bench.py)
+# (per-launch CUDA-event timing of every kernel class: _lib.PROFILE; bench.py)
 GEMM_SPAN = None     # set to {"buf": device uint64 array of 2*cap words armed to all-ones, "cap": cap, "meta": []}: every tcgen05 GEMM
 #                      launch i then stamps %globaltimer into words 2i (min after griddepcontrol.wait) and 2i+1 (~max at CTA exit)
 
@@ -105,16 +105,10 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
         bias_ptr = bias.ptr
     aux_arr = B200Array.empty((M, N), bfloat16) if aux else None
     epi = {None: 0, "none": 0, "gelu": 1, "relu": 2}[epilogue.lower() if isinstance(epilogue, str) else epilogue]
-    prof = GEMM_PROFILE
-    if prof is not None:
-        from .runtime import Event
-        e0 = Event().record(external=True)
     _arm_span(2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b)))
     call("nfb_gemm_bf16", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, a2.ptr, lda, b2.ptr, ldb, out.ptr,
          dtype_code(out.dtype), ldc_v, bias_ptr, res_ptr, ldr, aux_arr.ptr if aux_arr is not None else None, N, epi,
          1 if accumulate else 0, int(split_k), float(clip))
-    if prof is not None:
-        prof.append((e0, Event().record(external=True), 2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b))))
     return (out, aux_arr) if aux else out
 
 
@@ -149,15 +143,9 @@ def gemm_bf16_grouped(problems, trans_a=False, trans_b=False, accumulate=False):
         Cs.append(out.ptr); ldcs.append(out.strides[0] if M > 1 else max(N, out.strides[0]))
         flops += 2.0 * M * N * K
     ia, vpa, la = (C.c_int * n), (C.c_void_p * n), (C.c_int64 * n)
-    prof = GEMM_PROFILE
-    if prof is not None:
-        from .runtime import Event
-        e0 = Event().record(external=True)
     _arm_span(flops, ("grouped", tuple(zip(Ms, Ns, Ks)), bool(trans_a), bool(trans_b)))
     call("nfb_gemm_bf16_grouped", n, 1 if trans_a else 0, 1 if trans_b else 0, ia(*Ms), ia(*Ns), ia(*Ks), vpa(*As), la(*ldas), vpa(*Bs), la(*ldbs),
          vpa(*Cs), la(*ldcs), dtype_code(odt), 1 if accumulate else 0)
-    if prof is not None:
-        prof.append((e0, Event().record(external=True), flops, ("grouped", tuple(zip(Ms, Ns, Ks)), bool(trans_a), bool(trans_b))))
 
 
 def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None, bias=None, beta=0.0):

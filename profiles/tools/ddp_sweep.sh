@@ -1,0 +1,12 @@
+#!/bin/bash
+# data-parallel experiments at N GPUs: bench.py under torchrun with different GEMM SM limits / bucket sizes
+N=${1:-2}
+shift
+run() {
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 \
+    --no-profile --no-other-configs --no-ddp-parity "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$*', round(d['ms_per_step'],4), round(d['value']))"
+}
+run
+for lim in 132 124 116 108; do run --gemm-sm-limit $lim; done
+run --bucket-mb 50
+run --bucket-mb 200

@@ -16,14 +16,17 @@ def _ngpu():
     return _lib.device_count()
 
 
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense_embedding_grad", "sparse_embedding_grad"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_ddp_two_gpus_matches_one_gpu(tmp_path, precision):
+def test_ddp_two_gpus_matches_one_gpu(tmp_path, precision, sparse):
+    """sparse: the embedding table's row gradients travel as (ids, rows) in one all-gather after backward instead of inside a
+    dense bucket (DistributedDataParallel.defer_embedding_grad); the tied LM head's dense part is still bucketed."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     two, one = tmp_path / "two", tmp_path / "one"
     two.mkdir()
     one.mkdir()
-    env = {"NFB200_TEST_PRECISION": precision}
+    env = {"NFB200_TEST_PRECISION": precision, "NFB200_DDP_SPARSE_MIN": "1" if sparse else str(1 << 40)}
     _spawn("ddp_gpu", two, world=2, extra_env=env)
     _spawn("ddp_gpu", one, world=1, extra_env=env)
     d0, d1 = json.load(open(two / "ddp_0.json")), json.load(open(two / "ddp_1.json"))

@@ -320,7 +320,10 @@ def run_b200(args):
         R.synchronize()
 
     def wrap(model):
-        return DistributedDataParallel(model, bucket_size_mb=args.bucket_mb) if world > 1 else None
+        if world <= 1:
+            return None
+        return DistributedDataParallel(model, bucket_size_mb=args.bucket_mb, grad_dtype=args.grad_dtype if args.precision == "bf16" else "float32",
+                                       sparse_embedding_grads=args.sparse_embedding_grads)
 
     def timed(fn, n):
         e0, e1 = R.Event(), R.Event()
@@ -564,7 +567,8 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": "GPT-2 small (reference variant: RoPE+RMSNorm+SwiGLU, tied head) causal-LM train step (fwd + CE + bwd + AdamW)",
                        "per_gpu_batch": BATCH, "seq_len": SEQ, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       **({"gradient_buckets": f"{args.bucket_mb:g} MB NCCL all-reduce (ncclAvg, fp32) overlapped with backward, AdamW pipelined behind them",
+                       **({"gradient_buckets": f"{args.bucket_mb:g} MB NCCL all-reduce (ncclAvg, {args.grad_dtype if args.precision == 'bf16' else 'float32'} on the wire, fp32 arena) "
+                                               "overlapped with backward, AdamW pipelined behind them",
                            "gemm_sm_limit": args.gemm_sm_limit} if world > 1 else {}),
                        "precision": "bf16 tensor-core GEMM/attention operands, fp32 accumulate / residual stream / master weights / Adam moments" if args.precision == "bf16" else "fp32",
                        "l2": "no explicit flush: each step streams ~3 GB of weights/optimizer state and ~5 GB of activations, far above the 126 MB L2",
@@ -669,6 +673,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=100.0,
                     help="gradient all-reduce bucket size (the reference's default is 25; 100 measured 2.5 %% faster at 4 GPUs and 3.5 %% at 8, profiles/r01_ddp_explore.txt)")
+    ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
+                    help="data parallel, bf16 precision: dtype of the gradient buckets on the wire (fp32 arena either way)")
+    ap.add_argument("--sparse-embedding-grads", action="store_true", help="data parallel: exchange embedding-table row gradients as (ids, rows)")
     ap.add_argument("--gemm-sm-limit", type=int, default=-1,
                     help="data parallel: SMs the persistent GEMM grids may occupy (leaves the rest to NCCL's channel CTAs); -1 = all")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying a captured CUDA graph")

@@ -7,6 +7,8 @@ run() {
     --no-profile --no-other-configs --no-ddp-parity "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$*', round(d['ms_per_step'],4), round(d['value']))"
 }
 run
-for lim in 132 124 116 108; do run --gemm-sm-limit $lim; done
+run --sparse-embedding-grads
+run --grad-dtype float32
+run --grad-dtype float32 --bucket-mb 50
 run --bucket-mb 50
 run --bucket-mb 200

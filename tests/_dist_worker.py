@@ -81,7 +81,8 @@ def ddp_train(out, device):
     set_default_device(device)
     np.random.seed(0)
     model = GPT2(cfg)
-    ddp = dist.DistributedDataParallel(model, bucket_size_mb=0.25)
+    ddp = dist.DistributedDataParallel(model, bucket_size_mb=0.25, sparse_embedding_grads=bool(int(os.environ.get("NFB200_TEST_SPARSE", "0"))),
+                                       grad_dtype=os.environ.get("NFB200_TEST_GRAD_DTYPE", "float32"))
     which = os.environ.get("NFB200_TEST_OPT", "adamw")
     if which == "lion":
         from nfb200.optim import Lion

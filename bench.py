@@ -39,7 +39,7 @@ GPT2_SMALL = {"vocab_size": 50257, "n_positions": 1024, "n_embd": 768, "n_layer"
 BATCH, SEQ = 8, 512
 TRAIN_FLOP_PER_TOKEN = 712.88e6  # SURVEY App. C (GEMM + logits + attention, x3 for training)
 # dram__bytes_read.sum + dram__bytes_write.sum per k_gemm_tc launch, launch-weighted over one step (profiles/r02_ncu_gemm_full.txt)
-GEMM_DRAM_BYTES_PER_LAUNCH = 45.0e6
+GEMM_DRAM_BYTES_PER_LAUNCH = 47.0e6
 REF_DIR = os.path.join(ROOT, "oracle", "_ref", "neural_arch")
 
 

@@ -306,6 +306,8 @@ def run_b200(args):
     K.set_precision(args.precision)
     K.set_wgrad_overlap(args.wgrad_overlap)
     K.set_wgrad_group(args.wgrad_group)
+    if args.grad_dtype == "auto":
+        args.grad_dtype = "bfloat16" if (world >= 4 and args.precision == "bf16") else "float32"
     if world > 1:
         from nfb200.distributed import DistributedDataParallel, all_reduce_max_host, init_process_group
         from nfb200.distributed import barrier as dist_barrier
@@ -673,8 +675,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=100.0,
                     help="gradient all-reduce bucket size (the reference's default is 25; 100 measured 2.5 %% faster at 4 GPUs and 3.5 %% at 8, profiles/r01_ddp_explore.txt)")
-    ap.add_argument("--grad-dtype", default="float32", choices=["float32", "bfloat16"],
-                    help="data parallel, bf16 precision: dtype of the gradient buckets on the wire (fp32 arena either way)")
+    ap.add_argument("--grad-dtype", default="auto", choices=["auto", "float32", "bfloat16"],
+                    help="data parallel, bf16 precision: dtype of the gradient buckets on the wire (fp32 arena either way); auto = bfloat16 from 4 GPUs on "
+                         "(measured: 6.30 vs 6.46 ms at 8 GPUs, 6.14 vs 6.11 ms at 2, profiles/r02_ddp_sweep.txt)")
     ap.add_argument("--sparse-embedding-grads", action="store_true", help="data parallel: exchange embedding-table row gradients as (ids, rows)")
     ap.add_argument("--gemm-sm-limit", type=int, default=-1,
                     help="data parallel: SMs the persistent GEMM grids may occupy (leaves the rest to NCCL's channel CTAs); -1 = all")

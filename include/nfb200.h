@@ -139,6 +139,10 @@ int nfb_gemm_bf16_plan(int transB, int M, int N, int K, int accumulate, int epil
    (nn/optimized.py:286-317 computes them one np.matmul at a time).  Every output element gets exactly one store / reduce-add. */
 int nfb_gemm_bf16_grouped(int n, int transA, int transB, const int* Ms, const int* Ns, const int* Ks, const void* const* As, const int64_t* ldas,
                           const void* const* Bs, const int64_t* ldbs, void* const* Cs, const int64_t* ldcs, int c_dtype, int accumulate);
+/* Fused rotary embedding (models/language/gpt2.py:78-95 apply_rotary_pos_emb, rotate_half form): the NEXT nfb_gemm_bf16 launch rotates
+   output columns [0, cols) -- heads of 64 columns, position = row % S, tables (S, 32) fp32 -- in its bf16 TMA-store epilogue, before
+   the rounding to bf16 (the qkv projection: cols = 2 * d covers the q and k parts of the packed (T, 3, H, 64) output). */
+int nfb_gemm_bf16_set_rope(const float* cos_t, const float* sin_t, int S, int cols);
 int nfb_gemm_bf16_set_stream_k(int mode);            /* stream-K schedule (balanced (tile, k-block) ranges per SM pair + in-kernel fix-up) of SINGLE launches: 0 / 1 = classic (grouped launches always use it), 2 = whenever possible (test hook) */
 int nfb_gemm_bf16_set_sm_limit(int sms);             /* SMs the persistent GEMM grids may occupy (0 = all): data-parallel steps leave room for NCCL's channel CTAs */
 int nfb_gemm_bf16_set_span(void* dev_two_u64);      /* measurement: the NEXT launch writes min(%globaltimer at CTA entry) and ~max(%globaltimer at CTA exit) into two u64 words armed to all-ones */

@@ -88,6 +88,12 @@ struct GemmParams {
   float clip;           // > 0: clamp the result to [-clip, clip]
   int vec_ok;           // C / residual / aux pitches and bases allow 128-bit (fp32) / 64-bit (bf16) accesses
   int tma_store;        // epilogue through shared memory + TMA store / reduce-add (C 16-byte aligned rows, no residual, no aux)
+  // rotary position embedding fused into the bf16 TMA-store epilogue (the qkv projection of models/language/gpt2.py:78-95,
+  // 228-234): output columns [0, rope_cols) are heads of 64 columns rotated by (x1, x2) -> (x1 c - x2 s, x2 c + x1 s) with
+  // x2 = the column 32 further, position = row % rope_S, tables (rope_S, 32) fp32 -- before the rounding to bf16
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_S, rope_cols;
   unsigned long long* timeline;  // debug: per-CTA clock64 stamps of the pipeline events (NULL in production)
   unsigned long long* span;      // optional: span[0] = min %globaltimer at CTA entry, span[1] = ~max at CTA exit (bench roofline)
 };
@@ -634,7 +640,58 @@ k_gemm_tc(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmPar
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
           if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of shared memory
           __syncwarp();
-          if (p.c_bf16) {
+          if (p.c_bf16 && col0 < p.rope_cols) {
+            // ---- one head (64 columns) per step, both halves in registers: bias, rotation, clip, bf16
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(taddr, r0);
+            tmem_ld_32x32b_x32(taddr + 32u, r1);
+            tmem_ld_wait();
+            float v0[32], v1[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v0[j] = __uint_as_float(r0[j]); v1[j] = __uint_as_float(r1[j]); }
+            if (n_contrib) { add_partials(v0, c0); add_partials(v1, c0 + 32); }
+            if (add_bias) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j4 * 4));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j4 * 4));
+                v0[4 * j4] += b0.x; v0[4 * j4 + 1] += b0.y; v0[4 * j4 + 2] += b0.z; v0[4 * j4 + 3] += b0.w;
+                v1[4 * j4] += b1.x; v1[4 * j4 + 1] += b1.y; v1[4 * j4 + 2] += b1.z; v1[4 * j4 + 3] += b1.w;
+              }
+            }
+            {
+              const int pos = (row0 + lane) % p.rope_S;
+              const float4* ct = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * 32);
+              const float4* st = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 c4 = __ldg(ct + j4), s4 = __ldg(st + j4);
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = v0[4 * j4 + e], b = v1[4 * j4 + e];
+                  v0[4 * j4 + e] = a * cc[e] - b * ss[e];
+                  v1[4 * j4 + e] = b * cc[e] + a * ss[e];
+                }
+              }
+            }
+            if (p.clip > 0.f) {
+              const float lo = -p.clip, hi = p.clip;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { v0[j] = fminf(fmaxf(v0[j], lo), hi); v1[j] = fminf(fmaxf(v1[j], lo), hi); }
+            }
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {   // eight 16-byte slots (8 bf16 each): slots 0..3 = first half, 4..7 = second half
+              const float* src = sl < 4 ? v0 + 8 * sl : v1 + 8 * (sl - 4);
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(src[2 * e], src[2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((sl ^ sw) * 16)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
+          } else if (p.c_bf16) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t r[32];
@@ -1030,6 +1087,15 @@ static unsigned long long* g_span = nullptr;
 // measurement: two device u64 words (armed to all-ones) that the NEXT launch fills with min(%globaltimer at CTA entry) and
 // ~max(%globaltimer at CTA exit); NULL = off.  The pointer is consumed by one launch.
 NFB_API int nfb_gemm_bf16_set_span(void* dev_two_u64) { g_span = (unsigned long long*)dev_two_u64; return 0; }
+static const float* g_rope_cos = nullptr;
+static const float* g_rope_sin = nullptr;
+static int g_rope_S = 0, g_rope_cols = 0;
+// The NEXT nfb_gemm_bf16 launch rotates output columns [0, cols) (heads of 64 columns; position = row % S; tables (S, 32) fp32)
+// in its epilogue.  Needs a bf16 C with 16-byte rows and no residual / aux (the TMA-store epilogue), cols % 64 == 0, no epilogue op.
+NFB_API int nfb_gemm_bf16_set_rope(const float* cos_t, const float* sin_t, int S, int cols) {
+  g_rope_cos = cos_t; g_rope_sin = sin_t; g_rope_S = S; g_rope_cols = cols;
+  return 0;
+}
 NFB_API int nfb_gemm_bf16_force_tile(int block_n) { g_force_block_n = block_n; return 0; }
 NFB_API int nfb_gemm_bf16_force_cta_group(int cg) { g_force_cg = cg; return 0; }
 NFB_API int nfb_gemm_bf16_force_raster(int order) { g_force_raster = order; return 0; }   // test hook: 0 = auto, 1 = m fastest, 2 = n fastest
@@ -1413,6 +1479,14 @@ static int gemm_bf16_impl(int transA, int transB, int M, int N, int K, const voi
   // TMA-store epilogue: C rows must be 16-byte addressable; residual / aux outputs keep the register epilogue
   p.tma_store = (g_tma_store && !residual && !aux && ((uintptr_t)C % 16 == 0) && ((ldc * (c_dtype == NFB_BF16 ? 2 : 4)) % 16 == 0)) ? 1 : 0;
   if (!p.tma_store && slice_split > 1) return NFB_FAIL("gemm_bf16: the internal split-K needs the TMA-store epilogue");
+  if (g_rope_cols > 0 && slice_split <= 1) {
+    const int cols = g_rope_cols;
+    p.rope_cos = g_rope_cos; p.rope_sin = g_rope_sin; p.rope_S = g_rope_S; p.rope_cols = cols;
+    g_rope_cols = 0;   // consumed
+    if (!p.tma_store || c_dtype != NFB_BF16 || epilogue != 0 || cols % 64 != 0 || cols > N || best_bn % 64 != 0 || p.rope_S <= 0 || !p.rope_cos || !p.rope_sin ||
+        (bias && ((uintptr_t)bias % 16 != 0)))
+      return NFB_FAIL("gemm_bf16: the fused rotary epilogue needs a bf16 C with 16-byte rows, no residual / aux / activation, cols %% 64 == 0 (got cols=%d N=%d tile %d)", cols, N, best_bn);
+  }
   GemmOperands op = {M, N, K, A, lda, B, ldb, C, ldc};
   return launch_problems(1, &op, transA, transB, c_dtype, p, best_bn, cg, slice_split, slice_rows, sms);
 }

@@ -110,6 +110,7 @@ _SIGNATURES = {
     "nfb_gemm_bf16_plan": [i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)],
     "nfb_gemm_bf16_grouped": [i32, i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(vp), i64p, C.POINTER(vp), i64p,
                               C.POINTER(vp), i64p, i32, i32],
+    "nfb_gemm_bf16_set_rope": [vp, vp, i32, i32],
     "nfb_gemm_bf16_set_stream_k": [i32],
     "nfb_gemm_bf16_set_sm_limit": [i32],
     "nfb_gemm_bf16_set_span": [vp],

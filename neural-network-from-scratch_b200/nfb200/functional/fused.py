@@ -34,9 +34,19 @@ def _bf16_shadow(p: Tensor):
 
 
 # ====================================================================================== linear
+def fused_rope_available(x: Tensor, head_dim: int) -> bool:
+    """True when linear(..., rope=...) can rotate q / k in the projection's epilogue: device tensor, bf16 mode, head_dim 64."""
+    if not _dev(x) or head_dim != 64:
+        return False
+    from .. import kernels as K
+    return K.get_precision() == "bf16"
+
+
 def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None, out_dtype=None,
-           weight_layout: str = "out_in") -> Tensor:
-    """act(x @ W^T + b) [+ residual]; W is (out,in) ('out_in', nn/optimized.py) or (in,out) ('in_out', nn/linear.py)."""
+           weight_layout: str = "out_in", rope=None) -> Tensor:
+    """act(x @ W^T + b) [+ residual]; W is (out,in) ('out_in', nn/optimized.py) or (in,out) ('in_out', nn/linear.py).
+    rope = (seq_len, cols, head_dim) (only where fused_rope_available): the rotary embedding of output columns [0, cols) is applied
+    in the GEMM epilogue; the caller's backward must un-rotate the gradient of those columns (packed_qkv_attention does)."""
     n_in = weight.shape[1] if weight_layout == "out_in" else weight.shape[0]
     if x.shape[-1] != n_in:
         raise ValueError(f"Input features {x.shape[-1]} != expected {n_in}")
@@ -46,7 +56,7 @@ def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None,
         prec = K.get_precision()
         wb = _bf16_shadow(weight) if prec == "bf16" else None
         y, ctx = K.linear_forward(x.data, weight.data, None if bias is None else bias.data, activation, out_dtype,
-                                  None if residual is None else residual.data, wb, prec, weight_layout)
+                                  None if residual is None else residual.data, wb, prec, weight_layout, rope)
 
         def backward(g):
             from ..core.tensor import get_grad_clip
@@ -304,7 +314,8 @@ def scaled_dot_product_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, 
     return matmul(softmax(s, axis=-1), v)
 
 
-def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rope: bool = True, scale=None, mask=None) -> Tensor:
+def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rope: bool = True, scale=None, mask=None,
+                         rope_applied: bool = False) -> Tensor:
     """Attention on the output of a fused qkv projection.  qkv: (B,S,3*d) laid out as (B,S,3,H,D) (gpt2.py:228-234,
     vision_transformer.py:110-116).  Returns (B,S,d).  cuda + bf16: RoPE in place on the packed buffer, flash
     forward reading it in place, and a backward that hands back ONE packed (B,S,3d) gradient -- no transposes."""
@@ -317,10 +328,11 @@ def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rop
         from .. import kernels as K
         if K.get_precision() == "bf16" and D == 64:
             buf = K.to_bf16(qkv.data)
-            if buf is qkv.data or not buf.is_contiguous:
-                buf = buf.copy() if use_rope else buf.contiguous()
+            rotate_here = use_rope and not rope_applied   # rope_applied: the projection's epilogue already rotated q and k
+            if (buf is qkv.data and rotate_here) or not buf.is_contiguous:
+                buf = buf.copy() if rotate_here else buf.contiguous()
             p5 = buf.reshape(B, S, 3, n_heads, D)
-            if use_rope:
+            if rotate_here:
                 K.rope_packed_qk_inplace(p5, n_heads)
             qd = p5[:, :, 0].transpose(0, 2, 1, 3)
             kd = p5[:, :, 1].transpose(0, 2, 1, 3)

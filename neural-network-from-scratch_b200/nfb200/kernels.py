@@ -66,7 +66,7 @@ def _rowmajor_2d(x: B200Array):
 
 
 def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None, out_dtype=np.float32, bias=None,
-              residual=None, epilogue=None, accumulate=False, split_k=0, clip=0.0, aux=False, ldc=None):
+              residual=None, epilogue=None, accumulate=False, split_k=0, clip=0.0, aux=False, ldc=None, rope=None):
     """out[M,N] (+)= epi(op(a) @ op(b) + bias) + residual on the tcgen05 path.
 
     a: (M,K) or, with trans_a, (K,M);  b: (K,N) or, with trans_b, (N,K).  bf16 operands (fp32 inputs are cast).
@@ -105,6 +105,13 @@ def gemm_bf16(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None
         bias_ptr = bias.ptr
     aux_arr = B200Array.empty((M, N), bfloat16) if aux else None
     epi = {None: 0, "none": 0, "gelu": 1, "relu": 2}[epilogue.lower() if isinstance(epilogue, str) else epilogue]
+    if rope is not None:
+        # (seq_len, cols, head_dim): rotate output columns [0, cols) -- heads of 64 -- by the position row % seq_len in the epilogue
+        S_r, cols_r, D_r = rope
+        if D_r != 64 or out.dtype is not bfloat16:
+            raise ValueError("gemm_bf16: the fused rotary epilogue needs head_dim 64 and a bf16 output")
+        cos_t, sin_t = rope_tables(D_r, S_r)
+        call("nfb_gemm_bf16_set_rope", cos_t.ptr, sin_t.ptr, int(S_r), int(cols_r))
     _arm_span(2.0 * M * N * K, (M, N, K, bool(trans_a), bool(trans_b)))
     call("nfb_gemm_bf16", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, a2.ptr, lda, b2.ptr, ldb, out.ptr,
          dtype_code(out.dtype), ldc_v, bias_ptr, res_ptr, ldr, aux_arr.ptr if aux_arr is not None else None, N, epi,
@@ -176,7 +183,7 @@ def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None,
 # Linear (nn/optimized.py:149-317, nn/linear.py:202-205): y = act(x @ W^T + b) [+ residual]
 # ======================================================================================
 def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtype=None, residual=None, w_bf16=None,
-                   precision=None, weight_layout="out_in"):
+                   precision=None, weight_layout="out_in", rope=None):
     """x (..., in); W (out,in) [or (in,out) with weight_layout='in_out'].  Returns (y, ctx) where ctx is what
     linear_backward needs.  precision None -> the module-level mode."""
     precision = precision or _PRECISION
@@ -197,7 +204,7 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
         if act == "gelu":
             y, z = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue="gelu", aux=True)
         else:
-            y = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue=act)
+            y = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue=act, rope=rope)
             z = y if act == "relu" else None  # relu'(z) == (y > 0)
         ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16")
     else:

@@ -107,9 +107,13 @@ class GPT2Attention(Module):
         self.resid_dropout = Dropout(config.get("resid_pdrop", 0.1))
 
     def forward(self, hidden_states: Tensor, attention_mask=None, residual: Optional[Tensor] = None) -> Tensor:
-        qkv = self.c_attn(hidden_states)                                        # (B,S,3d) laid out (B,S,3,H,hd)
+        from ..functional.fused import fused_rope_available
+        fused = fused_rope_available(hidden_states, self.head_dim) and hidden_states.ndim == 3
+        # bf16 tensor-core path: the rotary embedding of q and k rides in the projection's epilogue (before the rounding to bf16)
+        rope = (hidden_states.shape[1], 2 * self.embed_dim, self.head_dim) if fused else None
+        qkv = self.c_attn(hidden_states, rope=rope) if fused else self.c_attn(hidden_states)   # (B,S,3d) laid out (B,S,3,H,hd)
         scale = (1.0 / np.sqrt(self.head_dim)) if self.scale_attn_weights else 1.0
-        ctx = F.packed_qkv_attention(qkv, self.num_heads, causal=True, use_rope=True, scale=float(scale), mask=attention_mask)
+        ctx = F.packed_qkv_attention(qkv, self.num_heads, causal=True, use_rope=True, scale=float(scale), mask=attention_mask, rope_applied=fused)
         return self.c_proj(ctx, residual=residual)                              # + residual in the GEMM epilogue
 
 

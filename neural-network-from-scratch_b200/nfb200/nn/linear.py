@@ -70,13 +70,13 @@ class Linear(Module):
     def _draw_bias(self, scheme: str, n: int) -> np.ndarray:
         return _init_bias(scheme, n)
 
-    def forward(self, x: Tensor, residual: Optional[Tensor] = None, out_dtype=None) -> Tensor:
+    def forward(self, x: Tensor, residual: Optional[Tensor] = None, out_dtype=None, rope=None) -> Tensor:
         if not isinstance(x, Tensor):
             x = Tensor(x, device=self.weight.device)
         if x.shape[-1] != self.in_features:
             raise ValueError(f"Input features {x.shape[-1]} != expected {self.in_features}")
         act = self.activation.lower() if isinstance(self.activation, str) else None
-        return F_linear(x, self.weight, self.bias, act if act in ("gelu", "relu") else None, residual, out_dtype, self._layout)
+        return F_linear(x, self.weight, self.bias, act if act in ("gelu", "relu") else None, residual, out_dtype, self._layout, rope)
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.has_bias}, activation={self.activation}"

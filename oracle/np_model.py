@@ -179,7 +179,8 @@ class GPT2OracleBF16(GPT2Oracle):
         gradient are bf16; weights are read through their bf16 shadow (nfb200/functional/fused.py:_bf16_shadow);
       * GEMM outputs that feed another tensor-core op are stored bf16 (qkv, gate|up, logits in a training step, every dX);
         outputs that join the residual stream stay fp32 (kernels.linear_forward);
-      * RoPE rotates the packed bf16 qkv buffer in place (csrc/attention.cu k_rope), forward and backward;
+      * RoPE: forward, q and k are rotated in the qkv GEMM's epilogue BEFORE the rounding to bf16 (csrc/gemm_tc.cu, rope_cols); backward,
+        the packed bf16 dqkv buffer is un-rotated in place (csrc/attention.cu k_rope);
       * flash attention: np_ops.attention_fwd_bf16 / attention_bwd_bf16;
       * SwiGLU and its backward read / write bf16 (csrc/elementwise.cu k_swiglu_fwd / k_swiglu_bwd);
       * cross entropy reads bf16 logits, does its math in fp32 and writes bf16 dlogits (csrc/softmax_ce.cu);
@@ -202,10 +203,11 @@ class GPT2OracleBF16(GPT2Oracle):
         c = {"x": x, "cos": cos, "sin": sin}
         h1f, c["ln1"] = O.rmsnorm_fwd(x, P[p + "ln_1.weight"], self.eps)
         h1 = r(h1f)
-        qkv = r(np.matmul(h1, W[p + "attn.c_attn.weight"].T) + P[p + "attn.c_attn.bias"])
-        q5 = qkv.reshape(B, S, 3, H, hd).transpose(2, 0, 3, 1, 4)
-        q, k, v = q5[0], q5[1], q5[2]
-        qr, kr = r(O.rope_fwd(q, cos, sin)), r(O.rope_fwd(k, cos, sin))
+        # the rotary embedding of q and k rides in the projection's epilogue: rotate the fp32 accumulator, THEN round to bf16
+        qkv_f = np.matmul(h1, W[p + "attn.c_attn.weight"].T) + P[p + "attn.c_attn.bias"]
+        q5 = qkv_f.reshape(B, S, 3, H, hd).transpose(2, 0, 3, 1, 4)
+        qr, kr, v = r(O.rope_fwd(q5[0], cos, sin)), r(O.rope_fwd(q5[1], cos, sin)), r(q5[2])
+        qkv = r(qkv_f)
         a, c["attn"] = O.attention_fwd_bf16(qr, kr, v, scale, "causal")
         a2 = a.transpose(0, 2, 1, 3).reshape(B, S, d)
         x2 = (np.matmul(a2, W[p + "attn.c_proj.weight"].T) + P[p + "attn.c_proj.bias"]) + x

@@ -31,8 +31,9 @@ for i, blk in enumerate(model.transformer.h):
     c = caches[i]
     cmp(f"L{i} x in", x.data, c["x"])
     h1 = blk.ln_1(x, out_dtype=bfloat16); cmp(f"L{i} ln_1 out", h1.data, c["h1"])
-    qkv = blk.attn.c_attn(h1); cmp(f"L{i} qkv", qkv.data, c["qkv"])
-    a2 = F.packed_qkv_attention(qkv, blk.attn.num_heads, causal=True, use_rope=True, scale=float(1.0 / np.sqrt(blk.attn.head_dim)))
+    qkv = blk.attn.c_attn(h1, rope=(S, 2 * d, blk.attn.head_dim))     # q, k rotated in the projection's epilogue
+    cmp(f"L{i} v part of qkv", qkv.data.reshape(B, S, 3, -1)[:, :, 2], c["qkv"].reshape(B, S, 3, -1)[:, :, 2])
+    a2 = F.packed_qkv_attention(qkv, blk.attn.num_heads, causal=True, use_rope=True, scale=float(1.0 / np.sqrt(blk.attn.head_dim)), rope_applied=True)
     cmp(f"L{i} attention out", a2.data, c["a2"])
     x2 = blk.attn.c_proj(a2, residual=x); cmp(f"L{i} x2 (proj + res)", x2.data, c["x2"])
     h2 = blk.ln_2(x2, out_dtype=bfloat16); cmp(f"L{i} ln_2 out", h2.data, c["h2"])

@@ -339,6 +339,41 @@ def test_grouped_launch_weight_gradients(be, cta_group, out_dtype):
         assert np.array_equal(g, g2)
 
 
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_fused_rotary_epilogue(be, cta_group, bn):
+    """qkv projection with the rotary embedding of q and k (models/language/gpt2.py:78-95) in the GEMM epilogue: output columns
+    [0, 2d) -- heads of 64 columns -- are rotated by the position row % S BEFORE the rounding to bf16; the v columns are not.
+    Against the fp64 projection + the oracle's rope_fwd, at the bf16 contract; and within one bf16 rounding of the unfused
+    route (projection rounded to bf16, then k_rope in place)."""
+    from nfb200 import _lib, kernels as Kn
+    from oracle import np_ops as O
+    rng = np.random.default_rng(21 + bn)
+    Bn, S, H, D, K = 3, 100, 4, 64, 200
+    d = H * D
+    x = rng.standard_normal((Bn * S, K)).astype(np.float32)
+    w = (rng.standard_normal((3 * d, K)) * 0.08).astype(np.float32)
+    bias = rng.standard_normal(3 * d).astype(np.float32)
+    z = (_ref(x, w, False, True) + bias).reshape(Bn, S, 3, H, D)
+    cos, sin = O.rope_tables(D, S)
+    want = z.copy()
+    for part in (0, 1):
+        want[:, :, part] = O.rope_fwd(z[:, :, part].transpose(0, 2, 1, 3), cos, sin).transpose(0, 2, 1, 3)
+    _lib.call("nfb_gemm_bf16_force_tile", bn)
+    try:
+        fused = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), out_dtype=be.bfloat16, rope=(S, 2 * d, D))
+        plain = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), out_dtype=be.bfloat16)
+    finally:
+        _lib.call("nfb_gemm_bf16_force_tile", 0)
+    Kn.rope_packed_qk_inplace(plain.reshape(Bn, S, 3, H, D), H)
+    got = fused.get().reshape(Bn, S, 3, H, D)
+    np.testing.assert_allclose(got, want, rtol=1e-2, atol=1e-2 * float(np.abs(want).max()) / 4)
+    assert np.array_equal(got[:, :, 2], _bf16(z[:, :, 2]))                                   # v: the plain bf16 projection
+    unfused = plain.get().reshape(Bn, S, 3, H, D)
+    np.testing.assert_allclose(got, unfused, rtol=2e-2, atol=2e-2 * float(np.abs(want).max()) / 4)
+    exact = _bf16(want)                                                                      # one rounding of the rotated fp32 value
+    assert np.mean(got != exact) < 0.02, np.mean(got != exact)                                # (fp32 summation-order flips only)
+
+
 def test_gemm_f32_wrapper(be):
     from nfb200 import kernels as Kn
     rng = np.random.default_rng(5)

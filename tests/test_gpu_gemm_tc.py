@@ -364,10 +364,10 @@ def test_fused_rotary_epilogue(be, cta_group, bn):
         plain = Kn.gemm_bf16(_to(be, x), _to(be, w), False, True, bias=_to(be, bias), out_dtype=be.bfloat16)
     finally:
         _lib.call("nfb_gemm_bf16_force_tile", 0)
-    Kn.rope_packed_qk_inplace(plain.reshape(Bn, S, 3, H, D), H)
     got = fused.get().reshape(Bn, S, 3, H, D)
+    assert np.array_equal(got[:, :, 2], plain.get().reshape(Bn, S, 3, H, D)[:, :, 2])        # v: exactly the plain bf16 projection
+    Kn.rope_packed_qk_inplace(plain.reshape(Bn, S, 3, H, D), H)
     np.testing.assert_allclose(got, want, rtol=1e-2, atol=1e-2 * float(np.abs(want).max()) / 4)
-    assert np.array_equal(got[:, :, 2], _bf16(z[:, :, 2]))                                   # v: the plain bf16 projection
     unfused = plain.get().reshape(Bn, S, 3, H, D)
     np.testing.assert_allclose(got, unfused, rtol=2e-2, atol=2e-2 * float(np.abs(want).max()) / 4)
     exact = _bf16(want)                                                                      # one rounding of the rotated fp32 value

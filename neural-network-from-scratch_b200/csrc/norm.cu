@@ -105,24 +105,7 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
     const float mean = (RMS || !mean_in) ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
     f4 xv[VPL], gv[VPL];
-    {
-      // this warp's NEXT row (a warp handles ~2 rows at T = 4096): pull its x / dy / skip-gradient lines into L2 while this row is
-      // being reduced, so the second row's loads are L2 hits instead of a second full HBM round trip (one prefetch per 128-byte line)
-      const int64_t nrow = row + nwarps;
-      if (nrow < rows) {
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const int c = k * 128 + lane * 4;
-          if (c < cols) {
-            if ((lane & (sizeof(TX) == 4 ? 7 : 15)) == 0) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nrow * cols + c));
-              if (dres) asm volatile("prefetch.global.L2 [%0];" ::"l"(dres + nrow * cols + c));
-            }
-            if ((lane & (sizeof(TY) == 4 ? 7 : 15)) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nrow * cols + c));
-          }
-        }
-      }
-    }
+    // (prefetching this warp's NEXT row into L2 here was tried in round 2: 13.7 -> 15.2 us under ncu, reverted)
     if (dres) {   // the skip-connection gradient is only needed at the very end: start pulling its lines into L2 / L1 now
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {

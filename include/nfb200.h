@@ -161,6 +161,7 @@ int nfb_rope(int dtype, void* x, const float* cos_t, const float* sin_t, int n_p
 int nfb_rope_interleaved(int dtype, void* x, const float* cos_t, const float* sin_t, int B, int S, int H, int head_dim, int64_t sb, int64_t ss,
                          int64_t sh, int inverse);
 int nfb_flash_attn_set_timeline(void* dev_buf);   /* debug: 256 x u64 clock64 stamps of the tcgen05 forward (NULL = off) */
+int nfb_flash_attn_set_poly(int fwd, int bwd);   /* tcgen05 attention: n of every 4 softmax exponentials go through a degree-4 polynomial on the FMA pipe instead of MUFU.EX2 (0, 1 or 2; the kernels are MUFU-bound at head_dim 64) */
 int nfb_flash_attn_set_tc(int on);   /* test hook: 0 = mma.sync flash kernels only, 1 = tcgen05 forward only, 3 = tcgen05 forward + backward (default) when the layout is TMA-addressable */
 int nfb_flash_attn_fwd(int dtype, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int S, int head_dim,
                        int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb, int64_t o_ss,

@@ -17,6 +17,10 @@
 // than 2^8, otherwise the stale maximum is kept (exact: the final division by the row sum uses the same maximum).
 // P is rounded to bf16 and handed to the P.V product through shared memory in the K-major SWIZZLE_128B layout.
 #include "common.cuh"
+#ifndef NFB_ATTN_POLY_FWD_DEFAULT
+#define NFB_ATTN_POLY_FWD_DEFAULT 0   // set from the measurements in profiles/r02_attn_poly.txt
+#define NFB_ATTN_POLY_BWD_DEFAULT 0
+#endif
 #include <cuda.h>
 #include <stdio.h>
 #include <map>
@@ -124,6 +128,26 @@ __device__ __forceinline__ float ex2(float x) {   // 2^x, one MUFU op (x <= ~8 h
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 polynomial (relative error
+// < 5e-5, far inside the bf16 rounding P receives), 2^n by an integer add into the exponent field.  Both attention kernels are
+// bound by the 16 ex2/clk/SM MUFU rate at head_dim 64; a share of the exponentials of every row goes through here instead
+// (POLY of every 4 element pairs / elements: 0 = none).  x <= ~8; anything below -127 (masked keys, -inf) comes out as 0.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -127.f);
+  const float magic = 12582912.f;                 // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  const float xf = x + magic;
+  const float f = x - (xf - magic);
+  float pl = fmaf(f, 0.009618129f, 0.05550411f);   // 2^f = sum (f ln 2)^k / k!
+  pl = fmaf(pl, f, 0.2402265f);
+  pl = fmaf(pl, f, 0.6931472f);
+  pl = fmaf(pl, f, 1.0f);
+  return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(xf) << 23));
+}
+template <int POLY>
+__device__ __forceinline__ float ex2_mix(float x, int slot) {   // slot: position of the element within its group of 4
+  if (slot < POLY) return exp2_poly(x);
+  return ex2(x);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (see gemm_tc.cu)
@@ -171,6 +195,7 @@ constexpr int SM_BAR = SM_P + 65536;             // barriers + TMEM slot
 constexpr int SM_MASK = SM_BAR + 256;            // KV_STAGES x 128 fp32: additive key mask (log2 domain) of the staged block; -inf beyond Skv
 constexpr int SM_TOTAL = SM_MASK + KV_STAGES * 512 + 1024;    // + alignment slack
 
+template <int POLY>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const AttnTcParams p) {
@@ -407,7 +432,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2(t[cc * 8 + 2 * e] - m2), p1 = ex2(t[cc * 8 + 2 * e + 1] - m2);
+          const float p0 = ex2_mix<POLY>(t[cc * 8 + 2 * e] - m2, e), p1 = ex2_mix<POLY>(t[cc * 8 + 2 * e + 1] - m2, e);
           rsa[(2 * e) & 7] += p0;
           rsa[(2 * e + 1) & 7] += p1;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
@@ -543,6 +568,7 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
 //   ELEM:  loop it: [s_full(it)] P(it) ; (it > 0: [dq_full(it-1)] drain dQ(it-1)) ; [dp_full(it)] dS(it)   ... final drain
 // S(it+1) is issued BEFORE dK(it) / dQ(it), so the exponentials of the next block run while those products and the
 // dQ drain of the previous block are in flight; the dS buffer of block it is only rewritten after dq_full(it).
+template <int POLY>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ, const AttnBwdTcParams p) {
@@ -799,7 +825,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (!diag && !tail && !kmask) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
+          const float p0 = ex2_mix<POLY>(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2), j & 3), p1 = ex2_mix<POLY>(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2), j & 3);
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[j] = *reinterpret_cast<uint32_t*>(&b2);
         }
@@ -821,7 +847,7 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float pneg = ex2(-1e4f * LOG2E - lse2);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float p0 = ex2(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2)), p1 = ex2(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2));
+          float p0 = ex2_mix<POLY>(fmaf(__uint_as_float(sr[2 * j]), sl2, -lse2), j & 3), p1 = ex2_mix<POLY>(fmaf(__uint_as_float(sr[2 * j + 1]), sl2, -lse2), j & 3);
           if (2 * j > lim) p0 = pneg;
           if (2 * j + 1 > lim) p1 = pneg;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
@@ -1038,6 +1064,20 @@ int make_map_dq_f32(CUtensorMap* out, const float* base, int BH, int S) {
   if (r != CUDA_SUCCESS) return NFB_FAIL("attention_tc: cuTensorMapEncodeTiled (dQ fp32) failed (%d) BH=%d S=%d", (int)r, BH, S);
   return 0;
 }
+static int g_poly_fwd = -1, g_poly_bwd = -1;   // -1: not set yet -> NFB_ATTN_POLY="f,b" from the environment, else the defaults below
+static void poly_defaults() {
+  if (g_poly_fwd >= 0) return;
+  int f = NFB_ATTN_POLY_FWD_DEFAULT, b = NFB_ATTN_POLY_BWD_DEFAULT;
+  if (const char* e = getenv("NFB_ATTN_POLY")) sscanf(e, "%d,%d", &f, &b);
+  g_poly_fwd = f < 0 ? 0 : (f > 2 ? 2 : f);
+  g_poly_bwd = b < 0 ? 0 : (b > 2 ? 2 : b);
+}
+// share of the softmax exponentials evaluated by a polynomial on the FMA pipe instead of MUFU.EX2: n of every 4 (0, 1 or 2)
+NFB_API int nfb_flash_attn_set_poly(int fwd, int bwd) {
+  g_poly_fwd = fwd < 0 ? 0 : (fwd > 2 ? 2 : fwd);
+  g_poly_bwd = bwd < 0 ? 0 : (bwd > 2 ? 2 : bwd);
+  return 0;
+}
 static int g_dq_f32_blocks = 4;   // more key blocks than this per query row -> fp32 dQ accumulation (bf16 partial sums lose ~2^-9 per add)
 NFB_API int nfb_flash_attn_set_dq_f32_blocks(int n) { g_dq_f32_blocks = n; return 0; }   // test hook: 0 = always fp32, large = always bf16
 NFB_API int nfb_flash_attn_set_timeline(void* dev_buf) { g_attn_timeline = (unsigned long long*)dev_buf; return 0; }   // debug: 256 x u64
@@ -1066,11 +1106,16 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
   p.timeline = g_attn_timeline;
   static bool configured = false;
   if (!configured) {
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
   dim3 grid((unsigned)(nfb_cdiv(S, 2 * TILE_Q) * B * H));
-  NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  poly_defaults();
+  if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<1>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<2>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  else NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<0>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   NFB_LAUNCH_CHECK();
   return 0;
 }
@@ -1141,11 +1186,16 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   p.dq_f32 = dq_f32 ? 1 : 0;
   static bool configured = false;
   if (!configured) {
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_bwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
     configured = true;
   }
   dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * Hkv * kv_split));
-  k_flash_bwd_tc<<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  poly_defaults();
+  if (g_poly_bwd == 1) k_flash_bwd_tc<1><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  else if (g_poly_bwd == 2) k_flash_bwd_tc<2><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  else k_flash_bwd_tc<0><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   if (part) {
     const long long vecs = (long long)B * Skv * Hkv * 8;
     const long long half_elems = (long long)B * Skv * Hkv * kv_split * HDIM;

@@ -121,6 +121,7 @@ _SIGNATURES = {
     # attention
     "nfb_rope": [i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, i64, i64, i64, i32],
     "nfb_flash_attn_set_tc": [i32],
+    "nfb_flash_attn_set_poly": [i32, i32],
     "nfb_flash_attn_set_timeline": [vp],
     "nfb_flash_attn_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, vp],
     "nfb_flash_attn_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64,

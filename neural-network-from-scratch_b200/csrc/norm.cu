@@ -183,12 +183,10 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
 // partial is [nblocks][NP][cols]: block (8, 32) owns 8 columns; threadIdx.y strides the row-blocks (<= 10 independent
 // loads per thread for 296 row-blocks, all in flight at once), then a fixed-order shared-memory sum over threadIdx.y and
 // a write / accumulate into dgamma (which = 0) or dbeta (which = 1).  Deterministic.
-__global__ void __launch_bounds__(256)
-k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int np, int cols, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, int accumulate) {
-  nfb_pdl_enter();
+__device__ __forceinline__ void norm_param_reduce_body(const float* __restrict__ partial, int nblocks, int np, int cols, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta, int accumulate, int block) {
   __shared__ float red[32][9];
-  const int i = blockIdx.x * 8 + threadIdx.x;   // index into [np][cols]
+  const int i = block * 8 + threadIdx.x;   // index into [np][cols]
   const int total = np * cols;
   float a = 0.f;
   if (i < total) {
@@ -205,6 +203,24 @@ k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int np, int 
     float* dst = which == 0 ? dgamma : dbeta;
     if (dst) dst[c] = accumulate ? dst[c] + r : r;
   }
+}
+__global__ void __launch_bounds__(256)
+k_norm_param_reduce(const float* __restrict__ partial, int nblocks, int np, int cols, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int accumulate) {
+  nfb_pdl_enter();
+  norm_param_reduce_body(partial, nblocks, np, cols, dgamma, dbeta, accumulate, blockIdx.x);
+}
+// Up to NR_BATCH parameter reductions in ONE launch (the auxiliary-stream path queues them: nothing but the optimizer / the
+// gradient all-reduce reads dgamma / dbeta, so the reductions of several norm layers wait for a flush point and go together).
+constexpr int NR_BATCH = 8;
+struct NormReduceJob { const float* partial; float* dgamma; float* dbeta; int nblocks, np, cols, accumulate; };
+struct NormReduceBatch { int n; int blk0[NR_BATCH + 1]; NormReduceJob job[NR_BATCH]; };
+__global__ void __launch_bounds__(256)
+k_norm_param_reduce_batched(const __grid_constant__ NormReduceBatch b) {
+  int j = 0;
+  while (j + 1 < b.n && (int)blockIdx.x >= b.blk0[j + 1]) ++j;
+  const NormReduceJob& q = b.job[j];
+  norm_param_reduce_body(q.partial, q.nblocks, q.np, q.cols, q.dgamma, q.dbeta, q.accumulate, (int)blockIdx.x - b.blk0[j]);
 }
 
 // generic fallback (cols not a multiple of 4 or > 1024): one block per row, three passes.
@@ -303,6 +319,47 @@ static int norm_fwd_t(const void* x, const void* res, void* sum_out, const float
   return 0;
 }
 
+// ---- auxiliary-stream parameter reductions: the block partials of a backward go to one of NR_RING grow-only workspaces (not the
+// stream-ordered allocator), the reduction is QUEUED, and norm_flush_pending launches up to NR_BATCH of them as one kernel on
+// the auxiliary stream behind an event of the compute stream.  A workspace is fenced by the event of the launch that read it.
+struct AuxWs { float* buf; size_t n; cudaEvent_t done; unsigned long long epoch; bool used; bool pending; };
+constexpr int NR_RING = 2 * NR_BATCH;
+static AuxWs g_nr_ws[NR_RING] = {};
+static int g_nr_next = 0;
+static NormReduceBatch g_nr_pending = {};
+static AuxWs* g_nr_owner[NR_BATCH] = {};
+static cudaStream_t g_nr_stream = nullptr;     // the compute stream the queued backward kernels ran on
+static cudaEvent_t g_nr_ready = nullptr;
+
+static int norm_flush_pending() {
+  if (g_nr_pending.n == 0) return 0;
+  NormReduceBatch& b = g_nr_pending;
+  int blocks = 0;
+  for (int j = 0; j < b.n; ++j) { b.blk0[j] = blocks; blocks += (b.job[j].np * b.job[j].cols + 7) / 8; }
+  b.blk0[b.n] = blocks;
+  cudaStream_t aux = nfb_aux_stream();
+  cudaStream_t where = (aux && aux != g_nr_stream) ? aux : g_nr_stream;
+  if (where != g_nr_stream) {
+    if (!g_nr_ready) NFB_CUDA(cudaEventCreateWithFlags(&g_nr_ready, cudaEventDisableTiming));
+    NFB_CUDA(cudaEventRecord(g_nr_ready, g_nr_stream));
+    NFB_CUDA(cudaStreamWaitEvent(where, g_nr_ready, 0));
+  }
+  nfb_count_launch();
+  k_norm_param_reduce_batched<<<blocks, dim3(8, 32), 0, where>>>(b);
+  for (int j = 0; j < b.n; ++j) {
+    AuxWs* w = g_nr_owner[j];
+    NFB_CUDA(cudaEventRecord(w->done, where));
+    w->used = true;
+    w->pending = false;
+    w->epoch = nfb_capture_epoch();
+  }
+  b.n = 0;
+  NFB_LAUNCH_CHECK();
+  return 0;
+}
+// Launch the queued norm-parameter reductions now (the host calls this before it joins / fences the auxiliary stream).
+NFB_API int nfb_norm_flush() { return norm_flush_pending(); }
+
 template <typename TX, typename TY, bool RMS>
 static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
                       void* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int cols, float clip, void* dx_twin) {
@@ -326,18 +383,14 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   // With an auxiliary stream the (tiny, optimizer-only) parameter reduction leaves the critical path: the block partials go
   // to one of two grow-only workspaces instead of the stream-ordered allocator, the reduce kernel runs on the aux stream
   // behind an event, and the workspace is fenced by the event of the reduce that last read it.
-  struct AuxWs { float* buf; size_t n; cudaEvent_t done; unsigned long long epoch; bool used; };
-  static AuxWs ws[2] = {};
-  static int ws_next = 0;
-  static cudaEvent_t ev_ready = nullptr;
   cudaStream_t aux = need_params ? nfb_aux_stream() : nullptr;
   if (aux == s) aux = nullptr;
   AuxWs* w = nullptr;
   const size_t part_elems = (size_t)NP * cols * grid;
   if (aux) {
-    w = &ws[ws_next];
-    ws_next ^= 1;
-    if (!ev_ready) NFB_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    w = &g_nr_ws[g_nr_next];
+    g_nr_next = (g_nr_next + 1) % NR_RING;
+    if (w->pending && norm_flush_pending()) return -1;   // the ring wrapped onto a reduction that has not been launched yet
     if (!w->done) NFB_CUDA(cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming));
     if (w->n < part_elems) {
       if (w->buf) NFB_CUDA(cudaFree(w->buf));   // implicit device sync
@@ -359,15 +412,21 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   }
 #undef LB
   if (need_params) {
-    nfb_count_launch();
     if (aux) {
-      NFB_CUDA(cudaEventRecord(ev_ready, s));
-      NFB_CUDA(cudaStreamWaitEvent(aux, ev_ready, 0));
-      k_norm_param_reduce<<<(NP * cols + 7) / 8, dim3(8, 32), 0, aux>>>(partial, grid, NP, cols, dgamma, dbeta, accumulate);
-      NFB_CUDA(cudaEventRecord(w->done, aux));
-      w->used = true;
-      w->epoch = nfb_capture_epoch();
+      // queued: launched with its neighbours by norm_flush_pending (NR_BATCH queued, nfb_norm_flush, or the ring wrapping)
+      bool clash = g_nr_pending.n > 0 && g_nr_stream != s;
+      for (int j = 0; j < g_nr_pending.n && !clash; ++j)   // the same parameter twice in one batch would race: keep them in order
+        clash = (dgamma && g_nr_pending.job[j].dgamma == dgamma) || (dbeta && g_nr_pending.job[j].dbeta == dbeta);
+      if (clash && norm_flush_pending()) return -1;
+      g_nr_stream = s;
+      NormReduceJob& q = g_nr_pending.job[g_nr_pending.n];
+      q.partial = partial; q.dgamma = dgamma; q.dbeta = dbeta; q.nblocks = grid; q.np = NP; q.cols = cols; q.accumulate = accumulate;
+      g_nr_owner[g_nr_pending.n] = w;
+      ++g_nr_pending.n;
+      w->pending = true;
+      if (g_nr_pending.n == NR_BATCH && norm_flush_pending()) return -1;
     } else {
+      nfb_count_launch();
       nfb_launch_pdl(k_norm_param_reduce, dim3((NP * cols + 7) / 8), dim3(8, 32), 0, s, partial, grid, NP, cols, dgamma, dbeta, accumulate);
       nfb_free(partial);
     }

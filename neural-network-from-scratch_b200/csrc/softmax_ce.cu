@@ -184,7 +184,13 @@ k_cross_entropy(const float* __restrict__ logits, const void* __restrict__ targe
 
 // exp(x - m) for x <= m as ONE FFMA + MUFU.EX2 (x * log2e - m * log2e); ~2 ulp, no overflow possible since the argument
 // is <= 0.  expf() costs ~10 instructions and made the wide-row kernels issue-bound (206 M exponentials per LM-head step).
-__device__ __forceinline__ float exp_sub_fast(float x, float m_log2e) { return exp2f(fmaf(x, 1.4426950408889634f, -m_log2e)); }
+// ex2.approx.ftz: exp2f() without it wraps the MUFU in a subnormal-range rescue (FSETP + 2 predicated FMULs per value); a
+// probability below 2^-126 flushed to zero changes nothing at any tolerance this library states.
+__device__ __forceinline__ float exp_sub_fast(float x, float m_log2e) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(x, 1.4426950408889634f, -m_log2e)));
+  return r;
+}
 
 // ---- register-resident variant for wide rows (the LM-head shapes: V = 50257, 30522).  One 1024-thread block per SM
 // keeps a whole logits row in registers (NV4 x 4 values per thread, element 4*(k*1024 + t) .. +3), so the row is read
@@ -266,53 +272,61 @@ k_cross_entropy_reg(const TL* __restrict__ logits, const void* __restrict__ targ
 
 // ---- bf16 logits, wide rows: the row lives in SHARED memory as the raw bf16 it was loaded as (100 KB at V = 50257),
 // fetched by ONE bulk-async copy (cp.async.bulk global -> shared, mbarrier completion: no registers, no LSU issue), and
-// two 512-thread blocks share an SM so that one block's three shared-memory passes (max, sum of exp, scale + store)
-// overlap the other block's HBM load / store phases.  exp is evaluated twice per element; that is cheaper than a third
-// trip through memory.  dlogits may alias the logits buffer.
+// double-buffered: one 1024-thread block per SM runs the three shared-memory passes (max, sum of exp, scale + store) of
+// row r while the copy of its next row lands in the other buffer.  exp is evaluated twice per element; that is cheaper
+// than a third trip through memory.  dlogits may alias the logits buffer (a block only ever prefetches its OWN next row).
 __device__ __forceinline__ void ce_unpack8(const uint4& u, float* v) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
   for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
 }
 template <typename TD>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(1024, 1)
 k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __restrict__ targets, int tgt_is_i64, float* __restrict__ loss,
                      TD* __restrict__ dlogits, int64_t rows, int V, int64_t ld, int64_t dld, float grad_scale, int* __restrict__ err) {
+  // One 1024-thread CTA per SM, TWO row buffers: the bulk copy of row r+1 is in flight while the three shared-memory passes
+  // (max, exp-sum, gradient) of row r run, and the gradient stores of row r drain under the passes of row r+1.  (The
+  // single-buffer 2-CTA version serialised copy -> passes per CTA and ran at memory time + MUFU time: 202 us for 4096 x 50257.)
   extern __shared__ __align__(128) unsigned char ce_smem[];
   __shared__ float red[32];
-  __shared__ __align__(8) unsigned long long bar;
-  const uint4* srow = reinterpret_cast<const uint4*>(ce_smem);
+  __shared__ __align__(8) unsigned long long bar[2];
   const int t = threadIdx.x;
   const int nv = (V + 7) >> 3;                 // 16-byte vectors per row (the pitch is padded to a multiple of 8 elements)
   const uint32_t row_bytes = (uint32_t)nv * 16u;
-  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar), row_a = (uint32_t)__cvta_generic_to_shared(ce_smem);
+  const uint32_t buf_pitch = (row_bytes + 127u) & ~127u;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[0]), smem_a = (uint32_t)__cvta_generic_to_shared(ce_smem);
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8u));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t phase = 0;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    if (t == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer vs this async write
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(row_a), "l"(logits + row * ld), "r"(row_bytes), "r"(bar_a) : "memory");
-    }
+  auto fetch = [&](int64_t row, int b) {       // thread 0 only; every generic read of buffer b is behind a __syncthreads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8u * b), "r"(row_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_a + buf_pitch * b), "l"(logits + row * ld), "r"(row_bytes), "r"(bar_a + 8u * b) : "memory");
+  };
+  if (t == 0 && (int64_t)blockIdx.x < rows) fetch(blockIdx.x, 0);
+  int it = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    const int b = it & 1;
+    if (t == 0 && row + gridDim.x < rows) fetch(row + gridDim.x, b ^ 1);
+    const uint4* srow = reinterpret_cast<const uint4*>(ce_smem + (size_t)buf_pitch * b);
     int64_t tg = tgt_is_i64 ? ((const int64_t*)targets)[row] : (int64_t)((const int32_t*)targets)[row];
     if (tg < 0) tg += V;  // numpy negative indexing
     const bool bad = tg < 0 || tg >= V;   // see k_cross_entropy: NaN loss, zero gradient row, error flag
     if (bad) tg = -1;
     {
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
       uint32_t ok = 0;
       while (!ok) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar_a), "r"(phase) : "memory");
+                     : "=r"(ok) : "r"(bar_a + 8u * b), "r"(phase) : "memory");
       }
-      phase ^= 1;
     }
     float m = -INFINITY;
-    for (int i = t; i < nv; i += 512) {
+    for (int i = t; i < nv; i += 1024) {
       float v[8];
       ce_unpack8(srow[i], v);
       const int c = i * 8;
@@ -326,7 +340,7 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
     m = block_max(m, red);
     const float ml2 = m * 1.4426950408889634f;
     float s = 0.f;
-    for (int i = t; i < nv; i += 512) {
+    for (int i = t; i < nv; i += 1024) {
       float v[8];
       ce_unpack8(srow[i], v);
       const int c = i * 8;
@@ -345,7 +359,7 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
         loss[row] = __int_as_float(0x7fc00000);
         if (err) *err = 1;
       } else {
-        float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tg]);
+        float xt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(srow)[tg]);
         loss[row] = -logf(exp_sub_fast(xt, ml2) * inv + 1e-8f);
       }
     }
@@ -353,7 +367,7 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
       TD* dr = dlogits + row * dld;
       const float sc = bad ? 0.f : inv * grad_scale;
       const int tvec = (int)(tg >> 3), te = (int)(tg & 7);
-      for (int i = t; i < nv; i += 512) {
+      for (int i = t; i < nv; i += 1024) {
         float v[8];
         ce_unpack8(srow[i], v);
         const int c = i * 8;
@@ -372,7 +386,7 @@ k_cross_entropy_bulk(const __nv_bfloat16* __restrict__ logits, const void* __res
         }
       }
     }
-    __syncthreads();   // everyone is done with the row buffer before the next bulk copy overwrites it
+    __syncthreads();   // everyone is done with buffer b before the copy of row r+2 overwrites it
   }
 }
 
@@ -436,18 +450,18 @@ NFB_API int nfb_cross_entropy_ex(int ldt, const void* logits, const void* target
       if (!dlogits || ddt == NFB_F32) return ce_launch_reg<float, float>((const float*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale);
       return ce_launch_reg<float, __nv_bfloat16>((const float*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale);
     }
-    // bf16 logits: shared-memory row + bulk-async copy, two blocks per SM (needs 16-byte aligned rows)
+    // bf16 logits: shared-memory rows + bulk-async copies, one block per SM (needs 16-byte aligned rows)
     if (ld % 8 == 0 && (uintptr_t)logits % 16 == 0 && g_ce_bulk) {
-      const size_t smem = (size_t)((V + 7) / 8) * 16;
+      const size_t smem = 2 * (((size_t)((V + 7) / 8) * 16 + 127) & ~(size_t)127);   // two row buffers
       cudaStream_t s = nfb_cur_stream();
-      int64_t grid = 2LL * nfb_sm_count();
+      int64_t grid = nfb_sm_count();
       if (grid > rows) grid = rows;
       if (!dlogits || ddt == NFB_BF16) {
         NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cross_entropy_bulk<__nv_bfloat16><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
+        k_cross_entropy_bulk<__nv_bfloat16><<<(unsigned)grid, 1024, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (__nv_bfloat16*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
       } else {
         NFB_CUDA(cudaFuncSetAttribute(k_cross_entropy_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cross_entropy_bulk<float><<<(unsigned)grid, 512, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
+        k_cross_entropy_bulk<float><<<(unsigned)grid, 1024, smem, s>>>((const __nv_bfloat16*)logits, targets, tgt_is_i64, loss, (float*)dlogits, rows, V, ld, dld, grad_scale, nfb_index_error_flag());
       }
       NFB_LAUNCH_CHECK();
       return 0;

@@ -206,7 +206,7 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
         else:
             y = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue=act, rope=rope)
             z = y if act == "relu" else None  # relu'(z) == (y > 0)
-        ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16")
+        ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16", rope)
     else:
         xf = x2 if x2.dtype == F32 else x2.astype(np.float32)
         z = gemm_f32(xf, W, False, tb, bias=b)
@@ -220,7 +220,7 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
             y = z
         if res2 is not None:
             y = y + res2
-        ctx = (xf, W, None, z if act else None, act, weight_layout, b is not None, "fp32")
+        ctx = (xf, W, None, z if act else None, act, weight_layout, b is not None, "fp32", None)
     return y.reshape(lead + (n_out,)), ctx
 
 
@@ -318,6 +318,7 @@ def join_side_stream():
     global _side_dirty
     flush_wgrad()
     if _side_dirty:
+        call("nfb_norm_flush")   # queued norm-parameter reductions (csrc/norm.cu) go out before the fence
         from .runtime import Event, compute_stream_wait
         compute_stream_wait(Event(timing=False).record(_side))
         _held.clear()
@@ -330,6 +331,7 @@ def side_stream_event():
     flush_wgrad()
     if not _side_dirty:
         return None
+    call("nfb_norm_flush")
     from .runtime import Event
     return Event(timing=False).record(_side)
 
@@ -341,6 +343,7 @@ def run_on_side_stream(fn, *keep, _flush=True):
     from .runtime import Event, Stream, current_stream_handle
     if _flush:
         flush_wgrad()   # queued weight gradients precede whatever consumes them on this stream
+        call("nfb_norm_flush")   # ... and so do the queued norm-parameter reductions (csrc/norm.cu)
     if _side is None:
         _side = Stream()
     _side.wait_event(Event(timing=False).record())   # operands are final on the compute stream
@@ -358,18 +361,28 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
     """Returns (dx, dW, db).  dW / db are ACCUMULATED into dW_out / db_out when given (gradient arena views),
     otherwise freshly allocated.  dX = dZ W ; dW = dZ^T X ; db = column sums of dZ."""
     from . import array as A
-    x2, W, wb, z, act, layout, has_bias, precision = ctx
+    x2, W, wb, z, act, layout, has_bias, precision, rope = ctx
     lead = dy.shape[:-1]
     n_out = dy.shape[-1]
     twin = getattr(dy, "twin", None)
     dz = dy.reshape(-1, n_out)
     out_in = layout == "out_in"
+    rope_db = None
     if precision == "bf16":
         dz = twin.reshape(-1, n_out) if (twin is not None and dy.dtype != bfloat16) else to_bf16(dz)
         if act == "gelu":
             dz = A.unary_bwd("gelu_tanh", z.reshape(dz.shape), dz)
         elif act == "relu":
             dz = A.unary_bwd("relu", to_bf16(z.reshape(dz.shape)), dz)
+        if rope is not None:
+            # the forward epilogue rotated columns [0, cols): un-rotate their gradient in place and take the bias gradient
+            # (column sums of the un-rotated rows) in the same pass -- one kernel where rope-inverse + colsum were two
+            # (in place when the producer handed over a buffer nobody else holds -- packed_qkv_attention's backward does)
+            if dz.dtype is not bfloat16 or not getattr(dy, "inplace_ok", False):
+                dz = dz.copy()
+            rope_db = (db_out if db_out is not None else B200Array.empty((n_out,), np.float32)) if has_bias else None
+            rope_bwd_colsum(dz, rope, rope_db, accumulate=db_out is not None)
+            has_bias = False              # the bias gradient is done; nothing left to queue below
         dx = None
         if need_dx:
             odt = dx_dtype if dx_dtype is not None else bfloat16
@@ -380,7 +393,7 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             # gradient-arena target: nothing reads it before the optimizer / the bucket all-reduce -> queue for a grouped launch
             pair = (dz, x2) if out_in else (x2, dz)
             queue_wgrad(pair[0], pair[1], dW_out, (dz, db_out) if (has_bias and db_out is not None) else None)
-            db = db_out if has_bias else None
+            db = db_out if has_bias else rope_db
             if has_bias and db_out is None:
                 db = _colsum(dz, None)
             return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
@@ -404,6 +417,8 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             wg()
         if has_bias and db is None:
             db = _colsum(dz, db_out)
+        if db is None:
+            db = rope_db
         return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
     # ---- fp32 path
     if dz.dtype != F32:
@@ -427,6 +442,20 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
     if has_bias:
         db = _colsum(dz, db_out)
     return dx, dW, db
+
+
+def rope_bwd_colsum(dz: B200Array, rope, db_out=None, accumulate=True, base=10000):
+    """dz (T, n_out) bf16 = gradient of a projection whose epilogue applied the rotary embedding to columns [0, cols) (rope =
+    (seq_len, cols, head_dim), linear_forward): un-rotates those columns IN PLACE and, when db_out is given, (accumulates) the
+    column sums of the un-rotated rows into it.  One kernel (csrc/reduce.cu k_colsum_fused<bf16, ROPE>)."""
+    S, cols, hd = rope
+    if hd != 64:
+        raise ValueError("rope_bwd_colsum: head_dim must be 64 (the fused rotary epilogue's layout)")
+    cos_t, sin_t = rope_tables(hd, S, base)
+    R, Cc = dz.shape
+    call("nfb_rope_bwd_colsum", dz.ptr, R, Cc, dz.strides[0] if R > 1 else Cc, cos_t.ptr, sin_t.ptr, S, cols,
+         db_out.ptr if db_out is not None else None, 1 if accumulate else 0)
+    return dz
 
 
 def _colsum(dz: B200Array, out=None) -> B200Array:

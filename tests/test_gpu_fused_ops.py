@@ -152,7 +152,7 @@ def _bf16_round(a):
     return r.astype(np.uint32).view(np.float32).reshape(np.shape(a))
 
 
-@pytest.mark.parametrize("rows,V", [(20, 50257), (300, 30522), (9, 8192), (5, 53248)])
+@pytest.mark.parametrize("rows,V", [(20, 50257), (300, 30522), (9, 8192), (5, 53248), (1000, 8195)])
 @pytest.mark.parametrize("mode", ["f32_reg", "bf16_bulk", "bf16_reg"])
 def test_cross_entropy_wide_rows_lm_head_layout(be, rows, V, mode):
     """The LM-head layout: (T, V) logits with the row pitch padded to 8 elements (garbage in the pad), fp32 through the

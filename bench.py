@@ -243,8 +243,6 @@ def work_of(name, a):
         return "elementwise", "byte", float(a[6]) * a[7] * a[8] * a[9] * max(1, a[4]) * 2 * DT_SIZE[a[0]]
     if name == "nfb_colsum":
         return "elementwise", "byte", float(a[2]) * a[3] * DT_SIZE[a[0]]
-    if name == "nfb_rope_bwd_colsum":   # read every column once, write the rotated ones back (bf16)
-        return "elementwise", "byte", float(a[1]) * (a[2] + a[7]) * 2
     if name == "nfb_gather_rows":
         return "elementwise", "byte", float(a[6]) * a[7] * (DT_SIZE[a[1]] + DT_SIZE[a[2]])
     if name == "nfb_scatter_add_rows":
@@ -263,7 +261,7 @@ def work_of(name, a):
 
 
 PROFILED = ("nfb_gemm_bf16", "nfb_gemm_bf16_grouped", "nfb_flash_attn_fwd_gqa", "nfb_flash_attn_bwd_gqa", "nfb_norm_fwd", "nfb_norm_bwd",
-            "nfb_cross_entropy_ex", "nfb_adam_step", "nfb_adam_step_ex", "nfb_swiglu_fwd", "nfb_swiglu_bwd", "nfb_rope", "nfb_colsum", "nfb_rope_bwd_colsum", "nfb_gather_rows",
+            "nfb_cross_entropy_ex", "nfb_adam_step", "nfb_adam_step_ex", "nfb_swiglu_fwd", "nfb_swiglu_bwd", "nfb_rope", "nfb_colsum", "nfb_gather_rows",
             "nfb_scatter_add_rows", "nfb_cast", "nfb_unary", "nfb_unary_bwd", "nfb_binary_scalar", "nfb_add3")
 
 

@@ -93,12 +93,6 @@ int nfb_add3(const float* a, const float* b, const float* c, float* out, int64_t
 int nfb_reduce(int op, int dtype, const void* x, void* out, int64_t outer, int64_t R, int64_t inner);
 int nfb_argreduce(int is_max, int dtype, const void* x, int64_t* out, int64_t outer, int64_t R, int64_t inner);
 int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, float* out, int accumulate);
-/* Backward of a projection whose epilogue applied the rotary embedding (nfb_gemm_bf16_set_rope; the qkv projection of
- * models/language/gpt2.py:78-95 + 228-234): x (R, C) bf16 with row pitch ld is the gradient of the projection output; columns
- * [0, rope_cols) are UN-rotated in place (heads of 64 columns, angle tables (S, 32) fp32, position = row %% S) and, when out is not
- * NULL, out[c] (+)= the column sums of the un-rotated rows (the bias gradient, functional/utils.py:33-96) -- one pass. */
-int nfb_rope_bwd_colsum(void* x, int64_t R, int C, int64_t ld, const float* rope_cos, const float* rope_sin, int S, int rope_cols,
-                        float* out, int accumulate);
 
 /* ---- normalisation: LayerNorm / RMSNorm forward + backward (nn/normalization.py:86-221,269-359;
  * models/language/gpt2.py:98-116; CuPy precedent CudaBackend.layernorm backends/cuda_backend.py:334-352).  kind 0 LN, 1 RMS. */

@@ -239,16 +239,10 @@ __global__ void k_colsum_stage2(const float* __restrict__ tmp, int chunks, int C
 // single-launch variant: 16-byte loads (8 bf16 / 4 fp32 columns per thread), block (32, 8) sums a row chunk of its
 // 32 x VEC columns, and the LAST block to finish a column strip (device counter, __threadfence) adds the chunk partials
 // in a fixed order -- deterministic, one kernel instead of two.
-// ROPE (bf16 only): x is the gradient of a projection whose epilogue rotated columns [0, rope_cols) (heads of 64 columns,
-// pairs (i, i + 32), angle table row = row index % rope_S -- gemm_tc.cu's fused rotary epilogue).  The rows are UN-rotated
-// in place on the way through (da = dy1 c + dy2 s ; db = dy2 c - dy1 s, rounded to bf16) and the column sums are taken of
-// the rounded un-rotated values: the inverse rotation and the bias gradient of the qkv projection in one pass over dqkv.
-// The partner half of a head sits four lanes away (8 columns per lane), so it arrives by one shuffle.
-template <typename T, bool ROPE>
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_colsum_fused(T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_len, float* __restrict__ tmp, unsigned* __restrict__ counters,
-               float* __restrict__ out, int accumulate, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int rope_S,
-               int rope_cols) {
+k_colsum_fused(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_len, float* __restrict__ tmp, unsigned* __restrict__ counters,
+               float* __restrict__ out, int accumulate) {
   nfb_pdl_enter();
   constexpr int VEC = 16 / (int)sizeof(T);
   __shared__ float red[8][32 * VEC + 1];
@@ -258,57 +252,7 @@ k_colsum_fused(T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_le
   float acc[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-  if (ROPE) {
-    // every lane walks the rows (the shuffle needs the whole warp); lanes past the last column carry zeros
-    const bool live = c0 < C, rot = c0 < rope_cols;
-    const int f0 = (c0 & 31);                       // first of this lane's 8 angle indices
-    const bool second = (c0 & 32) != 0;             // this lane holds the (i + 32) half of its head
-    for (int64_t rb = lo; rb < hi; rb += 32) {      // four rows per thread in flight
-      uint4 u4[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t r = rb + 8 * j + threadIdx.y;
-        u4[j] = make_uint4(0, 0, 0, 0);
-        if (live && r < hi) u4[j] = *reinterpret_cast<const uint4*>(x + r * ld + c0);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t r = rb + 8 * j + threadIdx.y;
-        const bool ok = live && r < hi;
-        const uint4 u = u4[j];
-        uint4 v;
-        v.x = __shfl_xor_sync(0xffffffffu, u.x, 4); v.y = __shfl_xor_sync(0xffffffffu, u.y, 4);
-        v.z = __shfl_xor_sync(0xffffffffu, u.z, 4); v.w = __shfl_xor_sync(0xffffffffu, u.w, 4);
-        if (!ok) continue;
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-        if (rot) {
-          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v);
-          const int pos = (int)(r % rope_S);
-          const float4* ct = reinterpret_cast<const float4*>(rope_cos + (size_t)pos * 32 + f0);
-          const float4* st = reinterpret_cast<const float4*>(rope_sin + (size_t)pos * 32 + f0);
-          const float4 ca = __ldg(ct), cb = __ldg(ct + 1), sa = __ldg(st), sb = __ldg(st + 1);
-          const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w}, ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-          uint4 w;
-          uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 a = __bfloat1622float2(h[k]), b = __bfloat1622float2(hp[k]);
-            const float o0 = second ? a.x * cc[2 * k] - b.x * ss[2 * k] : a.x * cc[2 * k] + b.x * ss[2 * k];
-            const float o1 = second ? a.y * cc[2 * k + 1] - b.y * ss[2 * k + 1] : a.y * cc[2 * k + 1] + b.y * ss[2 * k + 1];
-            __nv_bfloat162 o2 = __floats2bfloat162_rn(o0, o1);
-            wp[k] = *reinterpret_cast<uint32_t*>(&o2);
-            const float2 f = __bfloat1622float2(o2);
-            acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
-          }
-          *reinterpret_cast<uint4*>(x + r * ld + c0) = w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-        }
-      }
-    }
-    if (out == nullptr) return;   // un-rotation only (a projection without a bias)
-  } else if (c0 < C) {
+  if (c0 < C) {
     int64_t r = lo + threadIdx.y;
     for (; r + 56 < hi; r += 64) {   // eight independent 16-byte loads in flight per thread
       uint4 u[8];
@@ -373,67 +317,41 @@ k_colsum_fused(T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t chunk_le
   if (tid == 0) counters[blockIdx.x] = 0;   // ready for the next launch on this stream
 }
 
-// single-launch column sums (+ optional in-place inverse rotary on bf16 rows); returns 1 when the shape does not qualify
-static int colsum_fused_launch(int dtype, void* x, int64_t R, int C, int64_t ld, float* out, int accumulate, const float* rope_cos,
-                               const float* rope_sin, int rope_S, int rope_cols) {
-  cudaStream_t s = nfb_cur_stream();
-  const int esz = dtype == NFB_F32 ? 4 : 2, vec = 16 / esz;
-  const bool rope = rope_cols > 0;
-  if (!((dtype == NFB_F32 || dtype == NFB_BF16) && C % vec == 0 && ld % vec == 0 && ((uintptr_t)x % 16 == 0) && (R >= 64 || rope) && nfb_cdiv(C, 32 * vec) <= 4096))
-    return 1;
-  int strips = (int)nfb_cdiv(C, 32 * vec);
-  int chunks = (int)((2LL * nfb_sm_count() + strips - 1) / strips);
-  int64_t max_chunks = R / 64 > 0 ? R / 64 : 1;
-  if (chunks > max_chunks) chunks = (int)max_chunks;
-  if (chunks < 1) chunks = 1;
-  int64_t chunk_len = nfb_cdiv(R, chunks);
-  chunks = (int)nfb_cdiv(R, chunk_len);
-  // chunk partials live in a grow-only workspace PER STREAM (not in the stream-ordered caching allocator): bias gradients
-  // may be computed on the weight-gradient side stream, where an allocator block freed "in stream order" of the compute
-  // stream could be recycled while this kernel still runs
-  static std::map<cudaStream_t, std::pair<float*, size_t>> ws;
-  static std::map<cudaStream_t, unsigned*> ws_counters;
-  std::pair<float*, size_t>& w = ws[s];
-  const size_t need = (size_t)chunks * C;
-  if (w.second < need) {
-    if (w.first) NFB_CUDA(cudaFree(w.first));   // implicit device sync: earlier users have finished
-    NFB_CUDA(cudaMalloc((void**)&w.first, sizeof(float) * need));
-    w.second = need;
-  }
-  unsigned*& cnt = ws_counters[s];
-  if (!cnt) {
-    NFB_CUDA(cudaMalloc((void**)&cnt, 4096 * sizeof(unsigned)));
-    NFB_CUDA(cudaMemset(cnt, 0, 4096 * sizeof(unsigned)));
-  }
-  float* tmp = w.first;
-  dim3 grid(strips, chunks), block(32, 8);
-  if (rope) nfb_launch_pdl(k_colsum_fused<__nv_bfloat16, true>, grid, block, 0, s, (__nv_bfloat16*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate, rope_cos, rope_sin, rope_S, rope_cols);
-  else if (dtype == NFB_F32) nfb_launch_pdl(k_colsum_fused<float, false>, grid, block, 0, s, (float*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate, (const float*)nullptr, (const float*)nullptr, 0, 0);
-  else nfb_launch_pdl(k_colsum_fused<__nv_bfloat16, false>, grid, block, 0, s, (__nv_bfloat16*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate, (const float*)nullptr, (const float*)nullptr, 0, 0);
-  NFB_LAUNCH_CHECK();
-  return 0;
-}
-
-// x (R, C) bf16, row pitch ld: columns [0, rope_cols) are un-rotated in place (heads of 64 columns, angle tables (S, 32) fp32,
-// position = row % S) and, when out != NULL, out[c] (+)= the column sums of the un-rotated rows.  The backward of a projection
-// whose epilogue applied the rotary embedding (nfb_gemm_bf16_set_rope; models/language/gpt2.py:78-95): inverse rotation and
-// bias gradient in one pass.
-NFB_API int nfb_rope_bwd_colsum(void* x, int64_t R, int C, int64_t ld, const float* rope_cos, const float* rope_sin, int S, int rope_cols,
-                                float* out, int accumulate) {
-  if (R == 0 || C == 0) return 0;
-  if (rope_cols <= 0 || rope_cols % 64 != 0 || rope_cols > C || S <= 0 || !rope_cos || !rope_sin)
-    return NFB_FAIL("nfb_rope_bwd_colsum: rope_cols=%d must be a positive multiple of 64 <= C=%d, S=%d > 0, tables non-NULL", rope_cols, C, S);
-  int rc = colsum_fused_launch(NFB_BF16, x, R, C, ld, out, accumulate, rope_cos, rope_sin, S, rope_cols);
-  if (rc == 1) return NFB_FAIL("nfb_rope_bwd_colsum: needs 16-byte aligned bf16 rows with C %% 8 == 0 (C=%d ld=%lld)", C, (long long)ld);
-  return rc;
-}
-
 NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, float* out, int accumulate) {
   if (C == 0) return 0;
   cudaStream_t s = nfb_cur_stream();
-  {
-    int rc = colsum_fused_launch(dtype, const_cast<void*>(x), R, C, ld, out, accumulate, nullptr, nullptr, 0, 0);
-    if (rc != 1) return rc;
+  const int esz = dtype == NFB_F32 ? 4 : 2, vec = 16 / esz;
+  if ((dtype == NFB_F32 || dtype == NFB_BF16) && C % vec == 0 && ld % vec == 0 && ((uintptr_t)x % 16 == 0) && R >= 64 && nfb_cdiv(C, 32 * vec) <= 4096) {
+    int strips = (int)nfb_cdiv(C, 32 * vec);
+    int chunks = (int)((2LL * nfb_sm_count() + strips - 1) / strips);
+    int64_t max_chunks = R / 64 > 0 ? R / 64 : 1;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t chunk_len = nfb_cdiv(R, chunks);
+    chunks = (int)nfb_cdiv(R, chunk_len);
+    // chunk partials live in a grow-only workspace PER STREAM (not in the stream-ordered caching allocator): bias gradients
+    // may be computed on the weight-gradient side stream, where an allocator block freed "in stream order" of the compute
+    // stream could be recycled while this kernel still runs
+    static std::map<cudaStream_t, std::pair<float*, size_t>> ws;
+    static std::map<cudaStream_t, unsigned*> ws_counters;
+    std::pair<float*, size_t>& w = ws[s];
+    const size_t need = (size_t)chunks * C;
+    if (w.second < need) {
+      if (w.first) NFB_CUDA(cudaFree(w.first));   // implicit device sync: earlier users have finished
+      NFB_CUDA(cudaMalloc((void**)&w.first, sizeof(float) * need));
+      w.second = need;
+    }
+    unsigned*& cnt = ws_counters[s];
+    if (!cnt) {
+      NFB_CUDA(cudaMalloc((void**)&cnt, 4096 * sizeof(unsigned)));
+      NFB_CUDA(cudaMemset(cnt, 0, 4096 * sizeof(unsigned)));
+    }
+    float* tmp = w.first;
+    dim3 grid(strips, chunks), block(32, 8);
+    if (dtype == NFB_F32) nfb_launch_pdl(k_colsum_fused<float>, grid, block, 0, s, (const float*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate);
+    else nfb_launch_pdl(k_colsum_fused<__nv_bfloat16>, grid, block, 0, s, (const __nv_bfloat16*)x, R, C, ld, chunk_len, tmp, cnt, out, accumulate);
+    NFB_LAUNCH_CHECK();
+    return 0;
   }
   int col_blocks = (C + 63) / 64;
   int chunks = (int)((4LL * nfb_sm_count() + col_blocks - 1) / col_blocks);

@@ -76,7 +76,6 @@ _SIGNATURES = {
     "nfb_reduce": [i32, i32, vp, vp, i64, i64, i64],
     "nfb_argreduce": [i32, i32, vp, vp, i64, i64, i64],
     "nfb_colsum": [i32, vp, i64, i32, i64, vp, i32],
-    "nfb_rope_bwd_colsum": [vp, i64, i32, i64, vp, vp, i32, i32, vp, i32],
     # norms / softmax / loss
     "nfb_norm_fwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32],
     "nfb_norm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],

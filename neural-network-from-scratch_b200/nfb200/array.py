@@ -129,7 +129,7 @@ RED = {"sum": 0, "mean": 1, "max": 2, "min": 3, "prod": 4}
 
 
 class B200Array:
-    __slots__ = ("_buf", "_off", "shape", "strides", "dtype", "clipped", "twin", "inplace_ok", "__weakref__")
+    __slots__ = ("_buf", "_off", "shape", "strides", "dtype", "clipped", "twin", "__weakref__")
     __array_priority__ = 1000.0
 
     # ------------------------------------------------------------------ construction
@@ -140,7 +140,6 @@ class B200Array:
         self.strides = tuple(strides) if strides is not None else _contig_strides(self.shape)  # in ELEMENTS
         self._off = int(offset)  # in elements
         self.clipped = False  # gradient already clamped to +-clip by the kernel that produced it
-        self.inplace_ok = False  # a gradient buffer its producer hands over for good: the consumer's backward may overwrite it
         self.twin = None      # optional bf16 copy written by the producing kernel (feeds tensor-core GEMMs)
 
     @staticmethod

@@ -46,8 +46,7 @@ def linear(x: Tensor, weight: Tensor, bias=None, activation=None, residual=None,
            weight_layout: str = "out_in", rope=None) -> Tensor:
     """act(x @ W^T + b) [+ residual]; W is (out,in) ('out_in', nn/optimized.py) or (in,out) ('in_out', nn/linear.py).
     rope = (seq_len, cols, head_dim) (only where fused_rope_available): the rotary embedding of output columns [0, cols) is applied
-    in the GEMM epilogue and this node's backward un-rotates the gradient of those columns (together with the bias column sums);
-    consumers see rotated q / k and hand back the gradient of the ROTATED values (packed_qkv_attention(rope_applied=True))."""
+    in the GEMM epilogue; the caller's backward must un-rotate the gradient of those columns (packed_qkv_attention does)."""
     n_in = weight.shape[1] if weight_layout == "out_in" else weight.shape[0]
     if x.shape[-1] != n_in:
         raise ValueError(f"Input features {x.shape[-1]} != expected {n_in}")
@@ -344,13 +343,9 @@ def packed_qkv_attention(qkv: Tensor, n_heads: int, causal: bool = True, use_rop
             def backward(g):
                 g4 = K.to_bf16(g).reshape(B, S, n_heads, D).transpose(0, 2, 1, 3)
                 _, _, _, packed = K.attention_backward(g4, qd, kd, vd, o, lse, scale, causal, mk, packed=True)
-                if use_rope and not rope_applied:
+                if use_rope:
                     K.rope_packed_qk_inplace(packed, n_heads, inverse=True)
-                out_g = packed.reshape(B, S, three_d)
-                # rope_applied: the projection that rotated q / k in its epilogue un-rotates their gradient in its own
-                # backward (kernels.linear_backward: inverse rotation + bias column sums in one pass, in place on this buffer)
-                out_g.inplace_ok = True
-                return (out_g,)
+                return (packed.reshape(B, S, three_d),)
 
             return make_result(out, [qkv], backward, "packed_qkv_attention")
     from .shape import getitem, reshape, transpose

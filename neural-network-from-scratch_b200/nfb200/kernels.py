@@ -206,7 +206,7 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
         else:
             y = gemm_bf16(xb, wb, False, tb, out_dtype=odt, bias=b, residual=res2, epilogue=act, rope=rope)
             z = y if act == "relu" else None  # relu'(z) == (y > 0)
-        ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16", rope)
+        ctx = (xb, W, wb, z, act, weight_layout, b is not None, "bf16")
     else:
         xf = x2 if x2.dtype == F32 else x2.astype(np.float32)
         z = gemm_f32(xf, W, False, tb, bias=b)
@@ -220,7 +220,7 @@ def linear_forward(x: B200Array, W: B200Array, b=None, activation=None, out_dtyp
             y = z
         if res2 is not None:
             y = y + res2
-        ctx = (xf, W, None, z if act else None, act, weight_layout, b is not None, "fp32", None)
+        ctx = (xf, W, None, z if act else None, act, weight_layout, b is not None, "fp32")
     return y.reshape(lead + (n_out,)), ctx
 
 
@@ -361,28 +361,18 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
     """Returns (dx, dW, db).  dW / db are ACCUMULATED into dW_out / db_out when given (gradient arena views),
     otherwise freshly allocated.  dX = dZ W ; dW = dZ^T X ; db = column sums of dZ."""
     from . import array as A
-    x2, W, wb, z, act, layout, has_bias, precision, rope = ctx
+    x2, W, wb, z, act, layout, has_bias, precision = ctx
     lead = dy.shape[:-1]
     n_out = dy.shape[-1]
     twin = getattr(dy, "twin", None)
     dz = dy.reshape(-1, n_out)
     out_in = layout == "out_in"
-    rope_db = None
     if precision == "bf16":
         dz = twin.reshape(-1, n_out) if (twin is not None and dy.dtype != bfloat16) else to_bf16(dz)
         if act == "gelu":
             dz = A.unary_bwd("gelu_tanh", z.reshape(dz.shape), dz)
         elif act == "relu":
             dz = A.unary_bwd("relu", to_bf16(z.reshape(dz.shape)), dz)
-        if rope is not None:
-            # the forward epilogue rotated columns [0, cols): un-rotate their gradient in place and take the bias gradient
-            # (column sums of the un-rotated rows) in the same pass -- one kernel where rope-inverse + colsum were two
-            # (in place when the producer handed over a buffer nobody else holds -- packed_qkv_attention's backward does)
-            if dz.dtype is not bfloat16 or not getattr(dy, "inplace_ok", False):
-                dz = dz.copy()
-            rope_db = (db_out if db_out is not None else B200Array.empty((n_out,), np.float32)) if has_bias else None
-            rope_bwd_colsum(dz, rope, rope_db, accumulate=db_out is not None)
-            has_bias = False              # the bias gradient is done; nothing left to queue below
         dx = None
         if need_dx:
             odt = dx_dtype if dx_dtype is not None else bfloat16
@@ -393,7 +383,7 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             # gradient-arena target: nothing reads it before the optimizer / the bucket all-reduce -> queue for a grouped launch
             pair = (dz, x2) if out_in else (x2, dz)
             queue_wgrad(pair[0], pair[1], dW_out, (dz, db_out) if (has_bias and db_out is not None) else None)
-            db = db_out if has_bias else rope_db
+            db = db_out if has_bias else None
             if has_bias and db_out is None:
                 db = _colsum(dz, None)
             return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
@@ -417,8 +407,6 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
             wg()
         if has_bias and db is None:
             db = _colsum(dz, db_out)
-        if db is None:
-            db = rope_db
         return (dx.reshape(lead + (x2.shape[1],)) if dx is not None else None), dW_out, db
     # ---- fp32 path
     if dz.dtype != F32:
@@ -442,20 +430,6 @@ def linear_backward(dy: B200Array, ctx, need_dx=True, dW_out=None, db_out=None, 
     if has_bias:
         db = _colsum(dz, db_out)
     return dx, dW, db
-
-
-def rope_bwd_colsum(dz: B200Array, rope, db_out=None, accumulate=True, base=10000):
-    """dz (T, n_out) bf16 = gradient of a projection whose epilogue applied the rotary embedding to columns [0, cols) (rope =
-    (seq_len, cols, head_dim), linear_forward): un-rotates those columns IN PLACE and, when db_out is given, (accumulates) the
-    column sums of the un-rotated rows into it.  One kernel (csrc/reduce.cu k_colsum_fused<bf16, ROPE>)."""
-    S, cols, hd = rope
-    if hd != 64:
-        raise ValueError("rope_bwd_colsum: head_dim must be 64 (the fused rotary epilogue's layout)")
-    cos_t, sin_t = rope_tables(hd, S, base)
-    R, Cc = dz.shape
-    call("nfb_rope_bwd_colsum", dz.ptr, R, Cc, dz.strides[0] if R > 1 else Cc, cos_t.ptr, sin_t.ptr, S, cols,
-         db_out.ptr if db_out is not None else None, 1 if accumulate else 0)
-    return dz
 
 
 def _colsum(dz: B200Array, out=None) -> B200Array:

@@ -249,39 +249,3 @@ def test_cross_entropy_class_id_outside_the_vocabulary(be, rows, V, logits_bf16)
     assert not got_d[1].any() and not got_d[3].any()
     np.testing.assert_allclose(got_l[ok], want_l, rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(got_d[ok], probs / rows, rtol=1e-4, atol=1e-7)
-
-
-@pytest.mark.parametrize("B,S,H,bias", [(2, 512, 12, True), (3, 100, 4, True), (1, 70, 2, False), (8, 512, 12, True)])
-def test_rope_bwd_colsum_one_pass(be, B, S, H, bias):
-    """nfb_rope_bwd_colsum: the gradient of a packed qkv projection whose epilogue rotated q and k (models/language/gpt2.py:78-95)
-    is un-rotated in place -- da = dy1 c + dy2 s, db = dy2 c - dy1 s per (i, i + 32) pair of every 64-column head -- and the
-    bias gradient (column sums of the un-rotated, bf16-rounded rows; functional/utils.py:33-96) comes out of the same pass.
-    v columns pass through untouched."""
-    from nfb200 import kernels as Kn
-    from nfb200.array import B200Array, bfloat16
-    rng = np.random.default_rng(B * 1000 + S + H)
-    d = H * 64
-    R = B * S
-    g = rng.standard_normal((R, 3 * d)).astype(np.float32)
-    dev = Kn.to_bf16(B200Array.from_numpy(g))
-    g = dev.get().astype(np.float32)                      # the bf16 values the kernel sees
-    cos_t, sin_t = (t.get() for t in Kn.rope_tables(64, S))
-    pos = np.arange(R) % S
-    c, s = cos_t[pos][:, None, :], sin_t[pos][:, None, :]  # (R, 1, 32)
-    qk = g[:, :2 * d].reshape(R, 2 * H, 64)
-    a, b = qk[..., :32], qk[..., 32:]
-    want = g.copy()
-    want[:, :2 * d] = np.concatenate([a * c + b * s, b * c - a * s], axis=-1).reshape(R, 2 * d)
-    from test_gpu_fused_ops import _bf16_round
-    want_r = _bf16_round(want)
-    db0 = rng.standard_normal(3 * d).astype(np.float32)
-    db = B200Array.from_numpy(db0) if bias else None
-    Kn.rope_bwd_colsum(dev, (S, 2 * d, 64), db, accumulate=True)
-    got = dev.get().astype(np.float32)
-    assert np.array_equal(got[:, 2 * d:], g[:, 2 * d:])   # v: untouched
-    # a*c + b*s may be contracted into an FMA on the device: the bf16 rounding can then land one step away on a few elements
-    diff = np.abs(got - want_r)
-    assert np.all(diff <= np.abs(want_r) * 2.0 ** -7 + 1e-30)
-    assert np.mean(diff > 0) < 2e-3
-    if bias:
-        np.testing.assert_allclose(db.get(), db0 + got.astype(np.float64).sum(0), rtol=2e-5, atol=2e-4)

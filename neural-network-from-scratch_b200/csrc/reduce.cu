@@ -323,11 +323,14 @@ NFB_API int nfb_colsum(int dtype, const void* x, int64_t R, int C, int64_t ld, f
   const int esz = dtype == NFB_F32 ? 4 : 2, vec = 16 / esz;
   if ((dtype == NFB_F32 || dtype == NFB_BF16) && C % vec == 0 && ld % vec == 0 && ((uintptr_t)x % 16 == 0) && R >= 64 && nfb_cdiv(C, 32 * vec) <= 4096) {
     int strips = (int)nfb_cdiv(C, 32 * vec);
-    int chunks = (int)((2LL * nfb_sm_count() + strips - 1) / strips);
+    // ~4 blocks per SM, and a chunk length that is a MULTIPLE OF 64 rows: the kernel's fast loop takes 64 rows per trip (8 loads
+    // in flight per thread); a 125-row chunk (296 blocks over 4096 rows) ran its second half one load at a time -- 10.0 us for
+    // (4096, 2304) bf16, profiles/r02_bw_kernels.txt
+    int chunks = (int)((4LL * nfb_sm_count() + strips - 1) / strips);
     int64_t max_chunks = R / 64 > 0 ? R / 64 : 1;
     if (chunks > max_chunks) chunks = (int)max_chunks;
     if (chunks < 1) chunks = 1;
-    int64_t chunk_len = nfb_cdiv(R, chunks);
+    int64_t chunk_len = (nfb_cdiv(R, chunks) + 63) / 64 * 64;
     chunks = (int)nfb_cdiv(R, chunk_len);
     // chunk partials live in a grow-only workspace PER STREAM (not in the stream-ordered caching allocator): bias gradients
     // may be computed on the weight-gradient side stream, where an allocator block freed "in stream order" of the compute

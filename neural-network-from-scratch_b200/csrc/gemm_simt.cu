@@ -202,3 +202,56 @@ NFB_API int nfb_gemm_f64(int transA, int transB, int M, int N, int K, const doub
   NFB_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- fp32-accurate contraction ON THE TENSOR CORES: three-way bf16 split -------------------------------------------------
+// x = x1 + x2 + x3 with x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2) carries 24 significand bits, and
+//   A.B = A1B1 + (A1B2 + A2B1) + (A2B2 + A1B3 + A3B1) + O(2^-24 |A||B|).
+// Every bf16 x bf16 product is exact in fp32 and the tcgen05 pipe accumulates in fp32, so the six products are ONE bf16 GEMM
+// over a six-fold K: this kernel writes the operand with its K axis concatenated six times in the pattern
+//   role 0 (A): 1 1 2 2 1 3        role 1 (B): 1 2 1 2 3 1
+// k_axis 1: K runs along the columns -> out is (R, 6*C) row-major; k_axis 0: K runs along the rows -> out is (6*R, C).
+// The host (nfb200/kernels.py gemm_f32) then calls nfb_gemm_bf16 with K' = 6K and an fp32 C.  Replaces the FFMA kernel above
+// for large 2-D contractions of the fp32 mode (functional/arithmetic.py:441-575 at the north star's 1e-5 tolerance).
+__global__ void __launch_bounds__(256)
+k_split_bf16x3(const float* __restrict__ x, int64_t R, int64_t C, int64_t ld, int role, int k_axis, __nv_bfloat16* __restrict__ out) {
+  nfb_pdl_enter();
+  const int64_t c4n = C >> 2, total = R * c4n;
+  const int64_t seg = k_axis ? C : R * C;          // distance between consecutive copies, in elements
+  const int64_t pitch = k_axis ? 6 * C : C;        // output row pitch
+  const unsigned patA = 0x201100u;                 // copy j (j = 0 .. 5) takes part (pat >> 4j) & 15 (0-based): A = 0 0 1 1 0 2
+  const unsigned patB = 0x021010u;                 //                                                             B = 0 1 0 1 2 0
+  const unsigned pat = role == 0 ? patA : patB;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4n, c = (i - r * c4n) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint2 part[3];
+    __nv_bfloat16 h[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 a = __float2bfloat16_rn(f[e]);
+      const float r1 = f[e] - __bfloat162float(a);
+      const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(b);
+      h[0][e] = a; h[1][e] = b; h[2][e] = __float2bfloat16_rn(r2);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) part[q] = *reinterpret_cast<const uint2*>(h[q]);
+    __nv_bfloat16* o = out + r * pitch + c;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) *reinterpret_cast<uint2*>(o + j * seg) = part[(pat >> (4 * j)) & 15u];
+  }
+}
+
+NFB_API int nfb_split_bf16x3(const float* x, int64_t R, int64_t C, int64_t ld, int role, int k_axis, void* out) {
+  if (R == 0 || C == 0) return 0;
+  if (C % 4 != 0 || ld % 4 != 0 || (uintptr_t)x % 16 != 0 || (uintptr_t)out % 8 != 0)
+    return NFB_FAIL("nfb_split_bf16x3: needs C %% 4 == 0 and 16-byte aligned fp32 rows (C=%lld ld=%lld)", (long long)C, (long long)ld);
+  if (role != 0 && role != 1) return NFB_FAIL("nfb_split_bf16x3: role must be 0 (A) or 1 (B)");
+  const int64_t total = R * (C >> 2);
+  int grid = nfb_grid_for(total, 256);
+  nfb_launch_pdl(k_split_bf16x3, dim3(grid), dim3(256), 0, nfb_cur_stream(), x, R, C, ld, role, k_axis ? 1 : 0, (__nv_bfloat16*)out);
+  NFB_LAUNCH_CHECK();
+  return 0;
+}

@@ -102,6 +102,7 @@ _SIGNATURES = {
     # contractions
     "nfb_gemm_f32": [i32, i32, i32, i32, i32, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, i32, vp],
     "nfb_gemm_f64": [i32, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, i32],
+    "nfb_split_bf16x3": [vp, i64, i64, i64, i32, i32, vp],
     "nfb_gemm_bf16": [i32, i32, i32, i32, i32, vp, i64, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, i32, i32, i32, f32],
     "nfb_gemm_bf16_force_tile": [i32],
     "nfb_gemm_bf16_force_cta_group": [i32],

@@ -10,6 +10,8 @@ compute mode of the backend):
 from __future__ import annotations
 
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -155,8 +157,33 @@ def gemm_bf16_grouped(problems, trans_a=False, trans_b=False, accumulate=False):
          vpa(*Cs), la(*ldcs), dtype_code(odt), 1 if accumulate else 0)
 
 
+# fp32 contractions on the tensor cores (three-way bf16 split, six-fold K: csrc/gemm_simt.cu nfb_split_bf16x3).  Same 1e-5
+# contract as the FFMA kernel (O(2^-24) per product term, fp32 accumulation), ~3x its throughput on GPT-2-small layer shapes.
+_F32_TC = os.environ.get("NFB200_FP32_TENSOR_CORE", "1") != "0"
+_F32_TC_MIN_MNK = 1 << 24      # below this the two split passes cost more than the FFMA kernel
+
+
+def set_fp32_tensor_core(on: bool):
+    """fp32-mode 2-D contractions through the bf16x3 split on tcgen05 (True, default) or the FFMA kernel (False)."""
+    global _F32_TC
+    _F32_TC = bool(on)
+
+
+def _gemm_f32_split(a2, lda, b2, ldb, trans_a, trans_b, M, N, K, out, bias, accumulate):
+    # A' : (M, 6K) [K along the columns] or, with trans_a, (6K, M);  B' : (6K, N) or, with trans_b, (N, 6K)
+    ra, ca = a2.shape
+    rb, cb = b2.shape
+    ap = B200Array.empty((6 * ra, ca) if trans_a else (ra, 6 * ca), bfloat16)
+    bp = B200Array.empty((rb, 6 * cb) if trans_b else (6 * rb, cb), bfloat16)
+    call("nfb_split_bf16x3", a2.ptr, ra, ca, lda, 0, 0 if trans_a else 1, ap.ptr)
+    call("nfb_split_bf16x3", b2.ptr, rb, cb, ldb, 1, 1 if trans_b else 0, bp.ptr)
+    # split_k = 1: one pass over K' per output tile, no racing reduce-adds -> run-to-run deterministic like the FFMA kernel
+    return gemm_bf16(ap, bp, trans_a, trans_b, out=out, out_dtype=np.float32, bias=bias, accumulate=accumulate, split_k=1)
+
+
 def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None, bias=None, beta=0.0):
-    """fp32 SIMT contraction with the same calling convention as gemm_bf16 (2-D operands)."""
+    """fp32 contraction with the same calling convention as gemm_bf16 (2-D operands): the bf16x3 split on the tensor cores for
+    large aligned problems, the FFMA kernel otherwise."""
     def prep(x):
         if x.dtype != F32:
             x = x.astype(np.float32)
@@ -174,6 +201,10 @@ def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None,
         out = B200Array.empty((M, N), np.float32)
         beta = 0.0
     bias_c = bias.contiguous() if bias is not None else None
+    if (_F32_TC and beta in (0.0, 1.0) and float(M) * N * K >= _F32_TC_MIN_MNK and M % 8 == 0 and N % 8 == 0 and K % 8 == 0
+            and lda % 4 == 0 and ldb % 4 == 0 and a2.ptr % 16 == 0 and b2.ptr % 16 == 0 and out.dtype == F32 and out.strides[1] == 1
+            and (bias_c is None or bias_c.dtype == F32)):
+        return _gemm_f32_split(a2, lda, b2, ldb, trans_a, trans_b, M, N, K, out, bias_c, beta == 1.0)
     call("nfb_gemm_f32", 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, 1.0, a2.ptr, lda, 0, b2.ptr, ldb, 0, float(beta),
          out.ptr, out.strides[0] if M > 1 else N, 0, 1, bias_c.ptr if bias_c is not None else None)
     return out

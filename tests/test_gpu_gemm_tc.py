@@ -384,3 +384,42 @@ def test_gemm_f32_wrapper(be):
     np.testing.assert_allclose(got, x.astype(np.float64) @ w.T.astype(np.float64) + b, rtol=1e-5, atol=2e-5)
     got = Kn.gemm_f32(_to(be, x), _to(be, x), True, False).get()
     np.testing.assert_allclose(got, x.T.astype(np.float64) @ x.astype(np.float64), rtol=1e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(512, 768, 256, False, True), (1024, 2304, 768, False, False), (768, 768, 4096, True, False),
+                                         (4096, 768, 3072, False, True), (256, 264, 1032, True, True)])
+def test_fp32_contraction_through_the_bf16x3_split(be, M, N, K, ta, tb):
+    """fp32-mode contractions on the tensor cores: both operands split three ways into bf16 (24 significand bits), six products
+    as ONE bf16 GEMM over a six-fold K with fp32 accumulation (nfb_split_bf16x3 + nfb_gemm_bf16).  Held to the fp32 contract:
+    <= 1e-5 of the row scale against the float64 product (functional/arithmetic.py:441-575; the FFMA kernel is held to the same),
+    with bias and with accumulation into an existing C, and bit-identical run to run."""
+    from nfb200 import kernels as Kn
+    from nfb200.array import B200Array
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    a *= np.exp(rng.uniform(-6, 6, a.shape)).astype(np.float32)          # 5 decades of dynamic range inside every row
+    bias = rng.standard_normal(N).astype(np.float32)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    A64 = (a.T if ta else a).astype(np.float64)
+    B64 = (b.T if tb else b).astype(np.float64)
+    want = A64 @ B64
+    scale = np.abs(A64) @ np.abs(B64)                                     # the natural error scale of a dot product
+    da, db_, dbias = B200Array.from_numpy(a), B200Array.from_numpy(b), B200Array.from_numpy(bias)
+    Kn.set_fp32_tensor_core(True)
+    try:
+        got = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)
+        assert np.max(np.abs(got - want) / scale) < 2e-7                   # ~2^-22: far inside 1e-5
+        got2 = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)
+        assert np.array_equal(got, got2)
+        gb = Kn.gemm_f32(da, db_, ta, tb, bias=dbias).get().astype(np.float64)
+        assert np.max(np.abs(gb - (want + bias)) / (scale + np.abs(bias))) < 2e-7
+        out = B200Array.from_numpy(c0)
+        Kn.gemm_f32(da, db_, ta, tb, out=out, beta=1.0)
+        assert np.max(np.abs(out.get() - (want + c0)) / (scale + np.abs(c0))) < 2e-7
+        # against the FFMA kernel: both inside the contract, so they agree to it
+        Kn.set_fp32_tensor_core(False)
+        ref = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)
+        assert np.max(np.abs(ref - want) / scale) < 2e-6
+    finally:
+        Kn.set_fp32_tensor_core(True)

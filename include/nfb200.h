@@ -125,8 +125,8 @@ int nfb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const
 int nfb_gemm_f64(int transA, int transB, int M, int N, int K, const double* A, int64_t lda, int64_t strideA, const double* B, int64_t ldb,
                  int64_t strideB, double* C, int64_t ldc, int64_t strideC, int batch);   /* Backend.matmul on float64 arrays (not on the training path) */
 /* fp32-accurate contraction on the tensor cores: x (R, C) fp32 (row pitch ld) is split three ways into bf16 (x = x1 + x2 + x3,
- * 24 significand bits) and written with its K axis concatenated six times -- role 0 (A operand): parts 1 1 2 2 1 3, role 1 (B operand):
- * 1 2 1 2 3 1 -- as (R, 6*C) when k_axis = 1 (K along the columns) or (6*R, C) when k_axis = 0.  nfb_gemm_bf16 over the two outputs
+ * 24 significand bits) and written with its K axis concatenated six times -- role 0 (A operand): parts 2 1 3 1 2 1, role 1 (B operand):
+ * 2 3 1 2 1 1 (smallest products first) -- as (R, 6*C) when k_axis = 1 (K along the columns) or (6*R, C) when k_axis = 0.  nfb_gemm_bf16 over the two outputs
  * with K' = 6K and an fp32 C then equals the fp32 product to O(2^-24) (functional/arithmetic.py:441-575 at the 1e-5 tolerance). */
 int nfb_split_bf16x3(const float* x, int64_t R, int64_t C, int64_t ld, int role, int k_axis, void* out);
 int nfb_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,

@@ -209,7 +209,11 @@ NFB_API int nfb_gemm_f64(int transA, int transB, int M, int N, int K, const doub
 //   A.B = A1B1 + (A1B2 + A2B1) + (A2B2 + A1B3 + A3B1) + O(2^-24 |A||B|).
 // Every bf16 x bf16 product is exact in fp32 and the tcgen05 pipe accumulates in fp32, so the six products are ONE bf16 GEMM
 // over a six-fold K: this kernel writes the operand with its K axis concatenated six times in the pattern
-//   role 0 (A): 1 1 2 2 1 3        role 1 (B): 1 2 1 2 3 1
+//   role 0 (A): 2 1 3 1 2 1        role 1 (B): 2 3 1 2 1 1
+// i.e. SMALLEST TERMS FIRST (A2B2, A1B3, A3B1, then A1B2, A2B1, then A1B1).  The tensor pipe aligns the products of an MMA step to
+// the accumulator and truncates: second-order products (2^-16) added step after step INTO a large accumulator each lost their low
+// bits (measured 3e-6 of |A||B| with the large term first, against 3e-7 for the pipe's own accumulation error); accumulated on
+// their own first and merged once, they cost nothing (profiles/r02_fp32_split.txt).
 // k_axis 1: K runs along the columns -> out is (R, 6*C) row-major; k_axis 0: K runs along the rows -> out is (6*R, C).
 // The host (nfb200/kernels.py gemm_f32) then calls nfb_gemm_bf16 with K' = 6K and an fp32 C.  Replaces the FFMA kernel above
 // for large 2-D contractions of the fp32 mode (functional/arithmetic.py:441-575 at the north star's 1e-5 tolerance).
@@ -219,8 +223,8 @@ k_split_bf16x3(const float* __restrict__ x, int64_t R, int64_t C, int64_t ld, in
   const int64_t c4n = C >> 2, total = R * c4n;
   const int64_t seg = k_axis ? C : R * C;          // distance between consecutive copies, in elements
   const int64_t pitch = k_axis ? 6 * C : C;        // output row pitch
-  const unsigned patA = 0x201100u;                 // copy j (j = 0 .. 5) takes part (pat >> 4j) & 15 (0-based): A = 0 0 1 1 0 2
-  const unsigned patB = 0x021010u;                 //                                                             B = 0 1 0 1 2 0
+  const unsigned patA = 0x010201u;                 // copy j (j = 0 .. 5) takes part (pat >> 4j) & 15 (0-based): A = 1 0 2 0 1 0
+  const unsigned patB = 0x001021u;                 //                                                             B = 1 2 0 1 0 0
   const unsigned pat = role == 0 ? patA : patB;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / c4n, c = (i - r * c4n) << 2;

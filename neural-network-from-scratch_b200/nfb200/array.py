@@ -951,6 +951,13 @@ def matmul(a, b) -> B200Array:
     if out.size and K > 0:
         aa, ta, lda, sa = prep(a, M, K)
         bb, tb, ldb, sb = prep(b, K, N)
+        if not f64 and nb == 1 and float(M) * N * K >= (1 << 24):
+            # one large fp32 product: kernels.gemm_f32 (the bf16x3 split on the tensor cores when the shape qualifies, else FFMA)
+            from . import kernels as _K
+            a2 = aa.reshape(M, K) if not ta else aa.reshape(M, K).transpose(1, 0)
+            b2 = bb.reshape(K, N) if not tb else bb.reshape(K, N).transpose(1, 0)
+            _K.gemm_f32(a2, b2, bool(ta), bool(tb), out=out.reshape(M, N))
+            nb = 0   # done
         for b0 in range(0, nb, 65535):
             cnt = min(65535, nb - b0)
             if f64:

@@ -169,16 +169,26 @@ def set_fp32_tensor_core(on: bool):
     _F32_TC = bool(on)
 
 
+_F32_TC_KCHUNK = 4096          # the pipe's truncating fp32 accumulation grows with K (3e-7 of |A||B| at 768, 1e-6 at 8192): longer
+                               # contractions go in chunks whose results meet in round-to-nearest fp32 adds
+
+
 def _gemm_f32_split(a2, lda, b2, ldb, trans_a, trans_b, M, N, K, out, bias, accumulate):
     # A' : (M, 6K) [K along the columns] or, with trans_a, (6K, M);  B' : (6K, N) or, with trans_b, (N, 6K)
-    ra, ca = a2.shape
-    rb, cb = b2.shape
-    ap = B200Array.empty((6 * ra, ca) if trans_a else (ra, 6 * ca), bfloat16)
-    bp = B200Array.empty((rb, 6 * cb) if trans_b else (6 * rb, cb), bfloat16)
-    call("nfb_split_bf16x3", a2.ptr, ra, ca, lda, 0, 0 if trans_a else 1, ap.ptr)
-    call("nfb_split_bf16x3", b2.ptr, rb, cb, ldb, 1, 1 if trans_b else 0, bp.ptr)
-    # split_k = 1: one pass over K' per output tile, no racing reduce-adds -> run-to-run deterministic like the FFMA kernel
-    return gemm_bf16(ap, bp, trans_a, trans_b, out=out, out_dtype=np.float32, bias=bias, accumulate=accumulate, split_k=1)
+    for k0 in range(0, K, _F32_TC_KCHUNK):
+        kc = min(_F32_TC_KCHUNK, K - k0)
+        ac = a2[k0:k0 + kc, :] if trans_a else a2[:, k0:k0 + kc]
+        bc = b2[:, k0:k0 + kc] if trans_b else b2[k0:k0 + kc, :]
+        ra, ca = ac.shape
+        rb, cb = bc.shape
+        ap = B200Array.empty((6 * ra, ca) if trans_a else (ra, 6 * ca), bfloat16)
+        bp = B200Array.empty((rb, 6 * cb) if trans_b else (6 * rb, cb), bfloat16)
+        call("nfb_split_bf16x3", ac.ptr, ra, ca, lda, 0, 0 if trans_a else 1, ap.ptr)
+        call("nfb_split_bf16x3", bc.ptr, rb, cb, ldb, 1, 1 if trans_b else 0, bp.ptr)
+        # split_k = 1: one pass over K' per output tile, no racing reduce-adds -> run-to-run deterministic like the FFMA kernel
+        gemm_bf16(ap, bp, trans_a, trans_b, out=out, out_dtype=np.float32, bias=bias if k0 == 0 else None,
+                  accumulate=accumulate or k0 > 0, split_k=1)
+    return out
 
 
 def gemm_f32(a: B200Array, b: B200Array, trans_a=False, trans_b=False, out=None, bias=None, beta=0.0):

@@ -387,12 +387,14 @@ def test_gemm_f32_wrapper(be):
 
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(512, 768, 256, False, True), (1024, 2304, 768, False, False), (768, 768, 4096, True, False),
-                                         (4096, 768, 3072, False, True), (256, 264, 1032, True, True)])
+                                         (4096, 768, 3072, False, True), (256, 264, 1032, True, True), (256, 512, 9216, False, True),
+                                         (512, 256, 8200, True, False)])
 def test_fp32_contraction_through_the_bf16x3_split(be, M, N, K, ta, tb):
     """fp32-mode contractions on the tensor cores: both operands split three ways into bf16 (24 significand bits), six products
     as ONE bf16 GEMM over a six-fold K with fp32 accumulation (nfb_split_bf16x3 + nfb_gemm_bf16).  Held to the fp32 contract:
     <= 1e-5 of the row scale against the float64 product (functional/arithmetic.py:441-575; the FFMA kernel is held to the same),
-    with bias and with accumulation into an existing C, and bit-identical run to run."""
+    with bias and with accumulation into an existing C, and bit-identical run to run.  K > 4096 runs in chunks (the pipe's
+    truncating accumulation error grows with K) whose results meet in round-to-nearest fp32 adds."""
     from nfb200 import kernels as Kn
     from nfb200.array import B200Array
     rng = np.random.default_rng(M + N + K)
@@ -409,14 +411,14 @@ def test_fp32_contraction_through_the_bf16x3_split(be, M, N, K, ta, tb):
     Kn.set_fp32_tensor_core(True)
     try:
         got = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)
-        assert np.max(np.abs(got - want) / scale) < 2e-7                   # ~2^-22: far inside 1e-5
+        assert np.max(np.abs(got - want) / scale) < 2e-6                   # the tensor pipe's own fp32 accumulation error; far inside 1e-5
         got2 = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)
         assert np.array_equal(got, got2)
         gb = Kn.gemm_f32(da, db_, ta, tb, bias=dbias).get().astype(np.float64)
-        assert np.max(np.abs(gb - (want + bias)) / (scale + np.abs(bias))) < 2e-7
+        assert np.max(np.abs(gb - (want + bias)) / (scale + np.abs(bias))) < 2e-6
         out = B200Array.from_numpy(c0)
         Kn.gemm_f32(da, db_, ta, tb, out=out, beta=1.0)
-        assert np.max(np.abs(out.get() - (want + c0)) / (scale + np.abs(c0))) < 2e-7
+        assert np.max(np.abs(out.get() - (want + c0)) / (scale + np.abs(c0))) < 2e-6
         # against the FFMA kernel: both inside the contract, so they agree to it
         Kn.set_fp32_tensor_core(False)
         ref = Kn.gemm_f32(da, db_, ta, tb).get().astype(np.float64)

@@ -564,10 +564,11 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
 
 // Issue order of the MMA thread (tensor-core products retire in issue order) and the matching order of the elementwise
 // warps; iteration `it` handles query block i0 + it:
-//   MMA :  S(0) dP(0) | loop it: [p_full(it)] dV(it) ; [ds_full(it)] S(it+1) ; dK(it) ; [dq_free(it-1)] dQ(it) ; dP(it+1)
+//   MMA :  S(0) dP(0) | loop it: [p_full(it)] dV(it) ; S(it+1) ; [ds_full(it)] dK(it) ; [dq_free(it-1)] dQ(it) ; dP(it+1)
 //   ELEM:  loop it: [s_full(it)] P(it) ; (it > 0: [dq_full(it-1)] drain dQ(it-1)) ; [dp_full(it)] dS(it)   ... final drain
-// S(it+1) is issued BEFORE dK(it) / dQ(it), so the exponentials of the next block run while those products and the
-// dQ drain of the previous block are in flight; the dS buffer of block it is only rewritten after dq_full(it).
+// S(it+1) is issued as soon as P(it) has been written (the score columns are free then), so the next score block is in TMEM
+// long before the elementwise warps finish the dQ drain and dS of block it; the dS buffer of block it is only rewritten
+// after dq_full(it).
 template <int POLY>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -716,10 +717,16 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 256u, make_smem_desc(sP + k * 2048, 16384, 1024), make_smem_desc(sdO + st * 16384 + k * 2048, 8192, 1024), idesc_kv,
                     (it > 0 || k > 0) ? 1u : 0u);
-        if (more) mbar_wait(&q_full[st ^ 1], ((it + 1) >> 1) & 1);
+        // S(it+1) goes out right behind dV(it): the S columns were consumed when P(it) was written (p_full), so the next score block
+        // -- and the ~1.6 k clk from its issue to the elementwise warps seeing s_full -- no longer waits for dS(it); its s_full
+        // also certifies dV(it), i.e. that the P buffer may be rewritten
+        if (more) {
+          mbar_wait(&q_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(st ^ 1);
+        }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
-        if (more) issue_s(st ^ 1);      // S columns were consumed when P(it) was written; its s_full also certifies dV(it)
         // dK += dS^T Q_i ; dQ_i = dS K_j
 #pragma unroll
         for (int k = 0; k < 8; ++k)

@@ -530,12 +530,11 @@ constexpr int SB_DS = 131072;           // dS    32 KB
 constexpr int SB_DQ = 163840;           // dQ staging, bf16 [128 rows][128 B] = 16 KB (32 KB reserved)
 constexpr int SB_BAR = 196608;
 constexpr int SB_MASK = SB_BAR + 256;   // 128 fp32: additive key mask of this CTA's key block (log2 domain), -inf beyond Skv
-constexpr int SB_DELTA = SB_MASK + 512; // 2 stages x 128 fp32: delta_i = rowsum(dO_i o O_i) of the staged query block
-constexpr int SB_TOTAL = SB_DELTA + 1024 + 1024;
+constexpr int SB_TOTAL = SB_MASK + 512 + 1024 + 1024;
 
 struct AttnBwdTcParams {
   const float* lse;     // (B, H, S) natural log
-  const float* delta;   // (B, H, S) rowsum(dO o O), or NULL: computed in the kernel from `o` and the staged dO tile
+  const float* delta;   // (B, H, S) rowsum(dO o O): from k_attn_bwd_prep (or the caller)
   const __nv_bfloat16* o;   // forward output, same (b, s, h, d) strides as dO
   long long o_sb, o_ss, o_sh;
   __nv_bfloat16 *dk, *dv;
@@ -585,7 +584,6 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* ds_full = bars + 8;      // dS in smem (256 arrivals)
   uint64_t* dq_full = bars + 9;      // dQ_i partial in TMEM; dK(it) / dQ(it) have retired -> dS buffer free
   uint64_t* dq_free = bars + 10;     // dQ TMEM columns drained (256 arrivals)
-  uint64_t* delta_full = bars + 11;  // 2 stages: delta_i of the staged query block is in shared memory
   uint32_t* tmem_slot = (uint32_t*)(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -610,7 +608,6 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(dq_full, 1); mbar_init(dq_free, 256);
-    mbar_init(&delta_full[0], 1); mbar_init(&delta_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -626,18 +623,13 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (threadIdx.x == 0) tlb(p, 0);
 
   if (warp == 8) {
-    // ===================== TMA producer (lane 0) + delta (all lanes) =====================
-    // delta_i = sum_d dO[i, d] * O[i, d] of every staged query block (when the caller passed none): lane l owns rows
-    // 4l .. 4l+3 -- the O rows come straight from global memory (one 128-byte line each, 32 loads in flight per lane),
-    // the dO rows from the TMA-staged swizzled tile.  This warp runs a block ahead of the consumers and is otherwise
-    // idle, so the global-load latency never reaches the critical path.
+    // ===================== TMA producer (lane 0) =====================
     if (niter > 0) {
       if (lane == 0) {
         mbar_expect_tx(kv_full, 32768u);
         tma_load_4d(smem + SB_K, &tmK, kv_full, 0, h / p.kv_split, k0, b);
         tma_load_4d(smem + SB_V, &tmV, kv_full, 0, h / p.kv_split, k0, b);
       }
-      float* sdelta = reinterpret_cast<float*>(smem + SB_DELTA);
       for (int it = 0; it < niter; ++it) {
         const int st = it & 1;
         const int q0 = q0_of(it), hq = hq_of(it);
@@ -646,39 +638,6 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_expect_tx(&q_full[st], 32768u);
           tma_load_4d(smem + SB_Q + st * 16384, &tmQ, &q_full[st], 0, hq, q0, b);
           tma_load_4d(smem + SB_DO + st * 16384, &tmdO, &q_full[st], 0, hq, q0, b);
-        }
-        if (!p.delta) {
-          uint4 ov[4][8];
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int qi = q0 + lane * 4 + rr;
-            const uint4* orow = reinterpret_cast<const uint4*>(p.o + b * p.o_sb + hq * p.o_sh + (long long)qi * p.o_ss);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ov[rr][c] = qi < p.S ? __ldg(orow + c) : make_uint4(0, 0, 0, 0);
-          }
-          mbar_wait(&q_full[st], (it >> 1) & 1);   // the dO tile has landed
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int row = lane * 4 + rr;
-            const uint32_t dorow = smem_u32(smem + SB_DO) + (uint32_t)st * 16384u + (uint32_t)row * 128u;
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              uint4 dv4;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dv4.x), "=r"(dv4.y), "=r"(dv4.z), "=r"(dv4.w) : "r"(dorow + (uint32_t)((c ^ (row & 7)) * 16)));
-              const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&dv4);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&ov[rr][c]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-                acc0 = fmaf(fa.x, fb.x, acc0);
-                acc1 = fmaf(fa.y, fb.y, acc1);
-              }
-            }
-            sdelta[st * 128 + row] = acc0 + acc1;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&delta_full[st]);
         }
       }
     }
@@ -813,12 +772,27 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     };
 
+    // the row's LSE is loaded one block AHEAD: as the first instruction of an iteration its ~1.2 k clk global-load latency sat
+    // between dS(it-1) and P(it) on the critical path of these warps (profiles/r02_attn_timeline.txt)
+    auto lse_of = [&](int it_l) -> float {
+      const int qi_l = q0_of(it_l) + r;
+      const long long row_l = ((long long)b * p.H + hq_of(it_l)) * p.S;
+      // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
+      return qi_l < p.S ? p.lse[row_l + qi_l] : INFINITY;
+    };
+    auto delta_of = [&](int it_l) -> float {
+      const int qi_l = q0_of(it_l) + r;
+      const long long row_l = ((long long)b * p.H + hq_of(it_l)) * p.S;
+      return (p.delta && qi_l < p.S) ? p.delta[row_l + qi_l] : 0.f;
+    };
+    float lse_next = niter > 0 ? lse_of(0) : 0.f;
+    float dlt_next = niter > 0 ? delta_of(0) : 0.f;
     for (int it = 0; it < niter; ++it) {
       const int q0 = q0_of(it), qi = q0 + r;
       const long long row0 = ((long long)b * p.H + hq_of(it)) * p.S;   // (b, query head) row of lse / delta
-      const bool valid = qi < p.S;
-      // invalid (padding) rows: LSE = +inf makes P = 0, so nothing of them reaches dV / dK
-      const float lse2 = valid ? p.lse[row0 + qi] * LOG2E : INFINITY;
+      const float lse2 = lse_next * LOG2E;
+      const float dlt_ext = dlt_next;
+      if (it + 1 < niter) { lse_next = lse_of(it + 1); dlt_next = delta_of(it + 1); }
       // ---- P = exp2(score - LSE)
       mbar_wait(s_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it);
@@ -890,13 +864,8 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (it > 0) drain_dq(it - 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 2);
       // ---- dS = P o (dP - delta) * scale   (dS buffer: dK(it-1), dQ(it-1) retired -- dq_full(it-1) awaited in the drain)
-      float dlt;
-      if (p.delta) {
-        dlt = valid ? p.delta[row0 + qi] : 0.f;
-      } else {
-        mbar_wait(&delta_full[it & 1], (it >> 1) & 1);   // written by the producer warp a block ahead
-        dlt = reinterpret_cast<const float*>(smem + SB_DELTA)[(it & 1) * 128 + r];
-      }
+      const float dlt = dlt_ext;   // delta_i = rowsum(dO_i o O_i): formed by k_attn_bwd_prep (or passed in), loaded one block ahead
+      if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 5);
       mbar_wait(dp_full, it & 1);
       if (threadIdx.x == 0) tlb(p, 16 + 8 * it + 3);
       tc_fence_after();
@@ -966,6 +935,46 @@ k_flash_bwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// In front of the backward: dq := 0 (skipped when dq is NULL: the fp32 accumulation path clears its own buffer) and
+// delta[b, h, s] = sum_d dO[b, s, h, d] * O[b, s, h, d] (skipped when delta is NULL: the caller supplied it).  Eight threads per
+// (b, s, h) row, one 16-byte access each; consecutive rows walk the heads first, so a warp touches 4 x 128 contiguous bytes
+// of the (b, s, h, d) tensors.
+__global__ void __launch_bounds__(256)
+k_attn_bwd_prep(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta, __nv_bfloat16* __restrict__ dq,
+                int B, int H, int S, long long o_sb, long long o_ss, long long o_sh, long long q_sb, long long q_ss, long long q_sh) {
+  nfb_pdl_enter();
+  const long long total = (long long)B * S * H * 8;
+  const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;   // stride is a multiple of 32
+  for (long long i0 = start - (start & 7); i0 < total; i0 += stride) {   // the 8 threads of a row stay together (shuffles below)
+    const long long i = i0 + (start & 7);
+    const int c = (int)(i & 7);
+    long long row = i >> 3;
+    const int hh = (int)(row % H); row /= H;
+    const int sidx = (int)(row % S);
+    const long long bb = row / S;
+    if (dq) *reinterpret_cast<uint4*>(dq + bb * q_sb + (long long)sidx * q_ss + (long long)hh * q_sh + c * 8) = make_uint4(0, 0, 0, 0);
+    if (delta) {
+      const long long off = bb * o_sb + (long long)sidx * o_ss + (long long)hh * o_sh + c * 8;
+      const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(o + off)), b4 = __ldg(reinterpret_cast<const uint4*>(dout + off));
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+        acc0 = fmaf(fa.x, fb.x, acc0);
+        acc1 = fmaf(fa.y, fb.y, acc1);
+      }
+      float v = acc0 + acc1;
+      const unsigned gmask = 0xFFu << (threadIdx.x & 24);   // the row's 8 lanes (other rows of the warp may be past the end)
+      v += __shfl_xor_sync(gmask, v, 1);
+      v += __shfl_xor_sync(gmask, v, 2);
+      v += __shfl_xor_sync(gmask, v, 4);
+      if (c == 0) delta[(bb * H + hh) * S + sidx] = v;
+    }
   }
 }
 
@@ -1127,7 +1136,7 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
   return 0;
 }
 
-// backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) may be NULL (computed in the kernel from o and dO).  dq/dk/dv use the q / kv strides.
+// backward on the tensor cores; `delta` = rowsum(dO o O) (B, H, S) may be NULL (k_attn_bwd_prep forms it from o and dO).  dq/dk/dv use the q / kv strides.
 int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, const float* delta, void* dq, void* dk, void* dv,
                      int B, int H, int S, int Skv, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t kv_sb, int64_t kv_ss, int64_t kv_sh, int64_t o_sb,
                      int64_t o_ss, int64_t o_sh, float scale, int mask_mode, const float* key_mask, int kv_group) {
@@ -1148,18 +1157,20 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
     NFB_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   } else {
   if (make_map_bshd(&tmdQ, dq, B, S, H, q_sb, q_ss, q_sh)) return -1;
-  // dq accumulates through reduce-adds: zero it first.  Its rows (b, s) hold H*64 contiguous elements at pitch q_ss when the
-  // heads are packed (q_sh == 64): one 2-D memset per batch entry; any other layout is cleared head by head.
-  if (q_sh == HDIM && (q_sb == (long long)S * q_ss || B == 1)) {   // the packed qkv layout: ONE strided clear of all B*S rows
-    NFB_CUDA(cudaMemset2DAsync(dq, (size_t)q_ss * 2, 0, (size_t)H * HDIM * 2, (size_t)B * S, st));
-  } else if (q_sh == HDIM) {
-    for (int bb = 0; bb < B; ++bb)
-      NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb, (size_t)q_ss * 2, 0, (size_t)H * HDIM * 2, (size_t)S, st));
-  } else {
-    for (int bb = 0; bb < B; ++bb)
-      for (int hh = 0; hh < H; ++hh)
-        NFB_CUDA(cudaMemset2DAsync((__nv_bfloat16*)dq + (long long)bb * q_sb + (long long)hh * q_sh, (size_t)q_ss * 2, 0, (size_t)HDIM * 2, (size_t)S, st));
   }
+  // ONE preparation kernel in front of the backward: it clears dq (which accumulates through reduce-adds; any stride pattern) and
+  // forms delta = rowsum(dO o O) per (b, h, query row) unless the caller passed it.  (Until round 2 the delta of each staged
+  // query block was computed inside the backward kernel by its TMA-producer warp -- that single warp needed ~6.9 k clk per
+  // block and PACED the whole loop: 49.4 -> 38.8 us at B8 H12 S512 causal with delta supplied, profiles/r02_attn_timeline.txt --
+  // and dq was cleared by a 2-D memset node.)
+  float* delta_buf = nullptr;
+  if (!delta && nfb_malloc(sizeof(float) * (size_t)B * H * S, (void**)&delta_buf)) { if (acc) nfb_free(acc); return -1; }
+  {
+    const long long items = (long long)B * S * H * 8;
+    nfb_launch_pdl(k_attn_bwd_prep, dim3((unsigned)nfb_grid_for(items, 256)), dim3(256), 0, st, (const __nv_bfloat16*)o, (const __nv_bfloat16*)dout,
+                   delta_buf, dq_f32 ? (__nv_bfloat16*)nullptr : (__nv_bfloat16*)dq, B, H, S, (long long)o_sb, (long long)o_ss, (long long)o_sh,
+                   (long long)q_sb, (long long)q_ss, (long long)q_sh);
+    nfb_count_launch();
   }
   // grouped-query grids with few key/value heads (multi-query attention: one) would leave most SMs idle: split each
   // group over kv_split CTAs, each writing its partial dK / dV into a slice of a scratch buffer summed afterwards
@@ -1176,10 +1187,10 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   }
   __nv_bfloat16* part = nullptr;
   if (kv_split > 1) {
-    if (nfb_malloc(sizeof(__nv_bfloat16) * 2 * (size_t)B * Skv * Hkv * kv_split * HDIM, (void**)&part)) { if (acc) nfb_free(acc); return -1; }
+    if (nfb_malloc(sizeof(__nv_bfloat16) * 2 * (size_t)B * Skv * Hkv * kv_split * HDIM, (void**)&part)) { if (acc) nfb_free(acc); if (delta_buf) nfb_free(delta_buf); return -1; }
   }
   AttnBwdTcParams p = {};
-  p.lse = lse; p.delta = delta; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
+  p.lse = lse; p.delta = delta ? delta : delta_buf; p.o = (const __nv_bfloat16*)o; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   if (part) {   // partial dK | dV: two contiguous (B, Skv, Hkv * kv_split, 64) halves
     const long long hp = (long long)Hkv * kv_split;
@@ -1214,6 +1225,7 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
     nfb_count_launch();
     nfb_free(part);
   }
+  if (delta_buf) nfb_free(delta_buf);
   if (dq_f32) {
     const long long vecs = (long long)B * H * S * 8;
     nfb_launch_pdl(k_dq_convert, dim3((unsigned)nfb_grid_for(vecs, 256)), dim3(256), 0, st, (const float*)acc, (__nv_bfloat16*)dq, B, H, S,

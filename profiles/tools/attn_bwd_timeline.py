@@ -20,4 +20,4 @@ print("loop end", t[1] - t0, "after reduce wait", t[2] - t0)
 for it in range(8):
     s = t[16 + 8 * it: 16 + 8 * it + 7]
     if s[0] == 0: break
-    print(f"it {it}: s_full {s[0]-t0} | P {s[1]-s[0]} | drain(prev) {s[2]-s[1]} | wait dP {s[3]-s[2]} | dS {s[4]-s[3]}")
+    print(f"it {it}: s_full {s[0]-t0} | P {s[1]-s[0]} | drain(prev) {s[2]-s[1]} | wait delta {s[5]-s[2]} | wait dP {s[3]-s[5]} | dS {s[4]-s[3]}")

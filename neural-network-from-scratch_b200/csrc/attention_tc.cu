@@ -1211,9 +1211,11 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   }
   dim3 grid((unsigned)(nfb_cdiv(Skv, TILE_K) * B * Hkv * kv_split));
   poly_defaults();
-  if (g_poly_bwd == 1) k_flash_bwd_tc<1><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
-  else if (g_poly_bwd == 2) k_flash_bwd_tc<2><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
-  else k_flash_bwd_tc<0><<<grid, BWD_THREADS, SB_TOTAL, st>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  // programmatic dependent launch behind k_attn_bwd_prep (small blocks, no shared memory: the backward CTAs co-reside and run their
+  // prologue -- barrier init, TMEM allocation, descriptor prefetch -- under its tail; every global access sits behind griddepcontrol.wait)
+  if (g_poly_bwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_bwd_tc<1>, grid, dim3(BWD_THREADS), (size_t)SB_TOTAL, st, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  else if (g_poly_bwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_bwd_tc<2>, grid, dim3(BWD_THREADS), (size_t)SB_TOTAL, st, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  else NFB_CUDA(nfb_launch_pdl(k_flash_bwd_tc<0>, grid, dim3(BWD_THREADS), (size_t)SB_TOTAL, st, tmQ, tmK, tmV, tmdO, tmdQ, p));
   if (part) {
     const long long vecs = (long long)B * Skv * Hkv * 8;
     const long long half_elems = (long long)B * Skv * Hkv * kv_split * HDIM;

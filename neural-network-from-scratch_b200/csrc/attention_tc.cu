@@ -946,15 +946,19 @@ __global__ void __launch_bounds__(256)
 k_attn_bwd_prep(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta, __nv_bfloat16* __restrict__ dq,
                 int B, int H, int S, long long o_sb, long long o_ss, long long o_sh, long long q_sb, long long q_ss, long long q_sh) {
   nfb_pdl_enter();
-  const long long total = (long long)B * S * H * 8;
-  const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;   // stride is a multiple of 32
-  for (long long i0 = start - (start & 7); i0 < total; i0 += stride) {   // the 8 threads of a row stay together (shuffles below)
-    const long long i = i0 + (start & 7);
-    const int c = (int)(i & 7);
-    long long row = i >> 3;
-    const int hh = (int)(row % H); row /= H;
-    const int sidx = (int)(row % S);
-    const long long bb = row / S;
+  // 32-bit index arithmetic (the launcher checks B*S*H*8 < 2^31): four 64-bit divisions per row were most of this kernel's
+  // instructions (ncu: 62 % issue-active at 18 % of DRAM bandwidth)
+  const unsigned total = (unsigned)B * (unsigned)S * (unsigned)H * 8u;
+  const unsigned start = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;   // stride is a multiple of 32
+  for (unsigned i0 = start & ~7u; i0 < total; i0 += stride) {   // the 8 threads of a row stay together (shuffles below)
+    const unsigned i = i0 + (start & 7u);
+    const int c = (int)(i & 7u);
+    unsigned row = i >> 3;
+    const unsigned t1 = row / (unsigned)H;
+    const int hh = (int)(row - t1 * (unsigned)H);
+    const unsigned bq = t1 / (unsigned)S;
+    const int sidx = (int)(t1 - bq * (unsigned)S);
+    const long long bb = (long long)bq;
     if (dq) *reinterpret_cast<uint4*>(dq + bb * q_sb + (long long)sidx * q_ss + (long long)hh * q_sh + c * 8) = make_uint4(0, 0, 0, 0);
     if (delta) {
       const long long off = bb * o_sb + (long long)sidx * o_ss + (long long)hh * o_sh + c * 8;
@@ -1167,6 +1171,7 @@ int nfb_flash_bwd_tc(const void* q, const void* k, const void* v, const void* o,
   if (!delta && nfb_malloc(sizeof(float) * (size_t)B * H * S, (void**)&delta_buf)) { if (acc) nfb_free(acc); return -1; }
   {
     const long long items = (long long)B * S * H * 8;
+    if (items >= (1LL << 31)) { if (acc) nfb_free(acc); if (delta_buf) nfb_free(delta_buf); return NFB_FAIL("attention_tc backward: B*S*H = %lld rows exceed the preparation kernel's 32-bit index", items / 8); }
     nfb_launch_pdl(k_attn_bwd_prep, dim3((unsigned)nfb_grid_for(items, 256)), dim3(256), 0, st, (const __nv_bfloat16*)o, (const __nv_bfloat16*)dout,
                    delta_buf, dq_f32 ? (__nv_bfloat16*)nullptr : (__nv_bfloat16*)dq, B, H, S, (long long)o_sb, (long long)o_ss, (long long)o_sh,
                    (long long)q_sb, (long long)q_ss, (long long)q_sh);

@@ -303,14 +303,32 @@ k_colsum_fused(const T* __restrict__ x, int64_t R, int C, int64_t ld, int64_t ch
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // fixed-order sum of the chunk partials (one column per thread, loads unrolled 8-deep so they are in flight together)
+  // fixed-order sum of the chunk partials: thread (tx, ty) adds the partials ty, ty + 8, ... of its VEC columns (independent 16-byte
+  // loads, all in flight together), then the eight ty-sums meet in shared memory in ty order.  (One column per thread with 64
+  // partials, eight in flight, was eight dependent L2 round trips: ~5 us of an 11 us kernel, profiles/r02_ncu_attn_norm_colsum.txt.)
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (c0 < C) {
+#pragma unroll 8
+    for (unsigned b = threadIdx.y; b < gridDim.y; b += 8) {
+      const float4* tp = reinterpret_cast<const float4*>(tmp + (int64_t)b * C + c0);
+#pragma unroll
+      for (int k4 = 0; k4 < VEC / 4; ++k4) {
+        const float4 t = __ldcg(tp + k4);
+        acc[4 * k4] += t.x; acc[4 * k4 + 1] += t.y; acc[4 * k4 + 2] += t.z; acc[4 * k4 + 3] += t.w;
+      }
+    }
+  }
+  __syncthreads();   // (every thread of the last block is here: s_last is block-uniform)
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x * VEC + k] = acc[k];
+  __syncthreads();
   for (int cc = tid; cc < 32 * VEC; cc += 256) {
     const int col = blockIdx.x * 32 * VEC + cc;
     if (col < C) {
       float a = 0.f;
-      const float* tp = tmp + col;
-#pragma unroll 8
-      for (unsigned b = 0; b < gridDim.y; ++b) a += __ldcg(tp + (int64_t)b * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][cc];
       out[col] = accumulate ? out[col] + a : a;
     }
   }

@@ -7,7 +7,6 @@
 // Optional fusions: `res` (forward: s = x + res is normalised and written back to `sum_out`) and
 // `dres` (backward: dx += dres, the gradient arriving over the skip connection).
 #include "common.cuh"
-#include <stdio.h>
 #include <stdlib.h>
 
 #define WARPS_PER_BLOCK 4
@@ -176,142 +175,6 @@ k_norm_bwd(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __r
       float a = 0.f;
 #pragma unroll
       for (int ww = 0; ww < BWD_WARPS; ++ww) a += sh[ww][c];
-      partial[((int64_t)blockIdx.x * NP + which) * cols + c] = a;
-    }
-  }
-}
-
-// ---- backward, rows STAGED THROUGH SHARED MEMORY by bulk-async copies ------------------------------------------------------
-// The register-resident kernel above keeps 16 rows per SM in flight (16 warps x one row of x / dy in registers): at T = 4096 rows
-// every warp walks two rows one after the other and the kernel is latency-bound (ncu: 25 % of DRAM bandwidth, 21 % issue-active,
-// 15-16 us cold for 50 MB).  Here one 8-warp block per SM gives every warp a private ring of NB_SLOTS row slots (x | dres | dy,
-// 7.5 KB per row at 768 columns) filled by cp.async.bulk with mbarrier completion: up to 24 rows -- nearly the SM's whole share of
-// the tensor -- are in flight from the first cycle, no registers are held by loads, and the math is the one above.
-constexpr int NB_WARPS = 8;
-__device__ __forceinline__ uint32_t nb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void nb_bar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > 50000000u) { printf("nfb norm (staged): row copy wait timed out\n"); __trap(); }
-  }
-}
-template <int VPL, typename TX, typename TY, bool RMS>
-__global__ void __launch_bounds__(NB_WARPS * 32, 1)
-k_norm_bwd_staged(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                  const float* __restrict__ rstd_in, const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
-                  int64_t rows, int cols, float clip, __nv_bfloat16* __restrict__ dx_twin, int slots) {
-  nfb_pdl_enter();
-  constexpr int NP = RMS ? 1 : 2;
-  extern __shared__ __align__(128) unsigned char nb_sm[];
-  __shared__ __align__(8) unsigned long long bars[NB_WARPS][4];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t warp_global = (int64_t)blockIdx.x * NB_WARPS + w;
-  const int64_t nwarps = (int64_t)gridDim.x * NB_WARPS;
-  const float inv_n = 1.f / (float)cols;
-  const uint32_t xb = (uint32_t)cols * (uint32_t)sizeof(TX), gb = (uint32_t)cols * (uint32_t)sizeof(TY);
-  const uint32_t slot_bytes = xb + (dres ? xb : 0u) + gb;      // x | dres | dy ; all multiples of 16 (the launcher checks)
-  unsigned char* my = nb_sm + (size_t)w * slots * slot_bytes;
-  if (lane == 0) {
-    for (int sl = 0; sl < slots; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nb_smem_u32(&bars[w][sl])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int64_t n_my = warp_global < rows ? (rows - warp_global + nwarps - 1) / nwarps : 0;
-  auto issue = [&](int64_t i) {   // lane 0: row i of this warp -> slot i % slots
-    const int sl = (int)(i % slots);
-    const int64_t row = warp_global + i * nwarps;
-    const uint32_t bar = nb_smem_u32(&bars[w][sl]), dst = nb_smem_u32(my + (size_t)sl * slot_bytes);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's generic reads of this slot precede the async write
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(x + row * cols), "r"(xb), "r"(bar) : "memory");
-    if (dres) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + xb), "l"(dres + row * cols), "r"(xb), "r"(bar) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + xb + (dres ? xb : 0u)), "l"(dy + row * cols), "r"(gb), "r"(bar) : "memory");
-  };
-  if (lane == 0) for (int64_t i = 0; i < n_my && i < slots; ++i) issue(i);
-  f4 dg[VPL], db[RMS ? 1 : VPL];
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) dg[k] = {0.f, 0.f, 0.f, 0.f};
-  if (!RMS) {
-#pragma unroll
-    for (int k = 0; k < (RMS ? 1 : VPL); ++k) db[k] = {0.f, 0.f, 0.f, 0.f};
-  }
-  for (int64_t i = 0; i < n_my; ++i) {
-    const int64_t row = warp_global + i * nwarps;
-    const int sl = (int)(i % slots);
-    const float mean = (RMS || !mean_in) ? 0.f : mean_in[row];
-    const float rstd = rstd_in[row];
-    const unsigned char* sb = my + (size_t)sl * slot_bytes;
-    const TX* sx = reinterpret_cast<const TX*>(sb);
-    const TX* sr = reinterpret_cast<const TX*>(sb + xb);
-    const TY* sg = reinterpret_cast<const TY*>(sb + xb + (dres ? xb : 0u));
-    nb_bar_wait(nb_smem_u32(&bars[w][sl]), (uint32_t)((i / slots) & 1));
-    f4 xv[VPL], gv[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = k * 128 + lane * 4;
-      if (c < cols) { xv[k] = ld4<TX>(sx + c); gv[k] = ld4<TY>(sg + c); }
-      else { xv[k] = {mean, mean, mean, mean}; gv[k] = {0.f, 0.f, 0.f, 0.f}; }
-    }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = k * 128 + lane * 4;
-      const float4 gm = (gamma && c < cols) ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
-      xv[k] = {(xv[k].x - mean) * rstd, (xv[k].y - mean) * rstd, (xv[k].z - mean) * rstd, (xv[k].w - mean) * rstd};
-      dg[k].x += gv[k].x * xv[k].x; dg[k].y += gv[k].y * xv[k].y; dg[k].z += gv[k].z * xv[k].z; dg[k].w += gv[k].w * xv[k].w;
-      if (!RMS) { db[k].x += gv[k].x; db[k].y += gv[k].y; db[k].z += gv[k].z; db[k].w += gv[k].w; }
-      gv[k] = {gv[k].x * gm.x, gv[k].y * gm.y, gv[k].z * gm.z, gv[k].w * gm.w};
-      s1 += (gv[k].x + gv[k].y) + (gv[k].z + gv[k].w);
-      s2 += (gv[k].x * xv[k].x + gv[k].y * xv[k].y) + (gv[k].z * xv[k].z + gv[k].w * xv[k].w);
-    }
-    const float m1 = RMS ? 0.f : warp_sum(s1) * inv_n;
-    const float m2 = warp_sum(s2) * inv_n;
-    f4 o[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = k * 128 + lane * 4;
-      o[k].x = rstd * (gv[k].x - m1 - xv[k].x * m2);
-      o[k].y = rstd * (gv[k].y - m1 - xv[k].y * m2);
-      o[k].z = rstd * (gv[k].z - m1 - xv[k].z * m2);
-      o[k].w = rstd * (gv[k].w - m1 - xv[k].w * m2);
-      if (dres && c < cols) {
-        const f4 r = ld4<TX>(sr + c);
-        o[k].x += r.x; o[k].y += r.y; o[k].z += r.z; o[k].w += r.w;
-      }
-    }
-    // the slot has been read: refill it with this warp's row i + slots before the stores go out
-    __syncwarp();
-    if (lane == 0 && i + slots < n_my) issue(i + slots);
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = k * 128 + lane * 4;
-      if (c < cols) {
-        if (clip > 0.f) {
-          o[k].x = fminf(fmaxf(o[k].x, -clip), clip); o[k].y = fminf(fmaxf(o[k].y, -clip), clip);
-          o[k].z = fminf(fmaxf(o[k].z, -clip), clip); o[k].w = fminf(fmaxf(o[k].w, -clip), clip);
-        }
-        st4<TX>(dx + row * cols + c, o[k]);
-        if (dx_twin) st4<__nv_bfloat16>(dx_twin + row * cols + c, o[k]);
-      }
-    }
-  }
-  if (!partial) return;
-  __syncthreads();   // every warp is done with its slots: the ring becomes the [warp][columns] scratch of the block reduction
-  float* sh = reinterpret_cast<float*>(nb_sm);
-#pragma unroll
-  for (int which = 0; which < NP; ++which) {
-    if (which) __syncthreads();
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const f4 a = which == 0 ? dg[k] : db[RMS ? 0 : k];
-      *reinterpret_cast<float4*>(&sh[w * (VPL * 128) + k * 128 + lane * 4]) = make_float4(a.x, a.y, a.z, a.w);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-      float a = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < NB_WARPS; ++ww) a += sh[ww * (VPL * 128) + c];
       partial[((int64_t)blockIdx.x * NP + which) * cols + c] = a;
     }
   }
@@ -515,23 +378,6 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
   }
   if (grid < 1) grid = 1;
   constexpr int NP = RMS ? 1 : 2;
-  // rows staged through shared memory (k_norm_bwd_staged): one 8-warp block per SM, 2-3 row slots per warp
-  static const bool staged_on = !(getenv("NFB_NORM_STAGED") && atoi(getenv("NFB_NORM_STAGED")) == 0);
-  int slots = 0;
-  size_t staged_smem = 0;
-  if (staged_on && vpl > 0 && rows >= 4LL * nfb_sm_count()) {
-    const size_t xb = (size_t)cols * sizeof(TX), gb = (size_t)cols * sizeof(TY);
-    const size_t slot_bytes = xb + (dres ? xb : 0) + gb;
-    const bool aligned = xb % 16 == 0 && gb % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 && (!dres || (uintptr_t)dres % 16 == 0);
-    int fit = (int)((size_t)200 * 1024 / ((size_t)NB_WARPS * slot_bytes));
-    if (fit > 3) fit = 3;
-    if (aligned && fit >= 2 && (size_t)NB_WARPS * fit * slot_bytes >= (size_t)NB_WARPS * vpl * 128 * sizeof(float)) {
-      slots = fit;
-      staged_smem = (size_t)NB_WARPS * slots * slot_bytes;
-      const int64_t blocks = nfb_cdiv(rows, NB_WARPS);
-      grid = (int)(blocks < nfb_sm_count() ? blocks : nfb_sm_count());
-    }
-  }
   float* partial = nullptr;
   bool need_params = dgamma || dbeta;
   // With an auxiliary stream the (tiny, optimizer-only) parameter reduction leaves the critical path: the block partials go
@@ -555,15 +401,7 @@ static int norm_bwd_t(const void* dy, const void* x, const float* gamma, const f
     if (w->used && w->epoch == nfb_capture_epoch()) NFB_CUDA(cudaStreamWaitEvent(s, w->done, 0));
     partial = w->buf;
   } else if (need_params && nfb_malloc(sizeof(float) * part_elems, (void**)&partial)) return -1;
-#define LB(V)                                                                                                                                  \
-  do {                                                                                                                                         \
-    if (slots) {                                                                                                                               \
-      static bool configured = false;                                                                                                          \
-      if (!configured) { NFB_CUDA(cudaFuncSetAttribute(k_norm_bwd_staged<V, TX, TY, RMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; } \
-      nfb_launch_pdl(k_norm_bwd_staged<V, TX, TY, RMS>, dim3(grid), dim3(NB_WARPS * 32), staged_smem, s, (const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin, slots); \
-    } else                                                                                                                                     \
-      nfb_launch_pdl(k_norm_bwd<V, TX, TY, RMS>, dim3(grid), dim3(BWD_WARPS * 32), 0, s, (const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin); \
-  } while (0)
+#define LB(V) nfb_launch_pdl(k_norm_bwd<V, TX, TY, RMS>, dim3(grid), dim3(BWD_WARPS * 32), 0, s, (const TY*)dy, (const TX*)x, gamma, mean, rstd, (const TX*)dres, (TX*)dx, partial, rows, cols, clip, (__nv_bfloat16*)dx_twin)
   switch (vpl) {
     case 1: LB(1); break;
     case 2: LB(2); break;

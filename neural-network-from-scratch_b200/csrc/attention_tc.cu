@@ -43,16 +43,11 @@ struct AttnTcParams {
   const float* key_mask;
   unsigned long long* timeline;   // debug: clock64 stamps of CTA (0,0) (NULL in production)
   int kv_group;                   // query heads per key/value head (grouped-query attention): K/V maps have H / kv_group heads
-  int n_pairs, n_items;           // forward: query-tile pairs per (b, h) and items = n_pairs * B * H; a CTA works through several items
 };
 
 // ---------------------------------------------------------------- PTX helpers (same conventions as gemm_tc.cu)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_reinit(uint64_t* bar, uint32_t count) {   // a barrier that has been used: invalidate, then initialise
-  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -217,8 +212,16 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool causal = (p.mask_mode & 1) != 0;
-  const int nbh = p.B * p.H, npairs = p.n_pairs;
+  // 1-D grid, tile-pair-major; causal: the last tile pairs see the most keys -- ALL of those CTAs are scheduled first
+  // (longest-processing-time order over the 148 single-CTA SMs)
+  const int nbh = p.B * p.H, npairs = (int)gridDim.x / nbh;
+  const int pidx = (int)blockIdx.x / nbh, bh = (int)blockIdx.x % nbh, b = bh / p.H, h = bh % p.H;
+  const int pair = causal ? (npairs - 1 - pidx) : pidx;
+  const int q0A = pair * 2 * TILE_Q, q0B = q0A + TILE_Q;
   const int nkv_all = (p.Skv + TILE_K - 1) / TILE_K;
+  const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
+  const int nB = (q0B < p.S) ? (causal ? min(nkv_all, q0B / TILE_K + 1) : nkv_all) : 0;
+  const int nMax = max(nA, nB);
   if (threadIdx.x == 0) tl_cta(p, 0);
 
   if (warp == 8 && lane == 0) {
@@ -248,35 +251,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   nfb_pdl_wait();      // everything above overlapped the previous kernel's tail
   nfb_pdl_trigger();
   if (threadIdx.x == 0) tl(p, 0);
-
-  // ---- items.  Item k = (tile pair, b, h), pair-major; causal: the pairs that see the most keys come first.  The grid is at most one
-  // CTA per SM and CTA c takes items c, 2G-1-c, 2G+c, 4G-1-c, ... (a snake over the G CTAs: with items sorted by work, every CTA gets
-  // the same load to within one item -- B8 H12 S512 causal: 96 four-block pairs + 96 two-block pairs on 148 CTAs = four blocks each),
-  // paying barrier / TMEM / descriptor set-up once instead of once per pair and with no second wave of CTAs.  Between two items the
-  // CTA synchronises and re-initialises its mbarriers, so every phase count below starts from zero per item.
-  const int G = (int)gridDim.x;
-  for (int rnd = 0;; ++rnd) {
-  const int item = (rnd & 1) ? (rnd + 1) * G - 1 - (int)blockIdx.x : rnd * G + (int)blockIdx.x;
-  if (item >= p.n_items) break;
-  if (rnd > 0) {
-    tc_fence_before();
-    __syncthreads();   // every role is done with the previous item: its loads landed, its products retired (the MMA thread waited for
-                       // the last commit), its output is stored
-    if (warp == 8 && lane == 0) {
-      mbar_reinit(q_full, 1);
-      for (int s = 0; s < KV_STAGES; ++s) { mbar_reinit(&kv_full[s], 1); mbar_reinit(&kv_empty[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_reinit(&s_full[s], 1); mbar_reinit(&p_full[s], 128); mbar_reinit(&pv_done[s], 1); }
-      fence_barrier_init();
-    }
-    __syncthreads();
-    tc_fence_after();
-  }
-  const int pidx = item / nbh, bh = item % nbh, b = bh / p.H, h = bh % p.H;
-  const int pair = causal ? (npairs - 1 - pidx) : pidx;
-  const int q0A = pair * 2 * TILE_Q, q0B = q0A + TILE_Q;
-  const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
-  const int nB = (q0B < p.S) ? (causal ? min(nkv_all, q0B / TILE_K + 1) : nkv_all) : 0;
-  const int nMax = max(nA, nB);
 
   if (warp == 8) {
     // ===================== TMA producer (lane 0) + key-mask staging (all lanes) =====================
@@ -355,8 +329,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         umma_commit(&kv_empty[st]);   // every product that reads K / V block i has been issued
         tl(p, 19 + 4 * i);
       }
-      // the last commit has LANDED before this thread reaches the end-of-item barrier (the barriers are re-initialised behind it)
-      if (nMax > 0) mbar_wait(&kv_empty[(nMax - 1) % KV_STAGES], ((nMax - 1) / KV_STAGES) & 1);
     }
   } else {
     // ===================== softmax groups (thread = query row) =====================
@@ -517,7 +489,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (p.lse && qi < p.S) p.lse[(long long)bh * p.S + qi] = (m2 + log2f(lc)) * 0.6931471805599453f;
     }
   }
-  }   // items
 
   if (threadIdx.x == 0) tl(p, 1);
   tc_fence_before();
@@ -1160,11 +1131,7 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
     NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
-  p.n_pairs = (int)nfb_cdiv(S, 2 * TILE_Q);
-  p.n_items = p.n_pairs * B * H;
-  // at most one CTA per SM, each working through several (tile pair, b, h) items (NFB_ATTN_PERSISTENT=0: one CTA per item)
-  static const bool persistent = !(getenv("NFB_ATTN_PERSISTENT") && atoi(getenv("NFB_ATTN_PERSISTENT")) == 0);
-  dim3 grid((unsigned)((persistent && p.n_items > nfb_sm_count()) ? nfb_sm_count() : p.n_items));
+  dim3 grid((unsigned)(nfb_cdiv(S, 2 * TILE_Q) * B * H));
   poly_defaults();
   if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<1>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<2>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));

@@ -222,7 +222,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int nA = causal ? min(nkv_all, q0A / TILE_K + 1) : nkv_all;
   const int nB = (q0B < p.S) ? (causal ? min(nkv_all, q0B / TILE_K + 1) : nkv_all) : 0;
   const int nMax = max(nA, nB);
-  if (threadIdx.x == 0) tl_cta(p, 0);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -250,7 +249,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   nfb_pdl_wait();      // everything above overlapped the previous kernel's tail
   nfb_pdl_trigger();
-  if (threadIdx.x == 0) tl(p, 0);
+  if (threadIdx.x == 0) { tl(p, 0); tl_cta(p, 0); }   // (debug stamps: the CTA's span starts behind the dependency wait)
 
   if (warp == 8) {
     // ===================== TMA producer (lane 0) + key-mask staging (all lanes) =====================

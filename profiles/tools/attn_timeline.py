@@ -26,8 +26,11 @@ for g in (0, 1):
         print(f"softmax g{g} blk {i}: s_full {s[0]-t0} | ld {s[1]-s[0]} | max {s[2]-s[1]} | exp+sts {s[3]-s[2]} | arrive {s[4]-s[3]}")
 c = t[256:256 + 3 * 192].reshape(-1, 3)
 base = c[:, 0].min()
-print("CTA schedule (us from first start): cta start end sm")
+print("CTA schedule (us from first start; start = behind the dependency wait): cta start end duration sm")
 order = np.argsort(c[:, 0])
-for idx in list(order[:6]) + list(order[-50::5]):
-    print(idx, (c[idx, 0] - base) / 1e3, (c[idx, 1] - base) / 1e3, c[idx, 2])
+for idx in list(order[:4]) + list(order[96:100]) + list(order[-50::6]):
+    print(idx, (c[idx, 0] - base) / 1e3, (c[idx, 1] - base) / 1e3, round((c[idx, 1] - c[idx, 0]) / 1e3, 2), c[idx, 2])
+dur = (c[:, 1] - c[:, 0]) / 1e3
+print("durations us: heavy CTAs (0..95) mean %.2f min %.2f max %.2f | light, first wave (96..147) mean %.2f | light, second wave (148..191) mean %.2f" % (
+    dur[:96].mean(), dur[:96].min(), dur[:96].max(), dur[96:148].mean(), dur[148:192].mean()))
 print("last end us:", (c[:, 1].max() - base) / 1e3, " distinct SMs:", len(set(c[:, 2])))

@@ -501,334 +501,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 
 // =====================================================================================================================
-// FORWARD, short sequences (S, Skv <= 512): ONE CTA per (b, h), K/V blocks RESIDENT.  The pair kernel above pays ~5.8 us per
-// CTA on top of its 1.9 us rounds (pipeline fill, a last round in which one warp group idles, output drain) and launches
-// 2 CTAs per (b, h) whose causal ranges differ 2:1 (profiles/r02_attn_timeline.txt).  Here all (at most four) K/V blocks of the
-// head are staged ONCE, and the two softmax warp groups each walk TWO query tiles one after the other -- group 0 tiles
-// nq-1 and nq-4, group 1 tiles nq-2 and nq-3, i.e. 4 + 1 and 3 + 2 key blocks under a causal mask: equal work, no idle
-// group, one fill and one drain per head.  A group's query tile is reloaded into its single buffer once the last QK^T of
-// its first tile has retired (q_free); its step counter t runs over both tiles, so the s_full / p_full / pv_done phases
-// simply continue.  The softmax block body is the one of the kernel above.
-constexpr int RS_STAGES = 4;
-constexpr int RS_K = 32768;                        // SM_Q (2 x 16 KB) in front, as above
-constexpr int RS_V = RS_K + RS_STAGES * 16384;
-constexpr int RS_P = RS_V + RS_STAGES * 16384;     // 2 groups x 32 KB
-constexpr int RS_BAR = RS_P + 65536;
-constexpr int RS_MASK = RS_BAR + 256;              // RS_STAGES x 128 fp32
-constexpr int RS_TOTAL = RS_MASK + RS_STAGES * 512 + 768;   // = 232448 = the 227 KB a block may have; <= 768 B of alignment slack
-
-template <int POLY>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-k_flash_fwd_res(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                const AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  if (threadIdx.x == 0 && (smem - smem_raw) > 768) { printf("nfb attention_tc (resident forward): dynamic shared memory base misaligned by %d\n", (int)(smem - smem_raw)); __trap(); }
-  uint64_t* bars = (uint64_t*)(smem + RS_BAR);
-  uint64_t* q_full = bars;            // 2 (per group; second phase = the group's second tile)
-  uint64_t* q_free = bars + 2;        // 2 (per group): the last QK^T of the first tile has retired
-  uint64_t* kv_full = bars + 4;       // RS_STAGES, used once each
-  uint64_t* s_full = bars + 8;        // 2
-  uint64_t* p_full = bars + 10;       // 2 (128 arrivals)
-  uint64_t* pv_done = bars + 12;      // 2
-  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool causal = (p.mask_mode & 1) != 0;
-  const int bh = (int)blockIdx.x, b = bh / p.H, h = bh % p.H;
-  const int nq = (p.S + TILE_Q - 1) / TILE_Q, nkv_all = (p.Skv + TILE_K - 1) / TILE_K;   // both <= 4 (the launcher checks)
-  const int tile0[2] = {nq - 1, nq - 2}, tile1[2] = {nq - 4, nq - 3};                      // < 0: none
-  int n0[2], n1[2], T[2];
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    n0[g] = tile0[g] < 0 ? 0 : (causal ? min(nkv_all, tile0[g] + 1) : nkv_all);
-    n1[g] = tile1[g] < 0 ? 0 : (causal ? min(nkv_all, tile1[g] + 1) : nkv_all);
-    T[g] = n0[g] + n1[g];
-  }
-  const int nkv = max(n0[0], max(n0[1], max(n1[0], n1[1])));   // key blocks any tile of this head needs
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&q_full[s], 1);
-      mbar_init(&q_free[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&pv_done[s], 1);
-    }
-    for (int s = 0; s < RS_STAGES; ++s) mbar_init(&kv_full[s], 1);
-    fence_barrier_init();
-  }
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  nfb_pdl_wait();
-  nfb_pdl_trigger();
-
-  if (warp == 8) {
-    // ===================== TMA producer (lane 0) + key-mask staging (all lanes) =====================
-    if (lane == 0) {
-      for (int g = 0; g < 2; ++g)
-        if (n0[g] > 0) {
-          mbar_expect_tx(&q_full[g], 16384u);
-          tma_load_4d(smem + SM_Q + g * 16384, &tmQ, &q_full[g], 0, h, tile0[g] * TILE_Q, b);
-        }
-    }
-    const float* kmask_p = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
-    float* smask = reinterpret_cast<float*>(smem + RS_MASK);
-    for (int j = 0; j < nkv; ++j) {
-      const int j0 = j * TILE_K;
-      if (kmask_p || j0 + TILE_K > p.Skv) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kj = j0 + lane * 4 + e;
-          smask[j * 128 + lane * 4 + e] = kj < p.Skv ? (kmask_p ? __ldg(kmask_p + kj) * LOG2E : 0.f) : -INFINITY;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_expect_tx(&kv_full[j], 32768u);   // release: the mask words above are visible to whoever acquires kv_full
-        tma_load_4d(smem + RS_K + j * 16384, &tmK, &kv_full[j], 0, h / p.kv_group, j0, b);
-        tma_load_4d(smem + RS_V + j * 16384, &tmV, &kv_full[j], 0, h / p.kv_group, j0, b);
-      }
-    }
-    if (lane == 0) {
-      // second query tiles: group 1's first tile is the shorter one under a causal mask, so its buffer frees first
-      for (int gg = 0; gg < 2; ++gg) {
-        const int g = 1 - gg;
-        if (n1[g] > 0) {
-          mbar_wait(&q_free[g], 0);
-          mbar_expect_tx(&q_full[g], 16384u);
-          tma_load_4d(smem + SM_Q + g * 16384, &tmQ, &q_full[g], 0, h, tile1[g] * TILE_Q, b);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(0, 0, TILE_Q, TILE_K);   // S = Q K^T : A, B K-major, N = 128
-      const uint32_t idesc_o = make_idesc(0, 1, TILE_Q, HDIM);     // O += P V  : A K-major, B MN-major, N = 64
-      const uint32_t sQ = smem_u32(smem + SM_Q), sK = smem_u32(smem + RS_K), sV = smem_u32(smem + RS_V), sP = smem_u32(smem + RS_P);
-      auto issue_s = [&](int g, int st) {
-#pragma unroll
-        for (int k = 0; k < HDIM / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(g * 128), make_smem_desc(sQ + g * 16384 + k * 32, 16, 1024),
-                    make_smem_desc(sK + st * 16384 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-      };
-      auto issue_pv = [&](int g, int st, bool acc) {
-#pragma unroll
-        for (int k = 0; k < TILE_K / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(256 + g * 64), make_smem_desc(sP + g * 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(sV + st * 16384 + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
-      };
-      mbar_wait(&kv_full[0], 0);
-      for (int g = 0; g < 2; ++g)
-        if (T[g] > 0) {
-          mbar_wait(&q_full[g], 0);
-          tc_fence_after();
-          issue_s(g, 0);
-          umma_commit(&s_full[g]);
-          if (n0[g] == 1 && n1[g] > 0) umma_commit(&q_free[g]);   // that was the only QK^T of the first tile
-        }
-      const int maxT = max(T[0], T[1]);
-      for (int t = 0; t < maxT; ++t) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (t >= T[g]) continue;
-          const int blk = t < n0[g] ? t : t - n0[g];
-          mbar_wait(&p_full[g], t & 1);
-          tc_fence_after();
-          if (t + 1 < T[g]) {
-            // P_g(t) is in shared memory, so S_g(t) has been consumed: the group's next score block goes out FIRST
-            const int nblk = t + 1 < n0[g] ? t + 1 : t + 1 - n0[g];
-            if (t + 1 == n0[g]) mbar_wait(&q_full[g], 1);   // the second tile's queries have landed
-            mbar_wait(&kv_full[nblk], 0);
-            tc_fence_after();
-            issue_s(g, nblk);
-            umma_commit(&s_full[g]);
-            if (t + 1 == n0[g] - 1 && n1[g] > 0) umma_commit(&q_free[g]);   // the last QK^T of the first tile is in flight
-          }
-          issue_pv(g, blk, blk > 0);
-          umma_commit(&pv_done[g]);
-        }
-      }
-    }
-  } else {
-    // ===================== softmax groups (thread = query row) =====================
-    const int g = warp >> 2, quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t sP_row = smem_u32(smem + RS_P) + (uint32_t)g * 32768u + (uint32_t)r * 128u;
-    const int sw = r & 7;
-    const float sl2 = p.scale * LOG2E;
-    const float* kmask = (p.mask_mode & 2) ? p.key_mask + (long long)b * p.Skv : nullptr;
-    int stp = 0;   // step of this group over both of its tiles
-    for (int which = 0; which < 2; ++which) {
-      const int tile = which == 0 ? tile0[g] : tile1[g];
-      const int n = which == 0 ? n0[g] : n1[g];
-      if (n == 0) continue;
-      const int q0 = tile * TILE_Q, qi = q0 + r;
-      float m2 = -INFINITY, l = 0.f;    // running maximum (log2 domain) and row sum
-      for (int blk = 0; blk < n; ++blk, ++stp) {
-        mbar_wait(&s_full[g], stp & 1);
-        tc_fence_after();
-        uint32_t sr[128];
-  #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + (uint32_t)(g * 128 + c * 32), sr + c * 32);
-        tmem_ld_wait();
-        float t[128];
-        const int j0 = blk * TILE_K;
-        const bool diag = causal && (j0 + TILE_K - 1 > q0);   // some (row, key) of this block has key > row
-        const bool tail = j0 + TILE_K > p.Skv;
-        float bm;
-        if (!diag && !tail && !kmask) {
-          // eight independent running maxima: a single chain of 127 dependent FMNMX would cost ~500 clk of pure latency
-          // (there are only two softmax warps per scheduler to hide it)
-          float mx[8];
-  #pragma unroll
-          for (int a = 0; a < 8; ++a) mx[a] = __uint_as_float(sr[a]);
-  #pragma unroll
-          for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], __uint_as_float(sr[j]));
-          bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * sl2;
-  #pragma unroll
-          for (int j = 0; j < 128; ++j) t[j] = __uint_as_float(sr[j]) * sl2;
-        } else if (!diag) {
-          // key mask and / or ragged tail, no causal diagonal: one FFMA per element with the staged log2-domain mask
-          // (-inf beyond Skv); 16-byte broadcast reads of the mask row
-          mbar_wait(&kv_full[blk], 0);   // acquire the producer's mask words (long complete: S(i) needed this stage)
-          const float4* sm4 = reinterpret_cast<const float4*>(smem + RS_MASK + blk * 512);
-          float mx[8];
-  #pragma unroll
-          for (int j4 = 0; j4 < 32; ++j4) {
-            const float4 mk = sm4[j4];
-            t[4 * j4 + 0] = fmaf(__uint_as_float(sr[4 * j4 + 0]), sl2, mk.x);
-            t[4 * j4 + 1] = fmaf(__uint_as_float(sr[4 * j4 + 1]), sl2, mk.y);
-            t[4 * j4 + 2] = fmaf(__uint_as_float(sr[4 * j4 + 2]), sl2, mk.z);
-            t[4 * j4 + 3] = fmaf(__uint_as_float(sr[4 * j4 + 3]), sl2, mk.w);
-          }
-  #pragma unroll
-          for (int a = 0; a < 8; ++a) mx[a] = t[a];
-  #pragma unroll
-          for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], t[j]);
-          bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        } else if (!tail && !kmask) {
-          // causal diagonal block: keys j0 + j > qi are REPLACED by -1e4 (two instructions per element)
-          const int lim = qi - j0;
-          const float neg = -1e4f * LOG2E;
-          float mx[8];
-  #pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            const float v = (j > lim) ? neg : __uint_as_float(sr[j]) * sl2;
-            t[j] = v;
-            if (j < 8) mx[j] = v; else mx[j & 7] = fmaxf(mx[j & 7], v);
-          }
-          bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        } else {
-          bm = -INFINITY;
-  #pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            const int kj = j0 + j;
-            float v = __uint_as_float(sr[j]) * sl2;
-            if (causal && kj > qi) v = -1e4f * LOG2E;          // the reference REPLACES masked scores by -1e4
-            if (kmask) v += (kj < p.Skv ? __ldg(kmask + kj) : 0.f) * LOG2E;
-            if (kj >= p.Skv) v = -INFINITY;
-            t[j] = v;
-            bm = fmaxf(bm, v);
-          }
-        }
-        // lazy rescale: advance the maximum only when some row of this warp grew by more than 2^8
-        const bool need = (bm - m2) > 8.f;   // also true on the first block (m2 = -inf)
-        const bool rescale = __any_sync(0xffffffffu, need);
-        float c = 1.f;
-        if (rescale) {
-          const float m_new = fmaxf(m2, bm);
-          c = (m2 == -INFINITY) ? 0.f : ex2(m2 - m_new);
-          l *= c;
-          m2 = m_new;
-        }
-        // S_g(i) was issued BEFORE P_g(i-1).V(i-1): wait for that product before overwriting its P operand (and before
-        // touching O_g); it has normally retired long before the row maximum above is known
-        if (stp > 0) { mbar_wait(&pv_done[g], (stp - 1) & 1); tc_fence_after(); }
-        float rsa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        // P (bf16) -> shared memory, K-major SWIZZLE_128B: 16-byte slot c of row r at c ^ (r & 7), two 64-key panels
-  #pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          uint32_t w[4];
-  #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2_mix<POLY>(t[cc * 8 + 2 * e] - m2, e), p1 = ex2_mix<POLY>(t[cc * 8 + 2 * e + 1] - m2, e);
-            rsa[(2 * e) & 7] += p0;
-            rsa[(2 * e + 1) & 7] += p1;
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            w[e] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)(cc >> 3) * 16384u + (uint32_t)(((cc & 7) ^ sw) * 16)),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        }
-        l += ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3])) + ((rsa[4] + rsa[5]) + (rsa[6] + rsa[7]));
-        // the (rare) rescale of O_g comes last, when the score registers are dead.  O_g holds the products of blocks < i,
-        // all complete (pv_done above); P.V of this block is only issued after the arrive below.
-        if (rescale && blk > 0) {
-  #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t orr[32];
-            tmem_ld32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
-            tmem_ld_wait();
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * c);
-            tmem_st32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
-          }
-          tmem_st_wait();
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&p_full[g]);
-      }
-      {
-      mbar_wait(&pv_done[g], (stp - 1) & 1);
-      tc_fence_after();
-      const float lc = fmaxf(l, 1e-8f);   // the reference's 1e-8 floor (functional/activation.py:95)
-      const float inv = 1.f / lc;
-      __nv_bfloat16* orow = p.o + b * p.o_sb + h * p.o_sh + (long long)qi * p.o_ss;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t orr[32];
-        tmem_ld32(lane_addr + (uint32_t)(256 + g * 64 + cc * 32), orr);
-        tmem_ld_wait();
-        if (qi < p.S) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(orr[c * 8 + 2 * e]) * inv, __uint_as_float(orr[c * 8 + 2 * e + 1]) * inv);
-              w[e] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            *reinterpret_cast<uint4*>(orow + cc * 32 + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
-      if (p.lse && qi < p.S) p.lse[(long long)bh * p.S + qi] = (m2 + log2f(lc)) * 0.6931471805599453f;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-// =====================================================================================================================
 // BACKWARD.  One CTA per (batch, head, 128-key block j) -- 192 threads: warps 0-3 = elementwise group (thread = one
 // query row of the current 128-query block i), warp 4 = TMA producer, warp 5 = MMA issuer.  For every query block i
 // (i >= j when causal) five tensor-core products run on tiles that TMA delivers as plain [128 rows][64] SWIZZLE_128B
@@ -1458,25 +1130,8 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
     NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
-  poly_defaults();
-  // short sequences: one CTA per (b, h) with the K/V blocks resident (k_flash_fwd_res); NFB_ATTN_RESIDENT=0 keeps the pair kernel
-  static const bool resident_on = !(getenv("NFB_ATTN_RESIDENT") && atoi(getenv("NFB_ATTN_RESIDENT")) == 0);
-  if (resident_on && S <= 4 * TILE_Q && Skv <= 4 * TILE_K && S > TILE_Q) {
-    static bool res_configured = false;
-    if (!res_configured) {
-      NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_res<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL));
-      NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_res<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL));
-      NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_res<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL));
-      res_configured = true;
-    }
-    dim3 rgrid((unsigned)(B * H));
-    if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_res<1>, rgrid, dim3(ATC_THREADS), (size_t)RS_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-    else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_res<2>, rgrid, dim3(ATC_THREADS), (size_t)RS_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-    else NFB_CUDA(nfb_launch_pdl(k_flash_fwd_res<0>, rgrid, dim3(ATC_THREADS), (size_t)RS_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-    NFB_LAUNCH_CHECK();
-    return 0;
-  }
   dim3 grid((unsigned)(nfb_cdiv(S, 2 * TILE_Q) * B * H));
+  poly_defaults();
   if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<1>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<2>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   else NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<0>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));

@@ -96,15 +96,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// A operand in TENSOR MEMORY (lane = row, 16-bit elements packed two per 32-bit column in k order), B from shared memory
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -204,10 +195,7 @@ constexpr int SM_BAR = SM_P + 65536;             // barriers + TMEM slot
 constexpr int SM_MASK = SM_BAR + 256;            // KV_STAGES x 128 fp32: additive key mask (log2 domain) of the staged block; -inf beyond Skv
 constexpr int SM_TOTAL = SM_MASK + KV_STAGES * 512 + 1024;    // + alignment slack
 
-// TS: P goes to the P.V product through TENSOR memory (columns 384 + 64 g, bf16 pairs) instead of shared memory: per 128x128 block
-// that takes 32 KB of stores and 32 KB of MMA operand reads off the 128 B/clk shared-memory port, which the Q / K / V operand reads
-// of the same products already fill (the 12 MMAs of a block ran at ~108 clk each instead of 32-64, profiles/r02_attn_timeline.txt).
-template <int POLY, bool TS>
+template <int POLY>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const AttnTcParams p) {
@@ -305,14 +293,9 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       };
       auto issue_pv = [&](int g, int st, bool acc) {
 #pragma unroll
-        for (int k = 0; k < TILE_K / 16; ++k) {
-          if (TS)
-            umma_bf16_ts(tmem_base + (uint32_t)(256 + g * 64), tmem_base + (uint32_t)(384 + g * 64 + k * 8),
-                         make_smem_desc(sV + st * 16384 + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
-          else
-            umma_bf16(tmem_base + (uint32_t)(256 + g * 64), make_smem_desc(sP + g * 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(sV + st * 16384 + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < TILE_K / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(256 + g * 64), make_smem_desc(sP + g * 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(sV + st * 16384 + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -443,27 +426,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (i > 0) { mbar_wait(&pv_done[g], (i - 1) & 1); tc_fence_after(); }
       float rsa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       // P (bf16) -> shared memory, K-major SWIZZLE_128B: 16-byte slot c of row r at c ^ (r & 7), two 64-key panels
-      if (TS) {
-        // P (bf16 pairs) -> tensor memory columns 384 + 64 g: thread = row = TMEM lane, 32 packed columns per store
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const int cc = hf * 8 + c8;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float p0 = ex2_mix<POLY>(t[cc * 8 + 2 * e] - m2, e), p1 = ex2_mix<POLY>(t[cc * 8 + 2 * e + 1] - m2, e);
-              rsa[(2 * e) & 7] += p0;
-              rsa[(2 * e + 1) & 7] += p1;
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-              pk[c8 * 4 + e] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-          }
-          tmem_st32(lane_addr + (uint32_t)(384 + g * 64 + hf * 32), pk);
-        }
-        tmem_st_wait();
-      } else {
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) {
         uint32_t w[4];
@@ -477,7 +439,6 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (uint32_t)(cc >> 3) * 16384u + (uint32_t)(((cc & 7) ^ sw) * 16)),
                      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-      }
       }
       l += ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3])) + ((rsa[4] + rsa[5]) + (rsa[6] + rsa[7]));
       if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 3);
@@ -1164,20 +1125,16 @@ int nfb_flash_fwd_tc(const void* q, const void* k, const void* v, void* o, float
   p.timeline = g_attn_timeline;
   static bool configured = false;
   if (!configured) {
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    NFB_CUDA(cudaFuncSetAttribute(k_flash_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     configured = true;
   }
   dim3 grid((unsigned)(nfb_cdiv(S, 2 * TILE_Q) * B * H));
   poly_defaults();
-  // P through tensor memory (NFB_ATTN_P_TMEM=0: through shared memory, the round-1 path; the polynomial-exp2 variants keep it)
-  static const bool p_tmem = !(getenv("NFB_ATTN_P_TMEM") && atoi(getenv("NFB_ATTN_P_TMEM")) == 0);
-  if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<1, false>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-  else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<2, false>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-  else if (p_tmem) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<0, true>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
-  else NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<0, false>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  if (g_poly_fwd == 1) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<1>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  else if (g_poly_fwd == 2) NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<2>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
+  else NFB_CUDA(nfb_launch_pdl(k_flash_fwd_tc<0>, grid, dim3(ATC_THREADS), (size_t)SM_TOTAL, nfb_cur_stream(), tmQ, tmK, tmV, p));
   NFB_LAUNCH_CHECK();
   return 0;
 }

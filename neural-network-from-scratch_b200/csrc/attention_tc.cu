@@ -351,6 +351,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld_wait();
       if (quarter == 0 && lane == 0) tl(p, 64 + g * 64 + 8 * i + 1);
       float t[128];
+      float tmul = 1.f;   // exponent of element j = t[j] * tmul - m2
       const int j0 = i * TILE_K;
       const bool diag = causal && (j0 + TILE_K - 1 > (g == 0 ? q0A : q0B));   // some (row, key) of this block has key > row
       const bool tail = j0 + TILE_K > p.Skv;
@@ -364,8 +365,11 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], __uint_as_float(sr[j]));
         bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * sl2;
+        // the scores stay RAW: the scale rides in the FFMA that forms the exponent below (one instruction per element
+        // instead of a multiply here and a subtract there)
 #pragma unroll
-        for (int j = 0; j < 128; ++j) t[j] = __uint_as_float(sr[j]) * sl2;
+        for (int j = 0; j < 128; ++j) t[j] = __uint_as_float(sr[j]);
+        tmul = sl2;
       } else if (!diag) {
         // key mask and / or ragged tail, no causal diagonal: one FFMA per element with the staged log2-domain mask
         // (-inf beyond Skv); 16-byte broadcast reads of the mask row
@@ -431,7 +435,7 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2_mix<POLY>(t[cc * 8 + 2 * e] - m2, e), p1 = ex2_mix<POLY>(t[cc * 8 + 2 * e + 1] - m2, e);
+          const float p0 = ex2_mix<POLY>(fmaf(t[cc * 8 + 2 * e], tmul, -m2), e), p1 = ex2_mix<POLY>(fmaf(t[cc * 8 + 2 * e + 1], tmul, -m2), e);
           rsa[(2 * e) & 7] += p0;
           rsa[(2 * e + 1) & 7] += p1;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);

@@ -390,17 +390,19 @@ k_flash_fwd_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 8; j < 128; ++j) mx[j & 7] = fmaxf(mx[j & 7], t[j]);
         bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       } else if (!tail && !kmask) {
-        // causal diagonal block: keys j0 + j > qi are REPLACED by -1e4 (two instructions per element)
+        // causal diagonal block: keys j0 + j > qi are REPLACED by -1e4 -- as the RAW score whose scaled value that is, so this block
+        // too leaves the scale to the exponent's FFMA (compare + select per element, no multiply)
         const int lim = qi - j0;
-        const float neg = -1e4f * LOG2E;
+        const float negraw = -1e4f / p.scale;
         float mx[8];
 #pragma unroll
         for (int j = 0; j < 128; ++j) {
-          const float v = (j > lim) ? neg : __uint_as_float(sr[j]) * sl2;
+          const float v = (j > lim) ? negraw : __uint_as_float(sr[j]);
           t[j] = v;
           if (j < 8) mx[j] = v; else mx[j & 7] = fmaxf(mx[j & 7], v);
         }
-        bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+        bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * sl2;
+        tmul = sl2;
       } else {
         bm = -INFINITY;
 #pragma unroll

@@ -190,12 +190,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 2))
-    warm = 1 if args.warmup > 0 else 0
-    if os.path.isdir(REF_DIR):
-        r = cpu_reference_run(steps, warm, BATCH)
-    else:
-        r = cpu_oracle_run(steps, warm, BATCH)
+    # EXACTLY --steps timed steps after --warmup untimed ones, like the other arm; each step is a bounded sample of the workload
+    # (whole sequences of the batch) sized from a one-sequence probe so that the run ends within a few minutes
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    run = cpu_reference_run if os.path.isdir(REF_DIR) else cpu_oracle_run
+    probe = run(1, 1, 1)
+    budget_s = float(os.environ.get("NFB200_REFERENCE_BUDGET_S", "170"))
+    sample = int(budget_s / ((steps + warm) * max(probe["step_s"], 1e-3)))
+    sample = max(1, min(BATCH, sample))
+    r = run(steps, warm, sample)
     desc = r["sample"]
     line = {"impl": "reference", "metric": "training tokens/sec", "value": r["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

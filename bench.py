@@ -195,7 +195,7 @@ def run_reference(args):
     steps, warm = max(1, args.steps), max(0, args.warmup)
     run = cpu_reference_run if os.path.isdir(REF_DIR) else cpu_oracle_run
     probe = run(1, 1, 1)
-    budget_s = float(os.environ.get("NFB200_REFERENCE_BUDGET_S", "170"))
+    budget_s = float(os.environ.get("NFB200_REFERENCE_BUDGET_S", "120"))
     sample = int(budget_s / ((steps + warm) * max(probe["step_s"], 1e-3)))
     sample = max(1, min(BATCH, sample))
     r = run(steps, warm, sample)
